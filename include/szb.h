@@ -1,0 +1,186 @@
+/* szb.h -- C-ABI of the B200-native batched Newton / Rosenbrock backend for Solverz.
+ *
+ * One shared library, libszb.so, exports exactly the entry points below.  They are what a
+ * binding inside the reference would call in place of the three native pieces on its hot
+ * path (all paths relative to the Solverz 0.8.5 tree):
+ *
+ *   reference piece                                              replaced by
+ *   ------------------------------------------------------------ ---------------------------
+ *   generated F_/inner_F<N> (@njit)                              szb_eval_F
+ *     code_printer/python/module/module_printer.py:683-870
+ *   generated J_/inner_J<N> + coo_array(...).tocsc()             szb_eval_J
+ *     module_printer.py:140-458, sym_algebra/symbols.py:297-298
+ *   solve(A,b) -> scipy spsolve (SuperLU gssv)                   szb_lu_refactor + szb_lu_solve
+ *     solvers/laesolver.py:11-15
+ *   lu_decomposition(A) -> splu; .solve(b)                       szb_lu_refactor ; szb_lu_solve
+ *     solvers/laesolver.py:18-45
+ *   nr_method main loop                                          szb_newton / szb_newton_host
+ *     solvers/nlaesolver/nr.py:45-64
+ *   Rodas step loop                                              szb_rodas
+ *     solvers/daesolver/rodas/rodas.py:123-327
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary.
+ *   - every function returns 0 on success or a negative SZB_E* code and never throws; the
+ *     text of the last error of a handle is returned by szb_last_error (thread-unsafe per
+ *     handle, like the reference's module-global scratch buffers).
+ *   - run-time numerical failure is soft, as in the reference (nr.py:50-52, rodas.py:127-135):
+ *     it is reported per scenario in flags[] and never as an error code.
+ *   - layouts: scenario-major, row-major.  Y[B][n], F[B][n], JV[B][nnz_j] (CSC slot order of
+ *     the frozen pattern, jac.py:106-126 after duplicate summation), per-scenario parameter
+ *     p[B][len], shared parameter p[len].
+ *   - ownership: the caller owns every buffer passed to szb_bind and must keep it alive until
+ *     it is re-bound or the handle is destroyed.  The library owns only the workspaces it
+ *     allocates in szb_create / szb_set_batch and frees them in szb_destroy.
+ *   - all kernels are stream-ordered on the stream given; the only host synchronisations are
+ *     inside szb_newton / szb_rodas (reading the active-scenario count) and the *_host calls.
+ */
+#ifndef SZB_H
+#define SZB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SZB_API __attribute__((visibility("default")))
+#else
+#define SZB_API
+#endif
+
+#define SZB_ABI_VERSION 1
+
+/* error codes */
+#define SZB_OK 0
+#define SZB_EINVAL (-1)   /* bad argument / unbound slot                        */
+#define SZB_ECUDA (-2)    /* CUDA runtime error, see szb_last_error             */
+#define SZB_ENOMEM (-3)   /* host or device allocation failed                   */
+#define SZB_EMODEL (-4)   /* generated model library missing / ABI mismatch     */
+#define SZB_ESTATE (-5)   /* call sequence error (e.g. solve before refactor)   */
+
+/* per-scenario status written to flags[] by szb_newton / szb_rodas */
+#define SZB_FLAG_CONVERGED 0
+#define SZB_FLAG_MAXIT 1      /* nr.py:50-52                                   */
+#define SZB_FLAG_SINGULAR 2   /* zero / non-finite static pivot                */
+#define SZB_FLAG_DTMIN 3      /* rodas.py:127-130                              */
+#define SZB_FLAG_REJECTS 4    /* rodas.py:131-135                              */
+#define SZB_FLAG_NAN 5        /* NaN/Inf residual                              */
+#define SZB_FLAG_RUNNING 6    /* not finished (internal)                       */
+#define SZB_FLAG_NOTCONV 7    /* loop left with max|F| == tol (not < tol)      */
+
+/* szb_bind slots */
+#define SZB_SLOT_Y 0        /* double[B][n]     unknowns, updated in place               */
+#define SZB_SLOT_F 1        /* double[B][n]     residual                                 */
+#define SZB_SLOT_JV 2       /* double[B][nnz_j] Jacobian values                          */
+#define SZB_SLOT_RHS 3      /* double[B][n]     right-hand side / solution of lu_solve   */
+#define SZB_SLOT_PARAM0 16  /* + index in the model's parameter table                    */
+
+#define SZB_DTYPE_F64 0
+#define SZB_DTYPE_I32 1
+
+typedef struct szb_handle szb_handle;
+typedef void* szb_stream; /* cudaStream_t */
+
+/* Result of the host-side symbolic analysis (solverz_b200/lu/symbolic.py).  All arrays are
+ * host pointers, copied to the device by szb_create.  Index arrays are int32. */
+typedef struct szb_lu_symbolic {
+  int32_t n, nnz_a, ns;
+  int32_t lu_size, cb_size, cv_size; /* doubles per scenario: factors, contribution ws, fwd ws */
+  int32_t n_warp_lists, n_top, f_warp_max, f_top_max, s_warp_max, s_top_max;
+  const int32_t* rowp;      /* [n]   pivot k <- original row     */
+  const int32_t* colp;      /* [n]   pivot k <- original column  */
+  const int32_t* sn_piv0;   /* [ns]  */
+  const int32_t* sn_s;      /* [ns]  */
+  const int32_t* sn_f;      /* [ns]  */
+  const int32_t* idx_ptr;   /* [ns+1] */
+  const int32_t* idx;       /* front index lists */
+  const int32_t* rel_ptr;   /* [ns+1] */
+  const int32_t* rel;
+  const int32_t* child_ptr; /* [ns+1] */
+  const int32_t* child;
+  const int32_t* a_ptr;     /* [ns+1] */
+  const int32_t* a_src;     /* [nnz_a] */
+  const int32_t* a_dst;     /* [nnz_a] */
+  const int32_t* lp_off;    /* [ns] */
+  const int32_t* up_off;    /* [ns] */
+  const int32_t* cb_off;    /* [ns] */
+  const int32_t* wl_ptr;    /* [n_warp_lists+1] */
+  const int32_t* wl;
+  const int32_t* top;       /* [n_top] */
+} szb_lu_symbolic;
+
+typedef struct szb_desc {
+  int32_t abi_version;     /* SZB_ABI_VERSION */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t n;               /* unknowns per scenario */
+  int32_t nnz_j;           /* Jacobian value slots per scenario */
+  const char* model_lib;   /* path of the generated model library (szbm_* symbols), or NULL for
+                              a handle that only factors / solves */
+  szb_lu_symbolic lu;
+  const double* mass_vals; /* [nnz_j] mass matrix M scattered on the J pattern (DAE), or NULL */
+} szb_desc;
+
+/* options of szb_rodas -- field meanings follow solvers/option.py:4-51 */
+typedef struct szb_rodas_opt {
+  double t0, tend;
+  double rtol, atol, f_savety, fac1, fac2, facmax;
+  double hinit;  /* <= 0: 1e-6*(tend-t0), rodas.py:110-117 */
+  double hmax;   /* <= 0: |tend - t0|, rodas.py:76-77 */
+  int32_t scheme; /* 0 rodas4, 1 rodasp, 2 rodas5p, 3 rodas3, 4 rodas3d (param.py:4-202) */
+  int32_t fix_h;
+  int32_t max_steps; /* safety bound on accepted+rejected steps per scenario */
+  int32_t n_out;     /* number of dense-output times (0: only the final state) */
+  const double* t_out; /* host [n_out], increasing, inside [t0,tend] */
+} szb_rodas_opt;
+
+SZB_API int szb_abi_version(void);
+SZB_API const char* szb_last_error(const szb_handle* h); /* h == NULL: error of the last failed create */
+
+SZB_API int szb_create(const szb_desc* desc, szb_handle** out);
+SZB_API int szb_destroy(szb_handle* h);
+SZB_API int szb_set_batch(szb_handle* h, int32_t B);
+SZB_API int szb_bind(szb_handle* h, int32_t slot, void* dev_ptr, int64_t len, int32_t dtype);
+
+/* residual F(t, y, p) of every scenario into SLOT_F; max|F| per scenario is kept internally */
+SZB_API int szb_eval_F(szb_handle* h, double t, szb_stream stream);
+/* Jacobian values into SLOT_JV */
+SZB_API int szb_eval_J(szb_handle* h, double t, szb_stream stream);
+/* numeric refactorisation of  A = J            (h_gamma == 0)
+ *                             A = M - h_gamma*J (h_gamma != 0; M from desc.mass_vals) */
+SZB_API int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream);
+/* SLOT_RHS <- A^{-1} SLOT_RHS for nrhs right-hand sides stored as [nrhs][B][n] */
+SZB_API int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream);
+/* whole Newton solve, nr.py:45-64, on device buffers; iters/flags are device int32[B] */
+SZB_API int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, int32_t* flags_dev,
+               szb_stream stream);
+/* same with HOST buffers: copies y0 and the per-scenario parameters in, solves, copies y,
+ * iters and flags out.  params_host[i] may be NULL to keep what is already on the device. */
+SZB_API int szb_newton_host(szb_handle* h, double tol, int32_t max_it, double* y_host,
+                    const void* const* params_host, int32_t n_params, int32_t* iters_host,
+                    int32_t* flags_host, szb_stream stream);
+/* batched Rodas (rodas.py:7-344) on device buffers.  y_out_dev: [n_out or 1][B][n].
+ * stats_dev: int32 [B][8] = nstep, nfeval, nJeval, ndecomp, nreject, nsolve, flag, reserved */
+SZB_API int szb_rodas(szb_handle* h, const szb_rodas_opt* opt, double* y_out_dev, double* t_end_dev,
+              int32_t* stats_dev, szb_stream stream);
+
+/* introspection */
+SZB_API int szb_query(const szb_handle* h, int32_t what, int64_t* out);
+#define SZB_Q_N 0
+#define SZB_Q_NNZ_J 1
+#define SZB_Q_LU_SIZE 2
+#define SZB_Q_N_PARAMS 3
+#define SZB_Q_BATCH 4
+#define SZB_Q_LAUNCHES 5       /* kernels launched by this handle since creation */
+#define SZB_Q_WORKSPACE_BYTES 6
+/* per-kernel-class device time of the last szb_newton call, milliseconds (CUDA events):
+ * out[0..4] = F, J, LU refactor, solve+update, bookkeeping.  Only filled when profiling was
+ * switched on with szb_set_profile(h, 1). */
+SZB_API int szb_set_profile(szb_handle* h, int32_t on);
+SZB_API int szb_get_profile(const szb_handle* h, double* out5, int64_t* launches5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SZB_H */

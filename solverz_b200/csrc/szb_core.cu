@@ -1,0 +1,539 @@
+// szb_core.cu -- handle management, buffer binding and the batched Newton driver behind the
+// C-ABI of include/szb.h.  The Newton loop restates Solverz/solvers/nlaesolver/nr.py:45-64 per
+// scenario with an active mask; see szb_newton below for the exact correspondence.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "szb.h"
+#include "szb_internal.cuh"
+#include "szb_lu.cuh"
+#include "szb_model.h"
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+void szb_set_error(szb_handle* h, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+}
+
+namespace {
+
+template <typename T>
+int upload(szb_handle* h, const T* host, size_t count, T** dev) {
+  *dev = nullptr;
+  if (count == 0) count = 1;  // keep pointers non-null
+  void* p = nullptr;
+  SZB_CUDA(h, cudaMalloc(&p, count * sizeof(T)));
+  h->owned.push_back(p);
+  if (host) SZB_CUDA(h, cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  else SZB_CUDA(h, cudaMemset(p, 0, count * sizeof(T)));
+  *dev = static_cast<T*>(p);
+  return SZB_OK;
+}
+
+int dev_alloc(szb_handle* h, size_t bytes, void** out, std::vector<void*>& bag) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 8;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    szb_set_error(h, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return SZB_ENOMEM;
+  }
+  bag.push_back(p);
+  h->ws_bytes += static_cast<int64_t>(bytes);
+  *out = p;
+  return SZB_OK;
+}
+
+void free_bag(std::vector<void*>& bag) {
+  for (void* p : bag) cudaFree(p);
+  bag.clear();
+}
+
+// ---- small bookkeeping kernels ---------------------------------------------------------
+__global__ void newton_init_kernel(int* nstep, int* active, int* flags, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    nstep[b] = 0;
+    active[b] = 1;
+    flags[b] = SZB_FLAG_RUNNING;
+  }
+}
+
+// nr.py:48-56 and 63-64, per scenario.  `while max|df| > tol: if nstep > max_it: break; nstep += 1`
+__global__ void newton_check_kernel(const double* __restrict__ fnorm, int* __restrict__ nstep,
+                                    int* __restrict__ active, int* __restrict__ flags,
+                                    int* __restrict__ n_active, double tol, int max_it, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int mine = 0;
+  if (b < B && active[b]) {
+    const double fn = fnorm[b];
+    if (!(fn > tol)) {  // also taken for NaN, exactly like `nan > tol` in Python
+      active[b] = 0;
+      if (fn < tol) flags[b] = SZB_FLAG_CONVERGED;
+      else if (flags[b] == SZB_FLAG_SINGULAR) {}
+      else flags[b] = (fn != fn) ? SZB_FLAG_NAN : SZB_FLAG_NOTCONV;
+    } else if (nstep[b] > max_it) {
+      active[b] = 0;
+      if (flags[b] != SZB_FLAG_SINGULAR) flags[b] = isinf(fn) ? SZB_FLAG_NAN : SZB_FLAG_MAXIT;
+    } else {
+      nstep[b] += 1;
+      mine = 1;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_active, __popc(m));
+}
+
+}  // namespace
+
+static int need_model(szb_handle* h) {
+  if (!h) return SZB_EINVAL;
+  if (!h->launch_F) { szb_set_error(h, "no model library attached to this handle"); return SZB_EMODEL; }
+  if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
+  return SZB_OK;
+}
+
+int szb_eval_F_masked(szb_handle* h, double t, const int* active, cudaStream_t st) {
+  szbm_args a{};
+  a.B = h->B; a.t = t; a.Y = h->Y; a.F = h->F; a.JV = nullptr; a.fnorm = h->fnorm;
+  a.params = h->param_ptr.data(); a.active = active;
+  const int e = h->launch_F(&a, st);
+  if (e != 0) { szb_set_error(h, "F kernel launch: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return SZB_ECUDA; }
+  h->launches[0]++;
+  return SZB_OK;
+}
+
+int szb_eval_J_masked(szb_handle* h, double t, const int* active, cudaStream_t st) {
+  szbm_args a{};
+  a.B = h->B; a.t = t; a.Y = h->Y; a.F = nullptr; a.JV = h->JV; a.fnorm = nullptr;
+  a.params = h->param_ptr.data(); a.active = active;
+  const int e = h->launch_J(&a, st);
+  if (e != 0) { szb_set_error(h, "J kernel launch: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return SZB_ECUDA; }
+  h->launches[1]++;
+  return SZB_OK;
+}
+
+int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b, const int* active,
+                           cudaStream_t st) {
+  const double* mv = nullptr;
+  double scale = 1.0;
+  if (h_gamma != 0.0 || scale_b) {
+    if (!h->mass_vals) { szb_set_error(h, "szb_lu_refactor: h_gamma != 0 needs desc.mass_vals"); return SZB_EINVAL; }
+    mv = h->mass_vals;
+    scale = -h_gamma;
+  }
+  cudaError_t e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, mv, scale_b, scale, active,
+                                        h->flags, h->B, st);
+  if (e != cudaSuccess) { szb_set_error(h, "LU factor launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
+  h->launches[2]++;
+  h->factored = true;
+  return SZB_OK;
+}
+
+// =========================================================================================
+extern "C" {
+
+int szb_abi_version(void) { return SZB_ABI_VERSION; }
+
+const char* szb_last_error(const szb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int szb_destroy(szb_handle* h) {
+  if (!h) return SZB_OK;
+  cudaSetDevice(h->device);
+  free_bag(h->owned);
+  free_bag(h->batch_owned);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->model_dl) dlclose(h->model_dl);
+  delete h;
+  return SZB_OK;
+}
+
+int szb_create(const szb_desc* d, szb_handle** out) {
+  if (!d || !out) { szb_set_error(nullptr, "szb_create: null argument"); return SZB_EINVAL; }
+  *out = nullptr;
+  if (d->abi_version != SZB_ABI_VERSION) {
+    szb_set_error(nullptr, "szb_create: ABI version %d, library is %d", d->abi_version, SZB_ABI_VERSION);
+    return SZB_EINVAL;
+  }
+  const szb_lu_symbolic& L = d->lu;
+  if (d->n <= 0 || L.n != d->n || L.nnz_a != d->nnz_j || L.ns <= 0) {
+    szb_set_error(nullptr, "szb_create: inconsistent sizes (n=%d lu.n=%d nnz_j=%d lu.nnz_a=%d ns=%d)",
+                  d->n, L.n, d->nnz_j, L.nnz_a, L.ns);
+    return SZB_EINVAL;
+  }
+  szb_handle* h = new (std::nothrow) szb_handle();
+  if (!h) { szb_set_error(nullptr, "out of host memory"); return SZB_ENOMEM; }
+  h->device = d->device;
+  h->n = d->n;
+  h->nnz_j = d->nnz_j;
+  int rc = SZB_OK;
+  auto fail = [&](int code) { g_create_error = h->err; szb_destroy(h); return code; };
+  {
+    cudaError_t e = cudaSetDevice(d->device);
+    if (e != cudaSuccess) {
+      szb_set_error(h, "cudaSetDevice(%d): %s", d->device, cudaGetErrorString(e));
+      return fail(SZB_ECUDA);
+    }
+  }
+  szb::LuDev& S = h->S;
+  S.n = L.n; S.nnz_a = L.nnz_a; S.ns = L.ns;
+  S.lu_size = L.lu_size; S.cb_size = L.cb_size; S.cv_size = L.cv_size;
+  S.n_warp_lists = L.n_warp_lists; S.n_top = L.n_top;
+  S.f_warp_max = L.f_warp_max; S.f_top_max = L.f_top_max;
+  S.s_warp_max = L.s_warp_max; S.s_top_max = L.s_top_max;
+  const int ns = L.ns;
+#define UP(field, cnt)                                                               \
+  do {                                                                               \
+    int* p_ = nullptr;                                                               \
+    if ((rc = upload<int>(h, L.field, static_cast<size_t>(cnt), &p_)) != SZB_OK) return fail(rc); \
+    S.field = p_;                                                                    \
+  } while (0)
+  UP(rowp, L.n); UP(colp, L.n); UP(sn_piv0, ns); UP(sn_s, ns); UP(sn_f, ns);
+  UP(idx_ptr, ns + 1); UP(idx, L.idx_ptr[ns]); UP(rel_ptr, ns + 1); UP(rel, L.rel_ptr[ns]);
+  UP(child_ptr, ns + 1); UP(child, L.child_ptr[ns]);
+  UP(a_ptr, ns + 1); UP(a_src, L.nnz_a); UP(a_dst, L.nnz_a);
+  UP(lp_off, ns); UP(up_off, ns); UP(cb_off, ns);
+  UP(wl_ptr, L.n_warp_lists + 1); UP(wl, L.wl_ptr[L.n_warp_lists]); UP(top, L.n_top);
+#undef UP
+  if (d->mass_vals) {
+    double* p = nullptr;
+    if ((rc = upload<double>(h, d->mass_vals, d->nnz_j, &p)) != SZB_OK) return fail(rc);
+    h->mass_vals = p;
+  }
+  if (d->model_lib) {
+    h->model_dl = dlopen(d->model_lib, RTLD_NOW | RTLD_LOCAL);
+    if (!h->model_dl) {
+      szb_set_error(h, "dlopen(%s): %s", d->model_lib, dlerror());
+      return fail(SZB_EMODEL);
+    }
+    auto sym = [&](const char* name) { return dlsym(h->model_dl, name); };
+    auto abi = reinterpret_cast<int (*)()>(sym("szbm_abi_version"));
+    auto fn = reinterpret_cast<int (*)()>(sym("szbm_n"));
+    auto fnnz = reinterpret_cast<int (*)()>(sym("szbm_nnz_j"));
+    auto fnp = reinterpret_cast<int (*)()>(sym("szbm_n_params"));
+    auto fpi = reinterpret_cast<const szbm_param_info* (*)()>(sym("szbm_params"));
+    h->launch_F = reinterpret_cast<szb_handle::launch_fn>(sym("szbm_launch_F"));
+    h->launch_J = reinterpret_cast<szb_handle::launch_fn>(sym("szbm_launch_J"));
+    if (!abi || !fn || !fnnz || !fnp || !fpi || !h->launch_F || !h->launch_J) {
+      szb_set_error(h, "model library %s lacks szbm_* symbols", d->model_lib);
+      return fail(SZB_EMODEL);
+    }
+    if (abi() != SZBM_ABI_VERSION || fn() != d->n || fnnz() != d->nnz_j) {
+      szb_set_error(h, "model library mismatch: abi %d (want %d), n %d (want %d), nnz_j %d (want %d)",
+                    abi(), SZBM_ABI_VERSION, fn(), d->n, fnnz(), d->nnz_j);
+      return fail(SZB_EMODEL);
+    }
+    const int np = fnp();
+    const szbm_param_info* pi = fpi();
+    h->params.assign(pi, pi + np);
+    h->param_ptr.assign(np, nullptr);
+    h->param_bound.assign(np, 0);
+  }
+  {
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&h->pinned), 64);
+    if (e != cudaSuccess) { szb_set_error(h, "cudaMallocHost: %s", cudaGetErrorString(e)); return fail(SZB_ECUDA); }
+    for (auto& ev : h->ev) {
+      e = cudaEventCreate(&ev);
+      if (e != cudaSuccess) { szb_set_error(h, "cudaEventCreate: %s", cudaGetErrorString(e)); return fail(SZB_ECUDA); }
+    }
+  }
+  *out = h;
+  return SZB_OK;
+}
+
+int szb_set_batch(szb_handle* h, int32_t B) {
+  if (!h || B <= 0) { szb_set_error(h, "szb_set_batch: bad batch %d", B); return SZB_EINVAL; }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  free_bag(h->batch_owned);
+  h->ws_bytes = 0;
+  h->B = 0;
+  h->factored = false;
+  cudaError_t e = szb::lu_plan(h->S, B, &h->cfg);
+  if (e != cudaSuccess) {
+    szb_set_error(h, "LU launch plan failed (front %d / %d too large for shared memory?): %s",
+                  h->S.f_warp_max, h->S.f_top_max, cudaGetErrorString(e));
+    return SZB_ECUDA;
+  }
+  const size_t n = h->n, nz = h->nnz_j;
+  int rc;
+  void* p;
+#define ALLOC(dst, type, count)                                                         \
+  do {                                                                                  \
+    if ((rc = dev_alloc(h, sizeof(type) * (count), &p, h->batch_owned)) != SZB_OK) return rc; \
+    dst = static_cast<type*>(p);                                                        \
+  } while (0)
+  ALLOC(h->own_Y, double, B * n);
+  ALLOC(h->own_F, double, B * n);
+  ALLOC(h->own_JV, double, B * nz);
+  ALLOC(h->own_RHS, double, B * n);
+  ALLOC(h->LU, double, static_cast<size_t>(B) * h->S.lu_size);
+  const int gmax = h->cfg.grid_factor > h->cfg.grid_solve ? h->cfg.grid_factor : h->cfg.grid_solve;
+  ALLOC(h->CBW, double, static_cast<size_t>(gmax) * (h->S.cb_size > 0 ? h->S.cb_size : 1));
+  ALLOC(h->CVW, double, static_cast<size_t>(gmax) * (h->S.cv_size > 0 ? h->S.cv_size : 1));
+  ALLOC(h->XW, double, h->cfg.x_in_smem ? 1 : static_cast<size_t>(gmax) * n);
+  ALLOC(h->fnorm, double, B);
+  ALLOC(h->scale_b, double, B);
+  ALLOC(h->active, int, B);
+  ALLOC(h->nstep, int, B);
+  ALLOC(h->flags, int, B);
+  ALLOC(h->counter, int, 16);
+  for (size_t i = 0; i < h->params.size(); ++i) {
+    const auto& pi = h->params[i];
+    const size_t esz = pi.dtype == SZB_DTYPE_F64 ? 8 : 4;
+    const size_t cnt = static_cast<size_t>(pi.len) * (pi.per_scenario ? B : 1);
+    if ((rc = dev_alloc(h, esz * cnt, &p, h->batch_owned)) != SZB_OK) return rc;
+    SZB_CUDA(h, cudaMemset(p, 0, esz * (cnt ? cnt : 1)));
+    h->param_own.resize(h->params.size());
+    h->param_own[i] = p;
+    if (!h->param_bound[i]) h->param_ptr[i] = p;
+  }
+#undef ALLOC
+  SZB_CUDA(h, cudaMemset(h->flags, 0, sizeof(int) * B));
+  h->Y = h->bound_Y ? h->bound_Y : h->own_Y;
+  h->F = h->bound_F ? h->bound_F : h->own_F;
+  h->JV = h->bound_JV ? h->bound_JV : h->own_JV;
+  h->RHS = h->bound_RHS ? h->bound_RHS : h->own_RHS;
+  h->B = B;
+  return SZB_OK;
+}
+
+int szb_bind(szb_handle* h, int32_t slot, void* dev_ptr, int64_t len, int32_t dtype) {
+  if (!h) return SZB_EINVAL;
+  if (h->B <= 0) { szb_set_error(h, "szb_bind: call szb_set_batch first"); return SZB_ESTATE; }
+  const int64_t B = h->B, n = h->n;
+  auto want = [&](int64_t need, int32_t dt) {
+    if (dev_ptr && (len != need || dtype != dt)) {
+      szb_set_error(h, "szb_bind(slot %d): got len %lld dtype %d, expected len %lld dtype %d", slot,
+                    static_cast<long long>(len), dtype, static_cast<long long>(need), dt);
+      return false;
+    }
+    return true;
+  };
+  switch (slot) {
+    case SZB_SLOT_Y:
+      if (!want(B * n, SZB_DTYPE_F64)) return SZB_EINVAL;
+      h->bound_Y = static_cast<double*>(dev_ptr); h->Y = dev_ptr ? h->bound_Y : h->own_Y; return SZB_OK;
+    case SZB_SLOT_F:
+      if (!want(B * n, SZB_DTYPE_F64)) return SZB_EINVAL;
+      h->bound_F = static_cast<double*>(dev_ptr); h->F = dev_ptr ? h->bound_F : h->own_F; return SZB_OK;
+    case SZB_SLOT_JV:
+      if (!want(B * h->nnz_j, SZB_DTYPE_F64)) return SZB_EINVAL;
+      h->bound_JV = static_cast<double*>(dev_ptr); h->JV = dev_ptr ? h->bound_JV : h->own_JV; return SZB_OK;
+    case SZB_SLOT_RHS:
+      if (dev_ptr && (dtype != SZB_DTYPE_F64 || len < B * n || len % (B * n) != 0)) {
+        szb_set_error(h, "szb_bind(RHS): len %lld is not a multiple of B*n", static_cast<long long>(len));
+        return SZB_EINVAL;
+      }
+      h->bound_RHS = static_cast<double*>(dev_ptr); h->RHS = dev_ptr ? h->bound_RHS : h->own_RHS;
+      h->rhs_len = dev_ptr ? len : B * n;
+      return SZB_OK;
+    default: break;
+  }
+  const int i = slot - SZB_SLOT_PARAM0;
+  if (i < 0 || i >= static_cast<int>(h->params.size())) {
+    szb_set_error(h, "szb_bind: unknown slot %d", slot);
+    return SZB_EINVAL;
+  }
+  const auto& pi = h->params[i];
+  if (!want(pi.len * (pi.per_scenario ? B : 1), pi.dtype)) return SZB_EINVAL;
+  h->param_bound[i] = dev_ptr != nullptr;
+  h->param_ptr[i] = dev_ptr ? dev_ptr : h->param_own[i];
+  return SZB_OK;
+}
+
+int szb_eval_F(szb_handle* h, double t, szb_stream stream) {
+  int rc = need_model(h);
+  if (rc) return rc;
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  return szb_eval_F_masked(h, t, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int szb_eval_J(szb_handle* h, double t, szb_stream stream) {
+  int rc = need_model(h);
+  if (rc) return rc;
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  return szb_eval_J_masked(h, t, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream) {
+  if (!h) return SZB_EINVAL;
+  if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  return szb_lu_refactor_masked(h, h_gamma, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream) {
+  if (!h) return SZB_EINVAL;
+  if (!h->factored) { szb_set_error(h, "szb_lu_solve before szb_lu_refactor"); return SZB_ESTATE; }
+  const int64_t per = static_cast<int64_t>(h->B) * h->n;
+  const int64_t have = h->bound_RHS ? h->rhs_len : per;
+  if (nrhs < 1 || nrhs * per > have) {
+    szb_set_error(h, "szb_lu_solve: nrhs=%d does not fit the bound RHS buffer", nrhs);
+    return SZB_EINVAL;
+  }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  for (int r = 0; r < nrhs; ++r) {
+    double* x = h->RHS + r * per;
+    cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, x, x, h->CVW, h->XW, 0, nullptr, h->B,
+                                         static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
+    h->launches[3]++;
+  }
+  return SZB_OK;
+}
+
+// nr.py:45-64 for the whole batch.
+//   df = F(y)                                   -> szbm_launch_F (+ max|F| per scenario)
+//   while max|df| > tol:                        -> newton_check_kernel (active mask)
+//       if nstep > max_it: break
+//       nstep += 1
+//       y = y - solve(J(y), df)                 -> szbm_launch_J, lu_factor, lu_solve(mode 1)
+//       df = F(y)
+//   succeed = max|df| < tol                     -> flags[b]
+int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, int32_t* flags_dev,
+               szb_stream stream) {
+  int rc = need_model(h);
+  if (rc) return rc;
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = h->B;
+  const int tb = 256, gb = (B + tb - 1) / tb;
+  const bool prof = h->profile;
+  for (int i = 0; i < 5; ++i) h->prof_ms[i] = 0.0;
+  auto tic = [&]() { if (prof) cudaEventRecord(h->ev[0], st); };
+  auto toc = [&](int cls) {
+    if (!prof) return;
+    cudaEventRecord(h->ev[1], st);
+    cudaEventSynchronize(h->ev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->prof_ms[cls] += ms;
+  };
+  tic();
+  newton_init_kernel<<<gb, tb, 0, st>>>(h->nstep, h->active, h->flags, B);
+  h->launches[4]++;
+  toc(4);
+  tic();
+  if ((rc = szb_eval_F_masked(h, 0.0, h->active, st)) != SZB_OK) return rc;
+  toc(0);
+  int sweeps = 0;
+  for (;;) {
+    tic();
+    SZB_CUDA(h, cudaMemsetAsync(h->counter, 0, sizeof(int), st));
+    newton_check_kernel<<<gb, tb, 0, st>>>(h->fnorm, h->nstep, h->active, h->flags, h->counter, tol,
+                                           max_it, B);
+    h->launches[4]++;
+    SZB_CUDA(h, cudaMemcpyAsync(h->pinned, h->counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SZB_CUDA(h, cudaStreamSynchronize(st));
+    toc(4);
+    const int n_active = h->pinned[0];
+    if (n_active <= 0) break;
+    tic();
+    if ((rc = szb_eval_J_masked(h, 0.0, h->active, st)) != SZB_OK) return rc;
+    toc(1);
+    tic();
+    if ((rc = szb_lu_refactor_masked(h, 0.0, nullptr, h->active, st)) != SZB_OK) return rc;
+    toc(2);
+    tic();
+    {
+      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->F, h->Y, h->CVW, h->XW, 1, h->active,
+                                           B, st);
+      if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
+      h->launches[3]++;
+    }
+    toc(3);
+    tic();
+    if ((rc = szb_eval_F_masked(h, 0.0, h->active, st)) != SZB_OK) return rc;
+    toc(0);
+    if (++sweeps > max_it + 2) {  // cannot happen: every scenario stops after max_it+1 sweeps
+      szb_set_error(h, "szb_newton: internal sweep bound exceeded");
+      return SZB_ESTATE;
+    }
+  }
+  h->last_sweeps = sweeps;
+  if (iters_dev) SZB_CUDA(h, cudaMemcpyAsync(iters_dev, h->nstep, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+  if (flags_dev) SZB_CUDA(h, cudaMemcpyAsync(flags_dev, h->flags, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+  SZB_CUDA(h, cudaGetLastError());
+  return SZB_OK;
+}
+
+int szb_newton_host(szb_handle* h, double tol, int32_t max_it, double* y_host,
+                    const void* const* params_host, int32_t n_params, int32_t* iters_host,
+                    int32_t* flags_host, szb_stream stream) {
+  int rc = need_model(h);
+  if (rc) return rc;
+  if (!y_host) { szb_set_error(h, "szb_newton_host: y_host is null"); return SZB_EINVAL; }
+  if (n_params > static_cast<int>(h->params.size())) {
+    szb_set_error(h, "szb_newton_host: %d parameters given, model has %zu", n_params, h->params.size());
+    return SZB_EINVAL;
+  }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t B = h->B, n = h->n;
+  SZB_CUDA(h, cudaMemcpyAsync(h->Y, y_host, B * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < n_params; ++i) {
+    if (!params_host || !params_host[i]) continue;
+    const auto& pi = h->params[i];
+    const size_t bytes = (pi.dtype == SZB_DTYPE_F64 ? 8 : 4) * static_cast<size_t>(pi.len) * (pi.per_scenario ? B : 1);
+    SZB_CUDA(h, cudaMemcpyAsync(h->param_ptr[i], params_host[i], bytes, cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = szb_newton(h, tol, max_it, nullptr, nullptr, stream)) != SZB_OK) return rc;
+  SZB_CUDA(h, cudaMemcpyAsync(y_host, h->Y, B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (iters_host) SZB_CUDA(h, cudaMemcpyAsync(iters_host, h->nstep, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (flags_host) SZB_CUDA(h, cudaMemcpyAsync(flags_host, h->flags, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SZB_CUDA(h, cudaStreamSynchronize(st));
+  return SZB_OK;
+}
+
+int szb_query(const szb_handle* h, int32_t what, int64_t* out) {
+  if (!h || !out) return SZB_EINVAL;
+  switch (what) {
+    case SZB_Q_N: *out = h->n; return SZB_OK;
+    case SZB_Q_NNZ_J: *out = h->nnz_j; return SZB_OK;
+    case SZB_Q_LU_SIZE: *out = h->S.lu_size; return SZB_OK;
+    case SZB_Q_N_PARAMS: *out = static_cast<int64_t>(h->params.size()); return SZB_OK;
+    case SZB_Q_BATCH: *out = h->B; return SZB_OK;
+    case SZB_Q_LAUNCHES: {
+      int64_t s = 0;
+      for (int i = 0; i < 5; ++i) s += h->launches[i];
+      *out = s;
+      return SZB_OK;
+    }
+    case SZB_Q_WORKSPACE_BYTES: *out = h->ws_bytes; return SZB_OK;
+    default: return SZB_EINVAL;
+  }
+}
+
+int szb_set_profile(szb_handle* h, int32_t on) {
+  if (!h) return SZB_EINVAL;
+  h->profile = on != 0;
+  return SZB_OK;
+}
+
+int szb_get_profile(const szb_handle* h, double* out5, int64_t* launches5) {
+  if (!h) return SZB_EINVAL;
+  for (int i = 0; i < 5; ++i) {
+    if (out5) out5[i] = h->prof_ms[i];
+    if (launches5) launches5[i] = h->launches[i];
+  }
+  return SZB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// szb_internal.cuh -- the handle behind include/szb.h (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "szb.h"
+#include "szb_lu.cuh"
+#include "szb_model.h"
+
+struct szb_handle {
+  using launch_fn = int (*)(const szbm_args*, void*);
+
+  int device = 0;
+  int n = 0, nnz_j = 0, B = 0;
+  std::string err;
+  // LU schedule (device copies owned by `owned`)
+  szb::LuDev S{};
+  szb::LuLaunchCfg cfg{};
+  const double* mass_vals = nullptr;
+  // model library
+  void* model_dl = nullptr;
+  launch_fn launch_F = nullptr, launch_J = nullptr;
+  std::vector<szbm_param_info> params;
+  std::vector<void*> param_ptr;   // what the kernels see (bound or own)
+  std::vector<void*> param_own;
+  std::vector<char> param_bound;
+  // per-batch buffers
+  double *own_Y = nullptr, *own_F = nullptr, *own_JV = nullptr, *own_RHS = nullptr;
+  double *bound_Y = nullptr, *bound_F = nullptr, *bound_JV = nullptr, *bound_RHS = nullptr;
+  double *Y = nullptr, *F = nullptr, *JV = nullptr, *RHS = nullptr;
+  int64_t rhs_len = 0;
+  double *LU = nullptr, *CBW = nullptr, *CVW = nullptr, *XW = nullptr;
+  double *fnorm = nullptr, *scale_b = nullptr;
+  int *active = nullptr, *nstep = nullptr, *flags = nullptr, *counter = nullptr;
+  int* pinned = nullptr;  // 16 ints of pinned host memory
+  bool factored = false;
+  // bookkeeping
+  std::vector<void*> owned;        // freed in destroy
+  std::vector<void*> batch_owned;  // freed in set_batch / destroy
+  int64_t ws_bytes = 0;
+  int64_t launches[5] = {0, 0, 0, 0, 0};  // F, J, LU, solve, bookkeeping
+  bool profile = false;
+  double prof_ms[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int last_sweeps = 0;
+  // Rodas workspaces (allocated on first use)
+  std::vector<void*> rodas_owned;
+  int rodas_B = 0, rodas_stages = 0;
+};
+
+void szb_set_error(szb_handle* h, const char* fmt, ...);
+
+#define SZB_CUDA(h, call)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      szb_set_error((h), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return SZB_ECUDA;                                                                \
+    }                                                                                  \
+  } while (0)
+
+// shared by the drivers
+int szb_eval_F_masked(szb_handle* h, double t, const int* active, cudaStream_t st);
+int szb_eval_J_masked(szb_handle* h, double t, const int* active, cudaStream_t st);
+int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b, const int* active,
+                           cudaStream_t st);

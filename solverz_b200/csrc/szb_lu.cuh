@@ -1,0 +1,45 @@
+// szb_lu.cuh -- device-side view of the multifrontal schedule and launch prototypes.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace szb {
+
+// All arrays are device pointers (int32).  Built once per handle from szb_lu_symbolic.
+struct LuDev {
+  int n, nnz_a, ns;
+  int lu_size, cb_size, cv_size;
+  int n_warp_lists, n_top, f_warp_max, f_top_max, s_warp_max, s_top_max;
+  const int *rowp, *colp;
+  const int *sn_piv0, *sn_s, *sn_f;
+  const int *idx_ptr, *idx, *rel_ptr, *rel, *child_ptr, *child;
+  const int *a_ptr, *a_src, *a_dst;
+  const int *lp_off, *up_off, *cb_off;
+  const int *wl_ptr, *wl, *top;
+};
+
+struct LuLaunchCfg {
+  int threads;        // threads per block (multiple of 32, >= 32*n_warp_lists)
+  int grid_factor;    // resident blocks (persistent grid size)
+  size_t smem_factor; // dynamic shared memory of the factor kernel
+  int grid_solve;
+  size_t smem_solve;
+  int x_in_smem;      // solve kernel keeps the permuted vector in shared memory
+};
+
+// Chooses block/grid/smem for this schedule on the current device; returns cudaError_t.
+cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg);
+
+// A(b) = scale(b) * JV[b] (+ mvals)  ->  LU[b];  scale_b may be null (then scale_const).
+cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV,
+                             double* LU, double* CBW, const double* mvals, const double* scale_b,
+                             double scale_const, const int* active, int* flags, int B,
+                             cudaStream_t st);
+
+// mode 0:  X[b] <- A^{-1} RHS[b]         (X may alias RHS)
+// mode 1:  X[b] <- X[b] - A^{-1} RHS[b]  (Newton update y -= dx; X is Y)
+cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* LU,
+                            const double* RHS, double* X, double* CVW, double* XW, int mode,
+                            const int* active, int B, cudaStream_t st);
+
+}  // namespace szb

@@ -6,3 +6,5 @@ from .equations import Eqn, Ode, LoopEqn, LoopOde, Model, AE, DAE, FDAE
 from .variables import Vars, TimeVars, Address
 
 __version__ = "0.1.0"
+from .code_printer import module_printer, made_numerical
+from .solvers import Opt, Stats, aesol, daesol, nr_method

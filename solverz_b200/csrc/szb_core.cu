@@ -131,6 +131,7 @@ int szb_eval_J_masked(szb_handle* h, double t, const int* active, cudaStream_t s
 
 int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b, const int* active,
                            cudaStream_t st) {
+  if (!h->has_lu) { szb_set_error(h, "this handle was created without an LU schedule"); return SZB_ESTATE; }
   const double* mv = nullptr;
   double scale = 1.0;
   if (h_gamma != 0.0 || scale_b) {
@@ -173,7 +174,7 @@ int szb_create(const szb_desc* d, szb_handle** out) {
     return SZB_EINVAL;
   }
   const szb_lu_symbolic& L = d->lu;
-  if (d->n <= 0 || L.n != d->n || L.nnz_a != d->nnz_j || L.ns <= 0) {
+  if (d->n <= 0 || d->nnz_j < 0 || (L.ns != 0 && (L.n != d->n || L.nnz_a != d->nnz_j || L.ns < 0))) {
     szb_set_error(nullptr, "szb_create: inconsistent sizes (n=%d lu.n=%d nnz_j=%d lu.nnz_a=%d ns=%d)",
                   d->n, L.n, d->nnz_j, L.nnz_a, L.ns);
     return SZB_EINVAL;
@@ -193,6 +194,8 @@ int szb_create(const szb_desc* d, szb_handle** out) {
     }
   }
   szb::LuDev& S = h->S;
+  h->has_lu = L.ns > 0;
+  if (h->has_lu) {
   S.n = L.n; S.nnz_a = L.nnz_a; S.ns = L.ns;
   S.lu_size = L.lu_size; S.cb_size = L.cb_size; S.cv_size = L.cv_size;
   S.n_warp_lists = L.n_warp_lists; S.n_top = L.n_top;
@@ -212,6 +215,7 @@ int szb_create(const szb_desc* d, szb_handle** out) {
   UP(lp_off, ns); UP(up_off, ns); UP(cb_off, ns);
   UP(wl_ptr, L.n_warp_lists + 1); UP(wl, L.wl_ptr[L.n_warp_lists]); UP(top, L.n_top);
 #undef UP
+  }
   if (d->mass_vals) {
     double* p = nullptr;
     if ((rc = upload<double>(h, d->mass_vals, d->nnz_j, &p)) != SZB_OK) return fail(rc);
@@ -265,11 +269,13 @@ int szb_set_batch(szb_handle* h, int32_t B) {
   h->ws_bytes = 0;
   h->B = 0;
   h->factored = false;
-  cudaError_t e = szb::lu_plan(h->S, B, &h->cfg);
-  if (e != cudaSuccess) {
-    szb_set_error(h, "LU launch plan failed (front %d / %d too large for shared memory?): %s",
-                  h->S.f_warp_max, h->S.f_top_max, cudaGetErrorString(e));
-    return SZB_ECUDA;
+  if (h->has_lu) {
+    cudaError_t e = szb::lu_plan(h->S, B, &h->cfg);
+    if (e != cudaSuccess) {
+      szb_set_error(h, "LU launch plan failed (front %d / %d too large for shared memory?): %s",
+                    h->S.f_warp_max, h->S.f_top_max, cudaGetErrorString(e));
+      return SZB_ECUDA;
+    }
   }
   const size_t n = h->n, nz = h->nnz_j;
   int rc;
@@ -283,11 +289,13 @@ int szb_set_batch(szb_handle* h, int32_t B) {
   ALLOC(h->own_F, double, B * n);
   ALLOC(h->own_JV, double, B * nz);
   ALLOC(h->own_RHS, double, B * n);
-  ALLOC(h->LU, double, static_cast<size_t>(B) * h->S.lu_size);
-  const int gmax = h->cfg.grid_factor > h->cfg.grid_solve ? h->cfg.grid_factor : h->cfg.grid_solve;
-  ALLOC(h->CBW, double, static_cast<size_t>(gmax) * (h->S.cb_size > 0 ? h->S.cb_size : 1));
-  ALLOC(h->CVW, double, static_cast<size_t>(gmax) * (h->S.cv_size > 0 ? h->S.cv_size : 1));
-  ALLOC(h->XW, double, h->cfg.x_in_smem ? 1 : static_cast<size_t>(gmax) * n);
+  if (h->has_lu) {
+    ALLOC(h->LU, double, static_cast<size_t>(B) * h->S.lu_size);
+    const int gmax = h->cfg.grid_factor > h->cfg.grid_solve ? h->cfg.grid_factor : h->cfg.grid_solve;
+    ALLOC(h->CBW, double, static_cast<size_t>(gmax) * (h->S.cb_size > 0 ? h->S.cb_size : 1));
+    ALLOC(h->CVW, double, static_cast<size_t>(gmax) * (h->S.cv_size > 0 ? h->S.cv_size : 1));
+    ALLOC(h->XW, double, h->cfg.x_in_smem ? 1 : static_cast<size_t>(gmax) * n);
+  }
   ALLOC(h->fnorm, double, B);
   ALLOC(h->scale_b, double, B);
   ALLOC(h->active, int, B);
@@ -306,6 +314,7 @@ int szb_set_batch(szb_handle* h, int32_t B) {
   }
 #undef ALLOC
   SZB_CUDA(h, cudaMemset(h->flags, 0, sizeof(int) * B));
+  SZB_CUDA(h, cudaMemset(h->own_JV, 0, sizeof(double) * B * nz));
   h->Y = h->bound_Y ? h->bound_Y : h->own_Y;
   h->F = h->bound_F ? h->bound_F : h->own_F;
   h->JV = h->bound_JV ? h->bound_JV : h->own_JV;
@@ -411,6 +420,7 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
                szb_stream stream) {
   int rc = need_model(h);
   if (rc) return rc;
+  if (!h->has_lu) { szb_set_error(h, "this handle was created without an LU schedule"); return SZB_ESTATE; }
   SZB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int B = h->B;

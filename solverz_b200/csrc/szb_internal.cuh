@@ -37,6 +37,7 @@ struct szb_handle {
   int *active = nullptr, *nstep = nullptr, *flags = nullptr, *counter = nullptr;
   int* pinned = nullptr;  // 16 ints of pinned host memory
   bool factored = false;
+  bool has_lu = false;
   // bookkeeping
   std::vector<void*> owned;        // freed in destroy
   std::vector<void*> batch_owned;  // freed in set_batch / destroy

@@ -1,0 +1,4 @@
+from .option import Opt
+from .stats import Stats
+from .solution import aesol, daesol
+from .nr import nr_method

@@ -1,0 +1,104 @@
+"""GPU parity tests of the hot path on the synthetic polar power-flow model (configs #2/#3 at
+sizes the oracle finishes in seconds).  Mirrors the reference's three-way parity tests
+(tests/test_matrix_equation.py:111-158: J at every Newton step 1e-12, solutions 1e-10)."""
+import importlib
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as sla
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pf8(libszb, tmp_path_factory):
+    from solverz_b200 import module_printer
+    from solverz_b200.synthetic import polar_pf_model
+    d = tmp_path_factory.mktemp("mods")
+    eqs, y0, info = polar_pf_model(8, 8)
+    pkg = module_printer(eqs, y0, "pf8_test", directory=str(d)).render()
+    sys.path.insert(0, str(d))
+    mod = importlib.import_module("pf8_test")
+    return mod.mdl, mod.y, info
+
+
+def _oracle(info):
+    from oracle.pf import PFOracle
+    return PFOracle(info["Ybus"], info["pv"], info["pq"])
+
+
+def test_F_J_parity(pf8):
+    from solverz_b200.synthetic import pf_scenarios
+    mdl, y0, info = pf8
+    orc = _oracle(info)
+    B = 48
+    P, Q = pf_scenarios(info, B)
+    rng = np.random.default_rng(0)
+    Y = y0.array[None, :] + 0.05 * rng.standard_normal((B, mdl.n))
+    s = mdl.session(B)
+    s.set_params({"Pinj": P, "Qinj": Q})
+    s.set_y(Y)
+    F = s.eval_F().cpu().numpy()
+    JV = s.eval_J().cpu().numpy()
+    for b in range(B):
+        Fo = orc.F(Y[b], P[b], Q[b])
+        Jo = orc.J(Y[b])
+        Jg = sps.csc_matrix((JV[b], mdl.indices, mdl.indptr), shape=(mdl.n, mdl.n))
+        assert np.abs(F[b] - Fo).max() <= 1e-12 * max(1.0, np.abs(Fo).max())
+        assert abs(Jg - Jo).max() <= 1e-12 * abs(Jo).max()
+
+
+def test_single_scenario_callables(pf8):
+    """mdl.F(y, p) / mdl.J(y, p) keep the reference's call shape for B = 1."""
+    mdl, y0, info = pf8
+    orc = _oracle(info)
+    F = mdl.F(y0.array, mdl.p)
+    J = mdl.J(y0.array, mdl.p)
+    assert np.abs(F - orc.F(y0.array, info["Pbase"], info["Qbase"])).max() <= 1e-13
+    assert abs(sps.csc_matrix(J) - orc.J(y0.array)).max() <= 1e-12 * abs(J).max()
+
+
+def test_lu_refactor_solve(pf8):
+    mdl, y0, info = pf8
+    orc = _oracle(info)
+    B = 40
+    rng = np.random.default_rng(1)
+    Y = y0.array[None, :] + 0.1 * rng.standard_normal((B, mdl.n))
+    s = mdl.session(B)
+    s.set_y(Y)
+    s.eval_J()
+    rhs = rng.standard_normal((B, mdl.n))
+    import torch
+    s.RHS.copy_(torch.as_tensor(rhs))
+    s.lu_refactor(0.0)
+    X = s.lu_solve(1).cpu().numpy()
+    for b in range(B):
+        Jo = orc.J(Y[b])
+        xr = sla.spsolve(Jo, rhs[b])
+        assert np.abs(X[b] - xr).max() <= 1e-10 * np.abs(xr).max()
+
+
+@pytest.mark.parametrize("nx,B", [(8, 64), (16, 32)])
+def test_newton_parity(libszb, tmp_path_factory, nx, B):
+    from oracle.nr import nr_method as oracle_nr
+    from solverz_b200 import Opt, module_printer, nr_method
+    from solverz_b200.synthetic import pf_scenarios, polar_pf_model
+    d = tmp_path_factory.mktemp(f"mods{nx}")
+    eqs, y0, info = polar_pf_model(nx, nx)
+    module_printer(eqs, y0, f"pfn{nx}", directory=str(d)).render()
+    sys.path.insert(0, str(d))
+    mdl = importlib.import_module(f"pfn{nx}").mdl
+    orc = _oracle(info)
+    P, Q = pf_scenarios(info, B)
+    mdl.p["Pinj"], mdl.p["Qinj"] = P, Q
+    sol = nr_method(mdl, np.tile(y0.array, (B, 1)), Opt(ite_tol=1e-8))
+    assert sol.stats.succeed.all()
+    for b in range(B):
+        ref = oracle_nr(lambda y: orc.F(y, P[b], Q[b]), orc.J, y0.array, 1e-8, 100)
+        assert np.abs(sol.y[b] - ref["y"]).max() <= 1e-10 * np.abs(ref["y"]).max()
+        assert int(sol.stats.nstep[b]) == ref["nstep"]
+        assert int(sol.stats.nfeval[b]) == ref["nfeval"]
+        # residual of the GPU solution judged by the oracle's F
+        assert np.abs(orc.F(sol.y[b], P[b], Q[b])).max() <= 1e-8

@@ -174,11 +174,13 @@ SZB_API int szb_query(const szb_handle* h, int32_t what, int64_t* out);
 #define SZB_Q_BATCH 4
 #define SZB_Q_LAUNCHES 5       /* kernels launched by this handle since creation */
 #define SZB_Q_WORKSPACE_BYTES 6
-/* per-kernel-class device time of the last szb_newton call, milliseconds (CUDA events):
- * out[0..4] = F, J, LU refactor, solve+update, bookkeeping.  Only filled when profiling was
- * switched on with szb_set_profile(h, 1). */
+/* per-kernel-class device time of the last szb_newton call, milliseconds, from CUDA event pairs
+ * recorded on the launching stream around every launch (no extra synchronisation):
+ * out5[0..4] = F, J, LU refactor, solve+update, bookkeeping; launches5 = launches per class since
+ * the handle was created; units5 = scenarios processed per class in the last call.  Only filled
+ * when profiling was switched on with szb_set_profile(h, 1). */
 SZB_API int szb_set_profile(szb_handle* h, int32_t on);
-SZB_API int szb_get_profile(const szb_handle* h, double* out5, int64_t* launches5);
+SZB_API int szb_get_profile(const szb_handle* h, double* out5, int64_t* launches5, int64_t* units5);
 
 #ifdef __cplusplus
 }

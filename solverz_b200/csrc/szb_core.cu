@@ -161,6 +161,7 @@ int szb_destroy(szb_handle* h) {
   free_bag(h->batch_owned);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_pool) cudaEventDestroy(e);
   if (h->model_dl) dlclose(h->model_dl);
   delete h;
   return SZB_OK;
@@ -426,15 +427,22 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
   const int B = h->B;
   const int tb = 256, gb = (B + tb - 1) / tb;
   const bool prof = h->profile;
-  for (int i = 0; i < 5; ++i) h->prof_ms[i] = 0.0;
-  auto tic = [&]() { if (prof) cudaEventRecord(h->ev[0], st); };
+  for (int i = 0; i < 5; ++i) { h->prof_ms[i] = 0.0; h->prof_units[i] = 0; }
+  // sync-free timing: event pairs are recorded around every launch and resolved after the loop
+  size_t ev_used = 0;
+  std::vector<int> ev_cls;
+  auto tic = [&]() {
+    if (!prof) return;
+    if (ev_used + 2 > h->ev_pool.size()) {
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+    }
+    cudaEventRecord(h->ev_pool[ev_used], st);
+  };
   auto toc = [&](int cls) {
     if (!prof) return;
-    cudaEventRecord(h->ev[1], st);
-    cudaEventSynchronize(h->ev[1]);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-    h->prof_ms[cls] += ms;
+    cudaEventRecord(h->ev_pool[ev_used + 1], st);
+    ev_used += 2;
+    ev_cls.push_back(cls);
   };
   tic();
   newton_init_kernel<<<gb, tb, 0, st>>>(h->nstep, h->active, h->flags, B);
@@ -443,6 +451,7 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
   tic();
   if ((rc = szb_eval_F_masked(h, 0.0, h->active, st)) != SZB_OK) return rc;
   toc(0);
+  h->prof_units[0] += B;
   int sweeps = 0;
   for (;;) {
     tic();
@@ -455,6 +464,7 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
     toc(4);
     const int n_active = h->pinned[0];
     if (n_active <= 0) break;
+    for (int i = 0; i < 4; ++i) h->prof_units[i] += n_active;
     tic();
     if ((rc = szb_eval_J_masked(h, 0.0, h->active, st)) != SZB_OK) return rc;
     toc(1);
@@ -478,6 +488,13 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
     }
   }
   h->last_sweeps = sweeps;
+  if (prof) {  // the loop ended right after a stream synchronisation: every event has completed
+    for (size_t i = 0; i < ev_cls.size(); ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]) == cudaSuccess)
+        h->prof_ms[ev_cls[i]] += ms;
+    }
+  }
   if (iters_dev) SZB_CUDA(h, cudaMemcpyAsync(iters_dev, h->nstep, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
   if (flags_dev) SZB_CUDA(h, cudaMemcpyAsync(flags_dev, h->flags, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
   SZB_CUDA(h, cudaGetLastError());
@@ -537,11 +554,12 @@ int szb_set_profile(szb_handle* h, int32_t on) {
   return SZB_OK;
 }
 
-int szb_get_profile(const szb_handle* h, double* out5, int64_t* launches5) {
+int szb_get_profile(const szb_handle* h, double* out5, int64_t* launches5, int64_t* units5) {
   if (!h) return SZB_EINVAL;
   for (int i = 0; i < 5; ++i) {
     if (out5) out5[i] = h->prof_ms[i];
     if (launches5) launches5[i] = h->launches[i];
+    if (units5) units5[i] = h->prof_units[i];
   }
   return SZB_OK;
 }

@@ -45,6 +45,8 @@ struct szb_handle {
   int64_t launches[5] = {0, 0, 0, 0, 0};  // F, J, LU, solve, bookkeeping
   bool profile = false;
   double prof_ms[5] = {0, 0, 0, 0, 0};
+  int64_t prof_units[5] = {0, 0, 0, 0, 0};  // scenarios processed per kernel class
+  std::vector<cudaEvent_t> ev_pool;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int last_sweeps = 0;
   // Rodas workspaces (allocated on first use)

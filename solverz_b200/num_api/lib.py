@@ -75,7 +75,7 @@ def load():
     lib.szb_rodas.argtypes = [H, C.POINTER(RodasOptC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.szb_query.argtypes = [H, C.c_int32, C.POINTER(C.c_int64)]
     lib.szb_set_profile.argtypes = [H, C.c_int32]
-    lib.szb_get_profile.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.szb_get_profile.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     if lib.szb_abi_version() != SZB_ABI_VERSION:
         raise SzbError(f"libszb.so ABI {lib.szb_abi_version()} != binding {SZB_ABI_VERSION}")
     _lib = lib

@@ -180,9 +180,10 @@ class BatchSession:
     def get_profile(self):
         ms = (C.c_double * 5)()
         ln = (C.c_int64 * 5)()
-        L.check(self.lib.szb_get_profile(self.h, ms, ln), self.h, "szb_get_profile")
+        un = (C.c_int64 * 5)()
+        L.check(self.lib.szb_get_profile(self.h, ms, ln, un), self.h, "szb_get_profile")
         names = ("F", "J", "lu_refactor", "lu_solve", "bookkeeping")
-        return {k: (ms[i], ln[i]) for i, k in enumerate(names)}
+        return {k: dict(ms=ms[i], launches=ln[i], units=un[i]) for i, k in enumerate(names)}
 
     def query(self, what: int) -> int:
         out = C.c_int64()

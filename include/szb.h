@@ -88,7 +88,8 @@ typedef void* szb_stream; /* cudaStream_t */
 typedef struct szb_lu_symbolic {
   int32_t n, nnz_a, ns;
   int32_t lu_size, cb_size, cv_size; /* doubles per scenario: factors, contribution ws, fwd ws */
-  int32_t n_warp_lists, n_top, f_warp_max, f_top_max, s_warp_max, s_top_max;
+  int32_t n_warp_lists, n_group_lists, n_top;
+  int32_t f_warp_max, f_group_max, f_top_max, s_warp_max, s_group_max, s_top_max;
   const int32_t* rowp;      /* [n]   pivot k <- original row     */
   const int32_t* colp;      /* [n]   pivot k <- original column  */
   const int32_t* sn_piv0;   /* [ns]  */
@@ -108,6 +109,8 @@ typedef struct szb_lu_symbolic {
   const int32_t* cb_off;    /* [ns] */
   const int32_t* wl_ptr;    /* [n_warp_lists+1] */
   const int32_t* wl;
+  const int32_t* gl_ptr;    /* [n_group_lists+1] */
+  const int32_t* gl;
   const int32_t* top;       /* [n_top] */
 } szb_lu_symbolic;
 

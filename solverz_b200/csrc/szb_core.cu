@@ -130,7 +130,7 @@ int szb_eval_J_masked(szb_handle* h, double t, const int* active, cudaStream_t s
 }
 
 int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b, const int* active,
-                           cudaStream_t st) {
+                           const double* rhs, double* yout, int store_l, cudaStream_t st) {
   if (!h->has_lu) { szb_set_error(h, "this handle was created without an LU schedule"); return SZB_ESTATE; }
   const double* mv = nullptr;
   double scale = 1.0;
@@ -139,11 +139,11 @@ int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b,
     mv = h->mass_vals;
     scale = -h_gamma;
   }
-  cudaError_t e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, mv, scale_b, scale, active,
-                                        h->flags, h->B, st);
+  cudaError_t e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, mv, scale_b, scale, rhs, yout,
+                                        store_l, active, h->flags, h->B, st);
   if (e != cudaSuccess) { szb_set_error(h, "LU factor launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
   h->launches[2]++;
-  h->factored = true;
+  h->factored = store_l != 0;
   return SZB_OK;
 }
 
@@ -199,9 +199,9 @@ int szb_create(const szb_desc* d, szb_handle** out) {
   if (h->has_lu) {
   S.n = L.n; S.nnz_a = L.nnz_a; S.ns = L.ns;
   S.lu_size = L.lu_size; S.cb_size = L.cb_size; S.cv_size = L.cv_size;
-  S.n_warp_lists = L.n_warp_lists; S.n_top = L.n_top;
-  S.f_warp_max = L.f_warp_max; S.f_top_max = L.f_top_max;
-  S.s_warp_max = L.s_warp_max; S.s_top_max = L.s_top_max;
+  S.n_warp_lists = L.n_warp_lists; S.n_group_lists = L.n_group_lists; S.n_top = L.n_top;
+  S.f_warp_max = L.f_warp_max; S.f_group_max = L.f_group_max; S.f_top_max = L.f_top_max;
+  S.s_warp_max = L.s_warp_max; S.s_group_max = L.s_group_max; S.s_top_max = L.s_top_max;
   const int ns = L.ns;
 #define UP(field, cnt)                                                               \
   do {                                                                               \
@@ -214,7 +214,8 @@ int szb_create(const szb_desc* d, szb_handle** out) {
   UP(child_ptr, ns + 1); UP(child, L.child_ptr[ns]);
   UP(a_ptr, ns + 1); UP(a_src, L.nnz_a); UP(a_dst, L.nnz_a);
   UP(lp_off, ns); UP(up_off, ns); UP(cb_off, ns);
-  UP(wl_ptr, L.n_warp_lists + 1); UP(wl, L.wl_ptr[L.n_warp_lists]); UP(top, L.n_top);
+  UP(wl_ptr, L.n_warp_lists + 1); UP(wl, L.wl_ptr[L.n_warp_lists]);
+  UP(gl_ptr, L.n_group_lists + 1); UP(gl, L.gl_ptr[L.n_group_lists]); UP(top, L.n_top);
 #undef UP
   }
   if (d->mass_vals) {
@@ -292,6 +293,7 @@ int szb_set_batch(szb_handle* h, int32_t B) {
   ALLOC(h->own_RHS, double, B * n);
   if (h->has_lu) {
     ALLOC(h->LU, double, static_cast<size_t>(B) * h->S.lu_size);
+    ALLOC(h->ybuf, double, B * n);
     const int gmax = h->cfg.grid_factor > h->cfg.grid_solve ? h->cfg.grid_factor : h->cfg.grid_solve;
     ALLOC(h->CBW, double, static_cast<size_t>(gmax) * (h->S.cb_size > 0 ? h->S.cb_size : 1));
     ALLOC(h->CVW, double, static_cast<size_t>(gmax) * (h->S.cv_size > 0 ? h->S.cv_size : 1));
@@ -386,7 +388,8 @@ int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream) {
   if (!h) return SZB_EINVAL;
   if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
   SZB_CUDA(h, cudaSetDevice(h->device));
-  return szb_lu_refactor_masked(h, h_gamma, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  return szb_lu_refactor_masked(h, h_gamma, nullptr, nullptr, nullptr, nullptr, 1,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream) {
@@ -401,7 +404,7 @@ int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream) {
   SZB_CUDA(h, cudaSetDevice(h->device));
   for (int r = 0; r < nrhs; ++r) {
     double* x = h->RHS + r * per;
-    cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, x, x, h->CVW, h->XW, 0, nullptr, h->B,
+    cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, x, x, h->CVW, h->XW, 1, 0, nullptr, h->B,
                                          static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
     h->launches[3]++;
@@ -469,12 +472,14 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
     if ((rc = szb_eval_J_masked(h, 0.0, h->active, st)) != SZB_OK) return rc;
     toc(1);
     tic();
-    if ((rc = szb_lu_refactor_masked(h, 0.0, nullptr, h->active, st)) != SZB_OK) return rc;
+    // factorisation with the residual riding along as an extra column: y = L^{-1} P F
+    if ((rc = szb_lu_refactor_masked(h, 0.0, nullptr, h->active, h->F, h->ybuf, 0, st)) != SZB_OK) return rc;
     toc(2);
     tic();
     {
-      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->F, h->Y, h->CVW, h->XW, 1, h->active,
-                                           B, st);
+      // backward substitution and Newton update  Y -= U^{-1} y
+      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->ybuf, h->Y, h->CVW, h->XW, 0, 1,
+                                           h->active, B, st);
       if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
       h->launches[3]++;
     }

@@ -32,7 +32,7 @@ struct szb_handle {
   double *bound_Y = nullptr, *bound_F = nullptr, *bound_JV = nullptr, *bound_RHS = nullptr;
   double *Y = nullptr, *F = nullptr, *JV = nullptr, *RHS = nullptr;
   int64_t rhs_len = 0;
-  double *LU = nullptr, *CBW = nullptr, *CVW = nullptr, *XW = nullptr;
+  double *LU = nullptr, *CBW = nullptr, *CVW = nullptr, *XW = nullptr, *ybuf = nullptr;
   double *fnorm = nullptr, *scale_b = nullptr;
   int *active = nullptr, *nstep = nullptr, *flags = nullptr, *counter = nullptr;
   int* pinned = nullptr;  // 16 ints of pinned host memory
@@ -69,4 +69,4 @@ void szb_set_error(szb_handle* h, const char* fmt, ...);
 int szb_eval_F_masked(szb_handle* h, double t, const int* active, cudaStream_t st);
 int szb_eval_J_masked(szb_handle* h, double t, const int* active, cudaStream_t st);
 int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b, const int* active,
-                           cudaStream_t st);
+                           const double* rhs, double* yout, int store_l, cudaStream_t st);

@@ -11,15 +11,21 @@
 //   * the host analysis (lu/symbolic.py) fixes pivots, ordering, supernodes and all index
 //     maps once; the kernels below are pure value arithmetic driven by int32 tables that are
 //     identical for all scenarios (L1/L2 resident);
-//   * phase 1: every warp walks its own list of small subtrees (fronts <= f_warp_max) with
-//     warp-synchronous dense partial LU in a private shared-memory front -- no CTA barrier;
-//     phase 2: the CTA eliminates the top of the tree together, front in shared memory;
-//   * contribution blocks travel through a small per-CTA stack in global memory (L2 resident,
-//     reused across scenarios by the persistent CTA), factors are written exactly once;
-//   * triangular solves follow the same two-phase tree walk; the forward sweep passes
-//     contribution vectors up the tree (no atomics => bitwise reproducible), the backward
-//     sweep only reads ancestors.  No tensor cores: nothing here is a dense contraction large
-//     enough to amortise them, the arithmetic is fp64 FMA fed from shared memory.
+//   * three levels of the elimination tree run with three kinds of thread groups:
+//       warp  : every warp walks its own list of small subtrees, front in a warp-private
+//               shared-memory buffer, __syncwarp only;
+//       group : a few warps (named barrier) share one medium front; groups run independent
+//               subtrees concurrently;
+//       CTA   : the few big fronts at the top use all threads.
+//     Inside a front: lane = row (conflict-free column-major shared memory with an odd leading
+//     dimension), warps stride over columns, right-looking rank-1 updates, one barrier/pivot;
+//   * the right-hand side can ride along as an extra front column, which fuses the forward
+//     substitution L y = b into the factorisation (Newton never needs L again);
+//   * contribution blocks travel through a per-CTA stack in global memory (L2 resident, reused
+//     across scenarios by the persistent CTA); factors are written exactly once;
+//   * triangular solves follow the same tree; the forward sweep passes contribution vectors up
+//     the tree (no atomics => bitwise reproducible), the backward sweep only reads ancestors.
+//   No tensor cores: fp64 FMA fed from shared memory; nothing here is a large dense contraction.
 #include "szb_lu.cuh"
 
 #include <cstdio>
@@ -30,151 +36,203 @@ namespace {
 
 constexpr int kWarp = 32;
 
-template <bool WARP>
-struct Grp {
-  __device__ static __forceinline__ int rank() { return WARP ? (threadIdx.x & 31) : threadIdx.x; }
-  __device__ static __forceinline__ int size() { return WARP ? kWarp : blockDim.x; }
-  __device__ static __forceinline__ void sync() {
-    if (WARP) __syncwarp(); else __syncthreads();
+// ---- thread groups ------------------------------------------------------------------------
+struct WarpGrp {
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int warp() const { return 0; }
+  __device__ __forceinline__ int nwarps() const { return 1; }
+  __device__ __forceinline__ int rank() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int size() const { return kWarp; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+struct NamedGrp {  // `nw` consecutive warps, hardware named barrier `id` (1..15)
+  int id, nw, w0;
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int warp() const { return (threadIdx.x >> 5) - w0; }
+  __device__ __forceinline__ int nwarps() const { return nw; }
+  __device__ __forceinline__ int rank() const { return threadIdx.x - (w0 << 5); }
+  __device__ __forceinline__ int size() const { return nw << 5; }
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nw << 5) : "memory");
   }
 };
+struct BlockGrp {
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int warp() const { return threadIdx.x >> 5; }
+  __device__ __forceinline__ int nwarps() const { return blockDim.x >> 5; }
+  __device__ __forceinline__ int rank() const { return threadIdx.x; }
+  __device__ __forceinline__ int size() const { return blockDim.x; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
 
-// t / m for 0 <= t < 2^22 without an integer division (exact)
-__device__ __forceinline__ int fdiv(int t, float invm) {
-  return __float2int_rz((static_cast<float>(t) + 0.5f) * invm);
-}
+struct FactorArgs {
+  const double* __restrict__ jv;     // matrix values of this scenario (CSC slots)
+  const double* __restrict__ mvals;  // optional mass values (shared)
+  double scale;
+  const double* __restrict__ rhs;    // optional right-hand side of this scenario (original order)
+  double* __restrict__ yout;         // forward-substituted rhs in pivot order (when rhs != null)
+  double* __restrict__ lu;           // factor storage of this scenario
+  double* __restrict__ cb;           // contribution workspace of this CTA
+  int store_l;                       // write the L21 rows of the panels
+  int* flag;
+};
 
 // ---------------------------------------------------------------------------------------
-// numeric factorisation of one supernode
+// numeric factorisation of one supernode; the front is column-major with leading dimension
+// ld = f | 1 and has f (+1 when a rhs rides along) columns
 // ---------------------------------------------------------------------------------------
-template <bool WARP>
-__device__ void factor_supernode(const LuDev& S, int k, double* __restrict__ Fm,
-                                 double* __restrict__ dinv, const double* __restrict__ jv,
-                                 const double* __restrict__ mvals, double scale,
-                                 double* __restrict__ lu, double* __restrict__ cb, int* flag) {
-  const int s = S.sn_s[k], f = S.sn_f[k], u = f - s;
-  const int r = Grp<WARP>::rank(), G = Grp<WARP>::size();
-  const int ff = f * f;
-  for (int t = r; t < ff; t += G) Fm[t] = 0.0;
-  Grp<WARP>::sync();
-  // original entries
+template <class G>
+__device__ void factor_supernode(const G g, const LuDev& S, const int k, double* __restrict__ Fm,
+                                 double* __restrict__ dinv, const FactorArgs& A) {
+  const int s = S.sn_s[k], f = S.sn_f[k], u = f - s, ld = f | 1;
+  const int lane = g.lane(), w = g.warp(), nw = g.nwarps(), r = g.rank(), G_ = g.size();
+  const int with_rhs = A.rhs != nullptr;
+  const int ncol = f + with_rhs;
+  // 1. clear
+  for (int t = r; t < ld * ncol; t += G_) Fm[t] = 0.0;
+  g.sync();
+  // 2. original entries (+ right-hand side of the pivot rows)
   {
     const int a1 = S.a_ptr[k + 1];
-    if (mvals) {
-      for (int e = S.a_ptr[k] + r; e < a1; e += G) {
+    if (A.mvals) {
+      for (int e = S.a_ptr[k] + r; e < a1; e += G_) {
         const int src = S.a_src[e];
-        Fm[S.a_dst[e]] = fma(scale, jv[src], mvals[src]);
+        Fm[S.a_dst[e]] = fma(A.scale, A.jv[src], A.mvals[src]);
       }
     } else {
-      for (int e = S.a_ptr[k] + r; e < a1; e += G) Fm[S.a_dst[e]] = scale * jv[S.a_src[e]];
+      for (int e = S.a_ptr[k] + r; e < a1; e += G_) Fm[S.a_dst[e]] = A.scale * A.jv[S.a_src[e]];
+    }
+    if (with_rhs) {
+      const int p0 = S.sn_piv0[k];
+      for (int t = r; t < s; t += G_) Fm[t + f * ld] = A.rhs[S.rowp[p0 + t]];
     }
   }
-  Grp<WARP>::sync();
-  // extend-add of the children's contribution blocks
+  g.sync();
+  // 3. extend-add of the children's contribution blocks (u_c x (u_c + 1), column-major)
   for (int ci = S.child_ptr[k]; ci < S.child_ptr[k + 1]; ++ci) {
     const int c = S.child[ci];
     const int uc = S.sn_f[c] - S.sn_s[c];
     if (uc == 0) continue;
     const int* __restrict__ rel = S.rel + S.rel_ptr[c];
-    const double* __restrict__ C = cb + S.cb_off[c];
-    const float inv = 1.0f / static_cast<float>(uc);
-    const int n2 = uc * uc;
-    for (int t = r; t < n2; t += G) {
-      const int j = fdiv(t, inv);
-      const int i = t - j * uc;
-      Fm[rel[i] + rel[j] * f] += C[t];
+    const double* __restrict__ C = A.cb + S.cb_off[c];
+    const int nc = uc + with_rhs;
+    for (int jc = w; jc < nc; jc += nw) {
+      const int dcol = (jc < uc) ? rel[jc] : f;
+      double* __restrict__ dst = Fm + dcol * ld;
+      const double* __restrict__ src = C + jc * uc;
+      for (int ic = lane; ic < uc; ic += kWarp) dst[rel[ic]] += src[ic];
     }
-    Grp<WARP>::sync();
+    g.sync();
   }
-  // right-looking elimination of the s pivots; L is kept unscaled until write-out
+  // 4. right-looking elimination of the s pivots; L stays unscaled until write-out
   for (int p = 0; p < s; ++p) {
-    const double piv = Fm[p + p * f];
+    const double piv = Fm[p + p * ld];
     const double inv = 1.0 / piv;
     if (r == 0) {
       dinv[p] = inv;
-      if (!(fabs(piv) > 0.0) || isinf(piv)) *flag = 2;
+      if (!(fabs(piv) > 0.0) || isinf(piv)) *A.flag = 2;
     }
-    const int m = f - p - 1;
-    double* __restrict__ colp = Fm + (p + 1) + p * f;        // L column (unscaled)
-    double* __restrict__ A22 = Fm + (p + 1) + (p + 1) * f;   // trailing block
-    const double* __restrict__ rowp = Fm + p + (p + 1) * f;  // U row, stride f
-    if (WARP) {
-      const float invm = 1.0f / static_cast<float>(m);
-      const int n2 = m * m;
-      for (int t = r; t < n2; t += kWarp) {
-        const int j = fdiv(t, invm);
-        const int i = t - j * m;
-        A22[i + j * f] = fma(-(colp[i] * inv), rowp[j * f], A22[i + j * f]);
-      }
-    } else {
-      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-      for (int j = w; j < m; j += nw) {
-        const double ukj = rowp[j * f];
-        for (int i = lane; i < m; i += kWarp)
-          A22[i + j * f] = fma(-(colp[i] * inv), ukj, A22[i + j * f]);
-      }
+    const int m = f - p - 1;          // trailing rows
+    const int nc = ncol - p - 1;      // trailing columns (incl. rhs)
+    const double* __restrict__ colp = Fm + (p + 1) + p * ld;
+    // multipliers of this lane's rows (up to 4 row chunks kept in registers)
+    double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+    if (lane < m) l0 = colp[lane] * inv;
+    if (lane + 32 < m) l1 = colp[lane + 32] * inv;
+    if (lane + 64 < m) l2 = colp[lane + 64] * inv;
+    if (lane + 96 < m) l3 = colp[lane + 96] * inv;
+    for (int jj = w; jj < nc; jj += nw) {
+      double* __restrict__ col = Fm + (p + 1) + (p + 1 + jj) * ld;
+      const double ukj = col[-1];     // element (p, j)
+      if (lane < m) col[lane] = fma(-l0, ukj, col[lane]);
+      if (lane + 32 < m) col[lane + 32] = fma(-l1, ukj, col[lane + 32]);
+      if (lane + 64 < m) col[lane + 64] = fma(-l2, ukj, col[lane + 64]);
+      if (lane + 96 < m) col[lane + 96] = fma(-l3, ukj, col[lane + 96]);
+      for (int i = lane + 128; i < m; i += kWarp) col[i] = fma(-(colp[i] * inv), ukj, col[i]);
     }
-    Grp<WARP>::sync();
+    g.sync();
   }
-  // write-out: [L11\U11; L21] panel (f x s, column-major), U12^T (u x s), contribution (u x u)
+  // 5. write-out
   {
-    double* __restrict__ Lp = lu + S.lp_off[k];
-    const int fs = f * s;
-    const float invf = 1.0f / static_cast<float>(f);
-    for (int t = r; t < fs; t += G) {
-      const int p = fdiv(t, invf);
-      const int i = t - p * f;
-      const double v = Fm[t];
-      Lp[t] = (i > p) ? v * dinv[p] : v;
+    double* __restrict__ Lp = A.lu + S.lp_off[k];           // f x s, column-major, ld = f
+    const int rows = A.store_l ? f : s;
+    for (int p = w; p < s; p += nw) {
+      const double di = dinv[p];
+      for (int i = lane; i < rows; i += kWarp) {
+        const double v = Fm[i + p * ld];
+        Lp[i + p * f] = (i > p) ? v * di : v;
+      }
     }
     if (u > 0) {
-      double* __restrict__ Up = lu + S.up_off[k];
-      const float invu = 1.0f / static_cast<float>(u);
-      const int us = u * s;
-      for (int t = r; t < us; t += G) {
-        const int rr = fdiv(t, invu);
-        const int c = t - rr * u;
-        Up[t] = Fm[rr + (s + c) * f];
-      }
-      double* __restrict__ C = cb + S.cb_off[k];
-      const int uu = u * u;
-      for (int t = r; t < uu; t += G) {
-        const int j = fdiv(t, invu);
-        const int i = t - j * u;
-        C[t] = Fm[(s + i) + (s + j) * f];
-      }
+      double* __restrict__ Up = A.lu + S.up_off[k];         // U12 rows: Up[c + r*u] = U12[r][c]
+      for (int rr = w; rr < s; rr += nw)
+        for (int c = lane; c < u; c += kWarp) Up[c + rr * u] = Fm[rr + (s + c) * ld];
+      double* __restrict__ C = A.cb + S.cb_off[k];          // u x (u+1), column-major
+      const int nc = u + with_rhs;
+      for (int j = w; j < nc; j += nw)
+        for (int i = lane; i < u; i += kWarp) C[i + j * u] = Fm[(s + i) + (s + j) * ld];
+    }
+    if (with_rhs) {
+      const int p0 = S.sn_piv0[k];
+      for (int t = r; t < s; t += G_) A.yout[p0 + t] = Fm[t + f * ld];
     }
   }
-  Grp<WARP>::sync();
+  g.sync();
 }
 
 __global__ void __launch_bounds__(1024, 1)
 lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restrict__ LU,
                  double* __restrict__ CBW, const double* __restrict__ mvals,
                  const double* __restrict__ scale_b, double scale_const,
+                 const double* __restrict__ RHS, double* __restrict__ YOUT, int store_l,
                  const int* __restrict__ active, int* __restrict__ flags, int B) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5;
-  const int fw2 = S.f_warp_max * S.f_warp_max;
-  const int ftop2 = S.f_top_max * S.f_top_max;
-  const int front_doubles = max(S.n_warp_lists * fw2, ftop2);
-  double* dinv_all = sm + front_doubles;  // n_warp_lists*s_warp_max  |  s_top_max
-  double* cb = CBW + static_cast<size_t>(blockIdx.x) * S.cb_size;
+  const int wstride = (S.f_warp_max | 1) * (S.f_warp_max + 1) + S.f_warp_max;
+  const int gstride = (S.f_group_max | 1) * (S.f_group_max + 1) + S.f_group_max;
+  const int wpg = (blockDim.x >> 5) / max(S.n_group_lists, 1);   // warps per group
+  FactorArgs A;
+  A.mvals = mvals;
+  A.store_l = store_l;
+  A.cb = CBW + static_cast<size_t>(blockIdx.x) * S.cb_size;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     if (active && !active[b]) continue;
-    const double* jv = JV + static_cast<size_t>(b) * S.nnz_a;
-    double* lu = LU + static_cast<size_t>(b) * S.lu_size;
-    const double scale = scale_b ? scale_b[b] : scale_const;
-    int* flag = flags + b;
+    A.jv = JV + static_cast<size_t>(b) * S.nnz_a;
+    A.lu = LU + static_cast<size_t>(b) * S.lu_size;
+    A.scale = scale_b ? scale_b[b] : scale_const;
+    A.rhs = RHS ? RHS + static_cast<size_t>(b) * S.n : nullptr;
+    A.yout = YOUT ? YOUT + static_cast<size_t>(b) * S.n : nullptr;
+    A.flag = flags + b;
+    // level 0: warps
     if (warp < S.n_warp_lists) {
-      double* Fm = sm + warp * fw2;
-      double* dinv = dinv_all + warp * S.s_warp_max;
+      double* Fm = sm + warp * wstride;
+      double* dinv = Fm + (S.f_warp_max | 1) * (S.f_warp_max + 1);
+      const WarpGrp g;
       for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q)
-        factor_supernode<true>(S, S.wl[q], Fm, dinv, jv, mvals, scale, lu, cb, flag);
+        factor_supernode(g, S, S.wl[q], Fm, dinv, A);
     }
     __syncthreads();
-    for (int q = 0; q < S.n_top; ++q)
-      factor_supernode<false>(S, S.top[q], sm, dinv_all, jv, mvals, scale, lu, cb, flag);
+    // level 1: groups of warps
+    if (S.n_group_lists > 0) {
+      const int gi = warp / wpg;
+      if (gi < S.n_group_lists) {
+        double* Fm = sm + gi * gstride;
+        double* dinv = Fm + (S.f_group_max | 1) * (S.f_group_max + 1);
+        NamedGrp g;
+        g.id = 1 + gi;
+        g.nw = wpg;
+        g.w0 = gi * wpg;
+        for (int q = S.gl_ptr[gi]; q < S.gl_ptr[gi + 1]; ++q)
+          factor_supernode(g, S, S.gl[q], Fm, dinv, A);
+      }
+      __syncthreads();
+    }
+    // level 2: the whole CTA
+    {
+      double* dinv = sm + (S.f_top_max | 1) * (S.f_top_max + 1);
+      const BlockGrp g;
+      for (int q = 0; q < S.n_top; ++q) factor_supernode(g, S, S.top[q], sm, dinv, A);
+    }
   }
 }
 
@@ -188,102 +246,122 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // forward: r = [b_piv ; 0] + sum_children cv_c ;  L11 x = r_piv ; cv_k = r_upd - L21 x
-template <bool WARP>
-__device__ void forward_supernode(const LuDev& S, int k, const double* __restrict__ lu,
-                                  double* __restrict__ xb, double* __restrict__ cv,
-                                  double* __restrict__ rv, double* __restrict__ T) {
+// rv: f doubles of scratch, T: s*s doubles of scratch (diagonal block staged once)
+template <class G>
+__device__ void forward_supernode(const G g, const LuDev& S, const int k,
+                                  const double* __restrict__ lu, double* __restrict__ xb,
+                                  double* __restrict__ cv, double* __restrict__ rv,
+                                  double* __restrict__ T) {
   const int s = S.sn_s[k], f = S.sn_f[k], u = f - s, p0 = S.sn_piv0[k];
-  const int r = Grp<WARP>::rank(), G = Grp<WARP>::size();
+  const int lane = g.lane(), w = g.warp(), nw = g.nwarps(), r = g.rank(), G_ = g.size();
   const double* __restrict__ Lp = lu + S.lp_off[k];
-  for (int t = r; t < f; t += G) rv[t] = (t < s) ? xb[p0 + t] : 0.0;
-  // stage the s x s diagonal block
-  {
-    const float invs = 1.0f / static_cast<float>(s);
-    const int ss = s * s;
-    for (int t = r; t < ss; t += G) {
-      const int p = fdiv(t, invs);
-      const int i = t - p * s;
-      T[t] = Lp[i + p * f];
-    }
-  }
-  Grp<WARP>::sync();
+  for (int t = r; t < f; t += G_) rv[t] = (t < s) ? xb[p0 + t] : 0.0;
+  for (int p = w; p < s; p += nw)
+    for (int i = lane; i < s; i += kWarp) T[i + p * s] = Lp[i + p * f];
+  g.sync();
   for (int ci = S.child_ptr[k]; ci < S.child_ptr[k + 1]; ++ci) {
     const int c = S.child[ci];
     const int c0 = S.rel_ptr[c], uc = S.rel_ptr[c + 1] - c0;
     if (uc == 0) continue;
-    for (int t = r; t < uc; t += G) rv[S.rel[c0 + t]] += cv[c0 + t];
-    Grp<WARP>::sync();
+    for (int t = r; t < uc; t += G_) rv[S.rel[c0 + t]] += cv[c0 + t];
+    g.sync();
   }
   for (int p = 0; p + 1 < s; ++p) {
     const double xp = rv[p];
-    for (int i = p + 1 + r; i < s; i += G) rv[i] = fma(-T[i + p * s], xp, rv[i]);
-    Grp<WARP>::sync();
+    for (int i = p + 1 + r; i < s; i += G_) rv[i] = fma(-T[i + p * s], xp, rv[i]);
+    g.sync();
   }
-  for (int t = r; t < s; t += G) xb[p0 + t] = rv[t];
+  for (int t = r; t < s; t += G_) xb[p0 + t] = rv[t];
   if (u > 0) {
     const int c0 = S.rel_ptr[k];
-    for (int i = r; i < u; i += G) {
+    for (int i = r; i < u; i += G_) {
       double acc = rv[s + i];
       const double* __restrict__ row = Lp + s + i;
       for (int p = 0; p < s; ++p) acc = fma(-row[p * f], rv[p], acc);
       cv[c0 + i] = acc;
     }
   }
-  Grp<WARP>::sync();
+  g.sync();
 }
 
 // backward: x_piv = U11^{-1} ( y_piv - U12 x_upd )
-template <bool WARP>
-__device__ void backward_supernode(const LuDev& S, int k, const double* __restrict__ lu,
-                                   double* __restrict__ xb, double* __restrict__ rv,
-                                   double* __restrict__ gv, double* __restrict__ T) {
+// rv: s doubles, gv: u doubles, T: s*s doubles
+template <class G>
+__device__ void backward_supernode(const G g, const LuDev& S, const int k,
+                                   const double* __restrict__ lu, double* __restrict__ xb,
+                                   double* __restrict__ rv, double* __restrict__ gv,
+                                   double* __restrict__ T) {
   const int s = S.sn_s[k], f = S.sn_f[k], u = f - s, p0 = S.sn_piv0[k];
-  const int r = Grp<WARP>::rank(), G = Grp<WARP>::size();
+  const int lane = g.lane(), w = g.warp(), nw = g.nwarps(), r = g.rank(), G_ = g.size();
   const double* __restrict__ Lp = lu + S.lp_off[k];
   const double* __restrict__ Ut = lu + S.up_off[k];
   const int* __restrict__ ids = S.idx + S.idx_ptr[k] + s;
-  for (int t = r; t < u; t += G) gv[t] = xb[ids[t]];
-  {
-    const float invs = 1.0f / static_cast<float>(s);
-    const int ss = s * s;
-    for (int t = r; t < ss; t += G) {
-      const int p = fdiv(t, invs);
-      const int i = t - p * s;
-      T[t] = Lp[i + p * f];
+  for (int t = r; t < u; t += G_) gv[t] = xb[ids[t]];
+  // stage the upper triangle (incl. diagonal) of the s x s block: column p, rows 0..p
+  for (int p = w; p < s; p += nw)
+    for (int i = lane; i <= p; i += kWarp) T[i + p * s] = Lp[i + p * f];
+  g.sync();
+  for (int rr = w; rr < s; rr += nw) {
+    double acc = 0.0;
+    const double* __restrict__ row = Ut + rr * u;
+    for (int c = lane; c < u; c += kWarp) acc = fma(row[c], gv[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) rv[rr] = xb[p0 + rr] - acc;
+  }
+  g.sync();
+  if (s <= kWarp) {
+    // one warp finishes the small triangle with shuffles, no further barriers
+    if (w == 0) {
+      double mine = (lane < s) ? rv[lane] : 0.0;
+      for (int p = s - 1; p >= 0; --p) {
+        const double xp = __shfl_sync(0xffffffffu, mine, p) / T[p + p * s];
+        if (lane == p) mine = xp;
+        else if (lane < p) mine = fma(-T[lane + p * s], xp, mine);
+      }
+      if (lane < s) xb[p0 + lane] = mine;
+    }
+  } else {
+    for (int p = s - 1; p >= 0; --p) {
+      const double xp = rv[p] / T[p + p * s];
+      for (int i = r; i < p; i += G_) rv[i] = fma(-T[i + p * s], xp, rv[i]);
+      if (r == 0) xb[p0 + p] = xp;
+      g.sync();
     }
   }
-  Grp<WARP>::sync();
-  {
-    const int lane = threadIdx.x & 31;
-    const int w = WARP ? 0 : (threadIdx.x >> 5);
-    const int nw = WARP ? 1 : (blockDim.x >> 5);
-    for (int rr = w; rr < s; rr += nw) {
-      double acc = 0.0;
-      const double* __restrict__ col = Ut + rr * u;
-      for (int c = lane; c < u; c += kWarp) acc = fma(col[c], gv[c], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) rv[rr] = xb[p0 + rr] - acc;
-    }
-  }
-  Grp<WARP>::sync();
-  for (int p = s - 1; p >= 0; --p) {
-    const double xp = rv[p] / T[p + p * s];
-    for (int i = r; i < p; i += G) rv[i] = fma(-T[i + p * s], xp, rv[i]);
-    if (r == 0) xb[p0 + p] = xp;
-    Grp<WARP>::sync();
-  }
+  g.sync();
 }
 
+struct SolveSmem {
+  int wstride, gstride;
+  int w_rv, w_T, g_rv, g_T, t_rv, t_T;
+};
+
+__device__ __forceinline__ SolveSmem solve_layout(const LuDev& S) {
+  SolveSmem L;
+  L.w_rv = 2 * S.f_warp_max;
+  L.w_T = S.s_warp_max * S.s_warp_max;
+  L.wstride = L.w_rv + L.w_T;
+  L.g_rv = 2 * S.f_group_max;
+  L.g_T = S.s_group_max * S.s_group_max;
+  L.gstride = L.g_rv + L.g_T;
+  L.t_rv = 2 * S.f_top_max;
+  L.t_T = S.s_top_max * S.s_top_max;
+  return L;
+}
+
+// do_fwd: run the forward sweep (RHS in original order); otherwise RHS already holds y in pivot
+// order (produced by the fused factorisation).
 __global__ void __launch_bounds__(1024, 1)
 lu_solve_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ RHS,
                 double* __restrict__ X, double* __restrict__ CVW, double* __restrict__ XW,
-                int x_in_smem, int mode, const int* __restrict__ active, int B) {
+                int x_in_smem, int do_fwd, int mode, const int* __restrict__ active, int B) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5;
   const int n = S.n;
   double* xb = x_in_smem ? sm : XW + static_cast<size_t>(blockIdx.x) * n;
   double* scratch = x_in_smem ? sm + n : sm;
-  const int per_warp = 2 * S.f_warp_max + S.s_warp_max * S.s_warp_max;
+  const SolveSmem L = solve_layout(S);
+  const int wpg = (blockDim.x >> 5) / max(S.n_group_lists, 1);
   double* cv = CVW + static_cast<size_t>(blockIdx.x) * S.cv_size;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     if (active && !active[b]) continue;
@@ -291,32 +369,60 @@ lu_solve_kernel(const LuDev S, const double* __restrict__ LU, const double* __re
     const double* rhs = RHS + static_cast<size_t>(b) * n;
     double* x = X + static_cast<size_t>(b) * n;
     __syncthreads();
-    for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = rhs[S.rowp[t]];
-    __syncthreads();
-    // forward
-    if (warp < S.n_warp_lists) {
-      double* rv = scratch + warp * per_warp;
-      double* T = rv + 2 * S.f_warp_max;
-      for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q)
-        forward_supernode<true>(S, S.wl[q], lu, xb, cv, rv, T);
+    if (do_fwd) {
+      for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = rhs[S.rowp[t]];
+    } else {
+      for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = rhs[t];
     }
     __syncthreads();
+    if (do_fwd) {
+      if (warp < S.n_warp_lists) {
+        double* rv = scratch + warp * L.wstride;
+        const WarpGrp g;
+        for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q)
+          forward_supernode(g, S, S.wl[q], lu, xb, cv, rv, rv + L.w_rv);
+      }
+      __syncthreads();
+      if (S.n_group_lists > 0) {
+        const int gi = warp / wpg;
+        if (gi < S.n_group_lists) {
+          double* rv = scratch + gi * L.gstride;
+          NamedGrp g;
+          g.id = 1 + gi; g.nw = wpg; g.w0 = gi * wpg;
+          for (int q = S.gl_ptr[gi]; q < S.gl_ptr[gi + 1]; ++q)
+            forward_supernode(g, S, S.gl[q], lu, xb, cv, rv, rv + L.g_rv);
+        }
+        __syncthreads();
+      }
+      {
+        const BlockGrp g;
+        for (int q = 0; q < S.n_top; ++q)
+          forward_supernode(g, S, S.top[q], lu, xb, cv, scratch, scratch + L.t_rv);
+      }
+    }
+    // backward: top, groups, warps
     {
-      double* rv = scratch;
-      double* T = rv + 2 * S.f_top_max;
-      for (int q = 0; q < S.n_top; ++q) forward_supernode<false>(S, S.top[q], lu, xb, cv, rv, T);
-      // backward
-      double* gv = rv + S.f_top_max;
+      const BlockGrp g;
       for (int q = S.n_top - 1; q >= 0; --q)
-        backward_supernode<false>(S, S.top[q], lu, xb, rv, gv, T);
+        backward_supernode(g, S, S.top[q], lu, xb, scratch, scratch + S.f_top_max, scratch + L.t_rv);
     }
     __syncthreads();
+    if (S.n_group_lists > 0) {
+      const int gi = warp / wpg;
+      if (gi < S.n_group_lists) {
+        double* rv = scratch + gi * L.gstride;
+        NamedGrp g;
+        g.id = 1 + gi; g.nw = wpg; g.w0 = gi * wpg;
+        for (int q = S.gl_ptr[gi + 1] - 1; q >= S.gl_ptr[gi]; --q)
+          backward_supernode(g, S, S.gl[q], lu, xb, rv, rv + S.f_group_max, rv + L.g_rv);
+      }
+      __syncthreads();
+    }
     if (warp < S.n_warp_lists) {
-      double* rv = scratch + warp * per_warp;
-      double* gv = rv + S.f_warp_max;
-      double* T = rv + 2 * S.f_warp_max;
+      double* rv = scratch + warp * L.wstride;
+      const WarpGrp g;
       for (int q = S.wl_ptr[warp + 1] - 1; q >= S.wl_ptr[warp]; --q)
-        backward_supernode<true>(S, S.wl[q], lu, xb, rv, gv, T);
+        backward_supernode(g, S, S.wl[q], lu, xb, rv, rv + S.f_warp_max, rv + L.w_rv);
     }
     __syncthreads();
     if (mode == 0) {
@@ -327,6 +433,8 @@ lu_solve_kernel(const LuDev S, const double* __restrict__ LU, const double* __re
   }
 }
 
+size_t smax(size_t a, size_t b) { return a > b ? a : b; }
+
 }  // namespace
 
 cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
@@ -335,29 +443,32 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   if (e != cudaSuccess) return e;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  int threads = 32 * (S.n_warp_lists > 0 ? S.n_warp_lists : 1);
-  if (S.n_top > 0 && threads < 256) threads = 256;
-  if (threads > 1024) threads = 1024;
-  cfg->threads = threads;
-  const size_t fw2 = static_cast<size_t>(S.f_warp_max) * S.f_warp_max;
-  const size_t ftop2 = static_cast<size_t>(S.f_top_max) * S.f_top_max;
-  size_t front = S.n_warp_lists * fw2;
-  if (ftop2 > front) front = ftop2;
-  size_t dinv = static_cast<size_t>(S.n_warp_lists) * S.s_warp_max;
-  if (static_cast<size_t>(S.s_top_max) > dinv) dinv = S.s_top_max;
-  cfg->smem_factor = (front + dinv) * sizeof(double);
+  // threads: one warp per warp list, and a whole number of warps per group
+  int warps = S.n_warp_lists > 0 ? S.n_warp_lists : 1;
+  if (S.n_group_lists > 0) {
+    const int per = (warps + S.n_group_lists - 1) / S.n_group_lists;
+    const int wpg = per < 2 ? 2 : per;
+    warps = wpg * S.n_group_lists;
+  }
+  if (S.n_top > 0 && warps < 8) warps = S.n_group_lists > 0 ? ((8 + S.n_group_lists - 1) / S.n_group_lists) * S.n_group_lists : 8;
+  if (warps > 32) return cudaErrorInvalidConfiguration;
+  cfg->threads = 32 * warps;
+  auto front = [](int f) { return static_cast<size_t>(f | 1) * (f + 1) + f; };
+  size_t fsm = S.n_warp_lists * front(S.f_warp_max);
+  fsm = smax(fsm, S.n_group_lists * front(S.f_group_max));
+  fsm = smax(fsm, S.n_top > 0 ? front(S.f_top_max) : 0);
+  cfg->smem_factor = fsm * sizeof(double);
   if (cfg->smem_factor > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
-  size_t per_warp = 2 * static_cast<size_t>(S.f_warp_max) + static_cast<size_t>(S.s_warp_max) * S.s_warp_max;
-  size_t top = 2 * static_cast<size_t>(S.f_top_max) + static_cast<size_t>(S.s_top_max) * S.s_top_max;
-  size_t scratch = S.n_warp_lists * per_warp;
-  if (top > scratch) scratch = top;
-  size_t with_x = (scratch + S.n) * sizeof(double);
+  size_t ssm = S.n_warp_lists * (2 * static_cast<size_t>(S.f_warp_max) + static_cast<size_t>(S.s_warp_max) * S.s_warp_max);
+  ssm = smax(ssm, S.n_group_lists * (2 * static_cast<size_t>(S.f_group_max) + static_cast<size_t>(S.s_group_max) * S.s_group_max));
+  ssm = smax(ssm, 2 * static_cast<size_t>(S.f_top_max) + static_cast<size_t>(S.s_top_max) * S.s_top_max);
+  const size_t with_x = (ssm + S.n) * sizeof(double);
   if (with_x <= static_cast<size_t>(smem_max)) {
     cfg->x_in_smem = 1;
     cfg->smem_solve = with_x;
   } else {
     cfg->x_in_smem = 0;
-    cfg->smem_solve = scratch * sizeof(double);
+    cfg->smem_solve = ssm * sizeof(double);
     if (cfg->smem_solve > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
   }
   e = cudaFuncSetAttribute(lu_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -367,8 +478,8 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
                            static_cast<int>(cfg->smem_solve));
   if (e != cudaSuccess) return e;
   int occ_f = 1, occ_s = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lu_factor_kernel, threads, cfg->smem_factor);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, lu_solve_kernel, threads, cfg->smem_solve);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lu_factor_kernel, cfg->threads, cfg->smem_factor);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, lu_solve_kernel, cfg->threads, cfg->smem_solve);
   if (occ_f < 1) occ_f = 1;
   if (occ_s < 1) occ_s = 1;
   cfg->grid_factor = sms * occ_f;
@@ -380,20 +491,20 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
 
 cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV, double* LU,
                              double* CBW, const double* mvals, const double* scale_b,
-                             double scale_const, const int* active, int* flags, int B,
-                             cudaStream_t st) {
+                             double scale_const, const double* RHS, double* YOUT, int store_l,
+                             const int* active, int* flags, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   lu_factor_kernel<<<cfg.grid_factor, cfg.threads, cfg.smem_factor, st>>>(
-      S, JV, LU, CBW, mvals, scale_b, scale_const, active, flags, B);
+      S, JV, LU, CBW, mvals, scale_b, scale_const, RHS, YOUT, store_l, active, flags, B);
   return cudaGetLastError();
 }
 
 cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* LU,
-                            const double* RHS, double* X, double* CVW, double* XW, int mode,
-                            const int* active, int B, cudaStream_t st) {
+                            const double* RHS, double* X, double* CVW, double* XW, int do_fwd,
+                            int mode, const int* active, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   lu_solve_kernel<<<cfg.grid_solve, cfg.threads, cfg.smem_solve, st>>>(
-      S, LU, RHS, X, CVW, XW, cfg.x_in_smem, mode, active, B);
+      S, LU, RHS, X, CVW, XW, cfg.x_in_smem, do_fwd, mode, active, B);
   return cudaGetLastError();
 }
 

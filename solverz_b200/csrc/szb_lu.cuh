@@ -9,13 +9,14 @@ namespace szb {
 struct LuDev {
   int n, nnz_a, ns;
   int lu_size, cb_size, cv_size;
-  int n_warp_lists, n_top, f_warp_max, f_top_max, s_warp_max, s_top_max;
+  int n_warp_lists, n_group_lists, n_top;
+  int f_warp_max, f_group_max, f_top_max, s_warp_max, s_group_max, s_top_max;
   const int *rowp, *colp;
   const int *sn_piv0, *sn_s, *sn_f;
   const int *idx_ptr, *idx, *rel_ptr, *rel, *child_ptr, *child;
   const int *a_ptr, *a_src, *a_dst;
   const int *lp_off, *up_off, *cb_off;
-  const int *wl_ptr, *wl, *top;
+  const int *wl_ptr, *wl, *gl_ptr, *gl, *top;
 };
 
 struct LuLaunchCfg {
@@ -31,15 +32,19 @@ struct LuLaunchCfg {
 cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg);
 
 // A(b) = scale(b) * JV[b] (+ mvals)  ->  LU[b];  scale_b may be null (then scale_const).
+// RHS / YOUT non-null: the right-hand side rides along (forward substitution fused), YOUT gets
+// y = L^{-1} P b in pivot order.  store_l == 0 skips writing the L21 rows (Newton never reuses L).
 cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV,
                              double* LU, double* CBW, const double* mvals, const double* scale_b,
-                             double scale_const, const int* active, int* flags, int B,
-                             cudaStream_t st);
+                             double scale_const, const double* RHS, double* YOUT, int store_l,
+                             const int* active, int* flags, int B, cudaStream_t st);
 
 // mode 0:  X[b] <- A^{-1} RHS[b]         (X may alias RHS)
 // mode 1:  X[b] <- X[b] - A^{-1} RHS[b]  (Newton update y -= dx; X is Y)
+// do_fwd 1: RHS is b in original order (forward + backward sweep)
+// do_fwd 0: RHS is y in pivot order from a fused factorisation (backward sweep only)
 cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* LU,
-                            const double* RHS, double* X, double* CVW, double* XW, int mode,
-                            const int* active, int B, cudaStream_t st);
+                            const double* RHS, double* X, double* CVW, double* XW, int do_fwd,
+                            int mode, const int* active, int B, cudaStream_t st);
 
 }  // namespace szb

@@ -302,20 +302,30 @@ class LUSymbolic:
     nnz_lu: int               # true nnz(L+U) of the symbolic factor (no supernode padding)
     flops: float              # factor flops per scenario (2 per multiply-add)
     f_max: int
-    # schedule: warp-level subtrees first, then block-level top supernodes
+    # schedule: warp-level subtrees, then group-level (a few warps) subtrees, then the CTA-level top
     n_warp_lists: int
     wl_ptr: np.ndarray        # warp work lists (supernode ids, each list in postorder)
     wl: np.ndarray
+    n_group_lists: int
+    gl_ptr: np.ndarray        # group work lists
+    gl: np.ndarray
     top: np.ndarray           # block-level supernodes in postorder
     f_warp_max: int
+    f_group_max: int
     f_top_max: int
     ordering: str = ""
+
+    @property
+    def order(self) -> np.ndarray:
+        """A valid sequential elimination order (children before parents)."""
+        return np.concatenate([self.wl, self.gl, self.top]).astype(np.int64)
 
     def stats(self) -> Dict[str, float]:
         return dict(n=self.n, nnzA=self.nnzA, nnz_lu=self.nnz_lu, lu_size=self.lu_size,
                     cb_size=self.cb_size, flops=self.flops, ns=self.ns, f_max=self.f_max,
-                    f_warp_max=self.f_warp_max, f_top_max=self.f_top_max,
-                    n_top=len(self.top), ordering=self.ordering)
+                    f_warp_max=self.f_warp_max, f_group_max=self.f_group_max, f_top_max=self.f_top_max,
+                    n_warp_sn=len(self.wl), n_group_sn=len(self.gl), n_top=len(self.top),
+                    ordering=self.ordering)
 
 
 def _flops_of(struct_sizes: np.ndarray) -> float:
@@ -325,7 +335,7 @@ def _flops_of(struct_sizes: np.ndarray) -> float:
 
 def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.ndarray,
            relax_frac: float, relax_small: int, warp_front_max: int, n_warps: int,
-           name: str) -> LUSymbolic:
+           group_front_max: int, n_groups: int, name: str) -> LUSymbolic:
     n = A.shape[0]
     parent, children, struct = _symbolic_structs(S, order)
     size = np.array([len(s) for s in struct], dtype=np.int64)
@@ -437,7 +447,8 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         loc_r[sel] = pr
         loc_c[sel] = pc
     a_src = by_owner.astype(np.int64)
-    a_dst = (loc_r[by_owner] + loc_c[by_owner] * sn_f[owner[by_owner]]).astype(np.int64)
+    sn_ld = sn_f | 1   # odd leading dimension: conflict-free shared-memory rows AND columns
+    a_dst = (loc_r[by_owner] + loc_c[by_owner] * sn_ld[owner[by_owner]]).astype(np.int64)
 
     # ---- factor storage
     lp_sz = sn_f * sn_s
@@ -452,39 +463,53 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         off += up_sz[k]
     lu_size = int(off)
 
-    # ---- schedule: maximal subtrees whose fronts all fit a warp  vs  block-level top
+    # ---- schedule: three levels of the tree.  A supernode is warp-level when every front in
+    # its subtree fits a warp-private buffer, group-level when every front fits a group buffer,
+    # CTA-level otherwise.  Each level's forest is split into independent subtrees that are
+    # assigned to work lists by longest-processing-time first.
     sub_fmax = sn_f.copy()
     sub_cost = (sn_s * sn_f * sn_f).astype(np.float64)
+    own_cost = sub_cost.copy()
     for k in range(ns):  # postorder: children before parents
         p = sn_parent[k]
         if p >= 0:
             sub_fmax[p] = max(sub_fmax[p], sub_fmax[k])
             sub_cost[p] += sub_cost[k]
-    is_warp = sub_fmax <= warp_front_max
-    roots = [k for k in range(ns) if is_warp[k] and (sn_parent[k] < 0 or not is_warp[sn_parent[k]])]
-    # subtree membership: a warp supernode belongs to the root above it
-    root_of = np.full(ns, -1, dtype=np.int64)
-    for k in range(ns - 1, -1, -1):
-        if is_warp[k]:
-            p = sn_parent[k]
-            root_of[k] = k if (p < 0 or not is_warp[p]) else root_of[p]
-    # longest-processing-time assignment of subtrees to warp lists
-    n_lists = max(1, min(n_warps, len(roots))) if roots else 0
-    loads = np.zeros(max(n_lists, 1))
-    assign = {}
-    for r in sorted(roots, key=lambda k: -sub_cost[k]):
-        w = int(np.argmin(loads))
-        assign[r] = w
-        loads[w] += sub_cost[r]
-    lists: List[List[int]] = [[] for _ in range(n_lists)]
-    for k in range(ns):
-        if is_warp[k]:
-            lists[assign[int(root_of[k])]].append(k)
-    wl_ptr = np.zeros(n_lists + 1, dtype=np.int64)
-    if n_lists:
-        wl_ptr[1:] = np.cumsum([len(l) for l in lists])
-    wl = np.array([k for l in lists for k in l], dtype=np.int64)
-    top = np.array([k for k in range(ns) if not is_warp[k]], dtype=np.int64)
+    level = np.where(sub_fmax <= warp_front_max, 0, np.where(sub_fmax <= group_front_max, 1, 2))
+
+    def make_lists(lv: int, n_max: int):
+        mine = level == lv
+        roots = [k for k in range(ns) if mine[k] and (sn_parent[k] < 0 or not mine[sn_parent[k]])]
+        root_of = np.full(ns, -1, dtype=np.int64)
+        cost = np.zeros(ns)
+        for k in range(ns - 1, -1, -1):
+            if mine[k]:
+                p = sn_parent[k]
+                root_of[k] = k if (p < 0 or not mine[p]) else root_of[p]
+        for k in range(ns):
+            if mine[k]:
+                cost[root_of[k]] += own_cost[k]
+        n_lists = max(1, min(n_max, len(roots))) if roots else 0
+        loads = np.zeros(max(n_lists, 1))
+        assign = {}
+        for r in sorted(roots, key=lambda k: -cost[k]):
+            w = int(np.argmin(loads))
+            assign[r] = w
+            loads[w] += cost[r]
+        lists: List[List[int]] = [[] for _ in range(n_lists)]
+        for k in range(ns):
+            if mine[k]:
+                lists[assign[int(root_of[k])]].append(k)
+        ptr = np.zeros(n_lists + 1, dtype=np.int64)
+        if n_lists:
+            ptr[1:] = np.cumsum([len(l) for l in lists])
+        flat = np.array([k for l in lists for k in l], dtype=np.int64)
+        return n_lists, lists, ptr, flat
+
+    n_lists, lists, wl_ptr, wl = make_lists(0, n_warps)
+    n_glists, glists, gl_ptr, gl = make_lists(1, n_groups)
+    top = np.array([k for k in range(ns) if level[k] == 2], dtype=np.int64)
+    is_warp = level == 0
 
     # ---- contribution-block workspace.  Each work list (and the top list) is a sequential
     # postorder walk, so the classic multifrontal stack is valid per list: when a supernode
@@ -493,7 +518,7 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
     # block is pushed in their place once its pivots are eliminated.  Blocks that cross from a
     # warp list to the top list live in a separate, never-reused region.
     cb_off = np.zeros(ns, dtype=np.int64)
-    cb_need = sn_u * sn_u
+    cb_need = sn_u * (sn_u + 1)   # u x u Schur block + one right-hand-side column
     cursor = 0
 
     def alloc_list(seq: Sequence[int], base: int) -> int:
@@ -514,7 +539,8 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         return peak
 
     # persistent region for blocks that cross lists (warp subtree roots -> top, top roots: none)
-    all_lists = [list(map(int, lists[w])) for w in range(n_lists)] + [list(map(int, top))]
+    all_lists = [list(map(int, l)) for l in lists] + [list(map(int, l)) for l in glists] + \
+                [list(map(int, top))]
     for seq in all_lists:
         inseq = set(seq)
         for k in seq:
@@ -530,13 +556,15 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         sn_f=sn_f, sn_parent=sn_parent, idx_ptr=idx_ptr, idx=idx, rel_ptr=rel_ptr, rel=rel,
         child_ptr=child_ptr, child=child, a_ptr=a_ptr, a_src=a_src, a_dst=a_dst, lp_off=lp_off,
         up_off=up_off, lu_size=lu_size, cb_off=cb_off, cb_size=cb_size, nnz_lu=nnz_lu,
-        flops=flops, f_max=int(sn_f.max()), n_warp_lists=n_lists, wl_ptr=wl_ptr, wl=wl, top=top,
-        f_warp_max=int(sn_f[is_warp].max()) if is_warp.any() else 0,
-        f_top_max=int(sn_f[~is_warp].max()) if (~is_warp).any() else 0, ordering=name)
+        flops=flops, f_max=int(sn_f.max()), n_warp_lists=n_lists, wl_ptr=wl_ptr, wl=wl,
+        n_group_lists=n_glists, gl_ptr=gl_ptr, gl=gl, top=top,
+        f_warp_max=int(sn_f[level == 0].max()) if (level == 0).any() else 0,
+        f_group_max=int(sn_f[level == 1].max()) if (level == 1).any() else 0,
+        f_top_max=int(sn_f[level == 2].max()) if (level == 2).any() else 0, ordering=name)
 
 
 def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
-            warp_front_max: int = 32, n_warps: int = 8,
+            warp_front_max: int = 24, n_warps: int = 32, group_front_max: int = 72, n_groups: int = 4,
             orderings: Sequence[str] = ("nd", "mmd")) -> LUSymbolic:
     """Analyse the pattern (and representative values) of ``A``; see the module docstring."""
     A = sp.csc_matrix(A)
@@ -584,4 +612,5 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
             best = (fl, name, order)
     assert best is not None
     _, name, order = best
-    return _build(A, rowperm, S, order, relax_frac, relax_small, warp_front_max, n_warps, name)
+    return _build(A, rowperm, S, order, relax_frac, relax_small, warp_front_max, n_warps,
+                  group_front_max, n_groups, name)

@@ -23,10 +23,11 @@ _i32p = C.POINTER(C.c_int32)
 
 class LuSymbolicC(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n", "nnz_a", "ns", "lu_size", "cb_size", "cv_size", "n_warp_lists",
-                                         "n_top", "f_warp_max", "f_top_max", "s_warp_max", "s_top_max")] + \
+                                         "n_group_lists", "n_top", "f_warp_max", "f_group_max", "f_top_max",
+                                         "s_warp_max", "s_group_max", "s_top_max")] + \
                [(k, _i32p) for k in ("rowp", "colp", "sn_piv0", "sn_s", "sn_f", "idx_ptr", "idx", "rel_ptr",
                                      "rel", "child_ptr", "child", "a_ptr", "a_src", "a_dst", "lp_off",
-                                     "up_off", "cb_off", "wl_ptr", "wl", "top")]
+                                     "up_off", "cb_off", "wl_ptr", "wl", "gl_ptr", "gl", "top")]
 
 
 class DescC(C.Structure):
@@ -96,15 +97,18 @@ def lu_symbolic_c(sym, keep: list) -> LuSymbolicC:
     ns = sym.ns
     s.n, s.nnz_a, s.ns = sym.n, sym.nnzA, ns
     s.lu_size, s.cb_size, s.cv_size = sym.lu_size, sym.cb_size, int(sym.rel_ptr[-1])
-    s.n_warp_lists, s.n_top = sym.n_warp_lists, len(sym.top)
-    s.f_warp_max, s.f_top_max = sym.f_warp_max, sym.f_top_max
-    wl_set = np.asarray(sym.wl, dtype=np.int64)
-    s.s_warp_max = int(sym.sn_s[wl_set].max()) if len(wl_set) else 0
-    s.s_top_max = int(sym.sn_s[np.asarray(sym.top, dtype=np.int64)].max()) if len(sym.top) else 0
+    s.n_warp_lists, s.n_group_lists, s.n_top = sym.n_warp_lists, sym.n_group_lists, len(sym.top)
+    s.f_warp_max, s.f_group_max, s.f_top_max = sym.f_warp_max, sym.f_group_max, sym.f_top_max
+
+    def smax(ids):
+        ids = np.asarray(ids, dtype=np.int64)
+        return int(sym.sn_s[ids].max()) if len(ids) else 0
+    s.s_warp_max, s.s_group_max, s.s_top_max = smax(sym.wl), smax(sym.gl), smax(sym.top)
     if max(sym.lu_size, sym.cb_size, int(sym.a_dst.max(initial=0))) >= 2 ** 31:
         raise SzbError("LU schedule exceeds int32 offsets")
     for name in ("rowp", "colp", "sn_piv0", "sn_s", "sn_f", "idx_ptr", "idx", "rel_ptr", "rel", "child_ptr",
-                 "child", "a_ptr", "a_src", "a_dst", "lp_off", "up_off", "cb_off", "wl_ptr", "wl", "top"):
+                 "child", "a_ptr", "a_src", "a_dst", "lp_off", "up_off", "cb_off", "wl_ptr", "wl", "gl_ptr",
+                 "gl", "top"):
         arr = np.ascontiguousarray(np.asarray(getattr(sym, name)), dtype=np.int32)
         if arr.size == 0:
             arr = np.zeros(1, dtype=np.int32)

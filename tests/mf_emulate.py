@@ -12,18 +12,19 @@ def factor(sym, jv, mvals=None, scale=1.0):
     """jv: values of the original matrix in CSC slot order. Returns (lu, ok)."""
     lu = np.zeros(sym.lu_size)
     cb = np.zeros(max(sym.cb_size, 1))
-    order = list(sym.wl) + list(sym.top)
+    order = list(sym.order)
     done = np.zeros(sym.ns, dtype=bool)
     for k in order:
         s, f = int(sym.sn_s[k]), int(sym.sn_f[k])
         u = f - s
-        F = np.zeros(f * f)
+        ld = f | 1
+        F = np.zeros(ld * f)
         a0, a1 = sym.a_ptr[k], sym.a_ptr[k + 1]
         v = scale * jv[sym.a_src[a0:a1]]
         if mvals is not None:
             v = v + mvals[sym.a_src[a0:a1]]
         np.add.at(F, sym.a_dst[a0:a1], v)
-        F = F.reshape(f, f, order="F").copy()
+        F = F.reshape(ld, f, order="F")[:f, :].copy()
         for c in sym.child[sym.child_ptr[k]:sym.child_ptr[k + 1]]:
             assert done[c]
             uc = int(sym.sn_f[c] - sym.sn_s[c])
@@ -45,7 +46,7 @@ def solve(sym, lu, b):
     n = sym.n
     xb = b[sym.rowp].astype(float).copy()
     cv = np.zeros(max(int(sym.rel_ptr[-1]), 1))
-    order = list(sym.wl) + list(sym.top)
+    order = list(sym.order)
     for k in order:
         s, f = int(sym.sn_s[k]), int(sym.sn_f[k])
         u = f - s

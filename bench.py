@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lu-opt", default="", help="JSON dict of lu.symbolic.analyze options (experiments)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -224,6 +225,10 @@ def main():
     mdl = importlib.import_module(name).mdl
     from solverz_b200.synthetic import pf_scenarios
 
+    if args.lu_opt:
+        mdl.lu_options = json.loads(args.lu_opt)
+        mdl._sym = None
+        mdl._pkl_path = None
     sess = mdl.session(B, local)
     sym = sess.sym
     P, Q = pf_scenarios(info, B, first=rank * B)

@@ -125,18 +125,37 @@ typedef struct szb_desc {
   const double* mass_vals; /* [nnz_j] mass matrix M scattered on the J pattern (DAE), or NULL */
 } szb_desc;
 
-/* options of szb_rodas -- field meanings follow solvers/option.py:4-51 */
+/* options of szb_rodas -- field meanings follow solvers/option.py:4-51; the tableau arrays are the
+ * derived coefficients of Rodas_param (solvers/daesolver/rodas/param.py:4-202) in its final layout:
+ * alpha[l*s + j] and gammatilde[l*s + j] multiply stage l in stage j (param.py stores the transposes) */
 typedef struct szb_rodas_opt {
   double t0, tend;
   double rtol, atol, f_savety, fac1, fac2, facmax;
   double hinit;  /* <= 0: 1e-6*(tend-t0), rodas.py:110-117 */
   double hmax;   /* <= 0: |tend - t0|, rodas.py:76-77 */
-  int32_t scheme; /* 0 rodas4, 1 rodasp, 2 rodas5p, 3 rodas3, 4 rodas3d (param.py:4-202) */
   int32_t fix_h;
-  int32_t max_steps; /* safety bound on accepted+rejected steps per scenario */
-  int32_t n_out;     /* number of dense-output times (0: only the final state) */
-  const double* t_out; /* host [n_out], increasing, inside [t0,tend] */
+  int32_t dfdt_mode;  /* 0: dF/dt == 0, what the reference's rendered-module path computes because its
+                         two F calls alias one buffer; 1: forward difference
+                         (rodas.py:347-352), what the inline made_numerical path computes */
+  int32_t max_steps;  /* safety bound on accepted+rejected steps per scenario (0: 1000000) */
+  int32_t n_out;      /* dense-output times (rodas.py:273-303); 0: none */
+  const double* t_out; /* host [n_out], increasing, t_out[0] == t0 */
+  int32_t record_cap; /* > 0: record every accepted step (what the reference returns for a
+                         two-point tspan), at most record_cap rows per scenario */
+  /* tableau */
+  int32_t s, pord;
+  double gamma;
+  const double *alpha, *gammatilde; /* host [s*s] */
+  const double *a, *g, *b, *bd, *c, *d, *e; /* host [s] */
 } szb_rodas_opt;
+
+typedef struct szb_rodas_out {
+  double* y_out;     /* device [n_out][B][n] or NULL */
+  double* t_end;     /* device [B]: time reached */
+  int32_t* stats;    /* device [B][8]: nstep, nfeval, nJeval, ndecomp, nreject, nsolve, flag, n_recorded */
+  double* y_steps;   /* device [record_cap][B][n] or NULL */
+  double* t_steps;   /* device [record_cap][B] or NULL */
+} szb_rodas_out;
 
 SZB_API int szb_abi_version(void);
 SZB_API const char* szb_last_error(const szb_handle* h); /* h == NULL: error of the last failed create */
@@ -163,10 +182,15 @@ SZB_API int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters
 SZB_API int szb_newton_host(szb_handle* h, double tol, int32_t max_it, double* y_host,
                     const void* const* params_host, int32_t n_params, int32_t* iters_host,
                     int32_t* flags_host, szb_stream stream);
-/* batched Rodas (rodas.py:7-344) on device buffers.  y_out_dev: [n_out or 1][B][n].
- * stats_dev: int32 [B][8] = nstep, nfeval, nJeval, ndecomp, nreject, nsolve, flag, reserved */
-SZB_API int szb_rodas(szb_handle* h, const szb_rodas_opt* opt, double* y_out_dev, double* t_end_dev,
-              int32_t* stats_dev, szb_stream stream);
+/* batched Rodas (rodas.py:7-344): integrates every scenario of SLOT_Y from t0 to tend with its own
+ * adaptive step; SLOT_Y holds the final states on return. */
+SZB_API int szb_rodas(szb_handle* h, const szb_rodas_opt* opt, const szb_rodas_out* out, szb_stream stream);
+/* row_col[r] = column of the unit entry of M in row r, or -1 for an algebraic row (host int32[n]);
+ * needed once before szb_rodas */
+SZB_API int szb_set_mass_rows(szb_handle* h, const int32_t* row_col, int32_t n);
+/* A = M + diag(row_mask) J  (row_mask_dev: device double[nnz_j] with 0/1 per Jacobian slot, or NULL
+ * for all ones) -- the matrix of the consistent-initialisation Newton of daeic.py:24-68 */
+SZB_API int szb_lu_refactor_masked_rows(szb_handle* h, const double* row_mask_dev, szb_stream stream);
 
 /* introspection */
 SZB_API int szb_query(const szb_handle* h, int32_t what, int64_t* out);

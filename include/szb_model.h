@@ -34,6 +34,7 @@ typedef struct szbm_param_info {
 typedef struct szbm_args {
   int32_t B;              /* scenarios */
   double t;               /* time (DAE/FDAE), ignored by AE models */
+  const double* t_b;      /* [B] per-scenario time, or NULL to use t */
   const double* Y;        /* [B][n] */
   double* F;              /* [B][n]       (launch_F) */
   double* JV;             /* [B][nnz_j]   (launch_J) */

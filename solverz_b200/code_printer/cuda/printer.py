@@ -360,13 +360,13 @@ SZB_HD static inline void szb_emit(double* __restrict__ JV, const int slot, cons
 _KERNELS = r'''
 #ifndef SZBM_HOST_CHECK
 struct szbm_kargs {
-  int B; double t; const double* Y; double* F; double* JV; double* fnorm; const int* active;
+  int B; double t; const double* t_b; const double* Y; double* F; double* JV; double* fnorm; const int* active;
 %(karg_fields)s
 };
 
 __device__ __forceinline__ szbm_ctx szbm_make_ctx(const szbm_kargs& a, const int b) {
   szbm_ctx c;
-  c.t = a.t;
+  c.t = a.t_b ? a.t_b[b] : a.t;
   c.Y = a.Y + (size_t)b * SZBM_N;
 %(ctx_fill)s
   return c;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(SZBM_THREADS) szbm_J_kernel(const szbm_kargs a
 static int szbm_launch(const szbm_args* a, void* stream, int which) {
   if (!a || a->B <= 0) return (int)cudaErrorInvalidValue;
   szbm_kargs k;
-  k.B = a->B; k.t = a->t; k.Y = a->Y; k.F = a->F; k.JV = a->JV; k.fnorm = a->fnorm; k.active = a->active;
+  k.B = a->B; k.t = a->t; k.t_b = a->t_b; k.Y = a->Y; k.F = a->F; k.JV = a->JV; k.fnorm = a->fnorm; k.active = a->active;
 %(karg_fill)s
   int grid = a->B < 65535 * 16 ? a->B : 65535 * 16;
   if (which == 0) szbm_F_kernel<<<grid, SZBM_THREADS, 0, (cudaStream_t)stream>>>(k);

@@ -109,6 +109,28 @@ static int need_model(szb_handle* h) {
   return SZB_OK;
 }
 
+int szb_launch_F(szb_handle* h, double t, const double* t_b, const double* Y, double* F, double* fnorm,
+                 const int* active, cudaStream_t st) {
+  szbm_args a{};
+  a.B = h->B; a.t = t; a.t_b = t_b; a.Y = Y; a.F = F; a.JV = nullptr; a.fnorm = fnorm;
+  a.params = h->param_ptr.data(); a.active = active;
+  const int e = h->launch_F(&a, st);
+  if (e != 0) { szb_set_error(h, "F kernel launch: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return SZB_ECUDA; }
+  h->launches[0]++;
+  return SZB_OK;
+}
+
+int szb_launch_J(szb_handle* h, double t, const double* t_b, const double* Y, double* JV, const int* active,
+                 cudaStream_t st) {
+  szbm_args a{};
+  a.B = h->B; a.t = t; a.t_b = t_b; a.Y = Y; a.F = nullptr; a.JV = JV; a.fnorm = nullptr;
+  a.params = h->param_ptr.data(); a.active = active;
+  const int e = h->launch_J(&a, st);
+  if (e != 0) { szb_set_error(h, "J kernel launch: %s", cudaGetErrorString(static_cast<cudaError_t>(e))); return SZB_ECUDA; }
+  h->launches[1]++;
+  return SZB_OK;
+}
+
 int szb_eval_F_masked(szb_handle* h, double t, const int* active, cudaStream_t st) {
   szbm_args a{};
   a.B = h->B; a.t = t; a.Y = h->Y; a.F = h->F; a.JV = nullptr; a.fnorm = h->fnorm;
@@ -130,17 +152,18 @@ int szb_eval_J_masked(szb_handle* h, double t, const int* active, cudaStream_t s
 }
 
 int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b, const int* active,
-                           const double* rhs, double* yout, int store_l, cudaStream_t st) {
+                           const double* rhs, double* yout, int store_l, cudaStream_t st,
+                           const double* slot_mask) {
   if (!h->has_lu) { szb_set_error(h, "this handle was created without an LU schedule"); return SZB_ESTATE; }
   const double* mv = nullptr;
   double scale = 1.0;
-  if (h_gamma != 0.0 || scale_b) {
+  if (h_gamma != 0.0 || scale_b || slot_mask) {
     if (!h->mass_vals) { szb_set_error(h, "szb_lu_refactor: h_gamma != 0 needs desc.mass_vals"); return SZB_EINVAL; }
     mv = h->mass_vals;
     scale = -h_gamma;
   }
-  cudaError_t e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, mv, scale_b, scale, rhs, yout,
-                                        store_l, active, h->flags, h->B, st);
+  cudaError_t e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, mv, slot_mask, scale_b, scale, rhs,
+                                        yout, store_l, active, h->flags, h->B, st);
   if (e != cudaSuccess) { szb_set_error(h, "LU factor launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
   h->launches[2]++;
   h->factored = store_l != 0;
@@ -159,6 +182,7 @@ int szb_destroy(szb_handle* h) {
   cudaSetDevice(h->device);
   free_bag(h->owned);
   free_bag(h->batch_owned);
+  free_bag(h->rodas_owned);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);
@@ -268,6 +292,8 @@ int szb_set_batch(szb_handle* h, int32_t B) {
   if (!h || B <= 0) { szb_set_error(h, "szb_set_batch: bad batch %d", B); return SZB_EINVAL; }
   SZB_CUDA(h, cudaSetDevice(h->device));
   free_bag(h->batch_owned);
+  free_bag(h->rodas_owned);
+  h->rodas_B = 0; h->rodas_stages = 0; h->rd_tout_cap = 0; h->rd_mcol_ready = false;
   h->ws_bytes = 0;
   h->B = 0;
   h->factored = false;
@@ -390,6 +416,14 @@ int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream) {
   SZB_CUDA(h, cudaSetDevice(h->device));
   return szb_lu_refactor_masked(h, h_gamma, nullptr, nullptr, nullptr, nullptr, 1,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int szb_lu_refactor_masked_rows(szb_handle* h, const double* row_mask_dev, szb_stream stream) {
+  if (!h) return SZB_EINVAL;
+  if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  return szb_lu_refactor_masked(h, -1.0, nullptr, nullptr, nullptr, nullptr, 1,
+                                static_cast<cudaStream_t>(stream), row_mask_dev);
 }
 
 int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream) {

@@ -52,6 +52,12 @@ struct szb_handle {
   // Rodas workspaces (allocated on first use)
   std::vector<void*> rodas_owned;
   int rodas_B = 0, rodas_stages = 0;
+  double *rd_K = nullptr, *rd_y1 = nullptr, *rd_sum2 = nullptr, *rd_dfdt = nullptr, *rd_F1 = nullptr;
+  double *rd_dbl = nullptr, *rd_tout = nullptr;
+  int *rd_int = nullptr, *rd_mcol = nullptr;
+  int rd_tout_cap = 0;
+  bool rd_mcol_ready = false;
+  std::vector<int> mass_row_col;   // row -> column of the unit mass entry, -1 for algebraic rows
 };
 
 void szb_set_error(szb_handle* h, const char* fmt, ...);
@@ -69,4 +75,9 @@ void szb_set_error(szb_handle* h, const char* fmt, ...);
 int szb_eval_F_masked(szb_handle* h, double t, const int* active, cudaStream_t st);
 int szb_eval_J_masked(szb_handle* h, double t, const int* active, cudaStream_t st);
 int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b, const int* active,
-                           const double* rhs, double* yout, int store_l, cudaStream_t st);
+                           const double* rhs, double* yout, int store_l, cudaStream_t st,
+                           const double* slot_mask = nullptr);
+int szb_launch_F(szb_handle* h, double t, const double* t_b, const double* Y, double* F, double* fnorm,
+                 const int* active, cudaStream_t st);
+int szb_launch_J(szb_handle* h, double t, const double* t_b, const double* Y, double* JV, const int* active,
+                 cudaStream_t st);

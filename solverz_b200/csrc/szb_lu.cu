@@ -68,6 +68,7 @@ struct BlockGrp {
 struct FactorArgs {
   const double* __restrict__ jv;     // matrix values of this scenario (CSC slots)
   const double* __restrict__ mvals;  // optional mass values (shared)
+  const double* __restrict__ smask;  // optional 0/1 mask per slot applied to jv (shared)
   double scale;
   const double* __restrict__ rhs;    // optional right-hand side of this scenario (original order)
   double* __restrict__ yout;         // forward-substituted rhs in pivot order (when rhs != null)
@@ -76,6 +77,50 @@ struct FactorArgs {
   int store_l;                       // write the L21 rows of the panels
   int* flag;
 };
+
+// divide the rows below the diagonal of column p by the pivot (one warp)
+__device__ __forceinline__ void scale_pivot_column(double* __restrict__ Fm, const int p, const int f,
+                                                   const int ld, const int lane, int* flag) {
+  double* __restrict__ col = Fm + p * ld;
+  const double piv = col[p];
+  const double inv = 1.0 / piv;
+  if (lane == 0 && (!(fabs(piv) > 0.0) || isinf(piv))) *flag = 2;
+  for (int i = p + 1 + lane; i < f; i += kWarp) col[i] *= inv;
+}
+
+// one right-looking step: columns j > p get  a_ij -= l_i * u_pj ; lane = row, NCH row chunks of 32
+// held in registers (NCH == 0: generic loop).  The warp that owns column p+1 scales it afterwards.
+template <int NCH>
+__device__ __forceinline__ void eliminate_step(double* __restrict__ Fm, const int p, const int m,
+                                               const int nc, const int ld, const int f, const int lane,
+                                               const int w, const int nw, const bool more, int* flag) {
+  const double* __restrict__ colp = Fm + (p + 1) + p * ld;
+  double l[NCH > 0 ? NCH : 1];
+  if (NCH > 0) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int i = lane + 32 * c;
+      l[c] = (c + 1 < NCH || i < m) ? colp[i] : 0.0;
+    }
+  }
+  for (int jj = w; jj < nc; jj += nw) {
+    double* __restrict__ col = Fm + (p + 1) + (p + 1 + jj) * ld;
+    const double ukj = col[-1];     // element (p, j)
+    if (NCH > 0) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int i = lane + 32 * c;
+        if (c + 1 < NCH || i < m) col[i] = fma(-l[c], ukj, col[i]);
+      }
+    } else {
+      for (int i = lane; i < m; i += kWarp) col[i] = fma(-colp[i], ukj, col[i]);
+    }
+    if (jj == 0 && more) {
+      __syncwarp();
+      scale_pivot_column(Fm, p + 1, f, ld, lane, flag);
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // numeric factorisation of one supernode; the front is column-major with leading dimension
@@ -94,7 +139,12 @@ __device__ void factor_supernode(const G g, const LuDev& S, const int k, double*
   // 2. original entries (+ right-hand side of the pivot rows)
   {
     const int a1 = S.a_ptr[k + 1];
-    if (A.mvals) {
+    if (A.mvals && A.smask) {
+      for (int e = S.a_ptr[k] + r; e < a1; e += G_) {
+        const int src = S.a_src[e];
+        Fm[S.a_dst[e]] = fma(A.scale * A.smask[src], A.jv[src], A.mvals[src]);
+      }
+    } else if (A.mvals) {
       for (int e = S.a_ptr[k] + r; e < a1; e += G_) {
         const int src = S.a_src[e];
         Fm[S.a_dst[e]] = fma(A.scale, A.jv[src], A.mvals[src]);
@@ -124,31 +174,22 @@ __device__ void factor_supernode(const G g, const LuDev& S, const int k, double*
     }
     g.sync();
   }
-  // 4. right-looking elimination of the s pivots; L stays unscaled until write-out
+  // 4. right-looking elimination of the s pivots.  Column p is already divided by its pivot when
+  // step p starts: the warp that updates column p+1 in step p scales it right away, so no warp
+  // repeats the division and there is exactly one barrier per pivot.
+  if (w == 0) scale_pivot_column(Fm, 0, f, ld, lane, A.flag);
+  g.sync();
   for (int p = 0; p < s; ++p) {
-    const double piv = Fm[p + p * ld];
-    const double inv = 1.0 / piv;
-    if (r == 0) {
-      dinv[p] = inv;
-      if (!(fabs(piv) > 0.0) || isinf(piv)) *A.flag = 2;
-    }
     const int m = f - p - 1;          // trailing rows
     const int nc = ncol - p - 1;      // trailing columns (incl. rhs)
-    const double* __restrict__ colp = Fm + (p + 1) + p * ld;
-    // multipliers of this lane's rows (up to 4 row chunks kept in registers)
-    double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
-    if (lane < m) l0 = colp[lane] * inv;
-    if (lane + 32 < m) l1 = colp[lane + 32] * inv;
-    if (lane + 64 < m) l2 = colp[lane + 64] * inv;
-    if (lane + 96 < m) l3 = colp[lane + 96] * inv;
-    for (int jj = w; jj < nc; jj += nw) {
-      double* __restrict__ col = Fm + (p + 1) + (p + 1 + jj) * ld;
-      const double ukj = col[-1];     // element (p, j)
-      if (lane < m) col[lane] = fma(-l0, ukj, col[lane]);
-      if (lane + 32 < m) col[lane + 32] = fma(-l1, ukj, col[lane + 32]);
-      if (lane + 64 < m) col[lane + 64] = fma(-l2, ukj, col[lane + 64]);
-      if (lane + 96 < m) col[lane + 96] = fma(-l3, ukj, col[lane + 96]);
-      for (int i = lane + 128; i < m; i += kWarp) col[i] = fma(-(colp[i] * inv), ukj, col[i]);
+    const bool more = p + 1 < s;
+    switch ((m + 31) >> 5) {
+      case 0: break;
+      case 1: eliminate_step<1>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
+      case 2: eliminate_step<2>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
+      case 3: eliminate_step<3>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
+      case 4: eliminate_step<4>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
+      default: eliminate_step<0>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
     }
     g.sync();
   }
@@ -156,13 +197,8 @@ __device__ void factor_supernode(const G g, const LuDev& S, const int k, double*
   {
     double* __restrict__ Lp = A.lu + S.lp_off[k];           // f x s, column-major, ld = f
     const int rows = A.store_l ? f : s;
-    for (int p = w; p < s; p += nw) {
-      const double di = dinv[p];
-      for (int i = lane; i < rows; i += kWarp) {
-        const double v = Fm[i + p * ld];
-        Lp[i + p * f] = (i > p) ? v * di : v;
-      }
-    }
+    for (int p = w; p < s; p += nw)
+      for (int i = lane; i < rows; i += kWarp) Lp[i + p * f] = Fm[i + p * ld];
     if (u > 0) {
       double* __restrict__ Up = A.lu + S.up_off[k];         // U12 rows: Up[c + r*u] = U12[r][c]
       for (int rr = w; rr < s; rr += nw)
@@ -183,6 +219,7 @@ __device__ void factor_supernode(const G g, const LuDev& S, const int k, double*
 __global__ void __launch_bounds__(1024, 1)
 lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restrict__ LU,
                  double* __restrict__ CBW, const double* __restrict__ mvals,
+                 const double* __restrict__ slot_mask,
                  const double* __restrict__ scale_b, double scale_const,
                  const double* __restrict__ RHS, double* __restrict__ YOUT, int store_l,
                  const int* __restrict__ active, int* __restrict__ flags, int B) {
@@ -191,8 +228,12 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
   const int wstride = (S.f_warp_max | 1) * (S.f_warp_max + 1) + S.f_warp_max;
   const int gstride = (S.f_group_max | 1) * (S.f_group_max + 1) + S.f_group_max;
   const int wpg = (blockDim.x >> 5) / max(S.n_group_lists, 1);   // warps per group
+#ifdef SZB_PHASE_TIMING
+  long long tph[4] = {0, 0, 0, 0};
+#endif
   FactorArgs A;
   A.mvals = mvals;
+  A.smask = slot_mask;
   A.store_l = store_l;
   A.cb = CBW + static_cast<size_t>(blockIdx.x) * S.cb_size;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -203,6 +244,9 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
     A.rhs = RHS ? RHS + static_cast<size_t>(b) * S.n : nullptr;
     A.yout = YOUT ? YOUT + static_cast<size_t>(b) * S.n : nullptr;
     A.flag = flags + b;
+#ifdef SZB_PHASE_TIMING
+    long long t0 = clock64();
+#endif
     // level 0: warps
     if (warp < S.n_warp_lists) {
       double* Fm = sm + warp * wstride;
@@ -212,6 +256,9 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
         factor_supernode(g, S, S.wl[q], Fm, dinv, A);
     }
     __syncthreads();
+#ifdef SZB_PHASE_TIMING
+    long long t1 = clock64();
+#endif
     // level 1: groups of warps
     if (S.n_group_lists > 0) {
       const int gi = warp / wpg;
@@ -227,13 +274,25 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
       }
       __syncthreads();
     }
+#ifdef SZB_PHASE_TIMING
+    long long t2 = clock64();
+#endif
     // level 2: the whole CTA
     {
       double* dinv = sm + (S.f_top_max | 1) * (S.f_top_max + 1);
       const BlockGrp g;
       for (int q = 0; q < S.n_top; ++q) factor_supernode(g, S, S.top[q], sm, dinv, A);
     }
+#ifdef SZB_PHASE_TIMING
+    long long t3 = clock64();
+    tph[0] += t1 - t0; tph[1] += t2 - t1; tph[2] += t3 - t2; tph[3] += 1;
+#endif
   }
+#ifdef SZB_PHASE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("[lu_factor phases] warp %lld group %lld top %lld cycles/scenario (%lld scenarios)\n",
+           tph[0] / max(tph[3], 1LL), tph[1] / max(tph[3], 1LL), tph[2] / max(tph[3], 1LL), tph[3]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -490,12 +549,12 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
 }
 
 cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV, double* LU,
-                             double* CBW, const double* mvals, const double* scale_b,
-                             double scale_const, const double* RHS, double* YOUT, int store_l,
-                             const int* active, int* flags, int B, cudaStream_t st) {
+                             double* CBW, const double* mvals, const double* slot_mask,
+                             const double* scale_b, double scale_const, const double* RHS, double* YOUT,
+                             int store_l, const int* active, int* flags, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   lu_factor_kernel<<<cfg.grid_factor, cfg.threads, cfg.smem_factor, st>>>(
-      S, JV, LU, CBW, mvals, scale_b, scale_const, RHS, YOUT, store_l, active, flags, B);
+      S, JV, LU, CBW, mvals, slot_mask, scale_b, scale_const, RHS, YOUT, store_l, active, flags, B);
   return cudaGetLastError();
 }
 

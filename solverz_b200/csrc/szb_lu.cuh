@@ -35,8 +35,8 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg);
 // RHS / YOUT non-null: the right-hand side rides along (forward substitution fused), YOUT gets
 // y = L^{-1} P b in pivot order.  store_l == 0 skips writing the L21 rows (Newton never reuses L).
 cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV,
-                             double* LU, double* CBW, const double* mvals, const double* scale_b,
-                             double scale_const, const double* RHS, double* YOUT, int store_l,
+                             double* LU, double* CBW, const double* mvals, const double* slot_mask,
+                             const double* scale_b, double scale_const, const double* RHS, double* YOUT, int store_l,
                              const int* active, int* flags, int B, cudaStream_t st);
 
 // mode 0:  X[b] <- A^{-1} RHS[b]         (X may alias RHS)

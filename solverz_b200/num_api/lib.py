@@ -35,11 +35,22 @@ class DescC(C.Structure):
                 ("model_lib", C.c_char_p), ("lu", LuSymbolicC), ("mass_vals", C.POINTER(C.c_double))]
 
 
+_dp = C.POINTER(C.c_double)
+
+
 class RodasOptC(C.Structure):
     _fields_ = [("t0", C.c_double), ("tend", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
                 ("f_savety", C.c_double), ("fac1", C.c_double), ("fac2", C.c_double), ("facmax", C.c_double),
-                ("hinit", C.c_double), ("hmax", C.c_double), ("scheme", C.c_int32), ("fix_h", C.c_int32),
-                ("max_steps", C.c_int32), ("n_out", C.c_int32), ("t_out", C.POINTER(C.c_double))]
+                ("hinit", C.c_double), ("hmax", C.c_double), ("fix_h", C.c_int32), ("dfdt_mode", C.c_int32),
+                ("max_steps", C.c_int32), ("n_out", C.c_int32), ("t_out", _dp), ("record_cap", C.c_int32),
+                ("s", C.c_int32), ("pord", C.c_int32), ("gamma", C.c_double), ("alpha", _dp),
+                ("gammatilde", _dp), ("a", _dp), ("g", _dp), ("b", _dp), ("bd", _dp), ("c", _dp), ("d", _dp),
+                ("e", _dp)]
+
+
+class RodasOutC(C.Structure):
+    _fields_ = [("y_out", C.c_void_p), ("t_end", C.c_void_p), ("stats", C.c_void_p), ("y_steps", C.c_void_p),
+                ("t_steps", C.c_void_p)]
 
 
 _lib = None
@@ -73,7 +84,9 @@ def load():
     lib.szb_newton.argtypes = [H, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.szb_newton_host.argtypes = [H, C.c_double, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.szb_rodas.argtypes = [H, C.POINTER(RodasOptC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.szb_rodas.argtypes = [H, C.POINTER(RodasOptC), C.POINTER(RodasOutC), C.c_void_p]
+    lib.szb_set_mass_rows.argtypes = [H, C.POINTER(C.c_int32), C.c_int32]
+    lib.szb_lu_refactor_masked_rows.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.szb_query.argtypes = [H, C.c_int32, C.POINTER(C.c_int64)]
     lib.szb_set_profile.argtypes = [H, C.c_int32]
     lib.szb_get_profile.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

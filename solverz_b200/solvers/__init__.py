@@ -2,3 +2,5 @@ from .option import Opt
 from .stats import Stats
 from .solution import aesol, daesol
 from .nr import nr_method
+from .rodas import Rodas
+from .rodas_param import Rodas_param

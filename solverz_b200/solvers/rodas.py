@@ -1,0 +1,200 @@
+"""Batched Rodas with the reference's ``Rodas(dae, tspan, y0, opt)`` surface.
+
+Reference: Solverz/solvers/daesolver/rodas/rodas.py:7-344 and the ``dae_io_parser`` decorator
+(solvers/parser.py:65-121).  The step loop runs in ``szb_rodas`` (csrc/szb_rodas.cu); this module
+does the consistent initialisation (``DaeIc``, daeic.py:24-68) and moves data.
+
+* ``y0`` 1-D / ``Vars``: one scenario, returns ``daesol(T, Y, stats)`` like the reference -- every
+  accepted step for a two-point ``tspan``, dense output at the given nodes otherwise.
+* ``y0`` ``[B, n]``: a batch; ``T`` is ``tspan`` (dense output) or ``[t0, t_reached]``, ``Y`` has shape
+  ``[B, nt, n]`` and the ``Stats`` counters are int arrays of length ``B``.
+* ``opt.dfdt`` (backend knob, default ``'module'``): ``'module'`` reproduces the reference's rendered
+  numba module, where dF/dt evaluates to 0; ``'fd'`` uses the forward difference
+  of rodas.py:347-352 as the inline ``made_numerical`` path does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ..num_api import lib as L
+from ..num_api.model import CudaModel
+from ..variables import TimeVars, Vars
+from .option import Opt
+from .rodas_param import Rodas_param
+from .solution import daesol
+from .stats import Stats
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def dae_ic(sess, t0: float, rtol: float):
+    """Batched restatement of DaeIc (daeic.py:24-68): Newton on the algebraic sub-system
+    J[AlgEqn, AlgVar] with the three-probe halving line search.  The sub-system is solved with the
+    full-size matrix  A = M + diag(alg rows) J  whose differential rows are unit rows."""
+    import torch
+    mdl = sess.model
+    n = mdl.n
+    de, dv = mdl.mass
+    dev = sess.Y.device
+    alg_eqn = torch.as_tensor(np.setdiff1d(np.arange(n), de), device=dev)
+    alg_var = torch.as_tensor(np.setdiff1d(np.arange(n), dv), device=dev)
+    tt = torch.full((sess.B,), float(t0), dtype=torch.float64, device=dev)
+    F0 = sess.eval_F(t0)
+    need = torch.linalg.norm(F0[:, alg_eqn], dim=1) > 1e-6
+    if not bool(need.any()):
+        return
+    # 0/1 mask per Jacobian slot: 1 on algebraic rows
+    rows = mdl.indices
+    is_alg_row = np.ones(n)
+    is_alg_row[de] = 0.0
+    mask = torch.as_tensor(is_alg_row[rows], device=dev)
+    y = sess.Y.clone()
+    done = ~need
+
+    def solve_alg(yy, rhs_alg):
+        sess.Y.copy_(yy)
+        sess.eval_J(t0)
+        L.check(sess.lib.szb_lu_refactor_masked_rows(sess.h, C.c_void_p(mask.data_ptr()), sess._stream()),
+                sess.h, "szb_lu_refactor_masked_rows")
+        sess.RHS.zero_()
+        sess.RHS[:, alg_eqn] = rhs_alg
+        x = sess.lu_solve(1)
+        return x[:, alg_var].clone()
+
+    tiny = float(np.spacing(t0))
+    for _ in range(15):
+        sess.Y.copy_(y)
+        Fn = sess.eval_F(t0).clone()
+        dY = solve_alg(y, -Fn[:, alg_eqn])
+        ya = y[:, alg_var]
+        nz = ya.abs() > tiny
+        res = torch.linalg.norm(torch.where(nz, dY / torch.where(nz, ya, torch.ones_like(ya)), torch.zeros_like(ya)), dim=1)
+        lam = torch.ones(sess.B, dtype=torch.float64, device=dev)
+        settled = done.clone()          # scenarios whose probe loop has ended
+        ynew = y.clone()
+        resnew = torch.zeros_like(res)
+        for _probe in range(3):
+            cand = y.clone()
+            cand[:, alg_var] = ya + lam[:, None] * dY
+            ynew = torch.where(settled[:, None], ynew, cand)
+            sess.Y.copy_(ynew)
+            Fnew = sess.eval_F(t0).clone()
+            ok = torch.linalg.norm(Fnew[:, alg_eqn], dim=1) <= 1e-5 * rtol
+            newly = ok & ~settled
+            y = torch.where(newly[:, None], ynew, y)
+            done = done | newly
+            settled = settled | newly
+            dYn = solve_alg(ynew, Fnew[:, alg_eqn])
+            rn = torch.linalg.norm(torch.where(nz, dYn / torch.where(nz, ya, torch.ones_like(ya)), torch.zeros_like(ya)), dim=1)
+            resnew = torch.where(settled, resnew, rn)
+            brk = (rn < 0.9 * res) & ~settled
+            settled = settled | brk
+            lam = torch.where(settled, lam, 0.5 * lam)
+        y = torch.where(done[:, None], y, ynew)
+        done = done | (resnew <= 1e-3 * rtol)
+        if bool(done.all()):
+            sess.Y.copy_(y)
+            return
+    raise ValueError("Need Better y0")
+
+
+def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
+    if opt is None:
+        opt = Opt()
+    if not isinstance(dae, CudaModel) or dae.kind != "DAE":
+        raise TypeError("Rodas of solverz_b200 needs a DAE model rendered with lang='cuda'")
+    if opt.event is not None:
+        raise NotImplementedError("events are host callbacks in the reference (rodas.py:200-271); device-side "
+                                  "event detection is not built in this round")
+    import torch
+    rp = Rodas_param(opt.scheme)
+    tspan = np.asarray(tspan, dtype=float)
+    t0, tend = float(tspan[0]), float(tspan[-1])
+    if t0 > tend:
+        raise ValueError(f't0: {t0} > tend: {tend}')
+    dense = len(tspan) > 2
+    if dense and not rp.has_dense_output:
+        raise NotImplementedError(f"dense output of {opt.scheme} (ntrp2, rodas.py:389-393) is not built")
+    vars_in = y0 if isinstance(y0, Vars) else None
+    y_arr = y0.array if isinstance(y0, Vars) else y0
+    on_device = isinstance(y_arr, torch.Tensor)
+    if not on_device:
+        y_arr = np.asarray(y_arr, dtype=float)
+    single = y_arr.ndim == 1
+    B = 1 if single else int(y_arr.shape[0])
+    s = dae.session(B)
+    s.set_params(dae.p)
+    s.set_y(y_arr)
+    n = dae.n
+    rc = np.full(n, -1, dtype=np.int32)
+    rc[np.asarray(dae.mass[0], dtype=np.int64)] = np.asarray(dae.mass[1], dtype=np.int32)
+    L.check(s.lib.szb_set_mass_rows(s.h, rc.ctypes.data_as(C.POINTER(C.c_int32)), n), s.h, "szb_set_mass_rows")
+    dae_ic(s, t0, opt.rtol)
+    if opt.hmax is None:
+        opt.hmax = abs(tend - t0)                     # rodas.py:76-77 (the reference mutates opt too)
+    dev = s.Y.device
+    o = L.RodasOptC()
+    o.t0, o.tend = t0, tend
+    o.rtol, o.atol, o.f_savety = opt.rtol, opt.atol, opt.f_savety
+    o.fac1, o.fac2, o.facmax = opt.fac1, opt.fac2, opt.facmax
+    o.hinit = -1.0 if opt.hinit is None else float(opt.hinit)
+    o.hmax = float(opt.hmax)
+    o.fix_h = 1 if opt.fix_h else 0
+    o.dfdt_mode = 1 if getattr(opt, "dfdt", "module") == "fd" else 0
+    o.max_steps = int(getattr(opt, "max_steps", 0))
+    keep = [np.ascontiguousarray(getattr(rp, k), dtype=np.float64) for k in
+            ("alpha", "gammatilde", "a", "g", "b", "bd", "c", "d", "e")]
+    o.s, o.pord, o.gamma = rp.s, rp.pord, rp.gamma
+    (o.alpha, o.gammatilde, o.a, o.g, o.b, o.bd, o.c, o.d, o.e) = [_dp(k) for k in keep]
+    out = L.RodasOutC()
+    t_end = torch.zeros(B, dtype=torch.float64, device=dev)
+    stats_d = torch.zeros((B, 8), dtype=torch.int32, device=dev)
+    out.t_end, out.stats = t_end.data_ptr(), stats_d.data_ptr()
+    y_out = y_steps = t_steps = None
+    if dense:
+        o.n_out = len(tspan)
+        tsp = np.ascontiguousarray(tspan)
+        o.t_out = _dp(tsp)
+        y_out = torch.zeros((len(tspan), B, n), dtype=torch.float64, device=dev)
+        out.y_out = y_out.data_ptr()
+    elif single:
+        cap = int(getattr(opt, "record_cap", 10001))
+        o.record_cap = cap
+        y_steps = torch.zeros((cap, B, n), dtype=torch.float64, device=dev)
+        t_steps = torch.zeros((cap, B), dtype=torch.float64, device=dev)
+        out.y_steps, out.t_steps = y_steps.data_ptr(), t_steps.data_ptr()
+    y_init = s.Y.clone()
+    L.check(s.lib.szb_rodas(s.h, C.byref(o), C.byref(out), s._stream()), s.h, "szb_rodas")
+    st = stats_d.cpu().numpy().astype(np.int64)
+    stats = Stats(opt.scheme)
+    names = ("nstep", "nfeval", "nJeval", "ndecomp", "nreject", "nsolve")
+    for i, k in enumerate(names):
+        setattr(stats, k, int(st[0, i]) if single else st[:, i].copy())
+    stats.flag = int(st[0, 6]) if single else st[:, 6].copy()
+    failed = st[:, 6] != 0
+    stats.ret = ("failed" if failed[0] else None) if single else np.where(failed, "failed", None)
+    # the reference never sets succeed for Rodas (stats.py:11 stays False); keep that for B = 1
+    stats.succeed = False if single else ~failed
+    if dense:
+        Yh = y_out.permute(1, 0, 2).contiguous()          # [B, nt, n]
+        T = tspan.copy()
+        if single:
+            reached = int(torch.as_tensor(st[0, 6] == 0))
+            Y = Yh[0].cpu().numpy()
+        else:
+            Y = Yh if on_device else Yh.cpu().numpy()
+    elif single:
+        nrec = int(st[0, 7])
+        T = t_steps[:nrec, 0].cpu().numpy()
+        Y = y_steps[:nrec, 0].cpu().numpy()
+    else:
+        T = np.stack([np.full(B, t0), t_end.cpu().numpy()], axis=1)
+        Yh = torch.stack([y_init, s.Y], dim=1)             # [B, 2, n]
+        Y = Yh.clone() if on_device else Yh.cpu().numpy()
+    if vars_in is not None and not isinstance(Y, torch.Tensor):
+        Y = TimeVars(vars_in.a, Y)
+    return daesol(T, Y, stats=stats)

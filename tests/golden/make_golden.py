@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz from the reference itself.  Runs ONLY in the build container:
+
+    mkdir -p /tmp/ref && cp -r /root/reference/Solverz /tmp/ref/
+    sed -i "s/Derivative(Function('F'), diff_var)/Derivative(Function('F')(diff_var), diff_var)/" \\
+        /tmp/ref/Solverz/equation/eqn.py          # sympy 1.14 compatibility
+    echo "__version__ = '0.8.5'" > /tmp/ref/Solverz/_version.py
+    PYTHONPATH=/tmp/ref:/root/repo NUMBA_CACHE_DIR=/tmp/numba-cache python tests/golden/make_golden.py
+
+The reference is imported from the patched private copy; nothing of it is written into the repo
+except the numeric vectors below.  The tests never import the reference.
+"""
+import importlib
+import re
+import sys
+import tempfile
+import zipfile
+from pathlib import Path
+
+import numpy as np
+import scipy.sparse as sps
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parents[1]))
+
+
+def sheet(z, idx):
+    xml = z.read(f"xl/worksheets/sheet{idx}.xml").decode()
+    cells = re.findall(r'<c r="([A-Z]+)(\d+)"[^>]*?(?:t="(\w+)")?[^>]*>(?:<v>([^<]*)</v>)?', xml)
+    rows = {}
+    for col, row, typ, val in cells:
+        if typ == "s" or val == "":
+            continue
+        rows.setdefault(int(row), {})[col] = float(val)
+    out = [[r[c] for c in sorted(r)] for _, r in sorted(rows.items()) if r]
+    return np.array(out[1:])   # first row = pandas header (column labels 0, 1)
+
+
+def golden_dae_test():
+    """tests/dae_test.xlsx of the reference (sheets rodas, rodas_dense) + the reference's own run."""
+    from Solverz import Eqn, Model, Ode, Opt, Rodas, Var, made_numerical
+    z = zipfile.ZipFile("/root/reference/tests/dae_test.xlsx")
+    rodas_sheet, dense_sheet = sheet(z, 2), sheet(z, 3)
+    m = Model()
+    m.x = Var('x', 1)
+    m.y = Var('y', 1)
+    m.f = Ode(name='f', f=-m.x ** 3 + 0.5 * m.y ** 2, diff_var=m.x)
+    m.g = Eqn(name='g', eqn=m.x ** 2 + m.y ** 2 - 2)
+    dae, y0 = m.create_instance()
+    nd = made_numerical(dae, y0, sparse=True)
+    s1 = Rodas(nd, [0, 20], y0, opt=Opt(hinit=0.1))
+    s2 = Rodas(nd, np.linspace(0, 20, 201), y0, Opt(hinit=0.1))
+    assert np.max(np.abs(rodas_sheet - s1.Y.array)) < 1e-8
+    assert np.max(np.abs(dense_sheet - s2.Y.array)) < 1e-8
+    out = dict(rodas_sheet=rodas_sheet, rodas_dense_sheet=dense_sheet, ref_T=s1.T, ref_Y=s1.Y.array,
+               ref_dense_Y=s2.Y.array,
+               ref_stats=np.array([s1.stats.nstep, s1.stats.nfeval, s1.stats.nJeval, s1.stats.ndecomp,
+                                   s1.stats.nreject, s1.stats.nsolve]))
+    for sch in ("rodasp", "rodas5p", "rodas3d"):
+        s = Rodas(nd, [0, 20], y0, opt=Opt(hinit=0.1, scheme=sch))
+        out[f"ref_{sch}_T"] = s.T
+        out[f"ref_{sch}_Y"] = s.Y.array
+        out[f"ref_{sch}_stats"] = np.array([s.stats.nstep, s.stats.nfeval, s.stats.nJeval, s.stats.ndecomp,
+                                            s.stats.nreject, s.stats.nsolve])
+    np.savez(HERE / "dae_test_rodas.npz", **out)
+
+
+def golden_pf(nx):
+    """Reference numba module of the polar power-flow model: F, J, Newton iterates."""
+    from Solverz import Eqn, LoopEqn, Model, Opt, Param, Set, Sum, Var, cos, module_printer, nr_method, sin
+    from solverz_b200.synthetic import lattice_grid, pf_scenarios
+    nb, Y = lattice_grid(nx, nx)
+    G = sps.csc_array(Y.real)
+    B = sps.csc_array(Y.imag)
+    npv = max(1, int(0.1 * nb))
+    pv = list(range(1, 1 + npv))
+    pq = list(range(1 + npv, nb))
+    rng = np.random.default_rng(1)
+    Pb = rng.uniform(-.05, .05, nb)
+    Qb = rng.uniform(-.02, .02, nb)
+    m = Model()
+    m.Va = Var('Va', np.zeros(nb))
+    m.Vm = Var('Vm', np.ones(nb))
+    m.G = Param('G', G, dim=2, sparse=True)
+    m.B = Param('B', B, dim=2, sparse=True)
+    m.Pinj = Param('Pinj', Pb)
+    m.Qinj = Param('Qinj', Qb)
+    m.Bus = Set('Bus', nb)
+    m.PVPQ = Set('PVPQ', np.array(pv + pq))
+    m.PQ = Set('PQ', np.array(pq))
+    i = m.PVPQ.idx('i')
+    j = m.Bus.idx('j')
+    m.P_eqn = LoopEqn('P_eqn', outer_index=i, body=m.Vm[i] * Sum(m.Vm[j] * m.G[i, j] * cos(m.Va[i] - m.Va[j]), j)
+                      + m.Vm[i] * Sum(m.Vm[j] * m.B[i, j] * sin(m.Va[i] - m.Va[j]), j) - m.Pinj[i], model=m)
+    k = m.PQ.idx('k')
+    m.Q_eqn = LoopEqn('Q_eqn', outer_index=k, body=m.Vm[k] * Sum(m.Vm[j] * m.G[k, j] * sin(m.Va[k] - m.Va[j]), j)
+                      - m.Vm[k] * Sum(m.Vm[j] * m.B[k, j] * cos(m.Va[k] - m.Va[j]), j) - m.Qinj[k], model=m)
+    m.ref_eqn = Eqn('Va_ref', m.Va[0])
+    m.vm_eqn = Eqn('Vm_fix', m.Vm[0:1 + npv] - 1)
+    spf, y0 = m.create_instance()
+    d = tempfile.mkdtemp()
+    module_printer(spf, y0, f"gold_pf{nx}", directory=d, jit=True).render()
+    sys.path.insert(0, d)
+    mod = importlib.import_module(f"gold_pf{nx}")
+    mdl = mod.mdl
+    rng = np.random.default_rng(7)
+    yp = y0.array + 0.05 * rng.standard_normal(2 * nb)
+    F0 = mdl.F(y0.array, mdl.p).copy()
+    J0 = sps.csc_matrix(mdl.J(y0.array, mdl.p))
+    Fp = mdl.F(yp, mdl.p).copy()
+    Jp = sps.csc_matrix(mdl.J(yp, mdl.p))
+    info = dict(nb=nb, Pbase=Pb, Qbase=Qb)
+    nsc = 6
+    P, Q = pf_scenarios(info, nsc)
+    sols, its, nfe = [], [], []
+    for b in range(nsc):
+        mdl.p["Pinj"] = P[b]
+        mdl.p["Qinj"] = Q[b]
+        s = nr_method(mdl, mod.y, Opt(ite_tol=1e-8))
+        sols.append(s.y.array.copy())
+        its.append(s.stats.nstep)
+        nfe.append(s.stats.nfeval)
+    np.savez(HERE / f"pf_ref_{nx}x{nx}.npz", y0=y0.array, yp=yp, F0=F0, Fp=Fp, J0_data=J0.data,
+             J_indices=J0.indices, J_indptr=J0.indptr, Jp_data=Jp.data, P=P, Q=Q, sol=np.array(sols),
+             nstep=np.array(its), nfeval=np.array(nfe))
+
+
+def golden_known_answers():
+    """Known answers of the reference's own tests, re-run on the reference here."""
+    from Solverz import Eqn, Mat_Mul, Model, Opt, Param, Var, made_numerical, nr_method
+    out = {}
+    m = Model()
+    m.x = Var('x', [0, 0])
+    m.b = Param('b', [0.5, 1])
+    m.A = Param('A', [[1, 3], [-1, 2]], dim=2, sparse=True)
+    m.eqnf = Eqn('eqnf', m.b - Mat_Mul(m.A, m.x))
+    smdl, y0 = m.create_instance()
+    mdl = made_numerical(smdl, y0, sparse=True)
+    sol = nr_method(mdl, y0)
+    out["matmul_linear_y"] = sol.y.array           # tests/test_matrix_equation.py:57-69 -> [-0.4, 0.3]
+    out["matmul_linear_nstep"] = np.array(sol.stats.nstep)
+    m = Model()
+    m.x = Var('x', [0.5, 0.5])
+    m.A = Param('A', [[2, 1], [1, 3]], dim=2, sparse=True)
+    m.b = Param('b', [4.0, 5.0])
+    m.eqn = Eqn('f', m.x * Mat_Mul(m.A, m.x) - m.b)
+    smdl, y0 = m.create_instance()
+    mdl = made_numerical(smdl, y0, sparse=True)
+    J = mdl.J(y0.array, mdl.p)
+    sol = nr_method(mdl, y0, Opt(ite_tol=1e-10))
+    out["mutable_J0"] = J.toarray()                # tests/test_matrix_equation.py:103-158
+    out["mutable_y"] = sol.y.array
+    out["mutable_nstep"] = np.array(sol.stats.nstep)
+    m = Model()
+    m.x = Var(name='x', value=2)
+    m.e = Eqn(name='e', eqn=m.x ** 2 - 1)
+    g, y0 = m.create_instance()
+    sol = nr_method(made_numerical(g, y0, sparse=True), y0, Opt(ite_tol=1e-8))
+    out["x2m1_y"] = sol.y.array                     # tests/test_0.py:1-17
+    out["x2m1_nstep"] = np.array(sol.stats.nstep)
+    np.savez(HERE / "known_answers.npz", **out)
+
+
+if __name__ == "__main__":
+    golden_dae_test()
+    golden_pf(8)
+    golden_known_answers()
+    print("golden fixtures written to", HERE)

@@ -1,0 +1,100 @@
+"""GPU parity of the batched Rodas against the oracle and the reference's own golden trajectories
+(tests/dae_test.xlsx sheets ``rodas`` / ``rodas_dense`` of the reference, 1e-8: tests/test_dae.py:44-53)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def _dae_test_model():
+    from solverz_b200 import Eqn, Model, Ode, Var, made_numerical
+    m = Model()
+    m.x = Var('x', 1)
+    m.y = Var('y', 1)
+    m.f = Ode(name='f', f=-m.x ** 3 + 0.5 * m.y ** 2, diff_var=m.x)
+    m.g = Eqn(name='g', eqn=m.x ** 2 + m.y ** 2 - 2)
+    dae, y0 = m.create_instance()
+    return made_numerical(dae, y0, sparse=True), y0
+
+
+def test_rodas_reference_golden(libszb):
+    from solverz_b200 import Opt, Rodas
+    g = np.load(GOLD / "dae_test_rodas.npz")
+    nd, y0 = _dae_test_model()
+    sol = Rodas(nd, [0, 20], y0, opt=Opt(hinit=0.1))
+    assert np.max(np.abs(g["rodas_sheet"] - sol.Y.array)) < 1e-8
+    np.testing.assert_allclose(sol.T, g["ref_T"], rtol=1e-10)
+    got = [sol.stats.nstep, sol.stats.nfeval, sol.stats.nJeval, sol.stats.ndecomp, sol.stats.nreject,
+           sol.stats.nsolve]
+    assert got == g["ref_stats"].tolist()
+    sol2 = Rodas(nd, np.linspace(0, 20, 201), y0, Opt(hinit=0.1))
+    assert np.max(np.abs(g["rodas_dense_sheet"] - sol2.Y.array)) < 1e-8
+
+
+@pytest.mark.parametrize("scheme", ["rodasp", "rodas5p", "rodas3d"])
+def test_rodas_schemes_vs_reference(libszb, scheme):
+    from solverz_b200 import Opt, Rodas
+    g = np.load(GOLD / "dae_test_rodas.npz")
+    nd, y0 = _dae_test_model()
+    sol = Rodas(nd, [0, 20], y0, opt=Opt(hinit=0.1, scheme=scheme))
+    assert sol.Y.array.shape == g[f"ref_{scheme}_Y"].shape
+    assert np.max(np.abs(g[f"ref_{scheme}_Y"] - sol.Y.array)) < 1e-8
+    got = [sol.stats.nstep, sol.stats.nfeval, sol.stats.nJeval, sol.stats.ndecomp, sol.stats.nreject,
+           sol.stats.nsolve]
+    assert got == g[f"ref_{scheme}_stats"].tolist()
+
+
+def test_rodas_batched_vs_oracle(libszb):
+    """Stiff ensemble: B copies of a small nonlinear DAE with per-scenario parameters and explicit time
+    dependence; every scenario against the oracle (same accepted / rejected step counts)."""
+    from oracle.rodas import rodas as oracle_rodas
+    from solverz_b200 import Eqn, Model, Ode, Opt, Param, Rodas, Var, made_numerical, t_sym, sin
+    from solverz_b200.solvers.rodas_param import Rodas_param
+    B = 12
+    rng = np.random.default_rng(3)
+    kk = 50.0 + 100.0 * rng.random((B, 1))
+    amp = 0.5 + rng.random((B, 1))
+    m = Model()
+    m.x = Var('x', [1.0, 0.5])
+    m.z = Var('z', [1.0, 0.25])
+    m.k = Param('k', [100.0], per_scenario=True)
+    m.a = Param('a', [1.0], per_scenario=True)
+    m.f = Ode('f', -m.k * (m.x - m.a * sin(t_sym)) + m.z, diff_var=m.x)
+    m.g = Eqn('g', m.z + 0.1 * m.a * m.z ** 3 - m.x ** 2 - 0.1 * m.a * m.x ** 6)
+    dae, y0 = m.create_instance()
+    nd = made_numerical(dae, y0, sparse=True)
+    nd.p["k"], nd.p["a"] = kk, amp
+    Y0 = np.tile(y0.array, (B, 1))
+    tsp = np.linspace(0, 2, 21)
+    for mode in ("module", "fd"):
+        opt = Opt(rtol=1e-4, atol=1e-7)
+        opt.dfdt = mode
+        sol = Rodas(nd, tsp, Y0, opt)
+        rp = Rodas_param("rodas4")
+        M = nd.M
+        for b in range(B):
+            k_, a_ = kk[b, 0], amp[b, 0]
+
+            def F(t, y):
+                x, z = y[:2], y[2:]
+                return np.concatenate([-k_ * (x - a_ * np.sin(t)) + z,
+                                       z + 0.1 * a_ * z ** 3 - x ** 2 - 0.1 * a_ * x ** 6])
+
+            def J(t, y):
+                x, z = y[:2], y[2:]
+                return sps.bmat([[sps.diags(np.full(2, -k_)), sps.identity(2)],
+                                 [sps.diags(-2 * x - 0.6 * a_ * x ** 5), sps.diags(1 + 0.3 * a_ * z ** 2)]]).tocsc()
+            ref = oracle_rodas(F, J, M, tsp, y0.array, rp, rtol=1e-4, atol=1e-7, dfdt_mode=1 if mode == "fd" else 0)
+            assert int(sol.stats.nstep[b]) == ref["stats"]["nstep"], (mode, b)
+            assert int(sol.stats.nreject[b]) == ref["stats"]["nreject"], (mode, b)
+            assert int(sol.stats.nfeval[b]) == ref["stats"]["nfeval"]
+            assert int(sol.stats.nJeval[b]) == ref["stats"]["nJeval"]
+            assert ref["stats"]["nstep"] > 5
+            # 'fd' divides a difference of two F values by ddt ~ 1e-10: one-ulp differences between
+            # CUDA's and numpy's sin() are amplified to ~1e-7 there; the module path has no such term
+            tol = 1e-8 if mode == "module" else 5e-5   # still below rtol = 1e-4
+            assert np.max(np.abs(sol.Y[b] - ref["Y"])) < tol, (mode, b)

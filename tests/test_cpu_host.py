@@ -1,0 +1,292 @@
+"""CPU tests of the host-side logic: symbolic LU analysis (walked by a numpy emulator of the kernels'
+schedule), front-end lowering / Jacobian derivation / CUDA printer (through the -DSZBM_HOST_CHECK build
+of the generated source), the C-ABI library, and the multi-rank sharding plan (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import scipy.sparse.linalg as sla
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLD = Path(__file__).parent / "golden"
+
+
+# ----------------------------------------------------------------------------- symbolic LU
+def _pf_jacobian(nx, seed=0):
+    from oracle.pf import PFOracle
+    from solverz_b200.synthetic import lattice_grid
+    nb, Y = lattice_grid(nx, nx)
+    npv = max(1, int(0.1 * nb))
+    orc = PFOracle(Y, np.arange(1, 1 + npv), np.arange(1 + npv, nb))
+    rng = np.random.default_rng(seed)
+    y = np.concatenate([0.05 * rng.standard_normal(nb), 1 + 0.05 * rng.standard_normal(nb)])
+    J = sps.csc_matrix(orc.J(y))
+    J.sort_indices()
+    return J, orc
+
+
+@pytest.mark.parametrize("nx,opts", [(6, {}), (12, {}), (12, dict(warp_front_max=8, group_front_max=20, n_warps=4, n_groups=2)),
+                                     (10, dict(orderings=("nd",))), (10, dict(orderings=("natural",)))])
+def test_symbolic_schedule_solves(nx, opts):
+    import mf_emulate as E
+    from solverz_b200.lu.symbolic import analyze
+    J, orc = _pf_jacobian(nx)
+    sym = analyze(J, **opts)
+    assert sorted(sym.order.tolist()) == list(range(sym.ns))
+    assert sorted(sym.rowp.tolist()) == list(range(sym.n)) and sorted(sym.colp.tolist()) == list(range(sym.n))
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal(sym.n)
+    # a *different* scenario with the same pattern: the static pivots must still work
+    J2, _ = _pf_jacobian(nx, seed=5)
+    assert np.array_equal(J.indices, J2.indices)
+    for A in (J, J2):
+        lu = E.factor(sym, A.data)
+        x = E.solve(sym, lu, b)
+        xr = sla.spsolve(A, b)
+        assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
+
+
+def test_symbolic_shifted_matrix_and_singular_pattern():
+    import mf_emulate as E
+    from solverz_b200.lu.symbolic import analyze
+    J, _ = _pf_jacobian(6)
+    n = J.shape[0]
+    mv = np.zeros(J.nnz)
+    d = sps.csc_matrix((np.ones(n // 2), (np.arange(n // 2), np.arange(n // 2))), shape=(n, n))
+    U = (abs(J) + d).tocsc()
+    U.sort_indices()
+    sym = analyze(U)
+    # M - h*gamma*J assembled as mvals + scale*jv, both given on the union pattern's CSC slots
+    def on_pattern(A):
+        A = sps.coo_matrix(A)
+        slot = {}
+        for c in range(n):
+            for p in range(U.indptr[c], U.indptr[c + 1]):
+                slot[(U.indices[p], c)] = p
+        out = np.zeros(U.nnz)
+        for r, c, v in zip(A.row, A.col, A.data):
+            out[slot[(r, c)]] += v
+        return out
+    jd, md = on_pattern(J), on_pattern(d)
+    lu = E.factor(sym, jd, mvals=md, scale=-0.01)
+    b = np.arange(n, dtype=float)
+    x = E.solve(sym, lu, b)
+    A = (d - 0.01 * J).tocsc()
+    assert np.abs(A @ x - b).max() <= 1e-11 * abs(A).max() * np.abs(x).max()   # backward stable
+    with pytest.raises(ValueError):
+        analyze(sps.csc_matrix(np.array([[1.0, 1.0], [0.0, 0.0]])))
+
+
+# ----------------------------------------------------------------------------- printer via host check
+def _host_lib(eqs, name, tmp_path):
+    from solverz_b200.code_printer.cuda import compile_host_check, print_model
+    from solverz_b200.jacobian import derive_jacobian
+    ir = eqs.to_ir()
+    pat = derive_jacobian(ir)
+    src = print_model(ir, pat, name)
+    cu = tmp_path / f"{name}.cu"
+    cu.write_text(src)
+    so = compile_host_check(cu, tmp_path / f"{name}_host.so")
+    return ir, pat, ctypes.CDLL(so), src
+
+
+def _eval(lib, ir, pat, Y, params, t=0.0):
+    Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=float)
+    B = Y.shape[0]
+    vals = []
+    for p in ir.params.values():
+        v = params.get(p.name, p.value)
+        v = np.ascontiguousarray(v, dtype=np.float64 if p.dtype == "f64" else np.int32)
+        if p.per_scenario and v.ndim == 1:
+            v = np.ascontiguousarray(np.tile(v, (B, 1)))
+        vals.append(v)
+    ptrs = (ctypes.c_void_p * max(len(vals), 1))(*[v.ctypes.data for v in vals])
+    F = np.zeros((B, ir.n))
+    JV = np.zeros((B, pat.nnz))
+    lib.szbm_host_F(B, ctypes.c_double(t), Y.ctypes.data_as(ctypes.c_void_p), ptrs, F.ctypes.data_as(ctypes.c_void_p))
+    lib.szbm_host_J(B, ctypes.c_double(t), Y.ctypes.data_as(ctypes.c_void_p), ptrs, JV.ctypes.data_as(ctypes.c_void_p))
+    return F, JV
+
+
+def test_printer_pf_matches_reference_golden(tmp_path):
+    """Generated row functions vs the reference's numba module output (golden) at 1e-12 -- the
+    three-way parity of the reference's tests/test_matrix_equation.py:111-158."""
+    from solverz_b200.synthetic import polar_pf_model
+    g = np.load(GOLD / "pf_ref_8x8.npz")
+    eqs, y0, info = polar_pf_model(8, 8)
+    ir, pat, lib, src = _host_lib(eqs, "pf8", tmp_path)
+    assert np.array_equal(pat.indices, g["J_indices"]) and np.array_equal(pat.indptr, g["J_indptr"])
+    for y, F, Jd in ((g["y0"], g["F0"], g["J0_data"]), (g["yp"], g["Fp"], g["Jp_data"])):
+        Fh, JVh = _eval(lib, ir, pat, y, {})
+        assert np.abs(Fh[0] - F).max() <= 1e-13
+        assert np.abs(JVh[0] - Jd).max() <= 1e-12 * np.abs(Jd).max()
+    assert "sincos(" in src and "szbm_launch_F" in src
+
+
+def test_printer_vector_eqn_matmul_and_known_values(tmp_path):
+    """F0 = [3, 1 + sin 1], J0 = [[2, 1], [2, cos 1]] (reference test_module_generator.py:64-127);
+    x * (A @ x) - b: J0 = [[2.5, 0.5], [0.5, 3.5]] (reference golden known_answers.npz)."""
+    from solverz_b200 import Eqn, Mat_Mul, Model, Param, Var, sin
+    m = Model()
+    m.x = Var('x', [1, 1])
+    m.f1 = Eqn('f1', 2 * m.x[0] + m.x[1])
+    m.f2 = Eqn('f2', m.x[0] ** 2 + sin(m.x[1]))
+    eqs, y0 = m.create_instance()
+    ir, pat, lib, _ = _host_lib(eqs, "ae1", tmp_path)
+    F, JV = _eval(lib, ir, pat, y0.array, {})
+    np.testing.assert_allclose(F[0], [3, 1 + np.sin(1)], rtol=1e-14)
+    J = sps.csc_matrix((JV[0], pat.indices, pat.indptr), shape=(2, 2)).toarray()
+    np.testing.assert_allclose(J, [[2, 1], [2, np.cos(1)]], rtol=1e-14)
+
+    k = np.load(GOLD / "known_answers.npz")
+    m = Model()
+    m.x = Var('x', [0.5, 0.5])
+    m.A = Param('A', [[2, 1], [1, 3]], dim=2, sparse=True)
+    m.b = Param('b', [4.0, 5.0])
+    m.eqn = Eqn('f', m.x * Mat_Mul(m.A, m.x) - m.b)
+    eqs, y0 = m.create_instance()
+    ir, pat, lib, _ = _host_lib(eqs, "mm1", tmp_path)
+    F, JV = _eval(lib, ir, pat, y0.array, {})
+    J = sps.csc_matrix((JV[0], pat.indices, pat.indptr), shape=(2, 2)).toarray()
+    np.testing.assert_allclose(J, k["mutable_J0"], rtol=1e-14)
+    np.testing.assert_allclose(F[0], 0.5 * (np.array([[2, 1], [1, 3.]]) @ [0.5, 0.5]) - [4, 5], rtol=1e-14)
+
+
+def test_printer_dae_time_series_and_functions(tmp_path):
+    """DAE ordering (Ode rows first, equations.py:672), mass matrix, TimeSeriesParam end clamp
+    (param.py:187-212), Abs / heaviside / exp / ln vocabulary; J against complex-step-free central
+    differences of the generated F."""
+    from solverz_b200 import Abs, Eqn, Model, Ode, Param, TimeSeriesParam, Var, exp, heaviside, ln, t_sym, cos
+    m = Model()
+    m.u = Var('u', [0.3, -0.2, 0.8])
+    m.w = Var('w', [1.5])
+    m.c = Param('c', [2.0, 3.0, 4.0], per_scenario=True)
+    m.load = TimeSeriesParam('load', v_series=[1.0, 2.0, 0.5], time_series=[0.0, 1.0, 3.0])
+    m.alg = Eqn('alg', m.w * m.w - m.load - exp(-m.w) + ln(m.w + 2) * heaviside(m.w))
+    m.ode = Ode('ode', -m.c * m.u + Abs(m.u) * cos(t_sym) + m.w, diff_var=m.u)
+    eqs, y0 = m.create_instance()
+    assert eqs.kind == "DAE"
+    ir, pat, lib, _ = _host_lib(eqs, "dae1", tmp_path)
+    assert [e.name for e in ir.eqs] == ["ode", "alg"]          # Ode first
+    r, c = ir.mass
+    assert r.tolist() == [0, 1, 2] and c.tolist() == [0, 1, 2]
+    cs = np.array([[2.0, 3.0, 4.0], [1.0, 1.5, 2.5]])
+    Y = np.array([[0.3, -0.2, 0.8, 1.5], [0.1, 0.4, -0.6, 0.7]])
+    for t, load in ((0.5, 1.5), (2.0, 1.25), (3.0, 0.5), (10.0, 0.5)):
+        F, JV = _eval(lib, ir, pat, Y, {"c": cs}, t)
+        for b in range(2):
+            u, w = Y[b, :3], Y[b, 3]
+            ref = np.concatenate([-cs[b] * u + np.abs(u) * np.cos(t) + w,
+                                  [w * w - load - np.exp(-w) + np.log(w + 2) * (w >= 0)]])
+            np.testing.assert_allclose(F[b], ref, rtol=1e-14, atol=1e-15)
+            J = sps.csc_matrix((JV[b], pat.indices, pat.indptr), shape=(4, 4)).toarray()
+            Jfd = np.zeros((4, 4))
+            for j in range(4):
+                h = 1e-6
+                yp, ym = Y.copy(), Y.copy()
+                yp[b, j] += h
+                ym[b, j] -= h
+                Jfd[:, j] = (_eval(lib, ir, pat, yp, {"c": cs}, t)[0][b] - _eval(lib, ir, pat, ym, {"c": cs}, t)[0][b]) / (2 * h)
+            np.testing.assert_allclose(J, Jfd, atol=1e-8)
+
+
+def test_front_end_errors():
+    from solverz_b200 import Eqn, LoopEqn, Model, Param, Set, Sum, Var
+    m = Model()
+    m.x = Var('x', [1.0, 2.0, 3.0])
+    m.y = Var('y', [1.0, 2.0])
+    m.e = Eqn('e', m.x + m.y)
+    with pytest.raises(ValueError, match="incompatible operand lengths"):
+        m.create_instance()
+    with pytest.raises(ValueError):
+        Set('Bad', [1, 1, 2])
+    with pytest.raises(ValueError):
+        Set('Neg', [-1, 2])
+    with pytest.raises(TypeError):
+        m.x[[0, 1]]
+    m2 = Model()
+    m2.x = Var('x', [1.0, 2.0])
+    m2.e = Eqn('e', m2.x[0])
+    with pytest.raises(ValueError, match="not equal"):
+        m2.create_instance()
+
+
+# ----------------------------------------------------------------------------- C-ABI
+def test_c_abi_exports_every_declared_symbol(libszb):
+    from solverz_b200.num_api import lib as L
+    hdr = (ROOT / "include" / "szb.h").read_text()
+    declared = set(re.findall(r"SZB_API\s+(?:const\s+)?\w+\*?\s+(szb_\w+)\(", hdr))
+    assert len(declared) >= 18
+    out = subprocess.run(["nm", "-D", "--defined-only", str(L.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (szb_\w+)", out))
+    assert declared <= exported, declared - exported
+    assert libszb.szb_abi_version() == 1
+    # error convention: NULL handle -> negative code, never a crash
+    assert libszb.szb_set_batch(None, 4) < 0
+    assert libszb.szb_destroy(None) == 0
+
+
+def test_model_library_exports(tmp_path):
+    """The nvcc-built model library exports the szbm_* entry points of include/szb_model.h."""
+    from solverz_b200 import module_printer
+    from solverz_b200.synthetic import polar_pf_model
+    eqs, y0, _ = polar_pf_model(4, 4)
+    pkg = module_printer(eqs, y0, "pf4_abi", directory=str(tmp_path)).render()
+    out = subprocess.run(["nm", "-D", "--defined-only", str(pkg / "libpf4_abi.so")], capture_output=True, text=True).stdout
+    hdr = (ROOT / "include" / "szb_model.h").read_text()
+    declared = set(re.findall(r"SZBM_API\s+(?:const\s+)?\w+\*?\s+(szbm_\w+)\(", hdr))
+    assert declared <= set(re.findall(r" T (szbm_\w+)", out))
+    assert sorted(p.name for p in pkg.iterdir() if not p.name.startswith(".")) == \
+        ["__init__.py", "dependency.py", "libpf4_abi.so", "num_func.cu", "param_and_setting.pkl"]
+    sass = subprocess.run(["cuobjdump", "-lelf", str(pkg / "libpf4_abi.so")], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path fails loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from solverz_b200 import Eqn, Model, Var, made_numerical, nr_method
+    from solverz_b200.num_api.lib import SzbError
+    m = Model()
+    m.x = Var('x', 2.0)
+    m.e = Eqn('e', m.x ** 2 - 1)
+    g, y0 = m.create_instance()
+    mdl = made_numerical(g, y0, sparse=True)      # printing + nvcc work without a GPU
+    with pytest.raises(SzbError, match="no CPU fallback"):
+        nr_method(mdl, y0)
+
+
+# ----------------------------------------------------------------------------- multi-rank plan
+def test_shard_plan_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from solverz_b200.parallel import shard_range, gather_results
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+B, n = 11, 3
+lo, hi = shard_range(B, r, w)
+y = torch.arange(lo, hi, dtype=torch.float64)[:, None].repeat(1, n) + 0.5
+it = torch.arange(lo, hi, dtype=torch.int32) %% 4
+fl = torch.zeros(hi - lo, dtype=torch.int32)
+Y, IT, FL = gather_results(y, it, fl, B)
+assert Y.shape == (B, n) and torch.equal(Y[:, 0], torch.arange(B, dtype=torch.float64) + 0.5)
+assert torch.equal(IT, torch.arange(B, dtype=torch.int32) %% 4) and int(FL.sum()) == 0
+dist.destroy_process_group()
+sys.stdout.write("rank " + str(r) + " ok " + str(lo) + " " + str(hi) + chr(10)); sys.stdout.flush()
+''' % str(ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok 0 6" in r.stdout and "rank 1 ok 6 11" in r.stdout

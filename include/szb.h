@@ -107,6 +107,8 @@ typedef struct szb_lu_symbolic {
   const int32_t* lp_off;    /* [ns] */
   const int32_t* up_off;    /* [ns] */
   const int32_t* cb_off;    /* [ns] */
+  const int32_t* ea_ptr;    /* [ns+1] extend-add tables: ea_dst[ea_ptr[c] + t] = position in the parent */
+  const int32_t* ea_dst;    /*        front of element t of the u_c x (u_c+1) contribution block of c   */
   const int32_t* wl_ptr;    /* [n_warp_lists+1] */
   const int32_t* wl;
   const int32_t* gl_ptr;    /* [n_group_lists+1] */

@@ -237,7 +237,7 @@ int szb_create(const szb_desc* d, szb_handle** out) {
   UP(idx_ptr, ns + 1); UP(idx, L.idx_ptr[ns]); UP(rel_ptr, ns + 1); UP(rel, L.rel_ptr[ns]);
   UP(child_ptr, ns + 1); UP(child, L.child_ptr[ns]);
   UP(a_ptr, ns + 1); UP(a_src, L.nnz_a); UP(a_dst, L.nnz_a);
-  UP(lp_off, ns); UP(up_off, ns); UP(cb_off, ns);
+  UP(lp_off, ns); UP(up_off, ns); UP(cb_off, ns); UP(ea_ptr, ns + 1); UP(ea_dst, L.ea_ptr[ns]);
   UP(wl_ptr, L.n_warp_lists + 1); UP(wl, L.wl_ptr[L.n_warp_lists]);
   UP(gl_ptr, L.n_group_lists + 1); UP(gl, L.gl_ptr[L.n_group_lists]); UP(top, L.n_top);
 #undef UP

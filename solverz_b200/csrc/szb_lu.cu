@@ -36,6 +36,12 @@ namespace {
 
 constexpr int kWarp = 32;
 
+// t / m for 0 <= t < 2^22 without an integer division: (t + 0.5)/m is never within 0.5/m of an
+// integer, far more than the 2^-23 relative rounding of the float product
+__device__ __forceinline__ int fdiv(int t, float invm) {
+  return __float2int_rz((static_cast<float>(t) + 0.5f) * invm);
+}
+
 // ---- thread groups ------------------------------------------------------------------------
 struct WarpGrp {
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
@@ -78,57 +84,169 @@ struct FactorArgs {
   int* flag;
 };
 
-// divide the rows below the diagonal of column p by the pivot (one warp)
-__device__ __forceinline__ void scale_pivot_column(double* __restrict__ Fm, const int p, const int f,
-                                                   const int ld, const int lane, int* flag) {
-  double* __restrict__ col = Fm + p * ld;
-  const double piv = col[p];
-  const double inv = 1.0 / piv;
-  if (lane == 0 && (!(fabs(piv) > 0.0) || isinf(piv))) *flag = 2;
-  for (int i = p + 1 + lane; i < f; i += kWarp) col[i] *= inv;
+__device__ __forceinline__ void check_pivot(const double piv, int* flag) {
+  if (!(fabs(piv) > 0.0) || isinf(piv)) *flag = 2;
 }
 
-// one right-looking step: columns j > p get  a_ij -= l_i * u_pj ; lane = row, NCH row chunks of 32
-// held in registers (NCH == 0: generic loop).  The warp that owns column p+1 scales it afterwards.
+// ---- single warp, fronts with at most 32 rows: right-looking rank-1 steps, lane = row.  When the
+// trailing block has m <= 16 (<= 8) rows, two (four) columns are updated per warp instruction so that
+// all lanes stay busy on the tiny fronts that make up most of the tree.
+__device__ __forceinline__ void eliminate_warp(double* __restrict__ Fm, const int s, const int f,
+                                               const int ncol, const int ld, const int lane, int* flag) {
+  for (int p = 0; p < s; ++p) {
+    const int m = f - p - 1;
+    const int nc = ncol - p - 1;
+    double* __restrict__ colp = Fm + (p + 1) + p * ld;
+    const double piv = colp[-1];
+    const double inv = 1.0 / piv;
+    if (lane == 0) check_pivot(piv, flag);
+    const int sh = m <= 8 ? 3 : (m <= 16 ? 4 : 5);     // rows per column slot = 1 << sh
+    const int i = lane & ((1 << sh) - 1);
+    const int cj = lane >> sh;                          // column slot of this lane
+    const int cpw = 32 >> sh;                           // columns per warp instruction
+    const bool row_ok = i < m;
+    double l = 0.0;
+    if (row_ok) l = colp[i] * inv;
+    __syncwarp();
+    if (cj == 0 && row_ok) colp[i] = l;                 // L stored scaled
+    double* __restrict__ col = Fm + (p + 1) + (p + 1 + cj) * ld;
+    const int step = cpw * ld;
+    for (int j = cj; j < nc; j += cpw, col += step) {
+      const double u = col[-1];
+      if (row_ok) col[i] = fma(-l, u, col[i]);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- several warps: blocked right-looking elimination, NB = 4 pivots per panel.
+// (1) warp 0 factors the panel (rows p0.., columns p0..p0+nb-1) in registers, lane = row, pivots
+//     exchanged with shuffles;  (2) every warp takes trailing columns: forward-substitutes the nb
+//     U values of the column with the unit-lower panel block and applies the rank-nb update to its
+//     row chunks with the multipliers kept in registers.  Two group barriers per panel.
+constexpr int kNB = 4;
+
 template <int NCH>
-__device__ __forceinline__ void eliminate_step(double* __restrict__ Fm, const int p, const int m,
-                                               const int nc, const int ld, const int f, const int lane,
-                                               const int w, const int nw, const bool more, int* flag) {
-  const double* __restrict__ colp = Fm + (p + 1) + p * ld;
-  double l[NCH > 0 ? NCH : 1];
-  if (NCH > 0) {
+__device__ __forceinline__ void panel_factor(double* __restrict__ Fm, const int p0, const int nb, const int f,
+                                             const int ld, const int lane, int* flag) {
+  double P[NCH][kNB];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int i = p0 + lane + 32 * c;
+#pragma unroll
+    for (int k = 0; k < kNB; ++k) P[c][k] = (i < f && k < nb) ? Fm[i + (p0 + k) * ld] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < kNB; ++k) {
+    if (k < nb) {
+      const double piv = __shfl_sync(0xffffffffu, P[0][k], k);
+      const double inv = 1.0 / piv;
+      if (lane == 0) check_pivot(piv, flag);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (c > 0 || lane > k) P[c][k] *= inv;
+#pragma unroll
+      for (int k2 = k + 1; k2 < kNB; ++k2) {
+        const double u = __shfl_sync(0xffffffffu, P[0][k2], k);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          if (c > 0 || lane > k) P[c][k2] = fma(-P[c][k], u, P[c][k2]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int i = p0 + lane + 32 * c;
+#pragma unroll
+    for (int k = 0; k < kNB; ++k)
+      if (i < f && k < nb) Fm[i + (p0 + k) * ld] = P[c][k];
+  }
+}
+
+template <int NCH>
+__device__ __forceinline__ void trailing_update(double* __restrict__ Fm, const int p0, const int nb,
+                                                const int f, const int ncol, const int ld, const int lane,
+                                                const int w, const int nw) {
+  const int r0 = p0 + nb;            // first trailing row / column
+  const int m = f - r0;
+  // unit-lower panel block (strictly lower part) and this lane's multipliers
+  const double* __restrict__ blk = Fm + p0 + p0 * ld;
+  const double L10 = nb > 1 ? blk[1] : 0.0;
+  const double L20 = nb > 2 ? blk[2] : 0.0, L21 = nb > 2 ? blk[2 + ld] : 0.0;
+  const double L30 = nb > 3 ? blk[3] : 0.0, L31 = nb > 3 ? blk[3 + ld] : 0.0, L32 = nb > 3 ? blk[3 + 2 * ld] : 0.0;
+  double l[NCH][kNB];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int i = lane + 32 * c;
+#pragma unroll
+    for (int k = 0; k < kNB; ++k) l[c][k] = (i < m && k < nb) ? Fm[(r0 + i) + (p0 + k) * ld] : 0.0;
+  }
+  for (int j = r0 + w; j < ncol; j += nw) {
+    double* __restrict__ col = Fm + j * ld;
+    const double u0 = col[p0];
+    double u1 = nb > 1 ? col[p0 + 1] : 0.0;
+    double u2 = nb > 2 ? col[p0 + 2] : 0.0;
+    double u3 = nb > 3 ? col[p0 + 3] : 0.0;
+    u1 = fma(-L10, u0, u1);
+    u2 = fma(-L21, u1, fma(-L20, u0, u2));
+    u3 = fma(-L32, u2, fma(-L31, u1, fma(-L30, u0, u3)));
+    if (lane == 0) {
+      if (nb > 1) col[p0 + 1] = u1;
+      if (nb > 2) col[p0 + 2] = u2;
+      if (nb > 3) col[p0 + 3] = u3;
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int i = lane + 32 * c;
-      l[c] = (c + 1 < NCH || i < m) ? colp[i] : 0.0;
+      if (c + 1 < NCH || i < m) {
+        double a = col[r0 + i];
+        a = fma(-l[c][0], u0, a);
+        a = fma(-l[c][1], u1, a);
+        a = fma(-l[c][2], u2, a);
+        a = fma(-l[c][3], u3, a);
+        col[r0 + i] = a;
+      }
     }
   }
-  for (int jj = w; jj < nc; jj += nw) {
-    double* __restrict__ col = Fm + (p + 1) + (p + 1 + jj) * ld;
-    const double ukj = col[-1];     // element (p, j)
-    if (NCH > 0) {
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int i = lane + 32 * c;
-        if (c + 1 < NCH || i < m) col[i] = fma(-l[c], ukj, col[i]);
+}
+
+template <class G>
+__device__ __forceinline__ void eliminate_blocked(const G g, double* __restrict__ Fm, const int s, const int f,
+                                                  const int ncol, const int ld, int* flag) {
+  const int lane = g.lane(), w = g.warp(), nw = g.nwarps();
+  for (int p0 = 0; p0 < s; p0 += kNB) {
+    const int nb = min(kNB, s - p0);
+    if (w == 0) {
+      switch ((f - p0 + 31) >> 5) {
+        case 1: panel_factor<1>(Fm, p0, nb, f, ld, lane, flag); break;
+        case 2: panel_factor<2>(Fm, p0, nb, f, ld, lane, flag); break;
+        case 3: panel_factor<3>(Fm, p0, nb, f, ld, lane, flag); break;
+        default: panel_factor<4>(Fm, p0, nb, f, ld, lane, flag); break;
       }
-    } else {
-      for (int i = lane; i < m; i += kWarp) col[i] = fma(-colp[i], ukj, col[i]);
     }
-    if (jj == 0 && more) {
-      __syncwarp();
-      scale_pivot_column(Fm, p + 1, f, ld, lane, flag);
+    g.sync();
+    const int m = f - p0 - nb;
+    if (ncol - p0 - nb > 0) {
+      switch ((m + 31) >> 5) {
+        case 0: trailing_update<1>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;   // only the rhs column
+        case 1: trailing_update<1>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;
+        case 2: trailing_update<2>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;
+        case 3: trailing_update<3>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;
+        default: trailing_update<4>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;
+      }
     }
+    g.sync();
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // numeric factorisation of one supernode; the front is column-major with leading dimension
-// ld = f | 1 and has f (+1 when a rhs rides along) columns
+// ld = f | 1 and has f (+1 when a rhs rides along) columns.  Fronts of multi-warp groups are
+// limited to 128 rows (4 row chunks per lane); lu_plan() rejects larger ones.
 // ---------------------------------------------------------------------------------------
 template <class G>
 __device__ void factor_supernode(const G g, const LuDev& S, const int k, double* __restrict__ Fm,
-                                 double* __restrict__ dinv, const FactorArgs& A) {
+                                 const FactorArgs& A) {
   const int s = S.sn_s[k], f = S.sn_f[k], u = f - s, ld = f | 1;
   const int lane = g.lane(), w = g.warp(), nw = g.nwarps(), r = g.rank(), G_ = g.size();
   const int with_rhs = A.rhs != nullptr;
@@ -158,55 +276,58 @@ __device__ void factor_supernode(const G g, const LuDev& S, const int k, double*
     }
   }
   g.sync();
-  // 3. extend-add of the children's contribution blocks (u_c x (u_c + 1), column-major)
+  // 3. extend-add of the children's contribution blocks (u_c x (u_c + 1), column-major); the
+  // destination of every element was computed on the host (ea_dst)
   for (int ci = S.child_ptr[k]; ci < S.child_ptr[k + 1]; ++ci) {
     const int c = S.child[ci];
     const int uc = S.sn_f[c] - S.sn_s[c];
     if (uc == 0) continue;
-    const int* __restrict__ rel = S.rel + S.rel_ptr[c];
+    const int* __restrict__ dst = S.ea_dst + S.ea_ptr[c];
     const double* __restrict__ C = A.cb + S.cb_off[c];
-    const int nc = uc + with_rhs;
-    for (int jc = w; jc < nc; jc += nw) {
-      const int dcol = (jc < uc) ? rel[jc] : f;
-      double* __restrict__ dst = Fm + dcol * ld;
-      const double* __restrict__ src = C + jc * uc;
-      for (int ic = lane; ic < uc; ic += kWarp) dst[rel[ic]] += src[ic];
-    }
+    const int cnt = uc * (uc + with_rhs);
+    for (int t = r; t < cnt; t += G_) Fm[dst[t]] += C[t];
     g.sync();
   }
-  // 4. right-looking elimination of the s pivots.  Column p is already divided by its pivot when
-  // step p starts: the warp that updates column p+1 in step p scales it right away, so no warp
-  // repeats the division and there is exactly one barrier per pivot.
-  if (w == 0) scale_pivot_column(Fm, 0, f, ld, lane, A.flag);
-  g.sync();
-  for (int p = 0; p < s; ++p) {
-    const int m = f - p - 1;          // trailing rows
-    const int nc = ncol - p - 1;      // trailing columns (incl. rhs)
-    const bool more = p + 1 < s;
-    switch ((m + 31) >> 5) {
-      case 0: break;
-      case 1: eliminate_step<1>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
-      case 2: eliminate_step<2>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
-      case 3: eliminate_step<3>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
-      case 4: eliminate_step<4>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
-      default: eliminate_step<0>(Fm, p, m, nc, ld, f, lane, w, nw, more, A.flag); break;
-    }
-    g.sync();
-  }
+  // 4. elimination of the s pivots
+  if (nw == 1) eliminate_warp(Fm, s, f, ncol, ld, lane, A.flag);
+  else eliminate_blocked(g, Fm, s, f, ncol, ld, A.flag);
   // 5. write-out
   {
     double* __restrict__ Lp = A.lu + S.lp_off[k];           // f x s, column-major, ld = f
     const int rows = A.store_l ? f : s;
-    for (int p = w; p < s; p += nw)
-      for (int i = lane; i < rows; i += kWarp) Lp[i + p * f] = Fm[i + p * ld];
+    if (nw == 1) {
+      const float invr = 1.0f / static_cast<float>(rows);
+      for (int t = r; t < rows * s; t += kWarp) {
+        const int p = fdiv(t, invr);
+        const int i = t - p * rows;
+        Lp[i + p * f] = Fm[i + p * ld];
+      }
+    } else {
+      for (int p = w; p < s; p += nw)
+        for (int i = lane; i < rows; i += kWarp) Lp[i + p * f] = Fm[i + p * ld];
+    }
     if (u > 0) {
       double* __restrict__ Up = A.lu + S.up_off[k];         // U12 rows: Up[c + r*u] = U12[r][c]
-      for (int rr = w; rr < s; rr += nw)
-        for (int c = lane; c < u; c += kWarp) Up[c + rr * u] = Fm[rr + (s + c) * ld];
       double* __restrict__ C = A.cb + S.cb_off[k];          // u x (u+1), column-major
       const int nc = u + with_rhs;
-      for (int j = w; j < nc; j += nw)
-        for (int i = lane; i < u; i += kWarp) C[i + j * u] = Fm[(s + i) + (s + j) * ld];
+      if (nw == 1) {
+        const float invu = 1.0f / static_cast<float>(u);
+        for (int t = r; t < u * s; t += kWarp) {
+          const int rr = fdiv(t, invu);
+          const int c = t - rr * u;
+          Up[t] = Fm[rr + (s + c) * ld];
+        }
+        for (int t = r; t < u * nc; t += kWarp) {
+          const int j = fdiv(t, invu);
+          const int i = t - j * u;
+          C[t] = Fm[(s + i) + (s + j) * ld];
+        }
+      } else {
+        for (int rr = w; rr < s; rr += nw)
+          for (int c = lane; c < u; c += kWarp) Up[c + rr * u] = Fm[rr + (s + c) * ld];
+        for (int j = w; j < nc; j += nw)
+          for (int i = lane; i < u; i += kWarp) C[i + j * u] = Fm[(s + i) + (s + j) * ld];
+      }
     }
     if (with_rhs) {
       const int p0 = S.sn_piv0[k];
@@ -225,8 +346,8 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
                  const int* __restrict__ active, int* __restrict__ flags, int B) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5;
-  const int wstride = (S.f_warp_max | 1) * (S.f_warp_max + 1) + S.f_warp_max;
-  const int gstride = (S.f_group_max | 1) * (S.f_group_max + 1) + S.f_group_max;
+  const int wstride = (S.f_warp_max | 1) * (S.f_warp_max + 1);
+  const int gstride = (S.f_group_max | 1) * (S.f_group_max + 1);
   const int wpg = (blockDim.x >> 5) / max(S.n_group_lists, 1);   // warps per group
 #ifdef SZB_PHASE_TIMING
   long long tph[4] = {0, 0, 0, 0};
@@ -250,10 +371,8 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
     // level 0: warps
     if (warp < S.n_warp_lists) {
       double* Fm = sm + warp * wstride;
-      double* dinv = Fm + (S.f_warp_max | 1) * (S.f_warp_max + 1);
       const WarpGrp g;
-      for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q)
-        factor_supernode(g, S, S.wl[q], Fm, dinv, A);
+      for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q) factor_supernode(g, S, S.wl[q], Fm, A);
     }
     __syncthreads();
 #ifdef SZB_PHASE_TIMING
@@ -264,13 +383,12 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
       const int gi = warp / wpg;
       if (gi < S.n_group_lists) {
         double* Fm = sm + gi * gstride;
-        double* dinv = Fm + (S.f_group_max | 1) * (S.f_group_max + 1);
         NamedGrp g;
         g.id = 1 + gi;
         g.nw = wpg;
         g.w0 = gi * wpg;
         for (int q = S.gl_ptr[gi]; q < S.gl_ptr[gi + 1]; ++q)
-          factor_supernode(g, S, S.gl[q], Fm, dinv, A);
+          factor_supernode(g, S, S.gl[q], Fm, A);
       }
       __syncthreads();
     }
@@ -279,9 +397,8 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
 #endif
     // level 2: the whole CTA
     {
-      double* dinv = sm + (S.f_top_max | 1) * (S.f_top_max + 1);
       const BlockGrp g;
-      for (int q = 0; q < S.n_top; ++q) factor_supernode(g, S, S.top[q], sm, dinv, A);
+      for (int q = 0; q < S.n_top; ++q) factor_supernode(g, S, S.top[q], sm, A);
     }
 #ifdef SZB_PHASE_TIMING
     long long t3 = clock64();
@@ -512,7 +629,9 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   if (S.n_top > 0 && warps < 8) warps = S.n_group_lists > 0 ? ((8 + S.n_group_lists - 1) / S.n_group_lists) * S.n_group_lists : 8;
   if (warps > 32) return cudaErrorInvalidConfiguration;
   cfg->threads = 32 * warps;
-  auto front = [](int f) { return static_cast<size_t>(f | 1) * (f + 1) + f; };
+  if (S.f_group_max > 128 || S.f_top_max > 128) return cudaErrorInvalidConfiguration;  // 4 row chunks per lane
+  if (S.f_warp_max > 32) return cudaErrorInvalidConfiguration;
+  auto front = [](int f) { return static_cast<size_t>(f | 1) * (f + 1); };
   size_t fsm = S.n_warp_lists * front(S.f_warp_max);
   fsm = smax(fsm, S.n_group_lists * front(S.f_group_max));
   fsm = smax(fsm, S.n_top > 0 ? front(S.f_top_max) : 0);

@@ -16,6 +16,7 @@ struct LuDev {
   const int *idx_ptr, *idx, *rel_ptr, *rel, *child_ptr, *child;
   const int *a_ptr, *a_src, *a_dst;
   const int *lp_off, *up_off, *cb_off;
+  const int *ea_ptr, *ea_dst;   // per child: destination of every contribution-block element in the parent front
   const int *wl_ptr, *wl, *gl_ptr, *gl, *top;
 };
 

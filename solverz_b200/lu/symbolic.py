@@ -297,7 +297,9 @@ class LUSymbolic:
     lp_off: np.ndarray        # offset of the f x s column-major [L11\U11; L21] panel
     up_off: np.ndarray        # offset of the u x s column-major U12^T panel
     lu_size: int              # doubles per scenario of factor storage (with padding)
-    cb_off: np.ndarray        # offset of the u x u contribution block in the workspace
+    cb_off: np.ndarray        # offset of the u x (u+1) contribution block in the workspace
+    ea_ptr: np.ndarray        # extend-add destination tables, one run of u(u+1) entries per supernode
+    ea_dst: np.ndarray
     cb_size: int              # doubles per resident scenario of contribution workspace
     nnz_lu: int               # true nnz(L+U) of the symbolic factor (no supernode padding)
     flops: float              # factor flops per scenario (2 per multiply-add)
@@ -551,11 +553,27 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         cursor += alloc_list(seq, cursor)
     cb_size = int(cursor)
 
+    # ---- extend-add destinations: element t = i + j*u of the u x (u+1) block of child c goes to
+    # rel[i] + col*ld_parent with col = rel[j] (Schur part) or f_parent (right-hand-side column)
+    ea_ptr = np.zeros(ns + 1, dtype=np.int64)
+    ea_ptr[1:] = np.cumsum(cb_need)
+    ea_dst = np.zeros(ea_ptr[-1], dtype=np.int64)
+    for k in range(ns):
+        p = sn_parent[k]
+        uk = int(sn_u[k])
+        if p < 0 or uk == 0:
+            continue
+        rl = rel[rel_ptr[k]:rel_ptr[k + 1]]
+        ldp = int(sn_ld[p])
+        cols = np.concatenate([rl, [sn_f[p]]])
+        ea_dst[ea_ptr[k]:ea_ptr[k + 1]] = (rl[None, :] + cols[:, None] * ldp).reshape(-1)
+
     return LUSymbolic(
         n=n, nnzA=int(Ac.nnz), rowp=rowp, colp=colp, ns=ns, sn_piv0=sn_piv0, sn_s=sn_s,
         sn_f=sn_f, sn_parent=sn_parent, idx_ptr=idx_ptr, idx=idx, rel_ptr=rel_ptr, rel=rel,
         child_ptr=child_ptr, child=child, a_ptr=a_ptr, a_src=a_src, a_dst=a_dst, lp_off=lp_off,
-        up_off=up_off, lu_size=lu_size, cb_off=cb_off, cb_size=cb_size, nnz_lu=nnz_lu,
+        up_off=up_off, lu_size=lu_size, cb_off=cb_off, ea_ptr=ea_ptr, ea_dst=ea_dst, cb_size=cb_size,
+        nnz_lu=nnz_lu,
         flops=flops, f_max=int(sn_f.max()), n_warp_lists=n_lists, wl_ptr=wl_ptr, wl=wl,
         n_group_lists=n_glists, gl_ptr=gl_ptr, gl=gl, top=top,
         f_warp_max=int(sn_f[level == 0].max()) if (level == 0).any() else 0,

@@ -27,7 +27,7 @@ class LuSymbolicC(C.Structure):
                                          "s_warp_max", "s_group_max", "s_top_max")] + \
                [(k, _i32p) for k in ("rowp", "colp", "sn_piv0", "sn_s", "sn_f", "idx_ptr", "idx", "rel_ptr",
                                      "rel", "child_ptr", "child", "a_ptr", "a_src", "a_dst", "lp_off",
-                                     "up_off", "cb_off", "wl_ptr", "wl", "gl_ptr", "gl", "top")]
+                                     "up_off", "cb_off", "ea_ptr", "ea_dst", "wl_ptr", "wl", "gl_ptr", "gl", "top")]
 
 
 class DescC(C.Structure):
@@ -120,8 +120,8 @@ def lu_symbolic_c(sym, keep: list) -> LuSymbolicC:
     if max(sym.lu_size, sym.cb_size, int(sym.a_dst.max(initial=0))) >= 2 ** 31:
         raise SzbError("LU schedule exceeds int32 offsets")
     for name in ("rowp", "colp", "sn_piv0", "sn_s", "sn_f", "idx_ptr", "idx", "rel_ptr", "rel", "child_ptr",
-                 "child", "a_ptr", "a_src", "a_dst", "lp_off", "up_off", "cb_off", "wl_ptr", "wl", "gl_ptr",
-                 "gl", "top"):
+                 "child", "a_ptr", "a_src", "a_dst", "lp_off", "up_off", "cb_off", "ea_ptr", "ea_dst", "wl_ptr",
+                 "wl", "gl_ptr", "gl", "top"):
         arr = np.ascontiguousarray(np.asarray(getattr(sym, name)), dtype=np.int32)
         if arr.size == 0:
             arr = np.zeros(1, dtype=np.int32)

@@ -119,23 +119,32 @@ __device__ __forceinline__ void eliminate_warp(double* __restrict__ Fm, const in
   }
 }
 
-// ---- several warps: blocked right-looking elimination, NB = 4 pivots per panel.
-// (1) warp 0 factors the panel (rows p0.., columns p0..p0+nb-1) in registers, lane = row, pivots
-//     exchanged with shuffles;  (2) every warp takes trailing columns: forward-substitutes the nb
-//     U values of the column with the unit-lower panel block and applies the rank-nb update to its
-//     row chunks with the multipliers kept in registers.  Two group barriers per panel.
-constexpr int kNB = 4;
+// ---- several warps: blocked right-looking elimination with look-ahead, NB = 4 pivots per panel.
+//
+//   panel t = pivots [p0, p0+nb).  After its factorisation  A22 -= L21 U12  with U12 = L11^{-1} A12
+//   is applied as  A22 -= Lt A12,  Lt = L21 L11^{-1}:  the update then only reads the *unsolved* top
+//   rows A12, so no per-column triangular solve sits in the inner loop; the rows of U (and the rhs
+//   entries of the pivot rows) are solved once, after the last panel (finalize_u).
+//   Warp 0 is the panel warp: in iteration t it first updates the columns of panel t+1 with panel
+//   t, factors them in registers (pivots exchanged with shuffles), and publishes L (in place) and
+//   Lt (double-buffered side panel) while the other warps update the rest of the trailing block --
+//   the panel factorisation is off the critical path and there is ONE barrier per 4 pivots.
+//   Workers split the trailing block 2-D: one 32-row chunk per warp, columns strided.
+#ifdef SZB_PHASE_TIMING
+__device__ long long g_dbg[16];
+#define SZB_T(i) if (nw > 8 && r == 0 && blockIdx.x == 0) { long long now_ = clock64(); g_dbg[i] += now_ - tprev_; tprev_ = now_; }
+#else
+#define SZB_T(i)
+#endif
 
+constexpr int kNB = 4;
+constexpr int kLtStride = 128;   // rows per Lt column (fronts of multi-warp groups have <= 128 rows)
+
+// Factor the nb columns held in P (rows r = p0 + lane + 32c), write L in place, Lt to `lt`.
 template <int NCH>
-__device__ __forceinline__ void panel_factor(double* __restrict__ Fm, const int p0, const int nb, const int f,
-                                             const int ld, const int lane, int* flag) {
-  double P[NCH][kNB];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int i = p0 + lane + 32 * c;
-#pragma unroll
-    for (int k = 0; k < kNB; ++k) P[c][k] = (i < f && k < nb) ? Fm[i + (p0 + k) * ld] : 0.0;
-  }
+__device__ __forceinline__ void panel_finish(double (&P)[NCH][kNB], double* __restrict__ Fm,
+                                             double* __restrict__ lt, const int p0, const int nb,
+                                             const int f, const int ld, const int lane, int* flag) {
 #pragma unroll
   for (int k = 0; k < kNB; ++k) {
     if (k < nb) {
@@ -154,6 +163,7 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Fm, const int 
       }
     }
   }
+  // L (scaled) and the U11 block go back in place
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int i = p0 + lane + 32 * c;
@@ -161,82 +171,201 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Fm, const int 
     for (int k = 0; k < kNB; ++k)
       if (i < f && k < nb) Fm[i + (p0 + k) * ld] = P[c][k];
   }
+  // Lt = L21 L11^{-1} for the rows below the panel (x L11 = l, L11 unit lower)
+  const double L10 = __shfl_sync(0xffffffffu, P[0][0], 1);
+  const double L20 = __shfl_sync(0xffffffffu, P[0][0], 2), L21 = __shfl_sync(0xffffffffu, P[0][1], 2);
+  const double L30 = __shfl_sync(0xffffffffu, P[0][0], 3), L31 = __shfl_sync(0xffffffffu, P[0][1], 3),
+               L32 = __shfl_sync(0xffffffffu, P[0][2], 3);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int i = lane + 32 * c - nb;            // row index relative to r0 = p0 + nb
+    if (i >= 0 && p0 + nb + i < f) {
+      const double x3 = nb > 3 ? P[c][3] : 0.0;
+      const double x2 = nb > 2 ? fma(-x3, L32, P[c][2]) : 0.0;
+      const double x1 = nb > 1 ? fma(-x3, L31, fma(-x2, L21, P[c][1])) : 0.0;
+      const double x0 = fma(-x3, L30, fma(-x2, L20, fma(-x1, L10, P[c][0])));
+      lt[i] = x0;
+      lt[kLtStride + i] = x1;
+      lt[2 * kLtStride + i] = x2;
+      lt[3 * kLtStride + i] = x3;
+    }
+  }
 }
 
+// first panel of a supernode: load and factor
 template <int NCH>
-__device__ __forceinline__ void trailing_update(double* __restrict__ Fm, const int p0, const int nb,
-                                                const int f, const int ncol, const int ld, const int lane,
-                                                const int w, const int nw) {
-  const int r0 = p0 + nb;            // first trailing row / column
+__device__ __forceinline__ void panel_first(double* __restrict__ Fm, double* __restrict__ lt, const int nb,
+                                            const int f, const int ld, const int lane, int* flag) {
+  double P[NCH][kNB];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int i = lane + 32 * c;
+#pragma unroll
+    for (int k = 0; k < kNB; ++k) P[c][k] = (i < f && k < nb) ? Fm[i + k * ld] : 0.0;
+  }
+  panel_finish<NCH>(P, Fm, lt, 0, nb, f, ld, lane, flag);
+}
+
+// look-ahead: update the nb1 columns of the next panel (rows >= r0) with panel [p0, p0+nb) using
+// its Lt in `lt_cur`, then factor them and publish Lt of the next panel in `lt_next`.
+template <int NCH>
+__device__ __forceinline__ void panel_next(double* __restrict__ Fm, const double* __restrict__ lt_cur,
+                                           double* __restrict__ lt_next, const int p0, const int nb,
+                                           const int nb1, const int f, const int ld, const int lane,
+                                           int* flag) {
+  const int r0 = p0 + nb;
+  double P[NCH][kNB];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int i = r0 + lane + 32 * c;
+#pragma unroll
+    for (int q = 0; q < kNB; ++q) P[c][q] = (i < f && q < nb1) ? Fm[i + (r0 + q) * ld] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < kNB; ++k) {
+    if (k < nb) {
+      double top[kNB];
+#pragma unroll
+      for (int q = 0; q < kNB; ++q) top[q] = q < nb1 ? Fm[(p0 + k) + (r0 + q) * ld] : 0.0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int i = lane + 32 * c;
+        const double l = (r0 + i < f) ? lt_cur[k * kLtStride + i] : 0.0;
+#pragma unroll
+        for (int q = 0; q < kNB; ++q) P[c][q] = fma(-l, top[q], P[c][q]);
+      }
+    }
+  }
+  panel_finish<NCH>(P, Fm, lt_next, r0, nb1, f, ld, lane, flag);
+}
+
+// worker: all NCH row chunks of columns jbeg + cg, jbeg + cg + CW, ...  The four unsolved top values
+// of a column are fetched once (broadcast) and reused for every chunk; multipliers live in registers.
+template <int NCH>
+__device__ __forceinline__ void trailing_worker(double* __restrict__ Fm, const double* __restrict__ lt,
+                                                const int p0, const int nb, const int f, const int ld,
+                                                const int jbeg, const int ncol, const int cg, const int CW,
+                                                const int lane) {
+  const int r0 = p0 + nb;
   const int m = f - r0;
-  // unit-lower panel block (strictly lower part) and this lane's multipliers
-  const double* __restrict__ blk = Fm + p0 + p0 * ld;
-  const double L10 = nb > 1 ? blk[1] : 0.0;
-  const double L20 = nb > 2 ? blk[2] : 0.0, L21 = nb > 2 ? blk[2 + ld] : 0.0;
-  const double L30 = nb > 3 ? blk[3] : 0.0, L31 = nb > 3 ? blk[3 + ld] : 0.0, L32 = nb > 3 ? blk[3 + 2 * ld] : 0.0;
   double l[NCH][kNB];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int i = lane + 32 * c;
 #pragma unroll
-    for (int k = 0; k < kNB; ++k) l[c][k] = (i < m && k < nb) ? Fm[(r0 + i) + (p0 + k) * ld] : 0.0;
+    for (int k = 0; k < kNB; ++k) l[c][k] = (i < m && k < nb) ? lt[k * kLtStride + i] : 0.0;
   }
-  for (int j = r0 + w; j < ncol; j += nw) {
-    double* __restrict__ col = Fm + j * ld;
-    const double u0 = col[p0];
-    double u1 = nb > 1 ? col[p0 + 1] : 0.0;
-    double u2 = nb > 2 ? col[p0 + 2] : 0.0;
-    double u3 = nb > 3 ? col[p0 + 3] : 0.0;
-    u1 = fma(-L10, u0, u1);
-    u2 = fma(-L21, u1, fma(-L20, u0, u2));
-    u3 = fma(-L32, u2, fma(-L31, u1, fma(-L30, u0, u3)));
-    if (lane == 0) {
-      if (nb > 1) col[p0 + 1] = u1;
-      if (nb > 2) col[p0 + 2] = u2;
-      if (nb > 3) col[p0 + 3] = u3;
+  const int k1 = nb > 1 ? 1 : 0, k2 = nb > 2 ? 2 : 0, k3 = nb > 3 ? 3 : 0;   // stay inside the panel rows
+  double* __restrict__ col = Fm + (jbeg + cg) * ld;
+  const int step = CW * ld;
+  for (int j = jbeg + cg; j < ncol; j += CW, col += step) {
+    const double a0 = col[p0], a1 = col[p0 + k1], a2 = col[p0 + k2], a3 = col[p0 + k3];
+    double a[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int i = lane + 32 * c;
+      a[c] = (c + 1 < NCH || i < m) ? col[r0 + i] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      a[c] = fma(-l[c][0], a0, a[c]);
+      a[c] = fma(-l[c][1], a1, a[c]);
+      a[c] = fma(-l[c][2], a2, a[c]);
+      a[c] = fma(-l[c][3], a3, a[c]);
     }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int i = lane + 32 * c;
-      if (c + 1 < NCH || i < m) {
-        double a = col[r0 + i];
-        a = fma(-l[c][0], u0, a);
-        a = fma(-l[c][1], u1, a);
-        a = fma(-l[c][2], u2, a);
-        a = fma(-l[c][3], u3, a);
-        col[r0 + i] = a;
+      if (c + 1 < NCH || i < m) col[r0 + i] = a[c];
+    }
+  }
+}
+
+// deferred triangular solves of the U rows: for every panel and every column right of it
+//   u = L11^{-1} a   (4 values per column, lanes over columns, warps over panels)
+__device__ __forceinline__ void finalize_u(double* __restrict__ Fm, const int s, const int ncol, const int ld,
+                                           const int lane, const int w, const int nw) {
+  const int npan = (s + kNB - 1) / kNB;
+  for (int t = w; t < npan; t += nw) {
+    const int p0 = t * kNB;
+    const int nb = min(kNB, s - p0);
+    if (nb < 2) continue;
+    const double* __restrict__ blk = Fm + p0 + p0 * ld;
+    const double L10 = blk[1];
+    const double L20 = nb > 2 ? blk[2] : 0.0, L21 = nb > 2 ? blk[2 + ld] : 0.0;
+    const double L30 = nb > 3 ? blk[3] : 0.0, L31 = nb > 3 ? blk[3 + ld] : 0.0, L32 = nb > 3 ? blk[3 + 2 * ld] : 0.0;
+    for (int j = p0 + nb + lane; j < ncol; j += kWarp) {
+      double* __restrict__ col = Fm + p0 + j * ld;
+      const double u0 = col[0];
+      const double u1 = fma(-L10, u0, col[1]);
+      col[1] = u1;
+      if (nb > 2) {
+        const double u2 = fma(-L21, u1, fma(-L20, u0, col[2]));
+        col[2] = u2;
+        if (nb > 3) col[3] = fma(-L32, u2, fma(-L31, u1, fma(-L30, u0, col[3])));
       }
     }
   }
 }
 
 template <class G>
-__device__ __forceinline__ void eliminate_blocked(const G g, double* __restrict__ Fm, const int s, const int f,
-                                                  const int ncol, const int ld, int* flag) {
+__device__ __forceinline__ void eliminate_blocked(const G g, double* __restrict__ Fm, double* __restrict__ ltbuf,
+                                                  const int s, const int f, const int ncol, const int ld,
+                                                  int* flag) {
   const int lane = g.lane(), w = g.warp(), nw = g.nwarps();
-  for (int p0 = 0; p0 < s; p0 += kNB) {
-    const int nb = min(kNB, s - p0);
-    if (w == 0) {
-      switch ((f - p0 + 31) >> 5) {
-        case 1: panel_factor<1>(Fm, p0, nb, f, ld, lane, flag); break;
-        case 2: panel_factor<2>(Fm, p0, nb, f, ld, lane, flag); break;
-        case 3: panel_factor<3>(Fm, p0, nb, f, ld, lane, flag); break;
-        default: panel_factor<4>(Fm, p0, nb, f, ld, lane, flag); break;
-      }
+  const int npan = (s + kNB - 1) / kNB;
+#ifdef SZB_PHASE_TIMING
+  const int r = g.rank();
+  long long tprev_ = clock64();
+#endif
+  if (w == 0) {
+    const int nb = min(kNB, s);
+    switch ((f + 31) >> 5) {
+      case 1: panel_first<1>(Fm, ltbuf, nb, f, ld, lane, flag); break;
+      case 2: panel_first<2>(Fm, ltbuf, nb, f, ld, lane, flag); break;
+      case 3: panel_first<3>(Fm, ltbuf, nb, f, ld, lane, flag); break;
+      default: panel_first<4>(Fm, ltbuf, nb, f, ld, lane, flag); break;
     }
-    g.sync();
-    const int m = f - p0 - nb;
-    if (ncol - p0 - nb > 0) {
-      switch ((m + 31) >> 5) {
-        case 0: trailing_update<1>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;   // only the rhs column
-        case 1: trailing_update<1>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;
-        case 2: trailing_update<2>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;
-        case 3: trailing_update<3>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;
-        default: trailing_update<4>(Fm, p0, nb, f, ncol, ld, lane, w, nw); break;
-      }
-    }
-    g.sync();
   }
+  g.sync();
+  SZB_T(4)
+  for (int t = 0; t < npan; ++t) {
+    const int p0 = t * kNB;
+    const int nb = min(kNB, s - p0);
+    const int r0 = p0 + nb;
+    const bool has_next = t + 1 < npan;
+    const int nb1 = has_next ? min(kNB, s - r0) : 0;
+    const double* lt_cur = ltbuf + (t & 1) * (kNB * kLtStride);
+    double* lt_next = ltbuf + ((t + 1) & 1) * (kNB * kLtStride);
+    if (has_next && w == 0) {
+      switch ((f - r0 + 31) >> 5) {
+        case 1: panel_next<1>(Fm, lt_cur, lt_next, p0, nb, nb1, f, ld, lane, flag); break;
+        case 2: panel_next<2>(Fm, lt_cur, lt_next, p0, nb, nb1, f, ld, lane, flag); break;
+        case 3: panel_next<3>(Fm, lt_cur, lt_next, p0, nb, nb1, f, ld, lane, flag); break;
+        default: panel_next<4>(Fm, lt_cur, lt_next, p0, nb, nb1, f, ld, lane, flag); break;
+      }
+    } else {
+      const int W = has_next ? nw - 1 : nw;          // worker warps
+      const int ww = has_next ? w - 1 : w;
+      const int m = f - r0;
+      const int jbeg = r0 + nb1;
+      if (jbeg < ncol) {
+        switch ((m + 31) >> 5) {                      // row chunks (0: only the rhs column is left)
+          case 0: break;
+          case 1: trailing_worker<1>(Fm, lt_cur, p0, nb, f, ld, jbeg, ncol, ww, W, lane); break;
+          case 2: trailing_worker<2>(Fm, lt_cur, p0, nb, f, ld, jbeg, ncol, ww, W, lane); break;
+          case 3: trailing_worker<3>(Fm, lt_cur, p0, nb, f, ld, jbeg, ncol, ww, W, lane); break;
+          default: trailing_worker<4>(Fm, lt_cur, p0, nb, f, ld, jbeg, ncol, ww, W, lane); break;
+        }
+      }
+    }
+    SZB_T(5)
+    g.sync();
+    SZB_T(6)
+  }
+  finalize_u(Fm, s, ncol, ld, lane, w, nw);
+  g.sync();
+  SZB_T(7)
 }
 
 // ---------------------------------------------------------------------------------------
@@ -246,29 +375,40 @@ __device__ __forceinline__ void eliminate_blocked(const G g, double* __restrict_
 // ---------------------------------------------------------------------------------------
 template <class G>
 __device__ void factor_supernode(const G g, const LuDev& S, const int k, double* __restrict__ Fm,
-                                 const FactorArgs& A) {
+                                 double* __restrict__ ltbuf, const FactorArgs& A) {
   const int s = S.sn_s[k], f = S.sn_f[k], u = f - s, ld = f | 1;
+#ifdef SZB_PHASE_TIMING
+  long long tprev_ = clock64();
+#endif
   const int lane = g.lane(), w = g.warp(), nw = g.nwarps(), r = g.rank(), G_ = g.size();
   const int with_rhs = A.rhs != nullptr;
   const int ncol = f + with_rhs;
   // 1. clear
   for (int t = r; t < ld * ncol; t += G_) Fm[t] = 0.0;
   g.sync();
-  // 2. original entries (+ right-hand side of the pivot rows)
+  // 2. original entries (+ right-hand side of the pivot rows).  Global loads are issued in batches
+  // of four before the dependent shared-memory stores so that their latencies overlap.
   {
-    const int a1 = S.a_ptr[k + 1];
-    if (A.mvals && A.smask) {
-      for (int e = S.a_ptr[k] + r; e < a1; e += G_) {
-        const int src = S.a_src[e];
-        Fm[S.a_dst[e]] = fma(A.scale * A.smask[src], A.jv[src], A.mvals[src]);
+    const int a0 = S.a_ptr[k], a1 = S.a_ptr[k + 1];
+    for (int e = a0 + r; e < a1; e += 4 * G_) {
+      int src[4], dst[4];
+      double v[4], mv[4], mk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ee = e + q * G_;
+        const bool ok = ee < a1;
+        src[q] = ok ? S.a_src[ee] : -1;
+        dst[q] = ok ? S.a_dst[ee] : 0;
       }
-    } else if (A.mvals) {
-      for (int e = S.a_ptr[k] + r; e < a1; e += G_) {
-        const int src = S.a_src[e];
-        Fm[S.a_dst[e]] = fma(A.scale, A.jv[src], A.mvals[src]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q] = src[q] >= 0 ? A.jv[src[q]] : 0.0;
+        mv[q] = (A.mvals && src[q] >= 0) ? A.mvals[src[q]] : 0.0;
+        mk[q] = (A.smask && src[q] >= 0) ? A.smask[src[q]] : 1.0;
       }
-    } else {
-      for (int e = S.a_ptr[k] + r; e < a1; e += G_) Fm[S.a_dst[e]] = A.scale * A.jv[S.a_src[e]];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (src[q] >= 0) Fm[dst[q]] = fma(A.scale * mk[q], v[q], mv[q]);
     }
     if (with_rhs) {
       const int p0 = S.sn_piv0[k];
@@ -276,21 +416,36 @@ __device__ void factor_supernode(const G g, const LuDev& S, const int k, double*
     }
   }
   g.sync();
+  SZB_T(0)
   // 3. extend-add of the children's contribution blocks (u_c x (u_c + 1), column-major); the
-  // destination of every element was computed on the host (ea_dst)
+  // destination of every element was computed on the host (ea_dst).  Loads batched as above.
   for (int ci = S.child_ptr[k]; ci < S.child_ptr[k + 1]; ++ci) {
     const int c = S.child[ci];
     const int uc = S.sn_f[c] - S.sn_s[c];
     if (uc == 0) continue;
-    const int* __restrict__ dst = S.ea_dst + S.ea_ptr[c];
+    const int* __restrict__ dstp = S.ea_dst + S.ea_ptr[c];
     const double* __restrict__ C = A.cb + S.cb_off[c];
     const int cnt = uc * (uc + with_rhs);
-    for (int t = r; t < cnt; t += G_) Fm[dst[t]] += C[t];
+    for (int t = r; t < cnt; t += 4 * G_) {
+      int d[4];
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int tt = t + q * G_;
+        d[q] = tt < cnt ? dstp[tt] : -1;
+        v[q] = tt < cnt ? C[tt] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (d[q] >= 0) Fm[d[q]] += v[q];
+    }
     g.sync();
   }
+  SZB_T(1)
   // 4. elimination of the s pivots
   if (nw == 1) eliminate_warp(Fm, s, f, ncol, ld, lane, A.flag);
-  else eliminate_blocked(g, Fm, s, f, ncol, ld, A.flag);
+  else eliminate_blocked(g, Fm, ltbuf, s, f, ncol, ld, A.flag);
+  SZB_T(2)
   // 5. write-out
   {
     double* __restrict__ Lp = A.lu + S.lp_off[k];           // f x s, column-major, ld = f
@@ -335,6 +490,7 @@ __device__ void factor_supernode(const G g, const LuDev& S, const int k, double*
     }
   }
   g.sync();
+  SZB_T(3)
 }
 
 __global__ void __launch_bounds__(1024, 1)
@@ -347,7 +503,9 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5;
   const int wstride = (S.f_warp_max | 1) * (S.f_warp_max + 1);
-  const int gstride = (S.f_group_max | 1) * (S.f_group_max + 1);
+  const int gfront = (S.f_group_max | 1) * (S.f_group_max + 1);
+  const int gstride = gfront + 2 * kNB * kLtStride;
+  const int tfront = (S.f_top_max | 1) * (S.f_top_max + 1);
   const int wpg = (blockDim.x >> 5) / max(S.n_group_lists, 1);   // warps per group
 #ifdef SZB_PHASE_TIMING
   long long tph[4] = {0, 0, 0, 0};
@@ -372,7 +530,7 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
     if (warp < S.n_warp_lists) {
       double* Fm = sm + warp * wstride;
       const WarpGrp g;
-      for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q) factor_supernode(g, S, S.wl[q], Fm, A);
+      for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q) factor_supernode(g, S, S.wl[q], Fm, nullptr, A);
     }
     __syncthreads();
 #ifdef SZB_PHASE_TIMING
@@ -388,7 +546,7 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
         g.nw = wpg;
         g.w0 = gi * wpg;
         for (int q = S.gl_ptr[gi]; q < S.gl_ptr[gi + 1]; ++q)
-          factor_supernode(g, S, S.gl[q], Fm, A);
+          factor_supernode(g, S, S.gl[q], Fm, Fm + gfront, A);
       }
       __syncthreads();
     }
@@ -398,7 +556,7 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
     // level 2: the whole CTA
     {
       const BlockGrp g;
-      for (int q = 0; q < S.n_top; ++q) factor_supernode(g, S, S.top[q], sm, A);
+      for (int q = 0; q < S.n_top; ++q) factor_supernode(g, S, S.top[q], sm, sm + tfront, A);
     }
 #ifdef SZB_PHASE_TIMING
     long long t3 = clock64();
@@ -407,8 +565,13 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
   }
 #ifdef SZB_PHASE_TIMING
   if (threadIdx.x == 0 && blockIdx.x == 0)
-    printf("[lu_factor phases] warp %lld group %lld top %lld cycles/scenario (%lld scenarios)\n",
-           tph[0] / max(tph[3], 1LL), tph[1] / max(tph[3], 1LL), tph[2] / max(tph[3], 1LL), tph[3]);
+    printf("[lu_factor phases] warp %lld group %lld top %lld cycles/scenario (%lld scenarios) | top: asm %lld ea %lld elim %lld write %lld\n",
+           tph[0] / max(tph[3], 1LL), tph[1] / max(tph[3], 1LL), tph[2] / max(tph[3], 1LL), tph[3],
+           g_dbg[0] / max(tph[3], 1LL), g_dbg[1] / max(tph[3], 1LL), g_dbg[2] / max(tph[3], 1LL), g_dbg[3] / max(tph[3], 1LL));
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("   elim split (thread 0): first-panel %lld  panel_next/own work %lld  barrier wait %lld  finalize %lld\n", g_dbg[4] / max(tph[3], 1LL),
+           g_dbg[5] / max(tph[3], 1LL), g_dbg[6] / max(tph[3], 1LL), g_dbg[7] / max(tph[3], 1LL));
+  if (threadIdx.x == 0 && blockIdx.x == 0) for (int i = 0; i < 8; ++i) g_dbg[i] = 0;
 #endif
 }
 
@@ -632,9 +795,10 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   if (S.f_group_max > 128 || S.f_top_max > 128) return cudaErrorInvalidConfiguration;  // 4 row chunks per lane
   if (S.f_warp_max > 32) return cudaErrorInvalidConfiguration;
   auto front = [](int f) { return static_cast<size_t>(f | 1) * (f + 1); };
+  const size_t ltb = 2 * 4 * 128;   // two Lt side panels (kNB x kLtStride doubles)
   size_t fsm = S.n_warp_lists * front(S.f_warp_max);
-  fsm = smax(fsm, S.n_group_lists * front(S.f_group_max));
-  fsm = smax(fsm, S.n_top > 0 ? front(S.f_top_max) : 0);
+  fsm = smax(fsm, S.n_group_lists * (front(S.f_group_max) + ltb));
+  fsm = smax(fsm, S.n_top > 0 ? front(S.f_top_max) + ltb : 0);
   cfg->smem_factor = fsm * sizeof(double);
   if (cfg->smem_factor > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
   size_t ssm = S.n_warp_lists * (2 * static_cast<size_t>(S.f_warp_max) + static_cast<size_t>(S.s_warp_max) * S.s_warp_max);

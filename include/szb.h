@@ -179,6 +179,9 @@ SZB_API int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream);
 /* whole Newton solve, nr.py:45-64, on device buffers; iters/flags are device int32[B] */
 SZB_API int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, int32_t* flags_dev,
                szb_stream stream);
+/* time t at which szb_newton evaluates F(t,y,p) and J(t,y,p) (0 by default); fdae_solver sets t0 + dt
+ * before each step (fdesolver.py:104-108) */
+SZB_API int szb_set_time(szb_handle* h, double t);
 /* same with HOST buffers: copies y0 and the per-scenario parameters in, solves, copies y,
  * iters and flags out.  params_host[i] may be NULL to keep what is already on the device. */
 SZB_API int szb_newton_host(szb_handle* h, double tol, int32_t max_it, double* y_host,

@@ -1,5 +1,5 @@
 """solverz_b200 -- B200-native batched Newton / Rosenbrock backend with the Solverz API surface."""
-from .sym import (Var, Param, TimeSeriesParam, Set, Idx, Sum, Mat_Mul, sin, cos, exp, ln, Abs, atan2, tan,
+from .sym import (Var, Param, TimeSeriesParam, AliasVar, Set, Idx, Sum, Mat_Mul, sin, cos, exp, ln, Abs, atan2, tan,
                   sqrt, Sign, heaviside, Saturation, In, GreaterThan, LessThan, And, Or, Not, Min)
 from .sym import t as t_sym
 from .equations import Eqn, Ode, LoopEqn, LoopOde, Model, AE, DAE, FDAE
@@ -7,4 +7,4 @@ from .variables import Vars, TimeVars, Address
 
 __version__ = "0.1.0"
 from .code_printer import module_printer, made_numerical
-from .solvers import Opt, Stats, aesol, daesol, nr_method, Rodas
+from .solvers import Opt, Stats, aesol, daesol, nr_method, Rodas, fdae_solver

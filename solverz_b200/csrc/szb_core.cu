@@ -486,7 +486,7 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
   h->launches[4]++;
   toc(4);
   tic();
-  if ((rc = szb_eval_F_masked(h, 0.0, h->active, st)) != SZB_OK) return rc;
+  if ((rc = szb_eval_F_masked(h, h->time, h->active, st)) != SZB_OK) return rc;
   toc(0);
   h->prof_units[0] += B;
   int sweeps = 0;
@@ -503,7 +503,7 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
     if (n_active <= 0) break;
     for (int i = 0; i < 4; ++i) h->prof_units[i] += n_active;
     tic();
-    if ((rc = szb_eval_J_masked(h, 0.0, h->active, st)) != SZB_OK) return rc;
+    if ((rc = szb_eval_J_masked(h, h->time, h->active, st)) != SZB_OK) return rc;
     toc(1);
     tic();
     // factorisation with the residual riding along as an extra column: y = L^{-1} P F
@@ -519,7 +519,7 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
     }
     toc(3);
     tic();
-    if ((rc = szb_eval_F_masked(h, 0.0, h->active, st)) != SZB_OK) return rc;
+    if ((rc = szb_eval_F_masked(h, h->time, h->active, st)) != SZB_OK) return rc;
     toc(0);
     if (++sweeps > max_it + 2) {  // cannot happen: every scenario stops after max_it+1 sweeps
       szb_set_error(h, "szb_newton: internal sweep bound exceeded");
@@ -585,6 +585,12 @@ int szb_query(const szb_handle* h, int32_t what, int64_t* out) {
     case SZB_Q_WORKSPACE_BYTES: *out = h->ws_bytes; return SZB_OK;
     default: return SZB_EINVAL;
   }
+}
+
+int szb_set_time(szb_handle* h, double t) {
+  if (!h) return SZB_EINVAL;
+  h->time = t;
+  return SZB_OK;
 }
 
 int szb_set_profile(szb_handle* h, int32_t on) {

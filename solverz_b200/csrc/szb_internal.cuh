@@ -36,6 +36,7 @@ struct szb_handle {
   double *fnorm = nullptr, *scale_b = nullptr;
   int *active = nullptr, *nstep = nullptr, *flags = nullptr, *counter = nullptr;
   int* pinned = nullptr;  // 16 ints of pinned host memory
+  double time = 0.0;   // t used by szb_newton for F(t,y,p) / J(t,y,p) (FDAE steps)
   bool factored = false;
   bool has_lu = false;
   // bookkeeping

@@ -22,7 +22,7 @@ import scipy.sparse as sps
 import sympy as sp
 
 from . import sym as S
-from .sym import Idx, Param, Set, TimeSeriesParam, Var
+from .sym import AliasVar, Idx, Param, Set, TimeSeriesParam, Var
 from .variables import Address, Vars
 
 __all__ = ["Eqn", "Ode", "LoopEqn", "LoopOde", "Model", "Equations", "AE", "DAE", "FDAE", "ModelIR",
@@ -455,8 +455,17 @@ class Model:
             elif isinstance(value, Param):
                 params[value.name] = value
         is_dae = any(isinstance(e, (Ode, LoopOde)) for e in eqns)
-        cls = DAE if is_dae else AE
-        eqs = cls(eqns, variables, params)
+        aliases = [p for p in params.values() if isinstance(p, AliasVar)]
+        nstep = max((a.step for a in aliases), default=0)
+        if is_dae and aliases:
+            raise ValueError("DAE object cannot have iAliasVar!")      # model/basic.py:70-72
+        for a in aliases:
+            if a.base_var not in variables:
+                raise ValueError(f"AliasVar of unknown variable {a.base_var!r}")
+            if a.value is None or a.size != variables[a.base_var].size:
+                a.value = variables[a.base_var].value.copy()
+        cls = DAE if is_dae else (FDAE if aliases else AE)
+        eqs = cls(eqns, variables, params, nstep)
         y0 = Vars(eqs.var_address, np.concatenate([variables[k].value for k in eqs.var_address.names])
                   if variables else np.zeros(0))
         eqs.to_ir()

@@ -155,6 +155,9 @@ class BatchSession:
         L.check(self.lib.szb_lu_solve(self.h, int(nrhs), self._stream()), self.h, "szb_lu_solve")
         return self.RHS
 
+    def set_time(self, t: float):
+        L.check(self.lib.szb_set_time(self.h, float(t)), self.h, "szb_set_time")
+
     def newton(self, tol: float, max_it: int):
         L.check(self.lib.szb_newton(self.h, float(tol), int(max_it), C.c_void_p(self.iters.data_ptr()),
                                     C.c_void_p(self.flags.data_ptr()), self._stream()), self.h, "szb_newton")
@@ -240,7 +243,17 @@ class CudaModel:
             return 0.0, args[0], args[1]
         if len(args) < 3:
             raise TypeError("F/J of a DAE/FDAE take (t, y, p, ...)")
-        return float(args[0]), args[1], args[2]
+        p = args[2]
+        if self.kind == "FDAE" and len(args) > 3:
+            # F_(t, y_, p_, y_0, y_1, ...): history vectors become the alias parameters
+            p = dict(p)
+            for i, yh in enumerate(args[3:]):
+                yh = np.asarray(yh.array if isinstance(yh, Vars) else yh, dtype=float)
+                for pm in self.params_meta:
+                    tag = f"_tag_{i}"
+                    if pm["name"].endswith(tag) and pm["name"][:-len(tag)] in self.a:
+                        p[pm["name"]] = yh[..., self.a[pm["name"][:-len(tag)]]]
+        return float(args[0]), args[1], p
 
     def _one(self):
         return self.session(1, with_lu=False)

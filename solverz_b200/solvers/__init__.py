@@ -4,3 +4,4 @@ from .solution import aesol, daesol
 from .nr import nr_method
 from .rodas import Rodas
 from .rodas_param import Rodas_param
+from .fdae import fdae_solver

@@ -211,12 +211,16 @@ class Param(_Indexable):
                 raise NotImplementedError("2-D parameters are frozen at build time (param.py:12-55)")
             self.value = sps.csr_matrix(value)
             self.value.sort_indices()
+        elif value is None:
+            self.value = None
         else:
             self.value = np.atleast_1d(np.asarray(value, dtype=np.int64 if self.is_int else float)).ravel()
         self.sym = _leaf(self, None, "")
 
     @property
     def size(self):
+        if self.value is None:
+            return 0
         return self.value.shape[0] if self.dim == 2 else self.value.size
 
     def __repr__(self):
@@ -257,6 +261,20 @@ class TimeSeriesParam(Param):
         out = self.value.copy()
         out[self.index] = vt
         return out
+
+
+class AliasVar(Param):
+    """Value of variable ``name`` at an earlier time node (reference: ``AliasVar``,
+    variable/ssymbol.py:111-115): ``step=1`` is y_0 (the node the step starts from), ``step=2`` is
+    y_{-1}, ...  Lowered to a per-scenario parameter named ``<name>_tag_<step-1>`` that
+    ``fdae_solver`` refreshes on the device between steps."""
+
+    def __init__(self, name: str, step: int = 1, value=None, init=None):
+        if step < 1:
+            raise ValueError("AliasVar: step must be >= 1")
+        self.base_var = name
+        self.step = int(step)
+        super().__init__(f"{name}_tag_{abs(step - 1)}", value, per_scenario=True)
 
 
 def Sum(expr, idx: Idx) -> sp.Symbol:
@@ -368,6 +386,6 @@ class Min(sp.Function):
         return LessThan(x, y) + (1 - GreaterThan(x, y) - LessThan(x, y)) if argindex == 1 else GreaterThan(x, y)
 
 
-__all__ = ["Var", "Param", "TimeSeriesParam", "Set", "Idx", "Sum", "Mat_Mul", "t", "sin", "cos", "exp",
+__all__ = ["Var", "Param", "TimeSeriesParam", "AliasVar", "Set", "Idx", "Sum", "Mat_Mul", "t", "sin", "cos", "exp",
            "ln", "Abs", "atan2", "tan", "sqrt", "Sign", "heaviside", "Saturation", "In", "GreaterThan",
            "LessThan", "And", "Or", "Not", "Min", "leaf_info", "sum_info"]

@@ -50,7 +50,7 @@ extern "C" {
 #define SZB_API
 #endif
 
-#define SZB_ABI_VERSION 1
+#define SZB_ABI_VERSION 2
 
 /* error codes */
 #define SZB_OK 0
@@ -90,6 +90,8 @@ typedef struct szb_lu_symbolic {
   int32_t lu_size, cb_size, cv_size; /* doubles per scenario: factors, contribution ws, fwd ws */
   int32_t n_warp_lists, n_group_lists, n_top;
   int32_t f_warp_max, f_group_max, f_top_max, s_warp_max, s_group_max, s_top_max;
+  int32_t threads, wpg;     /* threads per CTA and warps per group the tables below were laid out for */
+  int32_t n_sched, n_ga;    /* fronts in schedule order; (src, dst) pairs in the gather table */
   const int32_t* rowp;      /* [n]   pivot k <- original row     */
   const int32_t* colp;      /* [n]   pivot k <- original column  */
   const int32_t* sn_piv0;   /* [ns]  */
@@ -114,6 +116,10 @@ typedef struct szb_lu_symbolic {
   const int32_t* gl_ptr;    /* [n_group_lists+1] */
   const int32_t* gl;
   const int32_t* top;       /* [n_top] */
+  const int32_t* fh;        /* [n_sched][16] front descriptors in schedule order (warp lists, group lists,
+                               top): s, f, piv0, ga0, ga_iters, lp_off, up_off, cb_off, k, n_src, 0... */
+  const int32_t* ga;        /* [n_ga][2] gather table: per front a [ga_iters][group threads] block of
+                               (tagged source, front position); see solverz_b200/lu/schedule.py */
 } szb_lu_symbolic;
 
 typedef struct szb_desc {

@@ -226,6 +226,13 @@ int szb_create(const szb_desc* d, szb_handle** out) {
   S.n_warp_lists = L.n_warp_lists; S.n_group_lists = L.n_group_lists; S.n_top = L.n_top;
   S.f_warp_max = L.f_warp_max; S.f_group_max = L.f_group_max; S.f_top_max = L.f_top_max;
   S.s_warp_max = L.s_warp_max; S.s_group_max = L.s_group_max; S.s_top_max = L.s_top_max;
+  S.threads = L.threads; S.wpg = L.wpg;
+  S.n_warp_sn = L.wl_ptr[L.n_warp_lists];
+  S.n_group_sn = L.n_group_lists > 0 ? L.gl_ptr[L.n_group_lists] : 0;
+  if (L.n_sched != S.n_warp_sn + S.n_group_sn + L.n_top || L.n_ga <= 0 || !L.fh || !L.ga) {
+    szb_set_error(h, "szb_create: LU schedule tables missing or inconsistent (n_sched=%d)", L.n_sched);
+    return fail(SZB_EINVAL);
+  }
   const int ns = L.ns;
 #define UP(field, cnt)                                                               \
   do {                                                                               \
@@ -241,6 +248,13 @@ int szb_create(const szb_desc* d, szb_handle** out) {
   UP(wl_ptr, L.n_warp_lists + 1); UP(wl, L.wl_ptr[L.n_warp_lists]);
   UP(gl_ptr, L.n_group_lists + 1); UP(gl, L.gl_ptr[L.n_group_lists]); UP(top, L.n_top);
 #undef UP
+  {
+    int* p_ = nullptr;
+    if ((rc = upload<int>(h, L.fh, static_cast<size_t>(L.n_sched) * 16, &p_)) != SZB_OK) return fail(rc);
+    S.fh = reinterpret_cast<const int4*>(p_);
+    if ((rc = upload<int>(h, L.ga, static_cast<size_t>(L.n_ga) * 2, &p_)) != SZB_OK) return fail(rc);
+    S.ga = reinterpret_cast<const int2*>(p_);
+  }
   }
   if (d->mass_vals) {
     double* p = nullptr;

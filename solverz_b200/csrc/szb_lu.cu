@@ -18,7 +18,12 @@
 //               subtrees concurrently;
 //       CTA   : the few big fronts at the top use all threads.
 //     Inside a front: lane = row (conflict-free column-major shared memory with an odd leading
-//     dimension), warps stride over columns, right-looking rank-1 updates, one barrier/pivot;
+//     dimension); multi-warp fronts run a blocked (NB = 4) elimination whose only serial chain is
+//     a 4x4 diagonal-block problem on one warp, one barrier per panel;
+//   * a front is described by ONE 64-byte descriptor (prefetched a front ahead) and assembled in
+//     ONE pass over a host-built gather table (lu/schedule.py): matrix entries, right-hand side and
+//     all children's contribution blocks, every destination owned by one thread (no barriers
+//     between children, no atomics);
 //   * the right-hand side can ride along as an extra front column, which fuses the forward
 //     substitution L y = b into the factorisation (Newton never needs L again);
 //   * contribution blocks travel through a per-CTA stack in global memory (L2 resident, reused
@@ -35,6 +40,9 @@ namespace szb {
 namespace {
 
 constexpr int kWarp = 32;
+#ifndef SZB_FACTOR_THREADS
+#define SZB_FACTOR_THREADS 512
+#endif
 
 // t / m for 0 <= t < 2^22 without an integer division: (t + 0.5)/m is never within 0.5/m of an
 // integer, far more than the 2^-23 relative rounding of the float product
@@ -79,13 +87,109 @@ struct FactorArgs {
   const double* __restrict__ rhs;    // optional right-hand side of this scenario (original order)
   double* __restrict__ yout;         // forward-substituted rhs in pivot order (when rhs != null)
   double* __restrict__ lu;           // factor storage of this scenario
-  double* __restrict__ cb;           // contribution workspace of this CTA
+  double* cb;                        // contribution workspace of this CTA (written and re-read: no restrict)
   int store_l;                       // write the L21 rows of the panels
   int* flag;
 };
 
+// one front of the schedule (lu/schedule.py: 16 int32, 12 used on the device)
+struct FrontHdr {
+  int s, f, piv0, lp_off, up_off, cb_off;
+  int gaJ, itJ, gaC, itC, gaR, itR;
+};
+
+__device__ __forceinline__ FrontHdr load_hdr(const int4* __restrict__ fh, const int q) {
+  const int4 a = __ldg(fh + 4 * q), b = __ldg(fh + 4 * q + 1), c = __ldg(fh + 4 * q + 2);
+  FrontHdr H;
+  H.s = a.x; H.f = a.y; H.piv0 = a.z; H.lp_off = a.w;
+  H.up_off = b.x; H.cb_off = b.y; H.gaJ = b.z; H.itJ = b.w;
+  H.gaC = c.x; H.itC = c.y; H.gaR = c.z; H.itR = c.w;
+  return H;
+}
+
+// doubles of shared memory of a front of order f with its right-hand-side column (column-major,
+// odd leading dimension f|1), rounded to an even count so that buffers stay 16-byte aligned
+__host__ __device__ __forceinline__ int front_elems(const int f) { return (((f | 1) * (f + 1)) + 1) & ~1; }
+__host__ __device__ __forceinline__ int lt_stride(const int f) { return (f + 1) & ~1; }
+constexpr int kNB = 4;
+constexpr int kMinCols = 4;
+constexpr int kDiagBuf = 8;   // reciprocal pivots of two panels (double-buffered)
+// per-group scratch behind the front: Lt side panel (kNB x lt_stride) + kDiagBuf
+__host__ __device__ __forceinline__ int group_elems(const int f) { return front_elems(f) + kNB * lt_stride(f) + kDiagBuf; }
+
 __device__ __forceinline__ void check_pivot(const double piv, int* flag) {
   if (!(fabs(piv) > 0.0) || isinf(piv)) *flag = 2;
+}
+
+// 1/x to full double precision (not correctly rounded): 20-bit hardware seed + two Newton steps;
+// 56 cycles dependent instead of 80 for the IEEE division (tools/fp64_lat.cu)
+__device__ __forceinline__ double fast_rcp(const double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// ---- assembly: one pass over a block of the front's gather table (lu/schedule.py).  Loads are
+// issued in batches of four (table entries, then the values they address) before the dependent
+// shared-memory updates so that their latencies overlap; a destination is only ever touched by one
+// thread, so there is nothing to synchronise.
+template <class Fetch>
+__device__ __forceinline__ void gather_block(const int2* __restrict__ e, const int iters, const int G_,
+                                             double* __restrict__ Fm, const Fetch fetch) {
+  int it = 0;
+  for (; it + 4 <= iters; it += 4, e += 4 * G_) {
+    int2 en[4];
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) en[q] = __ldg(e + q * G_);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = en[q].x != -1 ? fetch(en[q].x) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (en[q].x != -1) Fm[en[q].y] += v[q];
+  }
+  if (it < iters) {
+    int2 en[3];
+    double v[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) en[q] = (it + q < iters) ? __ldg(e + q * G_) : make_int2(-1, 0);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) v[q] = en[q].x != -1 ? fetch(en[q].x) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (en[q].x != -1) Fm[en[q].y] += v[q];
+  }
+}
+
+__device__ __forceinline__ void assemble_front(const int rank, const int G_, const FrontHdr& H,
+                                               const int2* __restrict__ ga, double* __restrict__ Fm,
+                                               const FactorArgs& A) {
+  const double* __restrict__ jv = A.jv;
+  if (A.mvals == nullptr && A.smask == nullptr) {
+    const double sc = A.scale;
+    gather_block(ga + H.gaJ + rank, H.itJ, G_, Fm, [=](const int o) { return sc * jv[o]; });
+  } else {
+    const double sc = A.scale;
+    const double* __restrict__ mvals = A.mvals;
+    const double* __restrict__ smask = A.smask;
+    gather_block(ga + H.gaJ + rank, H.itJ, G_, Fm, [=](const int o) {
+      const double mv = mvals ? mvals[o] : 0.0;
+      const double mk = smask ? smask[o] : 1.0;
+      return fma(sc * mk, jv[o], mv);
+    });
+  }
+  const double* cb = A.cb;
+  gather_block(ga + H.gaC + rank, H.itC, G_, Fm, [=](const int o) { return cb[o]; });
+  if (A.rhs != nullptr) {
+    const double* rhs = A.rhs;
+    gather_block(ga + H.gaR + rank, H.itR, G_, Fm, [=](const int o) {
+      const double* base = (o & 0x40000000) ? cb : rhs;
+      return base[o & 0x3fffffff];
+    });
+  }
 }
 
 // ---- single warp, fronts with at most 32 rows: right-looking rank-1 steps, lane = row.  When the
@@ -98,7 +202,7 @@ __device__ __forceinline__ void eliminate_warp(double* __restrict__ Fm, const in
     const int nc = ncol - p - 1;
     double* __restrict__ colp = Fm + (p + 1) + p * ld;
     const double piv = colp[-1];
-    const double inv = 1.0 / piv;
+    const double inv = fast_rcp(piv);
     if (lane == 0) check_pivot(piv, flag);
     const int sh = m <= 8 ? 3 : (m <= 16 ? 4 : 5);     // rows per column slot = 1 << sh
     const int i = lane & ((1 << sh) - 1);
@@ -119,166 +223,249 @@ __device__ __forceinline__ void eliminate_warp(double* __restrict__ Fm, const in
   }
 }
 
-// ---- several warps: blocked right-looking elimination with look-ahead, NB = 4 pivots per panel.
+// ---- several warps: blocked right-looking elimination, NB = 4 pivots per panel, with the panel
+// factorisation reduced to a 4x4 problem on the critical path.
 //
-//   panel t = pivots [p0, p0+nb).  After its factorisation  A22 -= L21 U12  with U12 = L11^{-1} A12
-//   is applied as  A22 -= Lt A12,  Lt = L21 L11^{-1}:  the update then only reads the *unsolved* top
-//   rows A12, so no per-column triangular solve sits in the inner loop; the rows of U (and the rhs
-//   entries of the pivot rows) are solved once, after the last panel (finalize_u).
-//   Warp 0 is the panel warp: in iteration t it first updates the columns of panel t+1 with panel
-//   t, factors them in registers (pivots exchanged with shuffles), and publishes L (in place) and
-//   Lt (double-buffered side panel) while the other warps update the rest of the trailing block --
-//   the panel factorisation is off the critical path and there is ONE barrier per 4 pivots.
-//   Workers split the trailing block 2-D: one 32-row chunk per warp, columns strided.
-#ifdef SZB_PHASE_TIMING
-__device__ long long g_dbg[16];
-#define SZB_T(i) if (nw > 8 && r == 0 && blockIdx.x == 0) { long long now_ = clock64(); g_dbg[i] += now_ - tprev_; tprev_ = now_; }
-#else
-#define SZB_T(i)
-#endif
+//   panel t = pivots [p0, p0+nb), r0 = p0+nb.  With D = L11 U11 the diagonal block,
+//       L21 = A21 U11^{-1},   Lt = L21 L11^{-1} (= A21 D^{-1}),   A22 -= Lt A12
+//   so the trailing update only reads the *unsolved* top rows A12 and the Lt side panel: nothing
+//   in the front is rewritten before the update starts.  Per panel:
+//     phase A  one warp per 32-row chunk derives the L / Lt rows from the published 4x4 factors
+//              (16 flops a row), puts Lt into the side panel and streams L21 straight to the factor
+//              storage when it is wanted;
+//     phase B  all worker warps update the trailing block, two 32-row chunks x strided columns
+//              per warp, multipliers in registers;
+//   meanwhile warp 0 (the diagonal warp) prepares the NEXT diagonal block: it alone owns those
+//   nb1 x nb1 entries, applies panel t to them and factors them in registers, so the serial chain
+//   per panel is load -> 4x4 update -> 4x4 LU (4 dependent reciprocals) -> publish, off the
+//   workers' path (it only *arrives* at the barrier between the phases).  The U rows are solved
+//   once at the end (finalize_u), and L21 never goes back to shared memory.
+struct Tri {   // factors of a 4x4 diagonal block, identity-padded when the panel has nb < 4 pivots
+  double l10, l20, l21, l30, l31, l32, u01, u02, u03, u12, u13, u23, r0, r1, r2, r3;
+};
 
-constexpr int kNB = 4;
-constexpr int kLtStride = 128;   // rows per Lt column (fronts of multi-warp groups have <= 128 rows)
+__device__ __forceinline__ Tri load_tri(const double* __restrict__ Fm, const double* __restrict__ rd,
+                                        const int p0, const int nb, const int ld) {
+  const double* __restrict__ b = Fm + p0 + p0 * ld;
+  Tri T;
+  T.l10 = nb > 1 ? b[1] : 0.0;
+  T.u01 = nb > 1 ? b[ld] : 0.0;
+  T.l20 = nb > 2 ? b[2] : 0.0;
+  T.l21 = nb > 2 ? b[2 + ld] : 0.0;
+  T.u02 = nb > 2 ? b[2 * ld] : 0.0;
+  T.u12 = nb > 2 ? b[1 + 2 * ld] : 0.0;
+  T.l30 = nb > 3 ? b[3] : 0.0;
+  T.l31 = nb > 3 ? b[3 + ld] : 0.0;
+  T.l32 = nb > 3 ? b[3 + 2 * ld] : 0.0;
+  T.u03 = nb > 3 ? b[3 * ld] : 0.0;
+  T.u13 = nb > 3 ? b[1 + 3 * ld] : 0.0;
+  T.u23 = nb > 3 ? b[2 + 3 * ld] : 0.0;
+  T.r0 = rd[0]; T.r1 = rd[1]; T.r2 = rd[2]; T.r3 = rd[3];
+  return T;
+}
 
-// Factor the nb columns held in P (rows r = p0 + lane + 32c), write L in place, Lt to `lt`.
-template <int NCH>
-__device__ __forceinline__ void panel_finish(double (&P)[NCH][kNB], double* __restrict__ Fm,
-                                             double* __restrict__ lt, const int p0, const int nb,
-                                             const int f, const int ld, const int lane, int* flag) {
+// one row of A21 (zero-padded to 4) -> its row of L21 (l) and of Lt (x)
+__device__ __forceinline__ void row_solve(const Tri& T, const double a0, const double a1, const double a2,
+                                          const double a3, double (&l)[4], double (&x)[4]) {
+  l[0] = a0 * T.r0;
+  l[1] = fma(-l[0], T.u01, a1) * T.r1;
+  l[2] = fma(-l[1], T.u12, fma(-l[0], T.u02, a2)) * T.r2;
+  l[3] = fma(-l[2], T.u23, fma(-l[1], T.u13, fma(-l[0], T.u03, a3))) * T.r3;
+  x[3] = l[3];
+  x[2] = fma(-x[3], T.l32, l[2]);
+  x[1] = fma(-x[2], T.l21, fma(-x[3], T.l31, l[1]));
+  x[0] = fma(-x[1], T.l10, fma(-x[2], T.l20, fma(-x[3], T.l30, l[0])));
+}
+
+// LU of the nb x nb block at (q0, q0) by one warp, in place; reciprocal pivots to rd[0..3]
+// (1.0 beyond nb).  All lanes compute redundantly in registers (no shuffles), lane 0 writes.
+__device__ __forceinline__ void diag_factor(double* __restrict__ Fm, double* __restrict__ rd, const int q0,
+                                            const int nb, const int ld, const int lane, int* flag) {
+  double a[4][4];
+  double* __restrict__ b = Fm + q0 + q0 * ld;
 #pragma unroll
-  for (int k = 0; k < kNB; ++k) {
-    if (k < nb) {
-      const double piv = __shfl_sync(0xffffffffu, P[0][k], k);
-      const double inv = 1.0 / piv;
-      if (lane == 0) check_pivot(piv, flag);
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int c = 0; c < NCH; ++c)
-        if (c > 0 || lane > k) P[c][k] *= inv;
+    for (int i = 0; i < 4; ++i) a[i][j] = (i < nb && j < nb) ? b[i + j * ld] : (i == j ? 1.0 : 0.0);
+  double r[4];
 #pragma unroll
-      for (int k2 = k + 1; k2 < kNB; ++k2) {
-        const double u = __shfl_sync(0xffffffffu, P[0][k2], k);
+  for (int k = 0; k < 4; ++k) {
+    if (lane == 0 && k < nb) check_pivot(a[k][k], flag);
+    r[k] = fast_rcp(a[k][k]);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
-          if (c > 0 || lane > k) P[c][k2] = fma(-P[c][k], u, P[c][k2]);
-      }
+    for (int i = k + 1; i < 4; ++i) {
+      a[i][k] *= r[k];
+#pragma unroll
+      for (int j = k + 1; j < 4; ++j) a[i][j] = fma(-a[i][k], a[k][j], a[i][j]);
     }
   }
-  // L (scaled) and the U11 block go back in place
+  if (lane == 0) {
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int i = p0 + lane + 32 * c;
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int k = 0; k < kNB; ++k)
-      if (i < f && k < nb) Fm[i + (p0 + k) * ld] = P[c][k];
-  }
-  // Lt = L21 L11^{-1} for the rows below the panel (x L11 = l, L11 unit lower)
-  const double L10 = __shfl_sync(0xffffffffu, P[0][0], 1);
-  const double L20 = __shfl_sync(0xffffffffu, P[0][0], 2), L21 = __shfl_sync(0xffffffffu, P[0][1], 2);
-  const double L30 = __shfl_sync(0xffffffffu, P[0][0], 3), L31 = __shfl_sync(0xffffffffu, P[0][1], 3),
-               L32 = __shfl_sync(0xffffffffu, P[0][2], 3);
+      for (int i = 0; i < 4; ++i)
+        if (i < nb && j < nb) b[i + j * ld] = a[i][j];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int i = lane + 32 * c - nb;            // row index relative to r0 = p0 + nb
-    if (i >= 0 && p0 + nb + i < f) {
-      const double x3 = nb > 3 ? P[c][3] : 0.0;
-      const double x2 = nb > 2 ? fma(-x3, L32, P[c][2]) : 0.0;
-      const double x1 = nb > 1 ? fma(-x3, L31, fma(-x2, L21, P[c][1])) : 0.0;
-      const double x0 = fma(-x3, L30, fma(-x2, L20, fma(-x1, L10, P[c][0])));
-      lt[i] = x0;
-      lt[kLtStride + i] = x1;
-      lt[2 * kLtStride + i] = x2;
-      lt[3 * kLtStride + i] = x3;
-    }
+    for (int k = 0; k < 4; ++k) rd[k] = r[k];
   }
 }
 
-// first panel of a supernode: load and factor
-template <int NCH>
-__device__ __forceinline__ void panel_first(double* __restrict__ Fm, double* __restrict__ lt, const int nb,
-                                            const int f, const int ld, const int lane, int* flag) {
-  double P[NCH][kNB];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int i = lane + 32 * c;
-#pragma unroll
-    for (int k = 0; k < kNB; ++k) P[c][k] = (i < f && k < nb) ? Fm[i + k * ld] : 0.0;
-  }
-  panel_finish<NCH>(P, Fm, lt, 0, nb, f, ld, lane, flag);
-}
-
-// look-ahead: update the nb1 columns of the next panel (rows >= r0) with panel [p0, p0+nb) using
-// its Lt in `lt_cur`, then factor them and publish Lt of the next panel in `lt_next`.
-template <int NCH>
-__device__ __forceinline__ void panel_next(double* __restrict__ Fm, const double* __restrict__ lt_cur,
-                                           double* __restrict__ lt_next, const int p0, const int nb,
-                                           const int nb1, const int f, const int ld, const int lane,
-                                           int* flag) {
+// diagonal warp, iteration t: apply panel t (factors at (p0,p0), reciprocals rd_cur) to the next
+// diagonal block at (r0,r0), factor it, publish its reciprocals in rd_next.  Lane i < nb1 owns row i
+// of the update; the 4x4 LU is then done redundantly by all lanes.
+__device__ __forceinline__ void diag_next(double* __restrict__ Fm, const double* __restrict__ rd_cur,
+                                          double* __restrict__ rd_next, const int p0, const int nb,
+                                          const int nb1, const int ld, const int lane, int* flag) {
   const int r0 = p0 + nb;
-  double P[NCH][kNB];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int i = r0 + lane + 32 * c;
-#pragma unroll
-    for (int q = 0; q < kNB; ++q) P[c][q] = (i < f && q < nb1) ? Fm[i + (r0 + q) * ld] : 0.0;
-  }
-#pragma unroll
-  for (int k = 0; k < kNB; ++k) {
-    if (k < nb) {
-      double top[kNB];
-#pragma unroll
-      for (int q = 0; q < kNB; ++q) top[q] = q < nb1 ? Fm[(p0 + k) + (r0 + q) * ld] : 0.0;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int i = lane + 32 * c;
-        const double l = (r0 + i < f) ? lt_cur[k * kLtStride + i] : 0.0;
-#pragma unroll
-        for (int q = 0; q < kNB; ++q) P[c][q] = fma(-l, top[q], P[c][q]);
-      }
-    }
-  }
-  panel_finish<NCH>(P, Fm, lt_next, r0, nb1, f, ld, lane, flag);
-}
-
-// worker: all NCH row chunks of columns jbeg + cg, jbeg + cg + CW, ...  The four unsolved top values
-// of a column are fetched once (broadcast) and reused for every chunk; multipliers live in registers.
-template <int NCH>
-__device__ __forceinline__ void trailing_worker(double* __restrict__ Fm, const double* __restrict__ lt,
-                                                const int p0, const int nb, const int f, const int ld,
-                                                const int jbeg, const int ncol, const int cg, const int CW,
-                                                const int lane) {
-  const int r0 = p0 + nb;
-  const int m = f - r0;
-  double l[NCH][kNB];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int i = lane + 32 * c;
-#pragma unroll
-    for (int k = 0; k < kNB; ++k) l[c][k] = (i < m && k < nb) ? lt[k * kLtStride + i] : 0.0;
-  }
+  const Tri T = load_tri(Fm, rd_cur, p0, nb, ld);
+  const int i = min(lane, nb1 - 1);                    // idle lanes mirror a valid row, never store
+  const double* __restrict__ arow = Fm + (r0 + i) + p0 * ld;
+  const double a0 = arow[0];
+  const double a1 = nb > 1 ? arow[ld] : 0.0;
+  const double a2 = nb > 2 ? arow[2 * ld] : 0.0;
+  const double a3 = nb > 3 ? arow[3 * ld] : 0.0;
+  double l[4], x[4];
+  row_solve(T, a0, a1, a2, a3, l, x);
   const int k1 = nb > 1 ? 1 : 0, k2 = nb > 2 ? 2 : 0, k3 = nb > 3 ? 3 : 0;   // stay inside the panel rows
-  double* __restrict__ col = Fm + (jbeg + cg) * ld;
-  const int step = CW * ld;
-  for (int j = jbeg + cg; j < ncol; j += CW, col += step) {
-    const double a0 = col[p0], a1 = col[p0 + k1], a2 = col[p0 + k2], a3 = col[p0 + k3];
-    double a[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int i = lane + 32 * c;
-      a[c] = (c + 1 < NCH || i < m) ? col[r0 + i] : 0.0;
-    }
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      a[c] = fma(-l[c][0], a0, a[c]);
-      a[c] = fma(-l[c][1], a1, a[c]);
-      a[c] = fma(-l[c][2], a2, a[c]);
-      a[c] = fma(-l[c][3], a3, a[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int i = lane + 32 * c;
-      if (c + 1 < NCH || i < m) col[r0 + i] = a[c];
+  for (int j = 0; j < 4; ++j) {
+    if (j < nb1) {
+      double* __restrict__ col = Fm + (r0 + j) * ld;
+      double v = col[r0 + i];
+      v = fma(-x[0], col[p0], v);
+      v = fma(-x[1], col[p0 + k1], v);
+      v = fma(-x[2], col[p0 + k2], v);
+      v = fma(-x[3], col[p0 + k3], v);
+      if (lane < nb1) col[r0 + i] = v;
     }
   }
+  __syncwarp();
+  diag_factor(Fm, rd_next, r0, nb1, ld, lane, flag);
+}
+
+// phase A: rows r0 + 32c + lane of panel t -> Lt side panel (and L21 to the factor storage)
+__device__ __forceinline__ void lt_chunk(const double* __restrict__ Fm, const double* __restrict__ rd,
+                                         double* __restrict__ lt, const int lts, double* __restrict__ Lg,
+                                         const int p0, const int nb, const int f, const int ld, const int c,
+                                         const int lane) {
+  const int r0 = p0 + nb;
+  const int i = lane + 32 * c;                         // row relative to r0
+  const bool ok = r0 + i < f;
+  const Tri T = load_tri(Fm, rd, p0, nb, ld);
+  const double* __restrict__ arow = Fm + (r0 + i) + p0 * ld;
+  const double a0 = ok ? arow[0] : 0.0;
+  const double a1 = (ok && nb > 1) ? arow[ld] : 0.0;
+  const double a2 = (ok && nb > 2) ? arow[2 * ld] : 0.0;
+  const double a3 = (ok && nb > 3) ? arow[3 * ld] : 0.0;
+  double l[4], x[4];
+  row_solve(T, a0, a1, a2, a3, l, x);
+  if (ok) {
+    lt[i] = x[0];
+    lt[lts + i] = x[1];
+    lt[2 * lts + i] = x[2];
+    lt[3 * lts + i] = x[3];
+    if (Lg != nullptr) {                               // L21 rows go straight to the factor storage
+      double* __restrict__ dst = Lg + (r0 + i) + p0 * f;
+      dst[0] = l[0];
+      if (nb > 1) dst[f] = l[1];
+      if (nb > 2) dst[2 * f] = l[2];
+      if (nb > 3) dst[3 * f] = l[3];
+    }
+  }
+}
+
+// phase B: R 32-row chunks (rows r0 + row0 + lane + 32 r) of the columns r0 + cg, r0 + cg + CW, ... < ncol.
+// The 4 R multipliers of a lane stay in registers; a column costs 4 broadcast loads of the unsolved top
+// values, R loads, 4 R fused multiply-adds and R stores; two columns are in flight per trip.
+// FULL: the panel has 4 pivots (immediate offsets for the top rows).
+template <int R, bool FULL>
+__device__ __forceinline__ void trailing_update(double* __restrict__ Fm, const double* __restrict__ lt,
+                                                const int lts, const int p0, const int nb, const int nb1,
+                                                const int m, const int ld, const int ncol, const int row0,
+                                                const int cg, const int CW, const int lane) {
+  const int r0 = p0 + nb;
+  const int i0 = row0 + lane;
+  double x[R][4];
+  bool ok[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    ok[r] = i0 + 32 * r < m;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[r][k] = ok[r] ? lt[k * lts + i0 + 32 * r] : 0.0;
+  }
+  const int k1 = FULL ? 1 : (nb > 1 ? 1 : 0), k2 = FULL ? 2 : (nb > 2 ? 2 : 0), k3 = FULL ? 3 : (nb > 3 ? 3 : 0);
+  int j = r0 + cg;
+  double* __restrict__ tp = Fm + p0 + j * ld;            // top rows of column j
+  double* __restrict__ vp = Fm + r0 + i0 + j * ld;       // this lane's rows of column j
+  const int step = CW * ld;
+  // the first nb1 columns: rows < nb1 are the next diagonal block, owned by warp 0
+  for (; j < r0 + nb1 && j < ncol; j += CW, tp += step, vp += step) {
+    const double t0 = tp[0], t1 = tp[k1], t2 = tp[k2], t3 = tp[k3];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (ok[r] && (r > 0 || i0 >= nb1)) {
+        double v = vp[32 * r];
+        v = fma(-x[r][0], t0, v); v = fma(-x[r][1], t1, v); v = fma(-x[r][2], t2, v); v = fma(-x[r][3], t3, v);
+        vp[32 * r] = v;
+      }
+    }
+  }
+  // two columns per trip (independent chains), no trip-count arithmetic
+  for (; j + CW < ncol; j += 2 * CW, tp += 2 * step, vp += 2 * step) {
+    const double* __restrict__ tq = tp + step;
+    double* __restrict__ vq = vp + step;
+    const double t0 = tp[0], t1 = tp[k1], t2 = tp[k2], t3 = tp[k3];
+    const double s0 = tq[0], s1 = tq[k1], s2 = tq[k2], s3 = tq[k3];
+    double v[R], w[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      v[r] = ok[r] ? vp[32 * r] : 0.0;
+      w[r] = ok[r] ? vq[32 * r] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      v[r] = fma(-x[r][0], t0, v[r]); w[r] = fma(-x[r][0], s0, w[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      v[r] = fma(-x[r][1], t1, v[r]); w[r] = fma(-x[r][1], s1, w[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      v[r] = fma(-x[r][2], t2, v[r]); w[r] = fma(-x[r][2], s2, w[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      v[r] = fma(-x[r][3], t3, v[r]); w[r] = fma(-x[r][3], s3, w[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (ok[r]) { vp[32 * r] = v[r]; vq[32 * r] = w[r]; }
+    }
+  }
+  if (j < ncol) {
+    const double t0 = tp[0], t1 = tp[k1], t2 = tp[k2], t3 = tp[k3];
+    double v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = ok[r] ? vp[32 * r] : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      v[r] = fma(-x[r][0], t0, v[r]); v[r] = fma(-x[r][1], t1, v[r]);
+      v[r] = fma(-x[r][2], t2, v[r]); v[r] = fma(-x[r][3], t3, v[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (ok[r]) vp[32 * r] = v[r];
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void trailing_tile(double* __restrict__ Fm, const double* __restrict__ lt,
+                                              const int lts, const int p0, const int nb, const int nb1,
+                                              const int m, const int ld, const int ncol, const int row0,
+                                              const int cg, const int CW, const int lane) {
+  if (nb == kNB) trailing_update<R, true>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, row0, cg, CW, lane);
+  else trailing_update<R, false>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, row0, cg, CW, lane);
 }
 
 // deferred triangular solves of the U rows: for every panel and every column right of it
@@ -308,207 +495,235 @@ __device__ __forceinline__ void finalize_u(double* __restrict__ Fm, const int s,
   }
 }
 
-template <class G>
-__device__ __forceinline__ void eliminate_blocked(const G g, double* __restrict__ Fm, double* __restrict__ ltbuf,
-                                                  const int s, const int f, const int ncol, const int ld,
-                                                  int* flag) {
-  const int lane = g.lane(), w = g.warp(), nw = g.nwarps();
+// a group of `nw` consecutive warps with two hardware named barriers: `id` for the whole group,
+// `id + 8` between the worker phases (the diagonal warp only arrives there)
+struct PanelGrp {
+  int id, nw, w0;
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int warp() const { return (threadIdx.x >> 5) - w0; }
+  __device__ __forceinline__ int rank() const { return threadIdx.x - (w0 << 5); }
+  __device__ __forceinline__ int size() const { return nw << 5; }
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nw << 5) : "memory");
+  }
+  __device__ __forceinline__ void phase_sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(id + 8), "r"(nw << 5) : "memory");
+  }
+  __device__ __forceinline__ void phase_arrive() const {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id + 8), "r"(nw << 5) : "memory");
+  }
+};
+
+#ifdef SZB_PHASE_TIMING
+__device__ long long g_el[8 * 8];
+#define SZB_E(i) { const long long now_ = clock64(); el_[i] += now_ - te_; te_ = now_; }
+#else
+#define SZB_E(i)
+#endif
+__device__ __forceinline__ void eliminate_blocked(const PanelGrp g, double* __restrict__ Fm, double* __restrict__ lt,
+                                                  const int lts, double* __restrict__ rdbuf,
+                                                  double* __restrict__ Lg, const int s, const int f,
+                                                  const int ncol, const int ld, int* flag) {
+  const int lane = g.lane(), w = g.warp(), nw = g.nw;
   const int npan = (s + kNB - 1) / kNB;
 #ifdef SZB_PHASE_TIMING
-  const int r = g.rank();
-  long long tprev_ = clock64();
+  const bool dbg_ = blockIdx.x == 0 && g.id == 0 && (threadIdx.x & 127) == 0;
+  long long el_[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long te_ = clock64();
 #endif
-  if (w == 0) {
-    const int nb = min(kNB, s);
-    switch ((f + 31) >> 5) {
-      case 1: panel_first<1>(Fm, ltbuf, nb, f, ld, lane, flag); break;
-      case 2: panel_first<2>(Fm, ltbuf, nb, f, ld, lane, flag); break;
-      case 3: panel_first<3>(Fm, ltbuf, nb, f, ld, lane, flag); break;
-      default: panel_first<4>(Fm, ltbuf, nb, f, ld, lane, flag); break;
-    }
-  }
+  if (w == 0) diag_factor(Fm, rdbuf, 0, min(kNB, s), ld, lane, flag);
   g.sync();
-  SZB_T(4)
+  SZB_E(0)
   for (int t = 0; t < npan; ++t) {
     const int p0 = t * kNB;
     const int nb = min(kNB, s - p0);
     const int r0 = p0 + nb;
     const bool has_next = t + 1 < npan;
     const int nb1 = has_next ? min(kNB, s - r0) : 0;
-    const double* lt_cur = ltbuf + (t & 1) * (kNB * kLtStride);
-    double* lt_next = ltbuf + ((t + 1) & 1) * (kNB * kLtStride);
+    const double* rd_cur = rdbuf + (t & 1) * kNB;
     if (has_next && w == 0) {
-      switch ((f - r0 + 31) >> 5) {
-        case 1: panel_next<1>(Fm, lt_cur, lt_next, p0, nb, nb1, f, ld, lane, flag); break;
-        case 2: panel_next<2>(Fm, lt_cur, lt_next, p0, nb, nb1, f, ld, lane, flag); break;
-        case 3: panel_next<3>(Fm, lt_cur, lt_next, p0, nb, nb1, f, ld, lane, flag); break;
-        default: panel_next<4>(Fm, lt_cur, lt_next, p0, nb, nb1, f, ld, lane, flag); break;
-      }
+      g.phase_arrive();
+      diag_next(Fm, rd_cur, rdbuf + ((t + 1) & 1) * kNB, p0, nb, nb1, ld, lane, flag);
+      SZB_E(1)
     } else {
-      const int W = has_next ? nw - 1 : nw;          // worker warps
+      const int W = has_next ? nw - 1 : nw;            // worker warps
       const int ww = has_next ? w - 1 : w;
       const int m = f - r0;
-      const int jbeg = r0 + nb1;
-      if (jbeg < ncol) {
-        switch ((m + 31) >> 5) {                      // row chunks (0: only the rhs column is left)
-          case 0: break;
-          case 1: trailing_worker<1>(Fm, lt_cur, p0, nb, f, ld, jbeg, ncol, ww, W, lane); break;
-          case 2: trailing_worker<2>(Fm, lt_cur, p0, nb, f, ld, jbeg, ncol, ww, W, lane); break;
-          case 3: trailing_worker<3>(Fm, lt_cur, p0, nb, f, ld, jbeg, ncol, ww, W, lane); break;
-          default: trailing_worker<4>(Fm, lt_cur, p0, nb, f, ld, jbeg, ncol, ww, W, lane); break;
+      const int nch = (m + 31) >> 5;                   // 32-row chunks of the trailing block
+      for (int c = ww; c < nch; c += W) lt_chunk(Fm, rd_cur, lt, lts, Lg, p0, nb, f, ld, c, lane);
+      SZB_E(2)
+      g.phase_sync();
+      SZB_E(3)
+      if (nch > 0) {
+        // every worker takes all row chunks (up to four per tile row) of its own strided columns, but at
+        // least kMinCols columns each: a tile's set-up (multipliers, addresses) costs as much as a few
+        // columns of updates
+        const int nt = (nch + 3) >> 2;                 // tile rows of four chunks (1 unless f > 128)
+        const int CW = max(1, min(nt == 1 ? W : W >> 1, (ncol - r0) / kMinCols));
+        for (int tile = ww; tile < nt * CW; tile += W) {
+          const int tr = tile >= CW ? 1 : 0;           // nt <= 2
+          const int cg = tile - tr * CW;
+          const int rem = nch - 4 * tr;                // chunks in this tile row
+          if (rem >= 3) trailing_tile<4>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, tr << 7, cg, CW, lane);
+          else if (rem == 2) trailing_tile<2>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, tr << 7, cg, CW, lane);
+          else trailing_tile<1>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, tr << 7, cg, CW, lane);
         }
       }
     }
-    SZB_T(5)
+    SZB_E(4)
     g.sync();
-    SZB_T(6)
+    SZB_E(5)
   }
   finalize_u(Fm, s, ncol, ld, lane, w, nw);
   g.sync();
-  SZB_T(7)
+  SZB_E(6)
+#ifdef SZB_PHASE_TIMING
+  if (dbg_) for (int i = 0; i < 7; ++i) g_el[8 * (threadIdx.x >> 7 & 7) + i] += el_[i];
+#endif
+}
+
+#ifdef SZB_PHASE_TIMING
+#define SZB_T(i) { const long long now_ = clock64(); tacc_[(i) + 4 * lvl_] += now_ - tprev_; tprev_ = now_; }
+#define SZB_TPARAM , long long* tacc_, const int lvl_
+#define SZB_TSTART long long tprev_ = clock64();
+#else
+#define SZB_T(i)
+#define SZB_TPARAM
+#define SZB_TSTART
+#endif
+
+__device__ __forceinline__ void clear_front(double* __restrict__ Fm, const int n_el, const int rank, const int G_) {
+  double2* __restrict__ p = reinterpret_cast<double2*>(Fm);
+  const int n2 = (n_el + 1) >> 1;
+  for (int t = rank; t < n2; t += G_) p[t] = make_double2(0.0, 0.0);
 }
 
 // ---------------------------------------------------------------------------------------
-// numeric factorisation of one supernode; the front is column-major with leading dimension
-// ld = f | 1 and has f (+1 when a rhs rides along) columns.  Fronts of multi-warp groups are
-// limited to 128 rows (4 row chunks per lane); lu_plan() rejects larger ones.
+// numeric factorisation of one front; the front is column-major with leading dimension
+// ld = f | 1 and has f + 1 columns (the last one carries the right-hand side when one rides along).
 // ---------------------------------------------------------------------------------------
-template <class G>
-__device__ void factor_supernode(const G g, const LuDev& S, const int k, double* __restrict__ Fm,
-                                 double* __restrict__ ltbuf, const FactorArgs& A) {
-  const int s = S.sn_s[k], f = S.sn_f[k], u = f - s, ld = f | 1;
-#ifdef SZB_PHASE_TIMING
-  long long tprev_ = clock64();
-#endif
-  const int lane = g.lane(), w = g.warp(), nw = g.nwarps(), r = g.rank(), G_ = g.size();
+// one warp, front of at most 32 rows
+__device__ void factor_front_warp(const FrontHdr H, const int2* __restrict__ ga, double* __restrict__ Fm,
+                                  const FactorArgs& A SZB_TPARAM) {
+  SZB_TSTART
+  const int s = H.s, f = H.f, u = f - s, ld = f | 1;
+  const int lane = threadIdx.x & 31;
   const int with_rhs = A.rhs != nullptr;
   const int ncol = f + with_rhs;
-  // 1. clear
-  for (int t = r; t < ld * ncol; t += G_) Fm[t] = 0.0;
-  g.sync();
-  // 2. original entries (+ right-hand side of the pivot rows).  Global loads are issued in batches
-  // of four before the dependent shared-memory stores so that their latencies overlap.
-  {
-    const int a0 = S.a_ptr[k], a1 = S.a_ptr[k + 1];
-    for (int e = a0 + r; e < a1; e += 4 * G_) {
-      int src[4], dst[4];
-      double v[4], mv[4], mk[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int ee = e + q * G_;
-        const bool ok = ee < a1;
-        src[q] = ok ? S.a_src[ee] : -1;
-        dst[q] = ok ? S.a_dst[ee] : 0;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        v[q] = src[q] >= 0 ? A.jv[src[q]] : 0.0;
-        mv[q] = (A.mvals && src[q] >= 0) ? A.mvals[src[q]] : 0.0;
-        mk[q] = (A.smask && src[q] >= 0) ? A.smask[src[q]] : 1.0;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (src[q] >= 0) Fm[dst[q]] = fma(A.scale * mk[q], v[q], mv[q]);
-    }
-    if (with_rhs) {
-      const int p0 = S.sn_piv0[k];
-      for (int t = r; t < s; t += G_) Fm[t + f * ld] = A.rhs[S.rowp[p0 + t]];
-    }
-  }
-  g.sync();
+  clear_front(Fm, ld * (f + 1), lane, kWarp);
+  __syncwarp();
+  assemble_front(lane, kWarp, H, ga, Fm, A);
+  __syncwarp();
   SZB_T(0)
-  // 3. extend-add of the children's contribution blocks (u_c x (u_c + 1), column-major); the
-  // destination of every element was computed on the host (ea_dst).  Loads batched as above.
-  for (int ci = S.child_ptr[k]; ci < S.child_ptr[k + 1]; ++ci) {
-    const int c = S.child[ci];
-    const int uc = S.sn_f[c] - S.sn_s[c];
-    if (uc == 0) continue;
-    const int* __restrict__ dstp = S.ea_dst + S.ea_ptr[c];
-    const double* __restrict__ C = A.cb + S.cb_off[c];
-    const int cnt = uc * (uc + with_rhs);
-    for (int t = r; t < cnt; t += 4 * G_) {
-      int d[4];
-      double v[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int tt = t + q * G_;
-        d[q] = tt < cnt ? dstp[tt] : -1;
-        v[q] = tt < cnt ? C[tt] : 0.0;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (d[q] >= 0) Fm[d[q]] += v[q];
-    }
-    g.sync();
-  }
+  eliminate_warp(Fm, s, f, ncol, ld, lane, A.flag);
   SZB_T(1)
-  // 4. elimination of the s pivots
-  if (nw == 1) eliminate_warp(Fm, s, f, ncol, ld, lane, A.flag);
-  else eliminate_blocked(g, Fm, ltbuf, s, f, ncol, ld, A.flag);
-  SZB_T(2)
-  // 5. write-out
+  double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
   {
-    double* __restrict__ Lp = A.lu + S.lp_off[k];           // f x s, column-major, ld = f
     const int rows = A.store_l ? f : s;
-    if (nw == 1) {
-      const float invr = 1.0f / static_cast<float>(rows);
-      for (int t = r; t < rows * s; t += kWarp) {
-        const int p = fdiv(t, invr);
-        const int i = t - p * rows;
-        Lp[i + p * f] = Fm[i + p * ld];
-      }
-    } else {
-      for (int p = w; p < s; p += nw)
-        for (int i = lane; i < rows; i += kWarp) Lp[i + p * f] = Fm[i + p * ld];
-    }
-    if (u > 0) {
-      double* __restrict__ Up = A.lu + S.up_off[k];         // U12 rows: Up[c + r*u] = U12[r][c]
-      double* __restrict__ C = A.cb + S.cb_off[k];          // u x (u+1), column-major
-      const int nc = u + with_rhs;
-      if (nw == 1) {
-        const float invu = 1.0f / static_cast<float>(u);
-        for (int t = r; t < u * s; t += kWarp) {
-          const int rr = fdiv(t, invu);
-          const int c = t - rr * u;
-          Up[t] = Fm[rr + (s + c) * ld];
-        }
-        for (int t = r; t < u * nc; t += kWarp) {
-          const int j = fdiv(t, invu);
-          const int i = t - j * u;
-          C[t] = Fm[(s + i) + (s + j) * ld];
-        }
-      } else {
-        for (int rr = w; rr < s; rr += nw)
-          for (int c = lane; c < u; c += kWarp) Up[c + rr * u] = Fm[rr + (s + c) * ld];
-        for (int j = w; j < nc; j += nw)
-          for (int i = lane; i < u; i += kWarp) C[i + j * u] = Fm[(s + i) + (s + j) * ld];
-      }
-    }
-    if (with_rhs) {
-      const int p0 = S.sn_piv0[k];
-      for (int t = r; t < s; t += G_) A.yout[p0 + t] = Fm[t + f * ld];
+    const float invr = 1.0f / static_cast<float>(rows);
+    for (int t = lane; t < rows * s; t += kWarp) {
+      const int p = fdiv(t, invr);
+      const int i = t - p * rows;
+      Lp[i + p * f] = Fm[i + p * ld];
     }
   }
-  g.sync();
-  SZB_T(3)
+  if (u > 0) {
+    double* __restrict__ Up = A.lu + H.up_off;           // U12 rows: Up[c + r*u] = U12[r][c]
+    double* C = A.cb + H.cb_off;                         // u x (u+1), column-major
+    const int nc = u + with_rhs;
+    const float invu = 1.0f / static_cast<float>(u);
+    for (int t = lane; t < u * s; t += kWarp) {
+      const int rr = fdiv(t, invu);
+      const int c = t - rr * u;
+      Up[t] = Fm[rr + (s + c) * ld];
+    }
+    for (int t = lane; t < u * nc; t += kWarp) {
+      const int j = fdiv(t, invu);
+      const int i = t - j * u;
+      C[t] = Fm[(s + i) + (s + j) * ld];
+    }
+  }
+  if (with_rhs && lane < s) A.yout[H.piv0 + lane] = Fm[lane + f * ld];
+  __syncwarp();
+  SZB_T(2)
 }
 
-__global__ void __launch_bounds__(1024, 1)
+// a group of warps
+__device__ void factor_front_group(const PanelGrp g, const FrontHdr H, const int2* __restrict__ ga,
+                                   double* __restrict__ Fm, double* __restrict__ lt, const int lts,
+                                   double* __restrict__ rdbuf, const FactorArgs& A SZB_TPARAM) {
+  SZB_TSTART
+  const int s = H.s, f = H.f, u = f - s, ld = f | 1;
+  const int lane = g.lane(), w = g.warp(), nw = g.nw, r = g.rank(), G_ = g.size();
+  const int with_rhs = A.rhs != nullptr;
+  const int ncol = f + with_rhs;
+  clear_front(Fm, ld * (f + 1), r, G_);
+  g.sync();
+  assemble_front(r, G_, H, ga, Fm, A);
+  g.sync();
+  SZB_T(0)
+  double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
+  eliminate_blocked(g, Fm, lt, lts, rdbuf, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
+  SZB_T(1)
+  // rows below a column's own panel were streamed by the workers (or are not wanted)
+  for (int p = w; p < s; p += nw) {
+    const int pend = min(s, (p & ~(kNB - 1)) + kNB);
+    const double* __restrict__ src = Fm + p * ld;
+    double* __restrict__ dst = Lp + p * f;
+    for (int i = lane; i < pend; i += kWarp) dst[i] = src[i];
+  }
+  if (u > 0) {
+    // lanes over the long dimension, pointer walks over the short one: no index arithmetic inside
+    double* __restrict__ Up = A.lu + H.up_off;           // U12 rows: Up[c + r*u] = U12[r][c]
+    for (int c = lane; c < u; c += kWarp) {
+      const double* __restrict__ src = Fm + (s + c) * ld + w;
+      double* __restrict__ dst = Up + c + w * u;
+      for (int rr = w; rr < s; rr += nw, src += nw, dst += nw * u) *dst = *src;
+    }
+    double* C = A.cb + H.cb_off;                         // u x (u+1), column-major
+    const int nc = u + with_rhs;
+    for (int i = lane; i < u; i += kWarp) {
+      const double* __restrict__ src = Fm + (s + i) + (s + w) * ld;
+      double* dst = C + i + w * u;
+      for (int j = w; j < nc; j += nw, src += nw * ld, dst += nw * u) *dst = *src;
+    }
+  }
+  if (with_rhs)
+    for (int t = r; t < s; t += G_) A.yout[H.piv0 + t] = Fm[t + f * ld];
+  g.sync();
+  SZB_T(2)
+}
+
+__global__ void __launch_bounds__(SZB_FACTOR_THREADS, 1)
 lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restrict__ LU,
-                 double* __restrict__ CBW, const double* __restrict__ mvals,
+                 double* CBW, const double* __restrict__ mvals,
                  const double* __restrict__ slot_mask,
                  const double* __restrict__ scale_b, double scale_const,
                  const double* __restrict__ RHS, double* __restrict__ YOUT, int store_l,
                  const int* __restrict__ active, int* __restrict__ flags, int B) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5;
-  const int wstride = (S.f_warp_max | 1) * (S.f_warp_max + 1);
-  const int gfront = (S.f_group_max | 1) * (S.f_group_max + 1);
-  const int gstride = gfront + 2 * kNB * kLtStride;
-  const int tfront = (S.f_top_max | 1) * (S.f_top_max + 1);
-  const int wpg = (blockDim.x >> 5) / max(S.n_group_lists, 1);   // warps per group
+  const int wstride = front_elems(S.f_warp_max);
+  const int gfront = front_elems(S.f_group_max), glts = lt_stride(S.f_group_max);
+  const int gstride = group_elems(S.f_group_max);
+  const int tfront = front_elems(S.f_top_max), tlts = lt_stride(S.f_top_max);
+  const int wpg = S.wpg;
+  // the work lists are the same for every scenario: fetch their bounds once
+  int wq0 = 0, wq1 = 0, gq0 = 0, gq1 = 0;
+  if (warp < S.n_warp_lists) { wq0 = S.wl_ptr[warp]; wq1 = S.wl_ptr[warp + 1]; }
+  const int gi = wpg > 0 ? warp / wpg : 0;
+  const bool in_group = S.n_group_lists > 0 && gi < S.n_group_lists;
+  if (in_group) { gq0 = S.n_warp_sn + S.gl_ptr[gi]; gq1 = S.n_warp_sn + S.gl_ptr[gi + 1]; }
+  const int tq0 = S.n_warp_sn + S.n_group_sn;
 #ifdef SZB_PHASE_TIMING
-  long long tph[4] = {0, 0, 0, 0};
+  long long tacc_[16];
+  for (int i = 0; i < 16; ++i) tacc_[i] = 0;
+  long long nscen_ = 0;
+#define SZB_TARG(l) , tacc_, l
+#define SZB_LVL(i) { const long long now_ = clock64(); tacc_[12 + (i)] += now_ - tlev_; tlev_ = now_; }
+#else
+#define SZB_TARG(l)
+#define SZB_LVL(i)
 #endif
   FactorArgs A;
   A.mvals = mvals;
@@ -524,54 +739,70 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
     A.yout = YOUT ? YOUT + static_cast<size_t>(b) * S.n : nullptr;
     A.flag = flags + b;
 #ifdef SZB_PHASE_TIMING
-    long long t0 = clock64();
+    long long tlev_ = clock64();
+    ++nscen_;
 #endif
     // level 0: warps
-    if (warp < S.n_warp_lists) {
+    if (wq0 < wq1) {
       double* Fm = sm + warp * wstride;
-      const WarpGrp g;
-      for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q) factor_supernode(g, S, S.wl[q], Fm, nullptr, A);
+      FrontHdr H = load_hdr(S.fh, wq0);
+      for (int q = wq0; q < wq1; ++q) {
+        const FrontHdr Hn = load_hdr(S.fh, min(q + 1, wq1 - 1));   // prefetch the next descriptor
+        factor_front_warp(H, S.ga, Fm, A SZB_TARG(0));
+        H = Hn;
+      }
     }
     __syncthreads();
-#ifdef SZB_PHASE_TIMING
-    long long t1 = clock64();
-#endif
+    SZB_LVL(0)
     // level 1: groups of warps
     if (S.n_group_lists > 0) {
-      const int gi = warp / wpg;
-      if (gi < S.n_group_lists) {
+      if (in_group && gq0 < gq1) {
         double* Fm = sm + gi * gstride;
-        NamedGrp g;
+        PanelGrp g;
         g.id = 1 + gi;
         g.nw = wpg;
         g.w0 = gi * wpg;
-        for (int q = S.gl_ptr[gi]; q < S.gl_ptr[gi + 1]; ++q)
-          factor_supernode(g, S, S.gl[q], Fm, Fm + gfront, A);
+        FrontHdr H = load_hdr(S.fh, gq0);
+        for (int q = gq0; q < gq1; ++q) {
+          const FrontHdr Hn = load_hdr(S.fh, min(q + 1, gq1 - 1));
+          factor_front_group(g, H, S.ga, Fm, Fm + gfront, glts, Fm + gfront + kNB * glts, A SZB_TARG(1));
+          H = Hn;
+        }
       }
       __syncthreads();
     }
-#ifdef SZB_PHASE_TIMING
-    long long t2 = clock64();
-#endif
-    // level 2: the whole CTA
-    {
-      const BlockGrp g;
-      for (int q = 0; q < S.n_top; ++q) factor_supernode(g, S, S.top[q], sm, sm + tfront, A);
+    SZB_LVL(1)
+    // level 2: the whole CTA as one group (barrier 0)
+    if (S.n_top > 0) {
+      PanelGrp g;
+      g.id = 0;
+      g.nw = blockDim.x >> 5;
+      g.w0 = 0;
+      FrontHdr H = load_hdr(S.fh, tq0);
+      for (int q = 0; q < S.n_top; ++q) {
+        const FrontHdr Hn = load_hdr(S.fh, tq0 + min(q + 1, S.n_top - 1));
+        factor_front_group(g, H, S.ga, sm, sm + tfront, tlts, sm + tfront + kNB * tlts, A SZB_TARG(2));
+        H = Hn;
+      }
     }
-#ifdef SZB_PHASE_TIMING
-    long long t3 = clock64();
-    tph[0] += t1 - t0; tph[1] += t2 - t1; tph[2] += t3 - t2; tph[3] += 1;
-#endif
+    __syncthreads();   // the next scenario reuses the fronts and the contribution workspace
+    SZB_LVL(2)
   }
 #ifdef SZB_PHASE_TIMING
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-    printf("[lu_factor phases] warp %lld group %lld top %lld cycles/scenario (%lld scenarios) | top: asm %lld ea %lld elim %lld write %lld\n",
-           tph[0] / max(tph[3], 1LL), tph[1] / max(tph[3], 1LL), tph[2] / max(tph[3], 1LL), tph[3],
-           g_dbg[0] / max(tph[3], 1LL), g_dbg[1] / max(tph[3], 1LL), g_dbg[2] / max(tph[3], 1LL), g_dbg[3] / max(tph[3], 1LL));
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-    printf("   elim split (thread 0): first-panel %lld  panel_next/own work %lld  barrier wait %lld  finalize %lld\n", g_dbg[4] / max(tph[3], 1LL),
-           g_dbg[5] / max(tph[3], 1LL), g_dbg[6] / max(tph[3], 1LL), g_dbg[7] / max(tph[3], 1LL));
-  if (threadIdx.x == 0 && blockIdx.x == 0) for (int i = 0; i < 8; ++i) g_dbg[i] = 0;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long n_ = nscen_ > 0 ? nscen_ : 1;
+    printf("[lu_factor phases, cycles/scenario over %lld scenarios, thread 0]\n", n_);
+    const char* nm[3] = {"warp ", "group", "top  "};
+    for (int l = 0; l < 3; ++l)
+      printf("  %s level %8lld : clear+assemble %8lld  eliminate %8lld  write-out %8lld\n", nm[l], tacc_[12 + l] / n_,
+             tacc_[4 * l] / n_, tacc_[4 * l + 1] / n_, tacc_[4 * l + 2] / n_);
+    for (int wq = 0; wq < 8; ++wq) {
+      printf("  top elimination, warp %2d: first-diag %lld diag_next %lld phaseA %lld wait-phase %lld phaseB %lld wait-main %lld finalize %lld\n",
+             4 * wq, g_el[8 * wq] / n_, g_el[8 * wq + 1] / n_, g_el[8 * wq + 2] / n_, g_el[8 * wq + 3] / n_,
+             g_el[8 * wq + 4] / n_, g_el[8 * wq + 5] / n_, g_el[8 * wq + 6] / n_);
+      for (int i = 0; i < 8; ++i) g_el[8 * wq + i] = 0;
+    }
+  }
 #endif
 }
 
@@ -700,7 +931,7 @@ lu_solve_kernel(const LuDev S, const double* __restrict__ LU, const double* __re
   double* xb = x_in_smem ? sm : XW + static_cast<size_t>(blockIdx.x) * n;
   double* scratch = x_in_smem ? sm + n : sm;
   const SolveSmem L = solve_layout(S);
-  const int wpg = (blockDim.x >> 5) / max(S.n_group_lists, 1);
+  const int wpg = max(S.wpg, 1);
   double* cv = CVW + static_cast<size_t>(blockIdx.x) * S.cv_size;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     if (active && !active[b]) continue;
@@ -782,23 +1013,20 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   if (e != cudaSuccess) return e;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  // threads: one warp per warp list, and a whole number of warps per group
-  int warps = S.n_warp_lists > 0 ? S.n_warp_lists : 1;
-  if (S.n_group_lists > 0) {
-    const int per = (warps + S.n_group_lists - 1) / S.n_group_lists;
-    const int wpg = per < 2 ? 2 : per;
-    warps = wpg * S.n_group_lists;
-  }
-  if (S.n_top > 0 && warps < 8) warps = S.n_group_lists > 0 ? ((8 + S.n_group_lists - 1) / S.n_group_lists) * S.n_group_lists : 8;
-  if (warps > 32) return cudaErrorInvalidConfiguration;
-  cfg->threads = 32 * warps;
-  if (S.f_group_max > 128 || S.f_top_max > 128) return cudaErrorInvalidConfiguration;  // 4 row chunks per lane
-  if (S.f_warp_max > 32) return cudaErrorInvalidConfiguration;
-  auto front = [](int f) { return static_cast<size_t>(f | 1) * (f + 1); };
-  const size_t ltb = 2 * 4 * 128;   // two Lt side panels (kNB x kLtStride doubles)
-  size_t fsm = S.n_warp_lists * front(S.f_warp_max);
-  fsm = smax(fsm, S.n_group_lists * (front(S.f_group_max) + ltb));
-  fsm = smax(fsm, S.n_top > 0 ? front(S.f_top_max) + ltb : 0);
+  // threads per CTA and warps per group were fixed by the host schedule (lu/schedule.py::plan_threads):
+  // the gather tables are laid out for exactly these group sizes
+  const int warps = S.threads >> 5;
+  if (S.threads <= 0 || (S.threads & 31) || warps > 32 || warps < S.n_warp_lists ||
+      S.wpg * S.n_group_lists > warps || (S.n_group_lists > 0 && S.wpg < 2))
+    return cudaErrorInvalidConfiguration;
+  cfg->threads = S.threads;
+  if (S.f_warp_max > 32) return cudaErrorInvalidConfiguration;   // lane = row
+  if (S.n_group_lists > 7) return cudaErrorInvalidConfiguration;   // named barriers 1..7 (+8 for the phase barrier)
+  if (S.f_group_max > 256 || S.f_top_max > 256) return cudaErrorInvalidConfiguration;  // <= 2 tile rows of 128
+  if (S.threads > SZB_FACTOR_THREADS) return cudaErrorInvalidConfiguration;
+  size_t fsm = static_cast<size_t>(S.n_warp_lists) * front_elems(S.f_warp_max);
+  fsm = smax(fsm, static_cast<size_t>(S.n_group_lists) * group_elems(S.f_group_max));
+  fsm = smax(fsm, S.n_top > 0 ? static_cast<size_t>(group_elems(S.f_top_max)) : 0);
   cfg->smem_factor = fsm * sizeof(double);
   if (cfg->smem_factor > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
   size_t ssm = S.n_warp_lists * (2 * static_cast<size_t>(S.f_warp_max) + static_cast<size_t>(S.s_warp_max) * S.s_warp_max);

@@ -10,6 +10,8 @@ struct LuDev {
   int n, nnz_a, ns;
   int lu_size, cb_size, cv_size;
   int n_warp_lists, n_group_lists, n_top;
+  int n_warp_sn, n_group_sn;     // fronts in the warp lists / group lists (schedule order: warp, group, top)
+  int threads, wpg;              // threads per CTA, warps per group (fixed by the host schedule)
   int f_warp_max, f_group_max, f_top_max, s_warp_max, s_group_max, s_top_max;
   const int *rowp, *colp;
   const int *sn_piv0, *sn_s, *sn_f;
@@ -18,6 +20,8 @@ struct LuDev {
   const int *lp_off, *up_off, *cb_off;
   const int *ea_ptr, *ea_dst;   // per child: destination of every contribution-block element in the parent front
   const int *wl_ptr, *wl, *gl_ptr, *gl, *top;
+  const int4* fh;                // front headers, 4 x int4 each, schedule order (lu/schedule.py)
+  const int2* ga;                // gather table: (tagged source, front position)
 };
 
 struct LuLaunchCfg {

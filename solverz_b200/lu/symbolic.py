@@ -582,7 +582,7 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
 
 
 def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
-            warp_front_max: int = 24, n_warps: int = 32, group_front_max: int = 72, n_groups: int = 4,
+            warp_front_max: int = 32, n_warps: int = 16, group_front_max: int = 72, n_groups: int = 4,
             orderings: Sequence[str] = ("nd", "mmd")) -> LUSymbolic:
     """Analyse the pattern (and representative values) of ``A``; see the module docstring."""
     A = sp.csc_matrix(A)

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE.parent / "csrc" / "libszb.so"
 
-SZB_ABI_VERSION = 1
+SZB_ABI_VERSION = 2
 SLOT_Y, SLOT_F, SLOT_JV, SLOT_RHS, SLOT_PARAM0 = 0, 1, 2, 3, 16
 DTYPE_F64, DTYPE_I32 = 0, 1
 FLAG_NAMES = {0: "converged", 1: "max_it", 2: "singular", 3: "dt_min", 4: "rejects", 5: "nan", 6: "running",
@@ -24,10 +24,12 @@ _i32p = C.POINTER(C.c_int32)
 class LuSymbolicC(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n", "nnz_a", "ns", "lu_size", "cb_size", "cv_size", "n_warp_lists",
                                          "n_group_lists", "n_top", "f_warp_max", "f_group_max", "f_top_max",
-                                         "s_warp_max", "s_group_max", "s_top_max")] + \
+                                         "s_warp_max", "s_group_max", "s_top_max", "threads", "wpg",
+                                         "n_sched", "n_ga")] + \
                [(k, _i32p) for k in ("rowp", "colp", "sn_piv0", "sn_s", "sn_f", "idx_ptr", "idx", "rel_ptr",
                                      "rel", "child_ptr", "child", "a_ptr", "a_src", "a_dst", "lp_off",
-                                     "up_off", "cb_off", "ea_ptr", "ea_dst", "wl_ptr", "wl", "gl_ptr", "gl", "top")]
+                                     "up_off", "cb_off", "ea_ptr", "ea_dst", "wl_ptr", "wl", "gl_ptr", "gl", "top",
+                                     "fh", "ga")]
 
 
 class DescC(C.Structure):
@@ -126,6 +128,16 @@ def lu_symbolic_c(sym, keep: list) -> LuSymbolicC:
         arr = np.ascontiguousarray(np.asarray(getattr(sym, name)), dtype=np.int32)
         if arr.size == 0:
             arr = np.zeros(1, dtype=np.int32)
+        keep.append(arr)
+        setattr(s, name, arr.ctypes.data_as(_i32p))
+    # device schedule: front descriptors + gather tables for exactly this thread layout
+    from ..lu.schedule import build_tables, plan_threads
+    plan = plan_threads(sym)
+    tabs = build_tables(sym, plan["threads"], plan["wpg"])
+    s.threads, s.wpg = plan["threads"], plan["wpg"]
+    s.n_sched, s.n_ga = tabs["n_sched"], len(tabs["ga"])
+    for name in ("fh", "ga"):
+        arr = np.ascontiguousarray(tabs[name], dtype=np.int32)
         keep.append(arr)
         setattr(s, name, arr.ctypes.data_as(_i32p))
     return s

@@ -117,9 +117,10 @@ typedef struct szb_lu_symbolic {
   const int32_t* gl;
   const int32_t* top;       /* [n_top] */
   const int32_t* fh;        /* [n_sched][16] front descriptors in schedule order (warp lists, group lists,
-                               top): s, f, piv0, ga0, ga_iters, lp_off, up_off, cb_off, k, n_src, 0... */
-  const int32_t* ga;        /* [n_ga][2] gather table: per front a [ga_iters][group threads] block of
-                               (tagged source, front position); see solverz_b200/lu/schedule.py */
+                               top): s, f, piv0, lp_off, up_off, cb_off, gaJ, itJ, gaC, itC, gaR, itR, k, n_src,
+                               idx_ptr, 0 */
+  const int32_t* ga;        /* [n_ga][2] gather table: per front three [iterations][group threads] blocks
+                               (J slots, contribution offsets, right-hand side) of (source, front position); see solverz_b200/lu/schedule.py */
 } szb_lu_symbolic;
 
 typedef struct szb_desc {

@@ -334,10 +334,11 @@ int szb_set_batch(szb_handle* h, int32_t B) {
   if (h->has_lu) {
     ALLOC(h->LU, double, static_cast<size_t>(B) * h->S.lu_size);
     ALLOC(h->ybuf, double, B * n);
-    const int gmax = h->cfg.grid_factor > h->cfg.grid_solve ? h->cfg.grid_factor : h->cfg.grid_solve;
+    int gmax = h->cfg.grid_factor > h->cfg.grid_solve ? h->cfg.grid_factor : h->cfg.grid_solve;
+    if (h->cfg.grid_bwd > gmax) gmax = h->cfg.grid_bwd;
     ALLOC(h->CBW, double, static_cast<size_t>(gmax) * (h->S.cb_size > 0 ? h->S.cb_size : 1));
     ALLOC(h->CVW, double, static_cast<size_t>(gmax) * (h->S.cv_size > 0 ? h->S.cv_size : 1));
-    ALLOC(h->XW, double, h->cfg.x_in_smem ? 1 : static_cast<size_t>(gmax) * n);
+    ALLOC(h->XW, double, (h->cfg.x_in_smem && h->cfg.bwd_x_in_smem) ? 1 : static_cast<size_t>(gmax) * n);
   }
   ALLOC(h->fnorm, double, B);
   ALLOC(h->scale_b, double, B);
@@ -452,7 +453,7 @@ int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream) {
   SZB_CUDA(h, cudaSetDevice(h->device));
   for (int r = 0; r < nrhs; ++r) {
     double* x = h->RHS + r * per;
-    cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, x, x, h->CVW, h->XW, 1, 0, nullptr, h->B,
+    cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, x, x, h->CVW, h->XW, h->ybuf, 1, 0, nullptr, h->B,
                                          static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
     h->launches[3]++;
@@ -526,7 +527,7 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
     tic();
     {
       // backward substitution and Newton update  Y -= U^{-1} y
-      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->ybuf, h->Y, h->CVW, h->XW, 0, 1,
+      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->ybuf, h->Y, h->CVW, h->XW, nullptr, 0, 1,
                                            h->active, B, st);
       if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
       h->launches[3]++;

@@ -628,13 +628,14 @@ __device__ void factor_front_warp(const FrontHdr H, const int2* __restrict__ ga,
     }
   }
   if (u > 0) {
-    double* __restrict__ Up = A.lu + H.up_off;           // U12 rows: Up[c + r*u] = U12[r][c]
+    double* __restrict__ Up = A.lu + H.up_off;           // U12, s x u column-major: Up[r + c*s]
     double* C = A.cb + H.cb_off;                         // u x (u+1), column-major
     const int nc = u + with_rhs;
     const float invu = 1.0f / static_cast<float>(u);
+    const float invs = 1.0f / static_cast<float>(s);
     for (int t = lane; t < u * s; t += kWarp) {
-      const int rr = fdiv(t, invu);
-      const int c = t - rr * u;
+      const int c = fdiv(t, invs);
+      const int rr = t - c * s;
       Up[t] = Fm[rr + (s + c) * ld];
     }
     for (int t = lane; t < u * nc; t += kWarp) {
@@ -674,11 +675,14 @@ __device__ void factor_front_group(const PanelGrp g, const FrontHdr H, const int
   }
   if (u > 0) {
     // lanes over the long dimension, pointer walks over the short one: no index arithmetic inside
-    double* __restrict__ Up = A.lu + H.up_off;           // U12 rows: Up[c + r*u] = U12[r][c]
-    for (int c = lane; c < u; c += kWarp) {
-      const double* __restrict__ src = Fm + (s + c) * ld + w;
-      double* __restrict__ dst = Up + c + w * u;
-      for (int rr = w; rr < s; rr += nw, src += nw, dst += nw * u) *dst = *src;
+    double* __restrict__ Up = A.lu + H.up_off;           // U12, s x u column-major: Up[r + c*s]
+    {
+      const float invs = 1.0f / static_cast<float>(s);
+      for (int t = r; t < u * s; t += G_) {
+        const int c = fdiv(t, invs);
+        const int rr = t - c * s;
+        Up[t] = Fm[rr + (s + c) * ld];
+      }
     }
     double* C = A.cb + H.cb_off;                         // u x (u+1), column-major
     const int nc = u + with_rhs;
@@ -809,12 +813,6 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
 // ---------------------------------------------------------------------------------------
 // triangular solves
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // forward: r = [b_piv ; 0] + sum_children cv_c ;  L11 x = r_piv ; cv_k = r_upd - L21 x
 // rv: f doubles of scratch, T: s*s doubles of scratch (diagonal block staged once)
 template <class G>
@@ -854,53 +852,6 @@ __device__ void forward_supernode(const G g, const LuDev& S, const int k,
   g.sync();
 }
 
-// backward: x_piv = U11^{-1} ( y_piv - U12 x_upd )
-// rv: s doubles, gv: u doubles, T: s*s doubles
-template <class G>
-__device__ void backward_supernode(const G g, const LuDev& S, const int k,
-                                   const double* __restrict__ lu, double* __restrict__ xb,
-                                   double* __restrict__ rv, double* __restrict__ gv,
-                                   double* __restrict__ T) {
-  const int s = S.sn_s[k], f = S.sn_f[k], u = f - s, p0 = S.sn_piv0[k];
-  const int lane = g.lane(), w = g.warp(), nw = g.nwarps(), r = g.rank(), G_ = g.size();
-  const double* __restrict__ Lp = lu + S.lp_off[k];
-  const double* __restrict__ Ut = lu + S.up_off[k];
-  const int* __restrict__ ids = S.idx + S.idx_ptr[k] + s;
-  for (int t = r; t < u; t += G_) gv[t] = xb[ids[t]];
-  // stage the upper triangle (incl. diagonal) of the s x s block: column p, rows 0..p
-  for (int p = w; p < s; p += nw)
-    for (int i = lane; i <= p; i += kWarp) T[i + p * s] = Lp[i + p * f];
-  g.sync();
-  for (int rr = w; rr < s; rr += nw) {
-    double acc = 0.0;
-    const double* __restrict__ row = Ut + rr * u;
-    for (int c = lane; c < u; c += kWarp) acc = fma(row[c], gv[c], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) rv[rr] = xb[p0 + rr] - acc;
-  }
-  g.sync();
-  if (s <= kWarp) {
-    // one warp finishes the small triangle with shuffles, no further barriers
-    if (w == 0) {
-      double mine = (lane < s) ? rv[lane] : 0.0;
-      for (int p = s - 1; p >= 0; --p) {
-        const double xp = __shfl_sync(0xffffffffu, mine, p) / T[p + p * s];
-        if (lane == p) mine = xp;
-        else if (lane < p) mine = fma(-T[lane + p * s], xp, mine);
-      }
-      if (lane < s) xb[p0 + lane] = mine;
-    }
-  } else {
-    for (int p = s - 1; p >= 0; --p) {
-      const double xp = rv[p] / T[p + p * s];
-      for (int i = r; i < p; i += G_) rv[i] = fma(-T[i + p * s], xp, rv[i]);
-      if (r == 0) xb[p0 + p] = xp;
-      g.sync();
-    }
-  }
-  g.sync();
-}
-
 struct SolveSmem {
   int wstride, gstride;
   int w_rv, w_T, g_rv, g_T, t_rv, t_T;
@@ -919,12 +870,12 @@ __device__ __forceinline__ SolveSmem solve_layout(const LuDev& S) {
   return L;
 }
 
-// do_fwd: run the forward sweep (RHS in original order); otherwise RHS already holds y in pivot
-// order (produced by the fused factorisation).
-__global__ void __launch_bounds__(1024, 1)
-lu_solve_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ RHS,
-                double* __restrict__ X, double* __restrict__ CVW, double* __restrict__ XW,
-                int x_in_smem, int do_fwd, int mode, const int* __restrict__ active, int B) {
+// forward sweep  y = L^{-1} P b : RHS in original order -> YP in pivot order (what the fused
+// factorisation produces for Newton; Rodas' stage solves come through here)
+__global__ void __launch_bounds__(SZB_FACTOR_THREADS, 1)
+lu_forward_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ RHS,
+                  double* __restrict__ YP, double* __restrict__ CVW, double* __restrict__ XW,
+                  int x_in_smem, const int* __restrict__ active, int B) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5;
   const int n = S.n;
@@ -937,44 +888,14 @@ lu_solve_kernel(const LuDev S, const double* __restrict__ LU, const double* __re
     if (active && !active[b]) continue;
     const double* lu = LU + static_cast<size_t>(b) * S.lu_size;
     const double* rhs = RHS + static_cast<size_t>(b) * n;
-    double* x = X + static_cast<size_t>(b) * n;
     __syncthreads();
-    if (do_fwd) {
-      for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = rhs[S.rowp[t]];
-    } else {
-      for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = rhs[t];
-    }
+    for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = rhs[S.rowp[t]];
     __syncthreads();
-    if (do_fwd) {
-      if (warp < S.n_warp_lists) {
-        double* rv = scratch + warp * L.wstride;
-        const WarpGrp g;
-        for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q)
-          forward_supernode(g, S, S.wl[q], lu, xb, cv, rv, rv + L.w_rv);
-      }
-      __syncthreads();
-      if (S.n_group_lists > 0) {
-        const int gi = warp / wpg;
-        if (gi < S.n_group_lists) {
-          double* rv = scratch + gi * L.gstride;
-          NamedGrp g;
-          g.id = 1 + gi; g.nw = wpg; g.w0 = gi * wpg;
-          for (int q = S.gl_ptr[gi]; q < S.gl_ptr[gi + 1]; ++q)
-            forward_supernode(g, S, S.gl[q], lu, xb, cv, rv, rv + L.g_rv);
-        }
-        __syncthreads();
-      }
-      {
-        const BlockGrp g;
-        for (int q = 0; q < S.n_top; ++q)
-          forward_supernode(g, S, S.top[q], lu, xb, cv, scratch, scratch + L.t_rv);
-      }
-    }
-    // backward: top, groups, warps
-    {
-      const BlockGrp g;
-      for (int q = S.n_top - 1; q >= 0; --q)
-        backward_supernode(g, S, S.top[q], lu, xb, scratch, scratch + S.f_top_max, scratch + L.t_rv);
+    if (warp < S.n_warp_lists) {
+      double* rv = scratch + warp * L.wstride;
+      const WarpGrp g;
+      for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q)
+        forward_supernode(g, S, S.wl[q], lu, xb, cv, rv, rv + L.w_rv);
     }
     __syncthreads();
     if (S.n_group_lists > 0) {
@@ -983,16 +904,208 @@ lu_solve_kernel(const LuDev S, const double* __restrict__ LU, const double* __re
         double* rv = scratch + gi * L.gstride;
         NamedGrp g;
         g.id = 1 + gi; g.nw = wpg; g.w0 = gi * wpg;
-        for (int q = S.gl_ptr[gi + 1] - 1; q >= S.gl_ptr[gi]; --q)
-          backward_supernode(g, S, S.gl[q], lu, xb, rv, rv + S.f_group_max, rv + L.g_rv);
+        for (int q = S.gl_ptr[gi]; q < S.gl_ptr[gi + 1]; ++q)
+          forward_supernode(g, S, S.gl[q], lu, xb, cv, rv, rv + L.g_rv);
       }
       __syncthreads();
     }
-    if (warp < S.n_warp_lists) {
-      double* rv = scratch + warp * L.wstride;
-      const WarpGrp g;
-      for (int q = S.wl_ptr[warp + 1] - 1; q >= S.wl_ptr[warp]; --q)
-        backward_supernode(g, S, S.wl[q], lu, xb, rv, rv + S.f_warp_max, rv + L.w_rv);
+    {
+      const BlockGrp g;
+      for (int q = 0; q < S.n_top; ++q)
+        forward_supernode(g, S, S.top[q], lu, xb, cv, scratch, scratch + L.t_rv);
+    }
+    __syncthreads();
+    double* yp = YP + static_cast<size_t>(b) * n;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) yp[t] = xb[t];
+  }
+}
+
+// ---- backward sweep  x = U^{-1} y.  One WARP per front, lane = pivot row (blocks of 32 rows), no
+// barriers and no reductions: row i accumulates  y_i - sum_{j > i} U_ij x_j  over the U12 columns
+// (stored s x u column-major, so a column is one coalesced load), then over the later pivots of the
+// front, and the 32 x 32 triangle is finished with shuffles.  Everything read from the factors is
+// independent of x, so the loads of one front overlap the dependent chain; many small CTAs per SM
+// (several scenarios in flight) hide the rest of the latency.
+struct SolveHdr {
+  int s, f, piv0, lp_off, up_off, idx_off;
+};
+
+__device__ __forceinline__ SolveHdr load_solve_hdr(const int4* __restrict__ fh, const int q) {
+  const int4 a = __ldg(fh + 4 * q), b = __ldg(fh + 4 * q + 1), d = __ldg(fh + 4 * q + 3);
+  SolveHdr H;
+  H.s = a.x; H.f = a.y; H.piv0 = a.z; H.lp_off = a.w; H.up_off = b.x; H.idx_off = d.z;
+  return H;
+}
+
+constexpr int kTri = 4;   // pivots of the triangle whose columns are fetched together
+
+// pull the factor data of a front that comes up two fronts from now into L1: nothing the backward
+// sweep reads from the factors depends on x, so the only dependent chain left is arithmetic
+__device__ __forceinline__ void prefetch_front(const SolveHdr H, const double* __restrict__ lu, const int lane) {
+  const int s = H.s, f = H.f, u = f - s;
+  const char* up = reinterpret_cast<const char*>(lu + H.up_off);
+  const int nb = s * u * 8;
+  for (int o = lane * 128; o < nb; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(up + o));
+  const double* Lp = lu + H.lp_off;
+  for (int p = lane; p < s; p += 32) {
+    const char* c0 = reinterpret_cast<const char*>(Lp + p * f);
+    for (int o = 0; o <= p * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(c0 + o));
+  }
+}
+
+// columns p, p-1, ..., p-kTri+1 (down to pmin) of the panel, row min(io, column): one batch of loads
+__device__ __forceinline__ void load_tri_cols(const double* __restrict__ Lp, const int f, const int io,
+                                              const int p, const int pmin, double (&tv)[kTri]) {
+#pragma unroll
+  for (int q = 0; q < kTri; ++q) {
+    const int pq = p - q;
+    tv[q] = pq >= pmin ? Lp[min(io, pq) + pq * f] : 1.0;
+  }
+}
+
+__device__ void backward_front(const SolveHdr H, const double* __restrict__ lu, const int* __restrict__ idx,
+                               double* xb, const int lane) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0;
+  const double* __restrict__ Lp = lu + H.lp_off;       // f x s panel; rows <= column hold U11
+  const double* __restrict__ Up = lu + H.up_off;       // U12, s x u column-major
+  const int* __restrict__ ids = idx + H.idx_off + s;   // pivot-order indices of the update rows
+  for (int blk = (s - 1) >> 5; blk >= 0; --blk) {
+    const int i = 32 * blk + lane;
+    const bool ok = i < s;
+    const int bend = min(s, 32 * blk + 32), bbeg = 32 * blk;
+    const int io = ok ? i : 0;                          // idle lanes mirror row 0 (finite data), never store
+    // nothing read from the factors depends on x: fetch the first batch of triangle columns now so that
+    // its latency overlaps the accumulation below
+    double tv[kTri];
+    load_tri_cols(Lp, f, io, bend - 1, bbeg, tv);
+    double acc = xb[p0 + io];
+    // columns of U12, eight in flight
+    {
+      const double* __restrict__ up = Up + io;
+      int c = 0;
+      for (; c + 8 <= u; c += 8, up += 8 * s) {
+        int j[8];
+        double uv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { j[q] = __ldg(ids + c + q); uv[q] = up[q * s]; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fma(-uv[q], xb[j[q]], acc);
+      }
+      if (c < u) {
+        int j[8];
+        double uv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const bool in = c + q < u;
+          j[q] = in ? __ldg(ids + c + q) : 0;
+          uv[q] = in ? up[q * s] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double xv = (c + q < u) ? xb[j[q]] : 0.0;
+          acc = fma(-uv[q], xv, acc);
+        }
+      }
+    }
+    // pivots of this front behind the block (already solved)
+    {
+      const double* __restrict__ lp = Lp + io + bend * f;
+      int p = bend;
+      for (; p + 4 <= s; p += 4, lp += 4 * f) {
+        const double u0 = lp[0], u1 = lp[f], u2 = lp[2 * f], u3 = lp[3 * f];
+        acc = fma(-u0, xb[p0 + p], acc);
+        acc = fma(-u1, xb[p0 + p + 1], acc);
+        acc = fma(-u2, xb[p0 + p + 2], acc);
+        acc = fma(-u3, xb[p0 + p + 3], acc);
+      }
+      for (; p < s; ++p, lp += f) acc = fma(-lp[0], xb[p0 + p], acc);
+    }
+    // the triangle of the block, last pivot first, kTri pivots per batch: the next batch of columns is in
+    // flight while this one is solved, and the reciprocals of the diagonal are off the dependent chain
+    for (int p = bend - 1; p >= bbeg; p -= kTri) {
+      double tn[kTri];
+      load_tri_cols(Lp, f, io, p - kTri, bbeg, tn);
+      double rinv[kTri];
+#pragma unroll
+      for (int q = 0; q < kTri; ++q) rinv[q] = 1.0 / __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);
+#pragma unroll
+      for (int q = 0; q < kTri; ++q) {
+        const int pq = p - q;
+        if (pq >= bbeg) {
+          const double xp = __shfl_sync(0xffffffffu, acc, pq & 31) * rinv[q];
+          if (i == pq) acc = xp;
+          else if (i < pq) acc = fma(-tv[q], xp, acc);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kTri; ++q) tv[q] = tn[q];
+    }
+    if (ok) xb[p0 + i] = acc;
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(128, 6)
+lu_backward_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ YP,
+                   double* __restrict__ X, double* __restrict__ XW, int x_in_smem, int mode,
+                   const int* __restrict__ active, int B) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int n = S.n;
+  double* xb = x_in_smem ? sm : XW + static_cast<size_t>(blockIdx.x) * n;
+  const int gq_base = S.n_warp_sn, tq0 = S.n_warp_sn + S.n_group_sn;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    if (active && !active[b]) continue;
+    const double* __restrict__ lu = LU + static_cast<size_t>(b) * S.lu_size;
+    const double* __restrict__ yp = YP + static_cast<size_t>(b) * n;
+    double* __restrict__ x = X + static_cast<size_t>(b) * n;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = yp[t];
+    __syncthreads();
+    // the top of the tree is a chain: one warp walks it, root first
+    if (warp == 0 && S.n_top > 0) {
+      SolveHdr H = load_solve_hdr(S.fh, tq0 + S.n_top - 1);
+      SolveHdr Hn = load_solve_hdr(S.fh, tq0 + max(S.n_top - 2, 0));
+      prefetch_front(Hn, lu, lane);
+      for (int q = S.n_top - 1; q >= 0; --q) {
+        const SolveHdr Hnn = load_solve_hdr(S.fh, tq0 + max(q - 2, 0));
+        if (q >= 2) prefetch_front(Hnn, lu, lane);
+        backward_front(H, lu, S.idx, xb, lane);
+        H = Hn;
+        Hn = Hnn;
+      }
+    }
+    __syncthreads();
+    for (int g = warp; g < S.n_group_lists; g += nwarps) {
+      const int q0 = gq_base + S.gl_ptr[g], q1 = gq_base + S.gl_ptr[g + 1];
+      if (q0 < q1) {
+        SolveHdr H = load_solve_hdr(S.fh, q1 - 1);
+        SolveHdr Hn = load_solve_hdr(S.fh, max(q1 - 2, q0));
+        prefetch_front(Hn, lu, lane);
+        for (int q = q1 - 1; q >= q0; --q) {
+          const SolveHdr Hnn = load_solve_hdr(S.fh, max(q - 2, q0));
+          if (q - 2 >= q0) prefetch_front(Hnn, lu, lane);
+          backward_front(H, lu, S.idx, xb, lane);
+          H = Hn;
+          Hn = Hnn;
+        }
+      }
+    }
+    __syncthreads();
+    for (int l = warp; l < S.n_warp_lists; l += nwarps) {
+      const int q0 = S.wl_ptr[l], q1 = S.wl_ptr[l + 1];
+      if (q0 < q1) {
+        SolveHdr H = load_solve_hdr(S.fh, q1 - 1);
+        SolveHdr Hn = load_solve_hdr(S.fh, max(q1 - 2, q0));
+        prefetch_front(Hn, lu, lane);
+        for (int q = q1 - 1; q >= q0; --q) {
+          const SolveHdr Hnn = load_solve_hdr(S.fh, max(q - 2, q0));
+          if (q - 2 >= q0) prefetch_front(Hnn, lu, lane);
+          backward_front(H, lu, S.idx, xb, lane);
+          H = Hn;
+          Hn = Hnn;
+        }
+      }
     }
     __syncthreads();
     if (mode == 0) {
@@ -1041,21 +1154,32 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
     cfg->smem_solve = ssm * sizeof(double);
     if (cfg->smem_solve > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
   }
+  // backward sweep: small CTAs, the permuted vector in shared memory when at least two CTAs fit an SM
+  cfg->threads_bwd = 128;
+  cfg->bwd_x_in_smem = static_cast<size_t>(S.n) * sizeof(double) * 2 <= static_cast<size_t>(smem_max) ? 1 : 0;
+  cfg->smem_bwd = cfg->bwd_x_in_smem ? static_cast<size_t>(S.n) * sizeof(double) : 0;
   e = cudaFuncSetAttribute(lu_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(cfg->smem_factor));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(lu_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(cfg->smem_solve));
   if (e != cudaSuccess) return e;
-  int occ_f = 1, occ_s = 1;
+  e = cudaFuncSetAttribute(lu_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(cfg->smem_bwd));
+  if (e != cudaSuccess) return e;
+  int occ_f = 1, occ_s = 1, occ_b = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lu_factor_kernel, cfg->threads, cfg->smem_factor);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, lu_solve_kernel, cfg->threads, cfg->smem_solve);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, lu_forward_kernel, cfg->threads, cfg->smem_solve);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, lu_backward_kernel, cfg->threads_bwd, cfg->smem_bwd);
   if (occ_f < 1) occ_f = 1;
   if (occ_s < 1) occ_s = 1;
+  if (occ_b < 1) occ_b = 1;
   cfg->grid_factor = sms * occ_f;
   cfg->grid_solve = sms * occ_s;
+  cfg->grid_bwd = sms * occ_b;
   if (cfg->grid_factor > B) cfg->grid_factor = B > 0 ? B : 1;
   if (cfg->grid_solve > B) cfg->grid_solve = B > 0 ? B : 1;
+  if (cfg->grid_bwd > B) cfg->grid_bwd = B > 0 ? B : 1;
   return cudaSuccess;
 }
 
@@ -1070,11 +1194,19 @@ cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const doubl
 }
 
 cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* LU,
-                            const double* RHS, double* X, double* CVW, double* XW, int do_fwd,
+                            const double* RHS, double* X, double* CVW, double* XW, double* YW, int do_fwd,
                             int mode, const int* active, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  lu_solve_kernel<<<cfg.grid_solve, cfg.threads, cfg.smem_solve, st>>>(
-      S, LU, RHS, X, CVW, XW, cfg.x_in_smem, do_fwd, mode, active, B);
+  const double* yp = RHS;
+  if (do_fwd) {
+    lu_forward_kernel<<<cfg.grid_solve, cfg.threads, cfg.smem_solve, st>>>(
+        S, LU, RHS, YW, CVW, XW, cfg.x_in_smem, active, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    yp = YW;
+  }
+  lu_backward_kernel<<<cfg.grid_bwd, cfg.threads_bwd, cfg.smem_bwd, st>>>(
+      S, LU, yp, X, XW, cfg.bwd_x_in_smem, mode, active, B);
   return cudaGetLastError();
 }
 

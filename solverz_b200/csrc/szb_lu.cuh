@@ -30,7 +30,11 @@ struct LuLaunchCfg {
   size_t smem_factor; // dynamic shared memory of the factor kernel
   int grid_solve;
   size_t smem_solve;
-  int x_in_smem;      // solve kernel keeps the permuted vector in shared memory
+  int x_in_smem;      // forward kernel keeps the permuted vector in shared memory
+  int threads_bwd;    // backward sweep: threads per block, resident blocks, dynamic shared memory
+  int grid_bwd;
+  size_t smem_bwd;
+  int bwd_x_in_smem;
 };
 
 // Chooses block/grid/smem for this schedule on the current device; returns cudaError_t.
@@ -48,8 +52,9 @@ cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const doubl
 // mode 1:  X[b] <- X[b] - A^{-1} RHS[b]  (Newton update y -= dx; X is Y)
 // do_fwd 1: RHS is b in original order (forward + backward sweep)
 // do_fwd 0: RHS is y in pivot order from a fused factorisation (backward sweep only)
+// YW: [B][n] scratch for y in pivot order (used when do_fwd == 1)
 cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* LU,
-                            const double* RHS, double* X, double* CVW, double* XW, int do_fwd,
+                            const double* RHS, double* X, double* CVW, double* XW, double* YW, int do_fwd,
                             int mode, const int* active, int B, cudaStream_t st);
 
 }  // namespace szb

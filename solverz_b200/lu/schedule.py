@@ -7,7 +7,7 @@ plus three streamed tables instead of a chain of dependent index look-ups:
 
 ``fh``  front headers, 16 int32 each, in *schedule order* (warp lists, then group lists, then the
         CTA-level list; list ``w`` of a level is the contiguous run ``ptr[w]:ptr[w+1]``):
-        ``[s, f, piv0, lp_off, up_off, cb_off, gaJ, itJ, gaC, itC, gaR, itR, k, n_src, 0, 0]``
+        ``[s, f, piv0, lp_off, up_off, cb_off, gaJ, itJ, gaC, itC, gaR, itR, k, n_src, idx_ptr, 0]``
 
 ``ga``  gather tables, ``(src, dst)`` int32 pairs.  A front owns three blocks, each laid out
         ``[iterations][G]`` (G = threads of the group that owns the front): in iteration ``it`` thread
@@ -137,6 +137,7 @@ def build_tables(sym, threads: int, wpg: int) -> Dict[str, np.ndarray]:
             cursor += tab.shape[0] * G
         fh[q, 12] = k
         fh[q, 13] = len(dst)
+        fh[q, 14] = int(sym.idx_ptr[k])
         if cursor >= 2 ** 31:
             raise ValueError("gather table exceeds int32 offsets")
     ga = np.concatenate(blocks) if blocks else np.zeros((0, 2), dtype=np.uint32)

@@ -295,7 +295,7 @@ class LUSymbolic:
     a_src: np.ndarray         # J slot (CSC position in the original matrix)
     a_dst: np.ndarray         # r + c*f position in the column-major front
     lp_off: np.ndarray        # offset of the f x s column-major [L11\U11; L21] panel
-    up_off: np.ndarray        # offset of the u x s column-major U12^T panel
+    up_off: np.ndarray        # offset of the s x u column-major U12 panel
     lu_size: int              # doubles per scenario of factor storage (with padding)
     cb_off: np.ndarray        # offset of the u x (u+1) contribution block in the workspace
     ea_ptr: np.ndarray        # extend-add destination tables, one run of u(u+1) entries per supernode

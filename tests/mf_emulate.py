@@ -36,7 +36,7 @@ def factor(sym, jv, mvals=None, scale=1.0):
             F[p + 1:, p] *= 1.0 / piv
             F[p + 1:, p + 1:] -= np.outer(F[p + 1:, p], F[p, p + 1:])
         lu[sym.lp_off[k]:sym.lp_off[k] + f * s] = F[:, :s].reshape(-1, order="F")
-        lu[sym.up_off[k]:sym.up_off[k] + u * s] = F[:s, s:].T.reshape(-1, order="F")
+        lu[sym.up_off[k]:sym.up_off[k] + u * s] = F[:s, s:].reshape(-1, order="F")
         cb[sym.cb_off[k]:sym.cb_off[k] + u * u] = F[s:, s:].reshape(-1, order="F")
         done[k] = True
     return lu
@@ -66,9 +66,9 @@ def solve(sym, lu, b):
         u = f - s
         p0 = int(sym.sn_piv0[k])
         Lp = lu[sym.lp_off[k]:sym.lp_off[k] + f * s].reshape(f, s, order="F")
-        Ut = lu[sym.up_off[k]:sym.up_off[k] + u * s].reshape(u, s, order="F")
+        U12 = lu[sym.up_off[k]:sym.up_off[k] + u * s].reshape(s, u, order="F")
         ids = sym.idx[sym.idx_ptr[k] + s:sym.idx_ptr[k + 1]]
-        r = xb[p0:p0 + s] - Ut.T @ xb[ids]
+        r = xb[p0:p0 + s] - U12 @ xb[ids]
         for p in range(s - 1, -1, -1):
             r[p] /= Lp[p, p]
             r[:p] -= Lp[:p, p] * r[p]
@@ -190,7 +190,7 @@ def factor_tables(sym, tabs, jv, rhs=None, mvals=None, scale=1.0, store_l=True):
                 pend = min(s, (p // 4) * 4 + 4)
                 panel[pend:, p] = Lout[pend:, p] if store_l else 0.0
         lu[lp_off:lp_off + f * s] = panel.reshape(-1, order="F")
-        lu[up_off:up_off + u * s] = F[:s, s:f].T.reshape(-1, order="F")
+        lu[up_off:up_off + u * s] = F[:s, s:f].reshape(-1, order="F")
         cb[cb_off:cb_off + u * (u + 1)] = F[s:, s:f + 1].reshape(-1, order="F")
         y[p0:p0 + s] = F[:s, f]
     return lu, y

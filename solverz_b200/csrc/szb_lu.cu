@@ -95,14 +95,14 @@ struct FactorArgs {
 // one front of the schedule (lu/schedule.py: 16 int32, 12 used on the device)
 struct FrontHdr {
   int s, f, piv0, lp_off, up_off, cb_off;
-  int gaJ, itJ, gaC, itC, gaR, itR;
+  int gaO, itO, gaC, itC, gaR, itR;
 };
 
 __device__ __forceinline__ FrontHdr load_hdr(const int4* __restrict__ fh, const int q) {
   const int4 a = __ldg(fh + 4 * q), b = __ldg(fh + 4 * q + 1), c = __ldg(fh + 4 * q + 2);
   FrontHdr H;
   H.s = a.x; H.f = a.y; H.piv0 = a.z; H.lp_off = a.w;
-  H.up_off = b.x; H.cb_off = b.y; H.gaJ = b.z; H.itJ = b.w;
+  H.up_off = b.x; H.cb_off = b.y; H.gaO = b.z; H.itO = b.w;
   H.gaC = c.x; H.itC = c.y; H.gaR = c.z; H.itR = c.w;
   return H;
 }
@@ -132,64 +132,118 @@ __device__ __forceinline__ double fast_rcp(const double x) {
   return fma(r, e, r);
 }
 
-// ---- assembly: one pass over a block of the front's gather table (lu/schedule.py).  Loads are
-// issued in batches of four (table entries, then the values they address) before the dependent
-// shared-memory updates so that their latencies overlap; a destination is only ever touched by one
-// thread, so there is nothing to synchronise.
-template <class Fetch>
-__device__ __forceinline__ void gather_block(const int2* __restrict__ e, const int iters, const int G_,
-                                             double* __restrict__ Fm, const Fetch fetch) {
-  int it = 0;
-  for (; it + 4 <= iters; it += 4, e += 4 * G_) {
-    int2 en[4];
-    double v[4];
+// ---- assembly: one pass over the front's stream of gather entries (lu/schedule.py).  A batch of
+// kAsm entries per thread is in flight: entries first, then the values they address, then the
+// shared-memory updates; a destination is only ever touched by one thread, so there is nothing to
+// synchronise.  The first batch of a front is fetched while the previous front is still being
+// eliminated (AsmPre), which takes the table round trip off the critical path.
+constexpr int kAsm = 8;
+
+constexpr int kAsmO = 2;   // leading entries per thread whose values (original data) are prefetched too
+
+struct AsmPre {
+  int2 en[kAsm];
+  double ov[kAsmO];
+  int n_ov;        // how many of ov[] are valid (0 unless the plain A = J path prefetched them)
+};
+
+// number of entries per thread: the right-hand-side block is skipped when no rhs rides along
+__device__ __forceinline__ int asm_iters(const FrontHdr& H, const bool with_rhs) {
+  return H.itO + H.itC + (with_rhs ? H.itR : 0);
+}
+
+__device__ __forceinline__ void asm_prefetch(AsmPre& P, const FrontHdr& H, const int2* __restrict__ ga,
+                                             const int rank, const int G_, const bool with_rhs) {
+  const int iters = asm_iters(H, with_rhs);
+  const int2* __restrict__ e = ga + H.gaO + rank;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) en[q] = __ldg(e + q * G_);
+  for (int q = 0; q < kAsm; ++q) P.en[q] = q < iters ? __ldg(e + q * G_) : make_int2(-1, 0);
+  P.n_ov = 0;
+}
+
+// second half of the prefetch, issued once the entries have landed (after the elimination of the
+// previous front): the values of the leading original-data entries (Jacobian slots and right-hand
+// side rows come from HBM; nothing in them depends on the children)
+__device__ __forceinline__ void asm_prefetch_values(AsmPre& P, const FrontHdr& H, const FactorArgs& A) {
+#ifndef SZB_VALUE_PREFETCH   // measured slower: the dependent value loads stall the warp before the write-out
+  return;
+#endif
+  if (A.mvals != nullptr || A.smask != nullptr || A.scale != 1.0) return;
+  const int n = min(H.itO, kAsmO);
+  const bool with_rhs = A.rhs != nullptr;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = en[q].x != -1 ? fetch(en[q].x) : 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (en[q].x != -1) Fm[en[q].y] += v[q];
+  for (int q = 0; q < kAsmO; ++q) {
+    double v = 0.0;
+    if (q < n) {
+      const unsigned sr = static_cast<unsigned>(P.en[q].x);
+      const unsigned tag = sr >> 30;
+      const int off = static_cast<int>(sr & 0x3fffffffu);
+      if (tag == 1u) v = A.jv[off];
+      else if (tag == 2u && with_rhs) v = A.rhs[off];
+    }
+    P.ov[q] = v;
   }
-  if (it < iters) {
-    int2 en[3];
-    double v[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) en[q] = (it + q < iters) ? __ldg(e + q * G_) : make_int2(-1, 0);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) v[q] = en[q].x != -1 ? fetch(en[q].x) : 0.0;
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-      if (en[q].x != -1) Fm[en[q].y] += v[q];
+  P.n_ov = n;
+}
+
+template <bool PLAIN>
+__device__ __forceinline__ double asm_fetch(const unsigned sr, const FactorArgs& A) {
+  const unsigned tag = sr >> 30;
+  const int off = static_cast<int>(sr & 0x3fffffffu);
+  if (PLAIN) {   // A = J: the value fetch is a pointer select
+    const double* base = tag == 0u ? A.cb : (tag == 1u ? A.jv : A.rhs);
+    return base[off];
+  } else {
+    if (tag == 1u) {
+      const double mv = A.mvals ? A.mvals[off] : 0.0;
+      const double mk = A.smask ? A.smask[off] : 1.0;
+      return fma(A.scale * mk, A.jv[off], mv);
+    }
+    const double* base = tag == 0u ? A.cb : A.rhs;
+    return base[off];
   }
 }
 
-__device__ __forceinline__ void assemble_front(const int rank, const int G_, const FrontHdr& H,
+template <bool PLAIN>
+__device__ __forceinline__ void assemble_stream(const AsmPre& P, const int rank, const int G_, const FrontHdr& H,
+                                                const int2* __restrict__ ga, double* __restrict__ Fm,
+                                                const FactorArgs& A) {
+  const bool with_rhs = A.rhs != nullptr;
+  const int iters = asm_iters(H, with_rhs);
+  const int2* __restrict__ e = ga + H.gaO + rank;
+  // an entry is dead when it is padding, or a right-hand-side row while no right-hand side rides along
+  auto live = [=](const int2 en) {
+    return en.x != -1 && (with_rhs || (static_cast<unsigned>(en.x) >> 30) != 2u);
+  };
+  {
+    double v[kAsm];
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q) {
+      if (q < kAsmO && q < P.n_ov) v[q] = P.ov[q];
+      else v[q] = live(P.en[q]) ? asm_fetch<PLAIN>(static_cast<unsigned>(P.en[q].x), A) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q)
+      if (live(P.en[q])) Fm[P.en[q].y] += v[q];
+  }
+  for (int it = kAsm; it < iters; it += kAsm) {
+    int2 en[kAsm];
+    double v[kAsm];
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q) en[q] = it + q < iters ? __ldg(e + (it + q) * G_) : make_int2(-1, 0);
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q) v[q] = live(en[q]) ? asm_fetch<PLAIN>(static_cast<unsigned>(en[q].x), A) : 0.0;
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q)
+      if (live(en[q])) Fm[en[q].y] += v[q];
+  }
+}
+
+__device__ __forceinline__ void assemble_front(const AsmPre& P, const int rank, const int G_, const FrontHdr& H,
                                                const int2* __restrict__ ga, double* __restrict__ Fm,
                                                const FactorArgs& A) {
-  const double* __restrict__ jv = A.jv;
-  if (A.mvals == nullptr && A.smask == nullptr) {
-    const double sc = A.scale;
-    gather_block(ga + H.gaJ + rank, H.itJ, G_, Fm, [=](const int o) { return sc * jv[o]; });
-  } else {
-    const double sc = A.scale;
-    const double* __restrict__ mvals = A.mvals;
-    const double* __restrict__ smask = A.smask;
-    gather_block(ga + H.gaJ + rank, H.itJ, G_, Fm, [=](const int o) {
-      const double mv = mvals ? mvals[o] : 0.0;
-      const double mk = smask ? smask[o] : 1.0;
-      return fma(sc * mk, jv[o], mv);
-    });
-  }
-  const double* cb = A.cb;
-  gather_block(ga + H.gaC + rank, H.itC, G_, Fm, [=](const int o) { return cb[o]; });
-  if (A.rhs != nullptr) {
-    const double* rhs = A.rhs;
-    gather_block(ga + H.gaR + rank, H.itR, G_, Fm, [=](const int o) {
-      const double* base = (o & 0x40000000) ? cb : rhs;
-      return base[o & 0x3fffffff];
-    });
-  }
+  if (A.mvals == nullptr && A.smask == nullptr && A.scale == 1.0) assemble_stream<true>(P, rank, G_, H, ga, Fm, A);
+  else assemble_stream<false>(P, rank, G_, H, ga, Fm, A);
 }
 
 // ---- single warp, fronts with at most 32 rows: right-looking rank-1 steps, lane = row.  When the
@@ -197,29 +251,50 @@ __device__ __forceinline__ void assemble_front(const int rank, const int G_, con
 // all lanes stay busy on the tiny fronts that make up most of the tree.
 __device__ __forceinline__ void eliminate_warp(double* __restrict__ Fm, const int s, const int f,
                                                const int ncol, const int ld, const int lane, int* flag) {
+  // The reciprocal of the NEXT pivot is computed by every lane from three broadcast values while the
+  // trailing update of the current pivot runs, so the dependent chain per pivot is one shuffle, one
+  // multiply-add and the update loop -- not load -> reciprocal -> scale -> update.
+  double piv = Fm[0];
+  double inv = fast_rcp(piv);
   for (int p = 0; p < s; ++p) {
     const int m = f - p - 1;
     const int nc = ncol - p - 1;
     double* __restrict__ colp = Fm + (p + 1) + p * ld;
-    const double piv = colp[-1];
-    const double inv = fast_rcp(piv);
     if (lane == 0) check_pivot(piv, flag);
-    const int sh = m <= 8 ? 3 : (m <= 16 ? 4 : 5);     // rows per column slot = 1 << sh
+    const bool more = p + 1 < s;                        // then m >= 1
+    const double a_next = more ? colp[ld] : 1.0;        // F[p+1][p+1] before this step's update
+    const double c_next = more ? colp[ld - 1] : 0.0;    // F[p][p+1]
+    const int sh = m <= 8 ? 3 : (m <= 16 ? 4 : 5);      // rows per column slot = 1 << sh
     const int i = lane & ((1 << sh) - 1);
     const int cj = lane >> sh;                          // column slot of this lane
     const int cpw = 32 >> sh;                           // columns per warp instruction
     const bool row_ok = i < m;
-    double l = 0.0;
-    if (row_ok) l = colp[i] * inv;
-    __syncwarp();
-    if (cj == 0 && row_ok) colp[i] = l;                 // L stored scaled
+    const double l = row_ok ? colp[i] * inv : 0.0;
+    const double l_next = __shfl_sync(0xffffffffu, l, 0);   // l of row p+1 (lane 0: i = 0, slot 0)
+    if (cj == 0 && row_ok) colp[i] = l;                 // L stored scaled (only its own lane reads colp[i])
+    piv = fma(-l_next, c_next, a_next);                 // exactly what the update below stores at (p+1, p+1)
+    const double inv_next = fast_rcp(piv);
     double* __restrict__ col = Fm + (p + 1) + (p + 1 + cj) * ld;
     const int step = cpw * ld;
-    for (int j = cj; j < nc; j += cpw, col += step) {
-      const double u = col[-1];
-      if (row_ok) col[i] = fma(-l, u, col[i]);
+    for (int j = cj; j < nc; j += 4 * cpw, col += 4 * step) {
+      const bool k1 = j + cpw < nc, k2 = j + 2 * cpw < nc, k3 = j + 3 * cpw < nc;
+      const double u0 = col[-1];
+      const double u1 = k1 ? col[step - 1] : 0.0;
+      const double u2 = k2 ? col[2 * step - 1] : 0.0;
+      const double u3 = k3 ? col[3 * step - 1] : 0.0;
+      if (row_ok) {
+        const double v0 = col[i];
+        const double v1 = k1 ? col[step + i] : 0.0;
+        const double v2 = k2 ? col[2 * step + i] : 0.0;
+        const double v3 = k3 ? col[3 * step + i] : 0.0;
+        col[i] = fma(-l, u0, v0);
+        if (k1) col[step + i] = fma(-l, u1, v1);
+        if (k2) col[2 * step + i] = fma(-l, u2, v2);
+        if (k3) col[3 * step + i] = fma(-l, u3, v3);
+      }
     }
     __syncwarp();
+    inv = inv_next;
   }
 }
 
@@ -603,8 +678,8 @@ __device__ __forceinline__ void clear_front(double* __restrict__ Fm, const int n
 // ld = f | 1 and has f + 1 columns (the last one carries the right-hand side when one rides along).
 // ---------------------------------------------------------------------------------------
 // one warp, front of at most 32 rows
-__device__ void factor_front_warp(const FrontHdr H, const int2* __restrict__ ga, double* __restrict__ Fm,
-                                  const FactorArgs& A SZB_TPARAM) {
+__device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre& P, const int2* __restrict__ ga,
+                                  double* __restrict__ Fm, const FactorArgs& A SZB_TPARAM) {
   SZB_TSTART
   const int s = H.s, f = H.f, u = f - s, ld = f | 1;
   const int lane = threadIdx.x & 31;
@@ -612,10 +687,12 @@ __device__ void factor_front_warp(const FrontHdr H, const int2* __restrict__ ga,
   const int ncol = f + with_rhs;
   clear_front(Fm, ld * (f + 1), lane, kWarp);
   __syncwarp();
-  assemble_front(lane, kWarp, H, ga, Fm, A);
+  assemble_front(P, lane, kWarp, H, ga, Fm, A);
+  asm_prefetch(P, Hnext, ga, lane, kWarp, with_rhs != 0);   // in flight during the elimination
   __syncwarp();
   SZB_T(0)
   eliminate_warp(Fm, s, f, ncol, ld, lane, A.flag);
+  asm_prefetch_values(P, Hnext, A);                       // entries have landed; values fly during the write-out
   SZB_T(1)
   double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
   {
@@ -650,9 +727,9 @@ __device__ void factor_front_warp(const FrontHdr H, const int2* __restrict__ ga,
 }
 
 // a group of warps
-__device__ void factor_front_group(const PanelGrp g, const FrontHdr H, const int2* __restrict__ ga,
-                                   double* __restrict__ Fm, double* __restrict__ lt, const int lts,
-                                   double* __restrict__ rdbuf, const FactorArgs& A SZB_TPARAM) {
+__device__ void factor_front_group(const PanelGrp g, const FrontHdr H, const FrontHdr Hnext, AsmPre& P,
+                                   const int2* __restrict__ ga, double* __restrict__ Fm, double* __restrict__ lt,
+                                   const int lts, double* __restrict__ rdbuf, const FactorArgs& A SZB_TPARAM) {
   SZB_TSTART
   const int s = H.s, f = H.f, u = f - s, ld = f | 1;
   const int lane = g.lane(), w = g.warp(), nw = g.nw, r = g.rank(), G_ = g.size();
@@ -660,11 +737,13 @@ __device__ void factor_front_group(const PanelGrp g, const FrontHdr H, const int
   const int ncol = f + with_rhs;
   clear_front(Fm, ld * (f + 1), r, G_);
   g.sync();
-  assemble_front(r, G_, H, ga, Fm, A);
+  assemble_front(P, r, G_, H, ga, Fm, A);
+  asm_prefetch(P, Hnext, ga, r, G_, with_rhs != 0);         // in flight during the elimination
   g.sync();
   SZB_T(0)
   double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
   eliminate_blocked(g, Fm, lt, lts, rdbuf, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
+  asm_prefetch_values(P, Hnext, A);                       // entries have landed; values fly during the write-out
   SZB_T(1)
   // rows below a column's own panel were streamed by the workers (or are not wanted)
   for (int p = w; p < s; p += nw) {
@@ -750,9 +829,11 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
     if (wq0 < wq1) {
       double* Fm = sm + warp * wstride;
       FrontHdr H = load_hdr(S.fh, wq0);
+      AsmPre P;
+      asm_prefetch(P, H, S.ga, threadIdx.x & 31, kWarp, A.rhs != nullptr);
       for (int q = wq0; q < wq1; ++q) {
-        const FrontHdr Hn = load_hdr(S.fh, min(q + 1, wq1 - 1));   // prefetch the next descriptor
-        factor_front_warp(H, S.ga, Fm, A SZB_TARG(0));
+        const FrontHdr Hn = load_hdr(S.fh, min(q + 1, wq1 - 1));   // the next descriptor
+        factor_front_warp(H, Hn, P, S.ga, Fm, A SZB_TARG(0));
         H = Hn;
       }
     }
@@ -767,9 +848,11 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
         g.nw = wpg;
         g.w0 = gi * wpg;
         FrontHdr H = load_hdr(S.fh, gq0);
+        AsmPre P;
+        asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
         for (int q = gq0; q < gq1; ++q) {
           const FrontHdr Hn = load_hdr(S.fh, min(q + 1, gq1 - 1));
-          factor_front_group(g, H, S.ga, Fm, Fm + gfront, glts, Fm + gfront + kNB * glts, A SZB_TARG(1));
+          factor_front_group(g, H, Hn, P, S.ga, Fm, Fm + gfront, glts, Fm + gfront + kNB * glts, A SZB_TARG(1));
           H = Hn;
         }
       }
@@ -783,9 +866,11 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
       g.nw = blockDim.x >> 5;
       g.w0 = 0;
       FrontHdr H = load_hdr(S.fh, tq0);
+      AsmPre P;
+      asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
       for (int q = 0; q < S.n_top; ++q) {
         const FrontHdr Hn = load_hdr(S.fh, tq0 + min(q + 1, S.n_top - 1));
-        factor_front_group(g, H, S.ga, sm, sm + tfront, tlts, sm + tfront + kNB * tlts, A SZB_TARG(2));
+        factor_front_group(g, H, Hn, P, S.ga, sm, sm + tfront, tlts, sm + tfront + kNB * tlts, A SZB_TARG(2));
         H = Hn;
       }
     }

@@ -7,15 +7,20 @@ plus three streamed tables instead of a chain of dependent index look-ups:
 
 ``fh``  front headers, 16 int32 each, in *schedule order* (warp lists, then group lists, then the
         CTA-level list; list ``w`` of a level is the contiguous run ``ptr[w]:ptr[w+1]``):
-        ``[s, f, piv0, lp_off, up_off, cb_off, gaJ, itJ, gaC, itC, gaR, itR, k, n_src, idx_ptr, 0]``
+        ``[s, f, piv0, lp_off, up_off, cb_off, gaO, itO, gaC, itC, gaR, itR, k, n_src, idx_ptr, 0]``
 
 ``ga``  gather tables, ``(src, dst)`` int32 pairs.  A front owns three blocks, each laid out
         ``[iterations][G]`` (G = threads of the group that owns the front): in iteration ``it`` thread
         ``r`` adds the value addressed by ``src`` to front position ``dst`` (``src == -1``: no-op).
-          J block  ``src`` = Jacobian slot (scaled / masked / mass-shifted on the fly),
-          C block  ``src`` = offset in the contribution workspace (Schur parts of the children),
-          R block  right-hand-side column: ``src`` = original row of the right-hand side, or, with bit
-                   30 set, an offset in the contribution workspace (children's right-hand-side column).
+          O block  original data: Jacobian slots (scaled / masked / mass-shifted on the fly) and the
+                   rows of the right-hand side (ignored when no right-hand side rides along); none of
+                   it depends on the children, so its values are prefetched a front ahead,
+          C block  offsets in the contribution workspace (Schur parts of the children),
+          R block  the children's right-hand-side columns in the contribution workspace; skipped
+                   when no right-hand side rides along.
+        The three blocks of a front are contiguous, so a thread walks ONE stream of entries; bits 30-31
+        of ``src`` name the address space (0 contribution workspace, 1 Jacobian values, 2 right-hand
+        side), which makes the value fetch a pointer select instead of a branch.
         Every destination is owned by exactly one thread across the three blocks, and a thread meets
         its sources in a fixed order (matrix entry, children in schedule order), so the assembly
         needs no barrier between children, no atomics, and is bitwise reproducible.
@@ -29,10 +34,11 @@ from typing import Dict
 
 import numpy as np
 
-__all__ = ["plan_threads", "build_tables", "NOOP", "CB_BIT"]
+__all__ = ["plan_threads", "build_tables", "NOOP", "TAG_CB", "TAG_J", "TAG_RHS", "OFF_MASK"]
 
 NOOP = 0xFFFFFFFF
-CB_BIT = 1 << 30
+TAG_CB, TAG_J, TAG_RHS = 0, 1, 2
+OFF_MASK = (1 << 30) - 1
 HDR_WORDS = 16
 
 
@@ -58,17 +64,17 @@ def plan_threads(sym) -> Dict[str, int]:
 
 
 def _front_sources(sym, k: int):
-    """Sources of front k in assembly order: (dst, src, kind) with kind 0 = J, 1 = C, 2 = R."""
+    """Sources of front k in assembly order: (dst, src, kind) with kind 0 = O, 1 = C, 2 = R."""
     s, f = int(sym.sn_s[k]), int(sym.sn_f[k])
     ld = f | 1
     a0, a1 = int(sym.a_ptr[k]), int(sym.a_ptr[k + 1])
     dst = [np.asarray(sym.a_dst[a0:a1], dtype=np.int64)]
-    src = [np.asarray(sym.a_src[a0:a1], dtype=np.int64)]
+    src = [np.asarray(sym.a_src[a0:a1], dtype=np.int64) | (TAG_J << 30)]
     kind = [np.zeros(a1 - a0, dtype=np.int64)]
     p0 = int(sym.sn_piv0[k])
     dst.append(np.arange(s, dtype=np.int64) + f * ld)
-    src.append(np.asarray(sym.rowp[p0:p0 + s], dtype=np.int64))
-    kind.append(np.full(s, 2, dtype=np.int64))
+    src.append(np.asarray(sym.rowp[p0:p0 + s], dtype=np.int64) | (TAG_RHS << 30))
+    kind.append(np.zeros(s, dtype=np.int64))
     for c in sym.child[sym.child_ptr[k]:sym.child_ptr[k + 1]]:
         c = int(c)
         uc = int(sym.sn_f[c] - sym.sn_s[c])
@@ -76,12 +82,12 @@ def _front_sources(sym, k: int):
             continue
         e0 = int(sym.ea_ptr[c])
         cnt = uc * (uc + 1)
-        if int(sym.cb_off[c]) + cnt >= CB_BIT:
+        if int(sym.cb_off[c]) + cnt > OFF_MASK:
             raise ValueError("contribution workspace exceeds 2^30 doubles per resident scenario")
         dst.append(np.asarray(sym.ea_dst[e0:e0 + cnt], dtype=np.int64))
         off = int(sym.cb_off[c]) + np.arange(cnt, dtype=np.int64)
         is_rhs = np.arange(cnt) >= uc * uc
-        src.append(np.where(is_rhs, off | CB_BIT, off))
+        src.append(off | (TAG_CB << 30))
         kind.append(np.where(is_rhs, 2, 1).astype(np.int64))
     return np.concatenate(dst), np.concatenate(src), np.concatenate(kind)
 

@@ -140,7 +140,7 @@ def eliminate_blocked(F, s, f, ncol, NB=4):
 
 def factor_tables(sym, tabs, jv, rhs=None, mvals=None, scale=1.0, store_l=True):
     """Walks the schedule of ``build_tables``; returns (lu, y) with y = L^{-1} P rhs in pivot order."""
-    from solverz_b200.lu.schedule import NOOP, CB_BIT
+    from solverz_b200.lu.schedule import NOOP, OFF_MASK, TAG_CB, TAG_J, TAG_RHS
     lu = np.zeros(sym.lu_size)
     cb = np.full(max(sym.cb_size, 1), np.nan)
     y = np.zeros(sym.n)
@@ -163,17 +163,20 @@ def factor_tables(sym, tabs, jv, rhs=None, mvals=None, scale=1.0, store_l=True):
                 live = src != NOOP
                 for r in np.flatnonzero(live):
                     assert owner.setdefault(int(dst[r]), int(r)) == int(r), "two threads share a destination"
-                off = src.astype(np.int64)
+                tag = src >> 30
+                off = (src & OFF_MASK).astype(np.int64)
                 v = np.zeros(G)
-                if b == 0:
-                    v[live] = scale * jv[off[live]] + (mvals[off[live]] if mvals is not None else 0.0)
-                elif b == 1:
-                    v[live] = cb[off[live]]
+                m = live & (tag == TAG_CB)
+                v[m] = cb[off[m]]
+                m = live & (tag == TAG_J)
+                assert b == 0 or not m.any()
+                v[m] = scale * jv[off[m]] + (mvals[off[m]] if mvals is not None else 0.0)
+                m = live & (tag == TAG_RHS)
+                assert b == 0 or not m.any()
+                if with_rhs:
+                    v[m] = rhs[off[m]]
                 else:
-                    iscb = live & ((src & CB_BIT) != 0)
-                    v[iscb] = cb[off[iscb] & (CB_BIT - 1)]
-                    isr = live & ~iscb
-                    v[isr] = rhs[off[isr]]
+                    live = live & ~m
                 Fm[dst[live]] += v[live]
         F = Fm.reshape(ld, ncol, order="F")[:f, :].copy()
         assert np.all(np.isfinite(F)), "front read an unwritten contribution"

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../solverz_b200/csrc"
 mkdir -p ../../build/timing
 F="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -I../../include -I."
-nvcc $F -DSZB_PHASE_TIMING -c szb_lu.cu -o ../../build/timing/szb_lu.o
+nvcc $F $SZB_EXTRA -DSZB_PHASE_TIMING -c szb_lu.cu -o ../../build/timing/szb_lu.o
 cp libszb.so ../../build/timing/libszb.keep.so
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o libszb.so szb_core.o ../../build/timing/szb_lu.o szb_rodas.o -lcudart -ldl
 cd ../..

@@ -162,7 +162,7 @@ int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b,
     mv = h->mass_vals;
     scale = -h_gamma;
   }
-  cudaError_t e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, mv, slot_mask, scale_b, scale, rhs,
+  cudaError_t e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, h->FBW, mv, slot_mask, scale_b, scale, rhs,
                                         yout, store_l, active, h->flags, h->B, st);
   if (e != cudaSuccess) { szb_set_error(h, "LU factor launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
   h->launches[2]++;
@@ -227,6 +227,8 @@ int szb_create(const szb_desc* d, szb_handle** out) {
   S.f_warp_max = L.f_warp_max; S.f_group_max = L.f_group_max; S.f_top_max = L.f_top_max;
   S.s_warp_max = L.s_warp_max; S.s_group_max = L.s_group_max; S.s_top_max = L.s_top_max;
   S.threads = L.threads; S.wpg = L.wpg;
+  S.f_max = L.f_warp_max > L.f_group_max ? L.f_warp_max : L.f_group_max;
+  if (L.f_top_max > S.f_max) S.f_max = L.f_top_max;
   S.n_warp_sn = L.wl_ptr[L.n_warp_lists];
   S.n_group_sn = L.n_group_lists > 0 ? L.gl_ptr[L.n_group_lists] : 0;
   if (L.n_sched != S.n_warp_sn + S.n_group_sn + L.n_top || L.n_ga <= 0 || !L.fh || !L.ga) {
@@ -337,6 +339,7 @@ int szb_set_batch(szb_handle* h, int32_t B) {
     int gmax = h->cfg.grid_factor > h->cfg.grid_solve ? h->cfg.grid_factor : h->cfg.grid_solve;
     if (h->cfg.grid_bwd > gmax) gmax = h->cfg.grid_bwd;
     ALLOC(h->CBW, double, static_cast<size_t>(gmax) * (h->S.cb_size > 0 ? h->S.cb_size : 1));
+    ALLOC(h->FBW, double, h->cfg.top_in_global ? static_cast<size_t>(h->cfg.grid_factor) * h->cfg.big_elems : 1);
     ALLOC(h->CVW, double, static_cast<size_t>(gmax) * (h->S.cv_size > 0 ? h->S.cv_size : 1));
     ALLOC(h->XW, double, (h->cfg.x_in_smem && h->cfg.bwd_x_in_smem) ? 1 : static_cast<size_t>(gmax) * n);
   }

@@ -50,35 +50,6 @@ __device__ __forceinline__ int fdiv(int t, float invm) {
   return __float2int_rz((static_cast<float>(t) + 0.5f) * invm);
 }
 
-// ---- thread groups ------------------------------------------------------------------------
-struct WarpGrp {
-  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
-  __device__ __forceinline__ int warp() const { return 0; }
-  __device__ __forceinline__ int nwarps() const { return 1; }
-  __device__ __forceinline__ int rank() const { return threadIdx.x & 31; }
-  __device__ __forceinline__ int size() const { return kWarp; }
-  __device__ __forceinline__ void sync() const { __syncwarp(); }
-};
-struct NamedGrp {  // `nw` consecutive warps, hardware named barrier `id` (1..15)
-  int id, nw, w0;
-  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
-  __device__ __forceinline__ int warp() const { return (threadIdx.x >> 5) - w0; }
-  __device__ __forceinline__ int nwarps() const { return nw; }
-  __device__ __forceinline__ int rank() const { return threadIdx.x - (w0 << 5); }
-  __device__ __forceinline__ int size() const { return nw << 5; }
-  __device__ __forceinline__ void sync() const {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nw << 5) : "memory");
-  }
-};
-struct BlockGrp {
-  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
-  __device__ __forceinline__ int warp() const { return threadIdx.x >> 5; }
-  __device__ __forceinline__ int nwarps() const { return blockDim.x >> 5; }
-  __device__ __forceinline__ int rank() const { return threadIdx.x; }
-  __device__ __forceinline__ int size() const { return blockDim.x; }
-  __device__ __forceinline__ void sync() const { __syncthreads(); }
-};
-
 struct FactorArgs {
   const double* __restrict__ jv;     // matrix values of this scenario (CSC slots)
   const double* __restrict__ mvals;  // optional mass values (shared)
@@ -634,9 +605,9 @@ __device__ __forceinline__ void eliminate_blocked(const PanelGrp g, double* __re
         // least kMinCols columns each: a tile's set-up (multipliers, addresses) costs as much as a few
         // columns of updates
         const int nt = (nch + 3) >> 2;                 // tile rows of four chunks (1 unless f > 128)
-        const int CW = max(1, min(nt == 1 ? W : W >> 1, (ncol - r0) / kMinCols));
+        const int CW = max(1, min(nt == 1 ? W : W / nt, (ncol - r0) / kMinCols));   // no division on the common path
         for (int tile = ww; tile < nt * CW; tile += W) {
-          const int tr = tile >= CW ? 1 : 0;           // nt <= 2
+          const int tr = nt == 1 ? 0 : tile / CW;
           const int cg = tile - tr * CW;
           const int rem = nch - 4 * tr;                // chunks in this tile row
           if (rem >= 3) trailing_tile<4>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, tr << 7, cg, CW, lane);
@@ -779,7 +750,7 @@ __device__ void factor_front_group(const PanelGrp g, const FrontHdr H, const Fro
 
 __global__ void __launch_bounds__(SZB_FACTOR_THREADS, 1)
 lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restrict__ LU,
-                 double* CBW, const double* __restrict__ mvals,
+                 double* CBW, double* FBW, const double* __restrict__ mvals,
                  const double* __restrict__ slot_mask,
                  const double* __restrict__ scale_b, double scale_const,
                  const double* __restrict__ RHS, double* __restrict__ YOUT, int store_l,
@@ -865,13 +836,26 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
       g.id = 0;
       g.nw = blockDim.x >> 5;
       g.w0 = 0;
+      // fronts too large for shared memory live in a per-CTA global workspace (L2): same code, the
+      // barriers order global memory within the CTA as well; only the side panels stay on chip
+      // (two call sites on purpose: with a run-time select the compiler would have to treat the
+      // shared-memory front as a generic pointer and lose the LDS/STS forms)
       FrontHdr H = load_hdr(S.fh, tq0);
       AsmPre P;
       asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
-      for (int q = 0; q < S.n_top; ++q) {
-        const FrontHdr Hn = load_hdr(S.fh, tq0 + min(q + 1, S.n_top - 1));
-        factor_front_group(g, H, Hn, P, S.ga, sm, sm + tfront, tlts, sm + tfront + kNB * tlts, A SZB_TARG(2));
-        H = Hn;
+      if (FBW == nullptr) {
+        for (int q = 0; q < S.n_top; ++q) {
+          const FrontHdr Hn = load_hdr(S.fh, tq0 + min(q + 1, S.n_top - 1));
+          factor_front_group(g, H, Hn, P, S.ga, sm, sm + tfront, tlts, sm + tfront + kNB * tlts, A SZB_TARG(2));
+          H = Hn;
+        }
+      } else {
+        double* Ft = FBW + static_cast<size_t>(blockIdx.x) * tfront;
+        for (int q = 0; q < S.n_top; ++q) {
+          const FrontHdr Hn = load_hdr(S.fh, tq0 + min(q + 1, S.n_top - 1));
+          factor_front_group(g, H, Hn, P, S.ga, Ft, sm, tlts, sm + kNB * tlts, A SZB_TARG(2));
+          H = Hn;
+        }
       }
     }
     __syncthreads();   // the next scenario reuses the fronts and the contribution workspace
@@ -898,109 +882,84 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
 // ---------------------------------------------------------------------------------------
 // triangular solves
 // ---------------------------------------------------------------------------------------
-// forward: r = [b_piv ; 0] + sum_children cv_c ;  L11 x = r_piv ; cv_k = r_upd - L21 x
-// rv: f doubles of scratch, T: s*s doubles of scratch (diagonal block staged once)
-template <class G>
-__device__ void forward_supernode(const G g, const LuDev& S, const int k,
-                                  const double* __restrict__ lu, double* __restrict__ xb,
-                                  double* __restrict__ cv, double* __restrict__ rv,
-                                  double* __restrict__ T) {
-  const int s = S.sn_s[k], f = S.sn_f[k], u = f - s, p0 = S.sn_piv0[k];
-  const int lane = g.lane(), w = g.warp(), nw = g.nwarps(), r = g.rank(), G_ = g.size();
-  const double* __restrict__ Lp = lu + S.lp_off[k];
-  for (int t = r; t < f; t += G_) rv[t] = (t < s) ? xb[p0 + t] : 0.0;
-  for (int p = w; p < s; p += nw)
-    for (int i = lane; i < s; i += kWarp) T[i + p * s] = Lp[i + p * f];
-  g.sync();
+struct SolveHdr {
+  int s, f, piv0, lp_off, up_off, idx_off, k;
+};
+
+__device__ __forceinline__ SolveHdr load_solve_hdr(const int4* __restrict__ fh, const int q) {
+  const int4 a = __ldg(fh + 4 * q), b = __ldg(fh + 4 * q + 1), d = __ldg(fh + 4 * q + 3);
+  SolveHdr H;
+  H.s = a.x; H.f = a.y; H.piv0 = a.z; H.lp_off = a.w; H.up_off = b.x; H.k = d.x; H.idx_off = d.z;
+  return H;
+}
+
+// ---- forward sweep  y = L^{-1} P b  (Rodas' stage solves and szb_lu_solve come through here; Newton
+// gets y from the fused factorisation).  One warp per front, lane = row:
+//   r = [b_piv ; 0] + sum_children cv_c ;  for every pivot p: r_i -= L_ip r_p (i > p, both the L11 and
+//   the L21 rows in one sweep down the panel column) ;  y_piv = r_piv ; cv_k = r_upd.
+// rv: f doubles of per-warp scratch.  Contribution vectors travel through the per-CTA workspace cv.
+__device__ void forward_front(const LuDev& S, const SolveHdr H, const double* __restrict__ lu,
+                              double* xb, double* cv, double* rv, const int lane) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0, k = H.k;
+  const double* __restrict__ Lp = lu + H.lp_off;
+  for (int t = lane; t < f; t += kWarp) rv[t] = t < s ? xb[p0 + t] : 0.0;
+  __syncwarp();
   for (int ci = S.child_ptr[k]; ci < S.child_ptr[k + 1]; ++ci) {
     const int c = S.child[ci];
     const int c0 = S.rel_ptr[c], uc = S.rel_ptr[c + 1] - c0;
-    if (uc == 0) continue;
-    for (int t = r; t < uc; t += G_) rv[S.rel[c0 + t]] += cv[c0 + t];
-    g.sync();
+    for (int t = lane; t < uc; t += kWarp) rv[S.rel[c0 + t]] += cv[c0 + t];
+    __syncwarp();
   }
-  for (int p = 0; p + 1 < s; ++p) {
+  for (int p = 0; p < s; ++p) {
     const double xp = rv[p];
-    for (int i = p + 1 + r; i < s; i += G_) rv[i] = fma(-T[i + p * s], xp, rv[i]);
-    g.sync();
+    const double* __restrict__ col = Lp + p * f;
+    int i = p + 1 + lane;
+    for (; i + kWarp < f; i += 2 * kWarp) {             // two chunks in flight
+      const double l0 = col[i], l1 = col[i + kWarp];
+      rv[i] = fma(-l0, xp, rv[i]);
+      rv[i + kWarp] = fma(-l1, xp, rv[i + kWarp]);
+    }
+    if (i < f) rv[i] = fma(-col[i], xp, rv[i]);
+    __syncwarp();
   }
-  for (int t = r; t < s; t += G_) xb[p0 + t] = rv[t];
+  for (int t = lane; t < s; t += kWarp) xb[p0 + t] = rv[t];
   if (u > 0) {
     const int c0 = S.rel_ptr[k];
-    for (int i = r; i < u; i += G_) {
-      double acc = rv[s + i];
-      const double* __restrict__ row = Lp + s + i;
-      for (int p = 0; p < s; ++p) acc = fma(-row[p * f], rv[p], acc);
-      cv[c0 + i] = acc;
-    }
+    for (int i = lane; i < u; i += kWarp) cv[c0 + i] = rv[s + i];
   }
-  g.sync();
+  __syncwarp();
 }
 
-struct SolveSmem {
-  int wstride, gstride;
-  int w_rv, w_T, g_rv, g_T, t_rv, t_T;
-};
-
-__device__ __forceinline__ SolveSmem solve_layout(const LuDev& S) {
-  SolveSmem L;
-  L.w_rv = 2 * S.f_warp_max;
-  L.w_T = S.s_warp_max * S.s_warp_max;
-  L.wstride = L.w_rv + L.w_T;
-  L.g_rv = 2 * S.f_group_max;
-  L.g_T = S.s_group_max * S.s_group_max;
-  L.gstride = L.g_rv + L.g_T;
-  L.t_rv = 2 * S.f_top_max;
-  L.t_T = S.s_top_max * S.s_top_max;
-  return L;
-}
-
-// forward sweep  y = L^{-1} P b : RHS in original order -> YP in pivot order (what the fused
-// factorisation produces for Newton; Rodas' stage solves come through here)
-__global__ void __launch_bounds__(SZB_FACTOR_THREADS, 1)
+__global__ void __launch_bounds__(128, 6)
 lu_forward_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ RHS,
-                  double* __restrict__ YP, double* __restrict__ CVW, double* __restrict__ XW,
+                  double* __restrict__ YP, double* CVW, double* __restrict__ XW,
                   int x_in_smem, const int* __restrict__ active, int B) {
   extern __shared__ double sm[];
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int n = S.n;
-  double* xb = x_in_smem ? sm : XW + static_cast<size_t>(blockIdx.x) * n;
-  double* scratch = x_in_smem ? sm + n : sm;
-  const SolveSmem L = solve_layout(S);
-  const int wpg = max(S.wpg, 1);
+  double* rv = sm + warp * S.f_max;
+  double* xb = x_in_smem ? sm + nwarps * S.f_max : XW + static_cast<size_t>(blockIdx.x) * n;
   double* cv = CVW + static_cast<size_t>(blockIdx.x) * S.cv_size;
+  const int gq_base = S.n_warp_sn, tq0 = S.n_warp_sn + S.n_group_sn;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     if (active && !active[b]) continue;
-    const double* lu = LU + static_cast<size_t>(b) * S.lu_size;
-    const double* rhs = RHS + static_cast<size_t>(b) * n;
+    const double* __restrict__ lu = LU + static_cast<size_t>(b) * S.lu_size;
+    const double* __restrict__ rhs = RHS + static_cast<size_t>(b) * n;
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = rhs[S.rowp[t]];
     __syncthreads();
-    if (warp < S.n_warp_lists) {
-      double* rv = scratch + warp * L.wstride;
-      const WarpGrp g;
-      for (int q = S.wl_ptr[warp]; q < S.wl_ptr[warp + 1]; ++q)
-        forward_supernode(g, S, S.wl[q], lu, xb, cv, rv, rv + L.w_rv);
-    }
+    for (int l = warp; l < S.n_warp_lists; l += nwarps)
+      for (int q = S.wl_ptr[l]; q < S.wl_ptr[l + 1]; ++q)
+        forward_front(S, load_solve_hdr(S.fh, q), lu, xb, cv, rv, lane);
     __syncthreads();
-    if (S.n_group_lists > 0) {
-      const int gi = warp / wpg;
-      if (gi < S.n_group_lists) {
-        double* rv = scratch + gi * L.gstride;
-        NamedGrp g;
-        g.id = 1 + gi; g.nw = wpg; g.w0 = gi * wpg;
-        for (int q = S.gl_ptr[gi]; q < S.gl_ptr[gi + 1]; ++q)
-          forward_supernode(g, S, S.gl[q], lu, xb, cv, rv, rv + L.g_rv);
-      }
-      __syncthreads();
-    }
-    {
-      const BlockGrp g;
-      for (int q = 0; q < S.n_top; ++q)
-        forward_supernode(g, S, S.top[q], lu, xb, cv, scratch, scratch + L.t_rv);
-    }
+    for (int g = warp; g < S.n_group_lists; g += nwarps)
+      for (int q = gq_base + S.gl_ptr[g]; q < gq_base + S.gl_ptr[g + 1]; ++q)
+        forward_front(S, load_solve_hdr(S.fh, q), lu, xb, cv, rv, lane);
     __syncthreads();
-    double* yp = YP + static_cast<size_t>(b) * n;
+    if (warp == 0)
+      for (int q = 0; q < S.n_top; ++q) forward_front(S, load_solve_hdr(S.fh, tq0 + q), lu, xb, cv, rv, lane);
+    __syncthreads();
+    double* __restrict__ yp = YP + static_cast<size_t>(b) * n;
     for (int t = threadIdx.x; t < n; t += blockDim.x) yp[t] = xb[t];
   }
 }
@@ -1011,17 +970,6 @@ lu_forward_kernel(const LuDev S, const double* __restrict__ LU, const double* __
 // front, and the 32 x 32 triangle is finished with shuffles.  Everything read from the factors is
 // independent of x, so the loads of one front overlap the dependent chain; many small CTAs per SM
 // (several scenarios in flight) hide the rest of the latency.
-struct SolveHdr {
-  int s, f, piv0, lp_off, up_off, idx_off;
-};
-
-__device__ __forceinline__ SolveHdr load_solve_hdr(const int4* __restrict__ fh, const int q) {
-  const int4 a = __ldg(fh + 4 * q), b = __ldg(fh + 4 * q + 1), d = __ldg(fh + 4 * q + 3);
-  SolveHdr H;
-  H.s = a.x; H.f = a.y; H.piv0 = a.z; H.lp_off = a.w; H.up_off = b.x; H.idx_off = d.z;
-  return H;
-}
-
 constexpr int kTri = 4;   // pivots of the triangle whose columns are fetched together
 
 // pull the factor data of a front that comes up two fronts from now into L1: nothing the backward
@@ -1220,23 +1168,32 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   cfg->threads = S.threads;
   if (S.f_warp_max > 32) return cudaErrorInvalidConfiguration;   // lane = row
   if (S.n_group_lists > 7) return cudaErrorInvalidConfiguration;   // named barriers 1..7 (+8 for the phase barrier)
-  if (S.f_group_max > 256 || S.f_top_max > 256) return cudaErrorInvalidConfiguration;  // <= 2 tile rows of 128
   if (S.threads > SZB_FACTOR_THREADS) return cudaErrorInvalidConfiguration;
   size_t fsm = static_cast<size_t>(S.n_warp_lists) * front_elems(S.f_warp_max);
   fsm = smax(fsm, static_cast<size_t>(S.n_group_lists) * group_elems(S.f_group_max));
-  fsm = smax(fsm, S.n_top > 0 ? static_cast<size_t>(group_elems(S.f_top_max)) : 0);
+  if (fsm * sizeof(double) > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
+  cfg->top_in_global = 0;
+  cfg->big_elems = 0;
+  if (S.n_top > 0) {
+    const size_t top_sm = static_cast<size_t>(group_elems(S.f_top_max));
+    if (top_sm * sizeof(double) <= static_cast<size_t>(smem_max)) {
+      fsm = smax(fsm, top_sm);
+    } else {   // CTA-level fronts in a global workspace, side panels in shared memory
+      cfg->top_in_global = 1;
+      cfg->big_elems = static_cast<size_t>(front_elems(S.f_top_max));
+      fsm = smax(fsm, static_cast<size_t>(kNB * lt_stride(S.f_top_max) + kDiagBuf));
+    }
+  }
   cfg->smem_factor = fsm * sizeof(double);
   if (cfg->smem_factor > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
-  size_t ssm = S.n_warp_lists * (2 * static_cast<size_t>(S.f_warp_max) + static_cast<size_t>(S.s_warp_max) * S.s_warp_max);
-  ssm = smax(ssm, S.n_group_lists * (2 * static_cast<size_t>(S.f_group_max) + static_cast<size_t>(S.s_group_max) * S.s_group_max));
-  ssm = smax(ssm, 2 * static_cast<size_t>(S.f_top_max) + static_cast<size_t>(S.s_top_max) * S.s_top_max);
-  const size_t with_x = (ssm + S.n) * sizeof(double);
-  if (with_x <= static_cast<size_t>(smem_max)) {
-    cfg->x_in_smem = 1;
-    cfg->smem_solve = with_x;
-  } else {
-    cfg->x_in_smem = 0;
-    cfg->smem_solve = ssm * sizeof(double);
+  // forward sweep: small CTAs, one scratch row vector per warp; the permuted vector in shared memory when
+  // at least two CTAs fit an SM
+  cfg->threads = S.threads;
+  cfg->threads_fwd = 128;
+  {
+    const size_t rvs = static_cast<size_t>(cfg->threads_fwd / 32) * S.f_max;
+    cfg->x_in_smem = (rvs + S.n) * sizeof(double) * 2 <= static_cast<size_t>(smem_max) ? 1 : 0;
+    cfg->smem_solve = (rvs + (cfg->x_in_smem ? S.n : 0)) * sizeof(double);
     if (cfg->smem_solve > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
   }
   // backward sweep: small CTAs, the permuted vector in shared memory when at least two CTAs fit an SM
@@ -1254,7 +1211,7 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   if (e != cudaSuccess) return e;
   int occ_f = 1, occ_s = 1, occ_b = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lu_factor_kernel, cfg->threads, cfg->smem_factor);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, lu_forward_kernel, cfg->threads, cfg->smem_solve);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, lu_forward_kernel, cfg->threads_fwd, cfg->smem_solve);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, lu_backward_kernel, cfg->threads_bwd, cfg->smem_bwd);
   if (occ_f < 1) occ_f = 1;
   if (occ_s < 1) occ_s = 1;
@@ -1269,12 +1226,13 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
 }
 
 cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV, double* LU,
-                             double* CBW, const double* mvals, const double* slot_mask,
+                             double* CBW, double* FBW, const double* mvals, const double* slot_mask,
                              const double* scale_b, double scale_const, const double* RHS, double* YOUT,
                              int store_l, const int* active, int* flags, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   lu_factor_kernel<<<cfg.grid_factor, cfg.threads, cfg.smem_factor, st>>>(
-      S, JV, LU, CBW, mvals, slot_mask, scale_b, scale_const, RHS, YOUT, store_l, active, flags, B);
+      S, JV, LU, CBW, cfg.top_in_global ? FBW : nullptr, mvals, slot_mask, scale_b, scale_const, RHS, YOUT, store_l,
+      active, flags, B);
   return cudaGetLastError();
 }
 
@@ -1284,7 +1242,7 @@ cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double
   if (B <= 0) return cudaSuccess;
   const double* yp = RHS;
   if (do_fwd) {
-    lu_forward_kernel<<<cfg.grid_solve, cfg.threads, cfg.smem_solve, st>>>(
+    lu_forward_kernel<<<cfg.grid_solve, cfg.threads_fwd, cfg.smem_solve, st>>>(
         S, LU, RHS, YW, CVW, XW, cfg.x_in_smem, active, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

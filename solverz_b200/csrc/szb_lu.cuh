@@ -13,6 +13,7 @@ struct LuDev {
   int n_warp_sn, n_group_sn;     // fronts in the warp lists / group lists (schedule order: warp, group, top)
   int threads, wpg;              // threads per CTA, warps per group (fixed by the host schedule)
   int f_warp_max, f_group_max, f_top_max, s_warp_max, s_group_max, s_top_max;
+  int f_max;                     // largest front order
   const int *rowp, *colp;
   const int *sn_piv0, *sn_s, *sn_f;
   const int *idx_ptr, *idx, *rel_ptr, *rel, *child_ptr, *child;
@@ -30,6 +31,9 @@ struct LuLaunchCfg {
   size_t smem_factor; // dynamic shared memory of the factor kernel
   int grid_solve;
   size_t smem_solve;
+  int top_in_global;  // CTA-level fronts do not fit shared memory: they live in a per-CTA global workspace
+  size_t big_elems;   // doubles of that workspace per resident block
+  int threads_fwd;    // forward sweep: threads per block
   int x_in_smem;      // forward kernel keeps the permuted vector in shared memory
   int threads_bwd;    // backward sweep: threads per block, resident blocks, dynamic shared memory
   int grid_bwd;
@@ -44,7 +48,7 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg);
 // RHS / YOUT non-null: the right-hand side rides along (forward substitution fused), YOUT gets
 // y = L^{-1} P b in pivot order.  store_l == 0 skips writing the L21 rows (Newton never reuses L).
 cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV,
-                             double* LU, double* CBW, const double* mvals, const double* slot_mask,
+                             double* LU, double* CBW, double* FBW, const double* mvals, const double* slot_mask,
                              const double* scale_b, double scale_const, const double* RHS, double* YOUT, int store_l,
                              const int* active, int* flags, int B, cudaStream_t st);
 

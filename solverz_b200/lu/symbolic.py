@@ -33,16 +33,86 @@ __all__ = ["LUSymbolic", "analyze"]
 # --------------------------------------------------------------------------------------
 # 1. static pivoting
 # --------------------------------------------------------------------------------------
-def static_row_matching(A: sp.csc_matrix) -> np.ndarray:
+def _heavy_matching(A: sp.csc_matrix) -> np.ndarray:
+    """Greedy heaviest-edge matching on |a_ij| / max_i |a_ij|, completed by augmenting paths that try
+    heavy edges first.  Not guaranteed optimal for the product objective, but on diagonally strong
+    matrices (power-flow, network, DAE Jacobians) it reproduces the optimum, and it costs O(nnz log nnz)
+    where SciPy's assignment solver needs minutes for n ~ 10^4."""
+    n = A.shape[0]
+    W = sp.coo_matrix(A)
+    absd = np.abs(W.data)
+    colmax = np.zeros(n)
+    np.maximum.at(colmax, W.col, absd)
+    colmax[colmax == 0.0] = 1.0
+    ratio = absd / colmax[W.col]
+    order = np.argsort(-ratio, kind="stable")
+    row_of = np.full(n, -1, dtype=np.int64)      # column -> matched row
+    col_of = np.full(n, -1, dtype=np.int64)      # row -> matched column
+    for i, j, r in zip(W.row[order].tolist(), W.col[order].tolist(), ratio[order].tolist()):
+        if r <= 0.0:
+            break
+        if row_of[j] < 0 and col_of[i] < 0:
+            row_of[j] = i
+            col_of[i] = j
+    free = np.flatnonzero(row_of < 0)
+    if len(free):
+        Ac = sp.csc_matrix((ratio, (W.row, W.col)), shape=(n, n))
+        indptr, indices, data = Ac.indptr, Ac.indices, Ac.data
+
+        def nbrs(j):
+            ks = range(indptr[j], indptr[j + 1])
+            return iter(sorted(ks, key=lambda k: -data[k]))
+
+        for j0 in free.tolist():
+            visited = set()
+            reached_from: Dict[int, int] = {}
+            stack = [(j0, nbrs(j0))]
+            found = -1
+            while stack and found < 0:
+                j, it = stack[-1]
+                advanced = False
+                for k in it:
+                    i = int(indices[k])
+                    if i in visited:
+                        continue
+                    visited.add(i)
+                    reached_from[i] = j
+                    if col_of[i] < 0:
+                        found = i
+                    else:
+                        j2 = int(col_of[i])
+                        stack.append((j2, nbrs(j2)))
+                    advanced = True
+                    break
+                if not advanced:
+                    stack.pop()
+            if found < 0:
+                raise ValueError("Jacobian pattern is structurally singular: no full matching")
+            i = found
+            while True:
+                j = reached_from[i]
+                prev = int(row_of[j])
+                row_of[j] = i
+                col_of[i] = j
+                if j == j0:
+                    break
+                i = prev
+    return row_of
+
+
+def static_row_matching(A: sp.csc_matrix, exact_below: int = 1500) -> np.ndarray:
     """Return ``rowperm`` with ``rowperm[c]`` = the original row matched to column ``c``.
 
     Maximises prod |a_{rowperm[c], c}| (MC64 job-5 style objective), so the permuted
     matrix has a zero-free, large diagonal.  Structural zeros that are stored explicitly
-    get a huge cost and are only used when the pattern leaves no alternative.
+    get a huge cost and are only used when the pattern leaves no alternative.  Above
+    ``exact_below`` unknowns the exact assignment solver is replaced by ``_heavy_matching``.
     """
+    n = A.shape[0]
+    if n >= exact_below:
+        return _heavy_matching(A)
     from scipy.sparse.csgraph import min_weight_full_bipartite_matching
 
-    n = A.shape[0]
     W = sp.coo_matrix(A)
     absd = np.abs(W.data)
     colmax = np.zeros(n)

@@ -102,3 +102,41 @@ def test_newton_parity(libszb, tmp_path_factory, nx, B):
         assert int(sol.stats.nfeval[b]) == ref["nfeval"]
         # residual of the GPU solution judged by the oracle's F
         assert np.abs(orc.F(sol.y[b], P[b], Q[b])).max() <= 1e-8
+
+
+def test_large_fronts_in_global_memory(libszb, tmp_path_factory):
+    """40x40 lattice (n = 3200): the separator fronts (order ~200) exceed shared memory, so the CTA-level
+    fronts run out of the per-CTA global workspace; factor + forward + backward against SuperLU, and the
+    Newton iteration against the oracle."""
+    import torch
+    from oracle.nr import nr_method as oracle_nr
+    from solverz_b200 import Opt, module_printer, nr_method
+    from solverz_b200.synthetic import pf_scenarios, polar_pf_model
+    d = tmp_path_factory.mktemp("mods40")
+    eqs, y0, info = polar_pf_model(40, 40)
+    module_printer(eqs, y0, "pfn40", directory=str(d)).render()
+    sys.path.insert(0, str(d))
+    mdl = importlib.import_module("pfn40").mdl
+    orc = _oracle(info)
+    B = 6
+    s = mdl.session(B)
+    assert s.sym.f_top_max > 167, "this test is meant to exercise fronts larger than shared memory"
+    rng = np.random.default_rng(3)
+    Y = y0.array[None, :] + 0.05 * rng.standard_normal((B, mdl.n))
+    s.set_y(Y)
+    s.eval_J()
+    rhs = rng.standard_normal((B, mdl.n))
+    s.RHS.copy_(torch.as_tensor(rhs))
+    s.lu_refactor(0.0)
+    X = s.lu_solve(1).cpu().numpy()
+    for b in range(B):
+        xr = sla.spsolve(orc.J(Y[b]), rhs[b])
+        assert np.abs(X[b] - xr).max() <= 1e-10 * np.abs(xr).max()
+    P, Q = pf_scenarios(info, B)
+    mdl.p["Pinj"], mdl.p["Qinj"] = P, Q
+    sol = nr_method(mdl, np.tile(y0.array, (B, 1)), Opt(ite_tol=1e-8))
+    assert sol.stats.succeed.all()
+    for b in range(B):
+        ref = oracle_nr(lambda y: orc.F(y, P[b], Q[b]), orc.J, y0.array, 1e-8, 100)
+        assert np.abs(sol.y[b] - ref["y"]).max() <= 1e-10 * np.abs(ref["y"]).max()
+        assert int(sol.stats.nstep[b]) == ref["nstep"]

@@ -46,6 +46,17 @@ def _peaks():
     return 6650.0, "fallback"
 
 
+def _ncu_traffic(cls: str, nx: int, B: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same workload (profiles/ncu_traffic.json); None when there is none."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text())
+    e = d.get(f"{cls}@nx{nx}B{B}")
+    return float(e["dram_bytes_per_launch"]) if e else None
+
+
 # ------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -354,9 +365,9 @@ def main():
     if dom:
         units_per_launch = prof[dom]["units"] / max(1, prof[dom]["launches"])
         roofline = {"bound": "hbm", "kernel": {"F": "szbm_F_kernel", "J": "szbm_J_kernel",
-                                               "lu_refactor": "lu_factor_kernel", "lu_solve": "lu_solve_kernel"}[dom],
+                                               "lu_refactor": "lu_factor_kernel", "lu_solve": "lu_backward_kernel"}[dom],
                     "achieved": classes[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": classes[dom]["frac"], "traffic": None, "peak_source": peak_kind,
+                    "frac": classes[dom]["frac"], "traffic": _ncu_traffic(dom, nx, B), "peak_source": peak_kind,
                     "alg_bytes_per_launch": alg[dom] * units_per_launch, "classes": classes}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

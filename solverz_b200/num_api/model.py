@@ -307,9 +307,12 @@ class CudaModel:
                     with open(self._pkl_path, "rb") as f:
                         d = pickle.load(f)
                     d["symbolic"] = self._sym
-                    with open(self._pkl_path, "wb") as f:
+                    # atomic replace: other ranks of a multi-GPU job import the same rendered package
+                    tmp = f"{self._pkl_path}.{os.getpid()}.tmp"
+                    with open(tmp, "wb") as f:
                         pickle.dump(d, f)
-                except OSError:
+                    os.replace(tmp, self._pkl_path)
+                except (OSError, pickle.UnpicklingError, EOFError):
                     pass
         return self._sym
 

@@ -137,7 +137,8 @@ def static_row_matching(A: sp.csc_matrix, exact_below: int = 1500) -> np.ndarray
 # --------------------------------------------------------------------------------------
 def _sym_pattern(B: sp.spmatrix) -> sp.csr_matrix:
     n = B.shape[0]
-    P = sp.csr_matrix((np.ones(B.nnz), B.nonzero()), shape=(n, n))
+    coo = sp.coo_matrix(B)            # stored entries, INCLUDING explicit zeros: they are structural
+    P = sp.csr_matrix((np.ones(coo.nnz), (coo.row, coo.col)), shape=(n, n))
     S = (P + P.T).tocsr()
     S.setdiag(0)
     S.eliminate_zeros()

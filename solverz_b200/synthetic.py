@@ -15,7 +15,7 @@ import scipy.sparse as sps
 from .equations import Eqn, LoopEqn, Model
 from .sym import Param, Set, Sum, Var, cos, sin
 
-__all__ = ["lattice_grid", "polar_pf_model", "pf_scenarios"]
+__all__ = ["lattice_grid", "polar_pf_model", "pf_scenarios", "swing_dae_model", "swing_fault_scenarios"]
 
 
 def lattice_grid(nx: int, ny: int, chord_frac: float = 0.02, seed: int = 0):
@@ -101,3 +101,100 @@ def pf_scenarios(info: Dict, B: int, first: int = 0, sigma: float = 0.2) -> Tupl
         P[b] = info["Pbase"] * (1.0 + sigma * rng.standard_normal(nb))
         Q[b] = info["Qbase"] * (1.0 + sigma * rng.standard_normal(nb))
     return P, Q
+
+
+# ------------------------------------------------------------------------------------------------
+# config #4: stiff DAE ensemble -- one machine (swing + flux decay + exciter) per bus of a lattice grid,
+# rectangular-coordinate stator and network current balance, bus-fault scenarios
+# ------------------------------------------------------------------------------------------------
+def swing_dae_model(nx: int, ny: int, ns=None, seed: int = 0, chord_frac: float = 0.02):
+    """Builds the model with the DSL in namespace ``ns`` (this package by default; the golden generator
+    passes the reference's ``Solverz`` module -- the two front-ends take the same statements, which is
+    the point of a drop-in).  Per machine i (at bus i):
+
+        delta' = wb (omega - 1)                        omega' = (Pm - (Ux Ix + Uy Iy) - D (omega - 1)) / Tj
+        Eq'    = (Efd - Eq - (xd - xdp) Id) / Td0      Efd'   = (Ka (Vref - |U|) - Efd) / Ta
+        0 = xdp Ix - Eq sin(delta) + Uy                0 = xdp Iy + Eq cos(delta) - Ux
+        0 = G Ux - B Uy + Fx - Ix                      0 = G Uy + B Ux + Fy - Iy
+        0 = Fx - gf(t) fmask Ux                        0 = Fy - gf(t) fmask Uy
+
+    with Id = Ix sin(delta) - Iy cos(delta), constant-admittance loads folded into Y, and the bus fault a
+    shunt conductance gf(t) (a TimeSeriesParam) at the buses selected by the 0/1 vector ``fmask``.  The fault
+    current (Fx, Fy) is a variable of its own: the reference's Jacobian drops d/dUx of ``gf*fmask*Ux`` when that
+    product shares an equation with ``Mat_Mul`` terms (found while generating the goldens), and a model the
+    reference differentiates correctly is what a parity fixture needs.
+    Returns (model, info); the model starts in equilibrium (gf = 0)."""
+    if ns is None:
+        import solverz_b200 as ns
+    own = ns.__name__ == "solverz_b200"
+    nb, Y = lattice_grid(nx, ny, chord_frac, seed)
+    rng = np.random.default_rng(seed + 7)
+    yload = rng.uniform(0.3, 0.8, nb) - 1j * rng.uniform(0.05, 0.2, nb)      # constant-admittance loads
+    Yt = (Y + sps.diags(yload)).tocsc()
+    G = sps.csc_array(Yt.real)
+    Bm = sps.csc_array(Yt.imag)
+    # equilibrium: pick the bus voltages, everything else follows
+    th = 0.05 * rng.standard_normal(nb)
+    U = (1.0 + 0.02 * rng.standard_normal(nb)) * np.exp(1j * th)
+    I = Yt @ U
+    xd, xdp = rng.uniform(0.8, 1.2, nb), rng.uniform(0.2, 0.4, nb)
+    E = U + 1j * xdp * I
+    Eq0, d0 = np.abs(E), np.angle(E)
+    Id0 = I.real * np.sin(d0) - I.imag * np.cos(d0)
+    Efd0 = Eq0 + (xd - xdp) * Id0
+    Pm = (U * np.conj(I)).real
+    Ka, Ta = rng.uniform(20.0, 50.0, nb), rng.uniform(0.05, 0.2, nb)
+    Vref = np.abs(U) + Efd0 / Ka
+    Tj, D, Td0 = rng.uniform(4.0, 10.0, nb), rng.uniform(1.0, 3.0, nb), rng.uniform(4.0, 8.0, nb)
+    wb = 2 * np.pi * 50.0
+    kw = dict(per_scenario=True) if own else {}
+    m = ns.Model()
+    m.delta = ns.Var('delta', d0)
+    m.omega = ns.Var('omega', np.ones(nb))
+    m.Eq = ns.Var('Eq', Eq0)
+    m.Efd = ns.Var('Efd', Efd0)
+    m.Ux = ns.Var('Ux', U.real)
+    m.Uy = ns.Var('Uy', U.imag)
+    m.Ix = ns.Var('Ix', I.real)
+    m.Iy = ns.Var('Iy', I.imag)
+    m.Fx = ns.Var('Fx', np.zeros(nb))
+    m.Fy = ns.Var('Fy', np.zeros(nb))
+    m.G = ns.Param('G', G, dim=2, sparse=True)
+    m.B = ns.Param('B', Bm, dim=2, sparse=True)
+    for nm, v in (("Pm", Pm), ("Dm", D), ("Tj", Tj), ("Td0", Td0), ("xd", xd), ("xdp", xdp), ("Ka", Ka),
+                  ("Ta", Ta), ("Vref", Vref)):
+        setattr(m, nm, ns.Param(nm, v))
+    m.fmask = ns.Param('fmask', np.zeros(nb), **kw)
+    m.gf = ns.TimeSeriesParam('gf', v_series=[0.0, 0.0, 5.0, 5.0, 0.0, 0.0],
+                              time_series=[0.0, 0.1, 0.101, 0.2, 0.201, 10.0], **kw)
+    sin, cos, Mat_Mul = ns.sin, ns.cos, ns.Mat_Mul
+    m.f_delta = ns.Ode('f_delta', wb * (m.omega - 1), diff_var=m.delta)
+    m.f_omega = ns.Ode('f_omega', (m.Pm - (m.Ux * m.Ix + m.Uy * m.Iy) - m.Dm * (m.omega - 1)) / m.Tj,
+                       diff_var=m.omega)
+    m.f_Eq = ns.Ode('f_Eq', (m.Efd - m.Eq - (m.xd - m.xdp) * (m.Ix * sin(m.delta) - m.Iy * cos(m.delta))) / m.Td0,
+                    diff_var=m.Eq)
+    m.f_Efd = ns.Ode('f_Efd', (m.Ka * (m.Vref - (m.Ux ** 2 + m.Uy ** 2) ** 0.5) - m.Efd) / m.Ta, diff_var=m.Efd)
+    m.g_sx = ns.Eqn('g_sx', m.xdp * m.Ix - m.Eq * sin(m.delta) + m.Uy)
+    m.g_sy = ns.Eqn('g_sy', m.xdp * m.Iy + m.Eq * cos(m.delta) - m.Ux)
+    m.g_nx = ns.Eqn('g_nx', Mat_Mul(m.G, m.Ux) - Mat_Mul(m.B, m.Uy) + m.Fx - m.Ix)
+    m.g_ny = ns.Eqn('g_ny', Mat_Mul(m.G, m.Uy) + Mat_Mul(m.B, m.Ux) + m.Fy - m.Iy)
+    m.g_fx = ns.Eqn('g_fx', m.Fx - m.gf * m.fmask * m.Ux)
+    m.g_fy = ns.Eqn('g_fy', m.Fy - m.gf * m.fmask * m.Uy)
+    info = dict(nb=nb, n=10 * nb, Ybus=Yt)
+    return m, info
+
+
+def swing_fault_scenarios(nb: int, B: int):
+    """Scenario b: fault at bus ``b mod nb`` from t_f = 0.1 + 0.01 (b mod 5) for 0.08 + 0.01 (b mod 3) s with
+    conductance 3 + (b mod 4).  Returns (fmask[B, nb], ts_t[B, 6], ts_v[B, 6])."""
+    fmask = np.zeros((B, nb))
+    tst = np.zeros((B, 6))
+    tsv = np.zeros((B, 6))
+    for b in range(B):
+        fmask[b, b % nb] = 1.0
+        t0 = 0.1 + 0.01 * (b % 5)
+        t1 = t0 + 0.08 + 0.01 * (b % 3)
+        g = 3.0 + (b % 4)
+        tst[b] = [0.0, t0, t0 + 1e-3, t1, t1 + 1e-3, 10.0]
+        tsv[b] = [0.0, 0.0, g, g, 0.0, 0.0]
+    return fmask, tst, tsv

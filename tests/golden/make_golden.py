@@ -161,8 +161,49 @@ def golden_known_answers():
     np.savez(HERE / "known_answers.npz", **out)
 
 
+def golden_swing(nx=3, B=6):
+    """Config #4 in miniature: the swing / flux-decay / exciter DAE ensemble of
+    ``solverz_b200.synthetic.swing_dae_model`` written with the REFERENCE's DSL (same builder, other
+    namespace), rendered by the reference's module_printer and integrated by the reference's Rodas, one
+    scenario at a time (bus fault = per-scenario ``fmask`` + ``gf`` time series, the way a Solverz user
+    mutates ``mdl.p`` between runs).  Module path => the reference's dF/dt is identically zero
+    (SURVEY.md 8a row R2), which is what ``Opt.dfdt = 'module'`` reproduces."""
+    import Solverz as ns
+    from solverz_b200.synthetic import swing_dae_model, swing_fault_scenarios
+    m, info = swing_dae_model(nx, nx, ns=ns)
+    dae, y0 = m.create_instance()
+    d = tempfile.mkdtemp()
+    ns.module_printer(dae, y0, "swing_ref", directory=d, jit=False).render()
+    sys.path.insert(0, d)
+    mod = importlib.import_module("swing_ref")
+    mdl, y = mod.mdl, mod.y
+    fmask, tst, tsv = swing_fault_scenarios(info["nb"], B)
+    tsp = np.linspace(0, 0.3, 13)
+    Y = np.zeros((B, len(tsp), len(y.array)))
+    stats = np.zeros((B, 6), dtype=np.int64)
+    F0 = mdl.F(0.0, y, mdl.p).copy()
+    J0 = mdl.J(0.0, y, mdl.p)
+    for b in range(B):
+        mdl.p["fmask"] = fmask[b]
+        mdl.p["gf"] = ns.TimeSeriesParam('gf', v_series=tsv[b], time_series=tst[b])
+        sol = ns.Rodas(mdl, tsp, y, ns.Opt(rtol=1e-4, atol=1e-7, hinit=1e-4))
+        Y[b] = sol.Y.array
+        st = sol.stats
+        stats[b] = [st.nstep, st.nfeval, st.nJeval, st.ndecomp, st.nreject, st.nsolve]
+        print("swing scenario", b, "stats", stats[b])
+    np.savez_compressed(HERE / "swing_ref_3x3.npz", tspan=tsp, Y=Y, stats=stats, y0=y.array, F0=F0,
+                        J0_data=J0.data, J0_indices=J0.indices, J0_indptr=J0.indptr,
+                        var_order=np.array(list(y.a.v.keys()) if hasattr(y.a, "v") else []))
+
+
 if __name__ == "__main__":
-    golden_dae_test()
-    golden_pf(8)
-    golden_known_answers()
+    which = sys.argv[1:] or ["dae", "pf", "known", "swing"]
+    if "dae" in which:
+        golden_dae_test()
+    if "pf" in which:
+        golden_pf(8)
+    if "known" in which:
+        golden_known_answers()
+    if "swing" in which:
+        golden_swing()
     print("golden fixtures written to", HERE)

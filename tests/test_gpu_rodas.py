@@ -98,3 +98,36 @@ def test_rodas_batched_vs_oracle(libszb):
             # CUDA's and numpy's sin() are amplified to ~1e-7 there; the module path has no such term
             tol = 1e-8 if mode == "module" else 5e-5   # still below rtol = 1e-4
             assert np.max(np.abs(sol.Y[b] - ref["Y"])) < tol, (mode, b)
+
+
+def test_rodas_swing_ensemble_vs_reference_golden(libszb):
+    """Config #4 in miniature: 9-machine swing / flux-decay / exciter DAE (n = 90, Mat_Mul network, per-scenario
+    bus fault through ``fmask`` + a TimeSeriesParam) integrated as ONE batch; every scenario against the
+    trajectory the reference's own rendered module + Rodas produced (tests/golden/swing_ref_3x3.npz).  The
+    reference takes 1000-2000 steps per scenario here (its module path has dF/dt = 0): accepted / rejected step
+    counts, F and J evaluation counts must be identical, the trajectories must agree far below rtol."""
+    from pathlib import Path
+    from solverz_b200 import Opt, Rodas, made_numerical
+    from solverz_b200.synthetic import swing_dae_model, swing_fault_scenarios
+    g = np.load(Path(__file__).parent / "golden" / "swing_ref_3x3.npz")
+    m, info = swing_dae_model(3, 3)
+    dae, y0 = m.create_instance()
+    nd = made_numerical(dae, y0, sparse=True)
+    B = g["Y"].shape[0]
+    fmask, tst, tsv = swing_fault_scenarios(info["nb"], B)
+    nd.p["fmask"] = fmask
+    nd.p["gf__ts_t"], nd.p["gf__ts_v"] = tst, tsv
+    opt = Opt(rtol=1e-4, atol=1e-7, hinit=1e-4)
+    opt.dfdt = "module"
+    sol = Rodas(nd, g["tspan"], np.tile(y0.array, (B, 1)), opt)
+    for b in range(B):
+        nstep, nfeval, nJ, ndec, nrej, nsolve = (int(v) for v in g["stats"][b])
+        assert int(sol.stats.nstep[b]) == nstep, (b, int(sol.stats.nstep[b]), nstep)
+        assert int(sol.stats.nreject[b]) == nrej, (b, int(sol.stats.nreject[b]), nrej)
+        assert int(sol.stats.nfeval[b]) == nfeval and int(sol.stats.nJeval[b]) == nJ
+        d = np.abs(sol.Y[b] - g["Y"][b]).max(axis=1)
+        # an output time that falls on a 1 ms fault ramp (knots of the time series) sits on a slope of
+        # ~3e3 / s: there the two runs may differ by rounding-level time offsets times that slope
+        on_ramp = np.array([np.min(np.abs(t - tst[b][1:5])) < 2e-3 for t in g["tspan"]])
+        assert d[~on_ramp].max() < 1e-6, (b, d)
+        assert d.max() < 1e-4 * max(1.0, np.abs(g["Y"][b]).max()), (b, d)

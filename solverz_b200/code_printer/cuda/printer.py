@@ -38,6 +38,15 @@ __all__ = ["print_model", "source_hash"]
 
 
 class _CPrinter(C99CodePrinter):
+    """C printer of one row function.  Custom functions plug in the way ``_numpycode`` does in the
+    reference (docs/src/advanced.md "Writing Custom Functions"; num_api/module_parser.py:13-39 injects
+    their numerical modules): a sympy ``Function`` subclass supplies ``_cudacode(self, printer) -> str``
+    (the C expression of a call) and, optionally, a class attribute ``_cuda_device_code`` holding the
+    ``SZB_HD static inline double name(...) {...}`` definition that expression calls; the definition is
+    emitted once into the generated translation unit."""
+
+    snippets: Dict[str, str] = {}     # filled while a model is printed (print_model resets it)
+
     def __init__(self, names: Dict[sp.Symbol, str]):
         super().__init__(dict(user_functions={
             "heaviside": "szb_heaviside", "Saturation": "szb_saturation", "In": "szb_in",
@@ -48,6 +57,14 @@ class _CPrinter(C99CodePrinter):
 
     def _print_Symbol(self, expr):
         return self.names.get(expr, expr.name)
+
+    def _print_Function(self, expr):
+        if hasattr(expr, "_cudacode"):
+            code = getattr(type(expr), "_cuda_device_code", None)
+            if code:
+                _CPrinter.snippets.setdefault(code.strip(), code.strip())   # keyed by text: classes may share a block
+            return expr._cudacode(self)
+        return super()._print_Function(expr)
 
     def _print_Pow(self, expr):
         b, e = expr.base, expr.exp
@@ -451,6 +468,7 @@ SZBM_API void szbm_host_J(int B, double t, const double* Y, const void* const* p
 def print_model(ir: ModelIR, pat: JacPattern, name: str = "model", threads: int = 256) -> str:
     """Return the CUDA source of the model library."""
     tabs = _Tables()
+    _CPrinter.snippets = {}
     f_funcs, j_funcs = [], []
     for k, (eq, jt) in enumerate(zip(ir.eqs, pat.templates)):
         f_funcs.append(_gen_F(ir, k, eq, jt, tabs))
@@ -483,6 +501,8 @@ def print_model(ir: ModelIR, pat: JacPattern, name: str = "model", threads: int 
     src += "static const szbm_param_info szbm_param_table[] = {\n" + "\n".join(ptable) + \
            ("\n" if ptable else "") + '  {0, 0, 0, 0}\n};\n\n'
     src += tabs.text() + "\n\n"
+    if _CPrinter.snippets:
+        src += "// device code of custom functions (_cuda_device_code)\n" + "\n".join(_CPrinter.snippets.values()) + "\n\n"
     src += "\n".join(f_funcs) + "\n" + "\n".join(j_funcs) + "\n"
     src += "SZB_HD static inline double szbm_row_F(const int row, const szbm_ctx& c) {\n" + "\n".join(disp_F) + "\n}\n"
     src += "SZB_HD static inline void szbm_row_J(const int row, const szbm_ctx& c, double* __restrict__ JV) {\n" + \

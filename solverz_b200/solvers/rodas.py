@@ -102,14 +102,36 @@ def dae_ic(sess, t0: float, rtol: float):
     raise ValueError("Need Better y0")
 
 
+def _rodas_events(dae: CudaModel, tspan, y0, opt: Opt):
+    """``Opt(event=...)``: the reference's event functions are Python callbacks on one trajectory
+    (rodas.py:99-107, 200-271), so this path takes one scenario and keeps the step controller on the
+    host; F, J, the factorisation and the stage solves are device calls (solvers/rodas_event.py)."""
+    from .rodas_event import DeviceOps, rodas_with_events
+    vars_in = y0 if isinstance(y0, Vars) else None
+    y_arr = np.asarray(y0.array if isinstance(y0, Vars) else y0, dtype=float)
+    if y_arr.ndim != 1:
+        raise NotImplementedError("event callbacks take one trajectory (rodas.py:200-271): pass a 1-D y0, or run "
+                                  "the batch without events")
+    s = dae.session(1)
+    s.set_params(dae.p)
+    s.set_y(y_arr)
+    dae_ic(s, float(tspan[0]), opt.rtol)
+    if opt.hmax is None:
+        opt.hmax = abs(float(tspan[-1]) - float(tspan[0]))          # rodas.py:76-77
+    y_init = s.Y[0].cpu().numpy().copy()
+    sol = rodas_with_events(DeviceOps(s), dae.M, tspan, y_init, opt, dfdt_mode=getattr(opt, "dfdt", "module") == "fd")
+    if vars_in is not None:                                         # parser.py:100-104
+        sol.Y = TimeVars(vars_in.a, sol.Y)
+        if sol.te is not None:
+            sol.ye = TimeVars(vars_in.a, sol.ye)
+    return sol
+
+
 def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
     if opt is None:
         opt = Opt()
     if not isinstance(dae, CudaModel) or dae.kind != "DAE":
         raise TypeError("Rodas of solverz_b200 needs a DAE model rendered with lang='cuda'")
-    if opt.event is not None:
-        raise NotImplementedError("events are host callbacks in the reference (rodas.py:200-271); device-side "
-                                  "event detection is not built in this round")
     import torch
     rp = Rodas_param(opt.scheme)
     tspan = np.asarray(tspan, dtype=float)
@@ -117,6 +139,8 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
     if t0 > tend:
         raise ValueError(f't0: {t0} > tend: {tend}')
     dense = len(tspan) > 2
+    if opt.event is not None:
+        return _rodas_events(dae, tspan, y0, opt)
     if dense and not rp.has_dense_output:
         raise NotImplementedError(f"dense output of {opt.scheme} (ntrp2, rodas.py:389-393) is not built")
     vars_in = y0 if isinstance(y0, Vars) else None

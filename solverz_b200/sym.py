@@ -304,7 +304,20 @@ def Mat_Mul(A: Param, x) -> sp.Symbol:
 sin, cos, exp, Abs, atan2 = sp.sin, sp.cos, sp.exp, sp.Abs, sp.atan2
 ln = sp.log
 tan, sqrt = sp.tan, sp.sqrt
-Sign = sp.sign
+
+
+class Sign(sp.Function):
+    """Reference ``Sign`` (functions.py:336-361): np.sign, treated as a constant when differentiated
+    (sympy's own ``sign`` would differentiate to a Dirac delta)."""
+    nargs = 1
+    is_real = True
+
+    def fdiff(self, argindex=1):
+        return sp.Integer(0)
+
+    def _cudacode(self, printer):
+        return f"szb_sign({printer._print(self.args[0])})"
+
 
 
 class heaviside(sp.Function):
@@ -386,6 +399,30 @@ class Min(sp.Function):
         return LessThan(x, y) + (1 - GreaterThan(x, y) - LessThan(x, y)) if argindex == 1 else GreaterThan(x, y)
 
 
+class switch(sp.Function):
+    """Reference ``switch(v_0, ..., v_{k-1}, flag)`` (functions.py:429-434, custom_function.py:71-89):
+    ``v_i`` where ``flag == i``, else 0; the derivative switches between the branch derivatives.
+    Printed through the same ``_cudacode`` hook user functions use."""
+    is_real = True
+
+    def _eval_derivative(self, s):
+        return switch(*[a.diff(s) for a in self.args[:-1]], self.args[-1])
+
+    def _cudacode(self, printer):
+        flag = printer._print(self.args[-1])
+        out = "0.0"
+        for i in reversed(range(len(self.args) - 1)):
+            out = f"(({flag}) == {i}.0 ? ({printer._print(self.args[i])}) : {out})"
+        return out
+
+
+def AntiWindUp(u, umin, umax, e):
+    """Reference ``AntiWindUp`` (functions.py:461-499): the integrator input ``e`` gated off while the
+    PI output sits on a limit and the error pushes further into it."""
+    zero = sp.Integer(0)
+    return e * Not(Or(And(GreaterThan(u, umax), GreaterThan(e, zero)), And(LessThan(u, umin), LessThan(e, zero))))
+
+
 __all__ = ["Var", "Param", "TimeSeriesParam", "AliasVar", "Set", "Idx", "Sum", "Mat_Mul", "t", "sin", "cos", "exp",
            "ln", "Abs", "atan2", "tan", "sqrt", "Sign", "heaviside", "Saturation", "In", "GreaterThan",
-           "LessThan", "And", "Or", "Not", "Min", "leaf_info", "sum_info"]
+           "LessThan", "And", "Or", "Not", "Min", "switch", "AntiWindUp", "leaf_info", "sum_info"]

@@ -83,7 +83,25 @@ class TimeVars:
     def __getitem__(self, item):
         if isinstance(item, str):
             return self.array[..., self.a[item]]
+        if self.array.ndim == 2:                       # one trajectory: variables.py:228-246
+            if isinstance(item, (int, np.integer)):
+                return Vars(self.a, self.array[item])
+            if isinstance(item, slice):
+                return TimeVars(self.a, self.array[item])
         return self.array[item]
 
     def __len__(self):
         return self.array.shape[-2]
+
+    @property
+    def len(self):
+        return self.array.shape[-2]
+
+    @property
+    def T(self):
+        return self.array.T
+
+    def append(self, other: "TimeVars"):
+        if self.a != other.a:
+            raise ValueError("Cannot concatenate two TimeVars with different variable addresses!")
+        self.array = np.concatenate([self.array, other.array], axis=-2)

@@ -196,8 +196,81 @@ def golden_swing(nx=3, B=6):
                         var_order=np.array(list(y.a.v.keys()) if hasattr(y.a, "v") else []))
 
 
+def golden_events():
+    """Config #1 (README.md:28-51, the bouncing ball with a terminal event) and the reference's event
+    tests (Solverz/solvers/test/test_rodas_event.py: ten bounces; the restricted three-body orbit with a
+    terminal and a non-terminal event, rodas4 and rodas3), run on the reference's inline path."""
+    from Solverz import Model, Ode, Opt, Rodas, Var, made_numerical
+    out = {}
+    m = Model()
+    m.h = Var('h', 0)
+    m.v = Var('v', 20)
+    m.f1 = Ode('f1', f=m.v, diff_var=m.h)
+    m.f2 = Ode('f2', f=-9.8, diff_var=m.v)
+    bball, y0 = m.create_instance()
+    nbball = made_numerical(bball, y0, sparse=True)
+
+    def ev_ball(t, y):
+        return np.array([y[0]]), np.array([1]), np.array([-1])
+
+    sol = Rodas(nbball, np.linspace(0, 30, 100), y0, Opt(event=ev_ball))
+    st = sol.stats
+    out.update(readme_T=sol.T, readme_Y=sol.Y.array, readme_te=sol.te, readme_ye=sol.ye.array, readme_ie=sol.ie,
+               readme_stats=np.array([st.nstep, st.nfeval, st.nJeval, st.ndecomp, st.nreject, st.nsolve]))
+    # ten bounces (test_rodas_event.py:7-46)
+    m = Model()
+    m.x = Var('x', [0, 20])
+    m.f1 = Ode('f1', m.x[1], m.x[0])
+    m.f2 = Ode('f2', -9.8, m.x[1])
+    bball, y0 = m.create_instance()
+    nbball = made_numerical(bball, y0, sparse=True)
+    opt = Opt(event=ev_ball)
+    te_all, tstart = [], 0
+    Tall, Yall = [np.array([0.0])], [y0.array.copy()[None, :]]
+    for _ in range(10):
+        sol = Rodas(nbball, np.linspace(tstart, 30, 100), y0, opt)
+        te_all.append(sol.te)
+        Tall.append(sol.T[1:])
+        Yall.append(sol.Y.array[1:])
+        y0['x'][0] = 0
+        y0['x'][1] = -0.9 * sol.Y[-1]['x'][1]
+        tstart = sol.T[-1]
+    out.update(bounce_te=np.concatenate(te_all), bounce_T=np.concatenate(Tall), bounce_Y=np.concatenate(Yall))
+    # orbit (test_rodas_event.py:49-89)
+    mu = 1 / 82.45
+    mustar = 1 - mu
+    m = Model()
+    m.y = Var('y', [1.2, 0, 0, -1.04935750983031990726])
+    m.f1 = Ode('f1', m.y[2], m.y[0])
+    m.f2 = Ode('f2', m.y[3], m.y[1])
+    r13 = ((m.y[0] + mu) ** 2 + m.y[1] ** 2) ** 1.5
+    r23 = ((m.y[0] - mustar) ** 2 + m.y[1] ** 2) ** 1.5
+    m.f3 = Ode('f3', 2 * m.y[3] + m.y[0] - mustar * ((m.y[0] + mu) / r13) - mu * ((m.y[0] - mustar) / r23), m.y[2])
+    m.f4 = Ode('f4', -2 * m.y[2] + m.y[1] - mustar * (m.y[1] / r13) - mu * (m.y[1] / r23), m.y[3])
+    orbit, y0 = m.create_instance()
+    norbit = made_numerical(orbit, y0, sparse=True)
+
+    def ev_orbit(t, y):
+        d = 2 * (y[0:2] - np.array([1.2, 0])).dot(y[2:4])
+        return np.array([d, d]), np.array([1, 0]), np.array([1, -1])
+
+    for sch in ("rodas4", "rodas3"):
+        sol = Rodas(norbit, [0, 7], y0, Opt(event=ev_orbit, rtol=1e-5, atol=1e-4, scheme=sch))
+        st = sol.stats
+        out[f"orbit_{sch}_te"] = sol.te
+        out[f"orbit_{sch}_ye"] = sol.ye.array
+        out[f"orbit_{sch}_ie"] = sol.ie
+        out[f"orbit_{sch}_T"] = sol.T
+        out[f"orbit_{sch}_Y"] = sol.Y.array
+        out[f"orbit_{sch}_stats"] = np.array([st.nstep, st.nfeval, st.nJeval, st.ndecomp, st.nreject, st.nsolve])
+    np.savez_compressed(HERE / "events_ref.npz", **out)
+    print("readme ball: T[-1] =", out["readme_T"][-1], "stats", out["readme_stats"])
+    print("bounce te", out["bounce_te"])
+    print("orbit te", out["orbit_rodas4_te"], out["orbit_rodas3_te"])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dae", "pf", "known", "swing"]
+    which = sys.argv[1:] or ["dae", "pf", "known", "swing", "events"]
     if "dae" in which:
         golden_dae_test()
     if "pf" in which:
@@ -206,4 +279,6 @@ if __name__ == "__main__":
         golden_known_answers()
     if "swing" in which:
         golden_swing()
+    if "events" in which:
+        golden_events()
     print("golden fixtures written to", HERE)

@@ -196,6 +196,66 @@ def test_printer_dae_time_series_and_functions(tmp_path):
             np.testing.assert_allclose(J, Jfd, atol=1e-8)
 
 
+def test_printer_control_vocabulary_and_custom_function(tmp_path):
+    """Saturation / AntiWindUp / switch / Min / atan2 / Sign (functions.py:307-606) against numpy, and a
+    user-defined function through the ``_cudacode`` + ``_cuda_device_code`` hook -- the CUDA analogue of
+    the reference's custom-function recipe (docs/src/advanced.md:1-80, num_api/test/test_udm.py): symbolic
+    derivatives from ``fdiff``, numerical code supplied by the function class."""
+    import sympy as sp
+    from solverz_b200 import AntiWindUp, Eqn, Model, Param, Saturation, Sign, Var, atan2, switch
+
+    class SoftMin(sp.Function):           # the documentation's Min example, smooth variant to exercise fdiff
+        nargs = 2
+        is_real = True
+        _cuda_device_code = """
+SZB_HD static inline double user_softmin(double x, double y) { return x <= y ? x : y; }
+SZB_HD static inline double user_dsoftmin(double x, double y, int k) { return (k == 0) == (x <= y) ? 1.0 : 0.0; }
+"""
+
+        def fdiff(self, argindex=1):
+            return DSoftMin(self.args[0], self.args[1], sp.Integer(argindex - 1))
+
+        def _cudacode(self, printer):
+            return f"user_softmin({printer._print(self.args[0])}, {printer._print(self.args[1])})"
+
+    class DSoftMin(sp.Function):
+        nargs = 3
+        is_real = True
+        _cuda_device_code = SoftMin._cuda_device_code
+
+        def fdiff(self, argindex=1):
+            return sp.Integer(0)
+
+        def _cudacode(self, printer):
+            return (f"user_dsoftmin({printer._print(self.args[0])}, {printer._print(self.args[1])}, "
+                    f"{int(self.args[2])})")
+
+    m = Model()
+    m.u = Var('u', [0.3, 1.7, -0.4])
+    m.e = Var('e', [0.5, 0.2, -0.1])
+    m.flag = Param('flag', [0.0, 1.0, 2.0])
+    m.f1 = Eqn('f1', Saturation(m.u, -0.2, 1.0) + AntiWindUp(m.u, -0.2, 1.0, m.e))
+    m.f2 = Eqn('f2', switch(m.u ** 2, 3 * m.e, m.flag) + atan2(m.u, m.e) + Sign(m.u) * SoftMin(m.u * m.u, m.e))
+    eqs, y0 = m.create_instance()
+    ir, pat, lib, src = _host_lib(eqs, "ctl", tmp_path)
+    assert src.count("double user_softmin(") == 1
+    for Y in (y0.array, np.array([1.5, -0.5, 0.1, 0.4, -0.3, 0.2]), np.array([-0.9, 0.2, 2.0, -0.6, 0.8, 0.05])):
+        F, JV = _eval(lib, ir, pat, Y, {})
+        u, e = Y[:3], Y[3:]
+        flag = np.array([0.0, 1.0, 2.0])
+        gate = ~(((u > 1.0) & (e > 0)) | ((u < -0.2) & (e < 0)))
+        f1 = np.clip(u, -0.2, 1.0) + e * gate
+        f2 = np.select([flag == 0, flag == 1], [u ** 2, 3 * e], 0) + np.arctan2(u, e) + np.sign(u) * np.minimum(u * u, e)
+        np.testing.assert_allclose(F[0], np.concatenate([f1, f2]), rtol=1e-14, atol=1e-15)
+        J = sps.csc_matrix((JV[0], pat.indices, pat.indptr), shape=(6, 6)).toarray()
+        r2 = u * u + e * e
+        d1u = ((u >= -0.2) & (u <= 1.0)).astype(float)
+        d2u = np.select([flag == 0, flag == 1], [2 * u, 0 * u], 0) + e / r2 + np.sign(u) * np.where(u * u <= e, 2 * u, 0)
+        d2e = np.select([flag == 0, flag == 1], [0 * u, 3 + 0 * u], 0) - u / r2 + np.sign(u) * np.where(u * u <= e, 0, 1.0)
+        Jref = np.block([[np.diag(d1u), np.diag(gate.astype(float))], [np.diag(d2u), np.diag(d2e)]])
+        np.testing.assert_allclose(J, Jref, rtol=1e-13, atol=1e-15)
+
+
 def test_printer_swing_dae_matches_reference_golden(tmp_path):
     """Config #4 in miniature (swing / flux decay / exciter per bus, Mat_Mul network, fault through a
     TimeSeriesParam): the generated F and J at (t = 0, y0) against the reference's rendered module."""

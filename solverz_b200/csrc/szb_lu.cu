@@ -80,13 +80,25 @@ __device__ __forceinline__ FrontHdr load_hdr(const int4* __restrict__ fh, const 
 
 // doubles of shared memory of a front of order f with its right-hand-side column (column-major,
 // odd leading dimension f|1), rounded to an even count so that buffers stay 16-byte aligned
-__host__ __device__ __forceinline__ int front_elems(const int f) { return (((f | 1) * (f + 1)) + 1) & ~1; }
-__host__ __device__ __forceinline__ int lt_stride(const int f) { return (f + 1) & ~1; }
+// Leading dimensions (lu/symbolic.py::front_ld builds the assembly tables with the same numbers):
+// warp-level fronts (lane = row, rank-1 steps) odd, so that rows AND columns are conflict-free;
+// multi-warp fronts ld = 2 (mod 4): the four column pairs of an mma.m8n8k4 accumulator fragment
+// (rows g, columns 2q and 2q+1) then fall on disjoint banks in each half-warp.  Multi-warp fronts also
+// carry 7 rows and 7 columns of zero padding, so that the 8x8 tiles of the tensor-core update never
+// need a mask: a tile that overhangs the front reads zeros and writes zeros.
+constexpr int kPad = 7;
+__host__ __device__ __forceinline__ int ld_warp(const int f) { return f | 1; }
+__host__ __device__ __forceinline__ int ld_blk(const int f) { return f + kPad + ((2 - (f + kPad)) & 3); }
+__host__ __device__ __forceinline__ int cols_blk(const int f) { return f + 1 + kPad; }
+__host__ __device__ __forceinline__ int front_elems_warp(const int f) { return ((ld_warp(f) * (f + 1)) + 1) & ~1; }
+__host__ __device__ __forceinline__ int front_elems_blk(const int f) { return ((ld_blk(f) * cols_blk(f)) + 1) & ~1; }
+// side-panel stride: covers the front rounded up to whole 8-row tiles, 4 (mod 16) so that the A
+// fragments (rows g, panel columns q) are conflict-free
+__host__ __device__ __forceinline__ int lt_stride(const int f) { return (((((f + 7) & ~7) + 11) >> 4) << 4) + 4; }
 constexpr int kNB = 4;
-constexpr int kMinCols = 4;
-constexpr int kDiagBuf = 8;   // reciprocal pivots of two panels (double-buffered)
-// per-group scratch behind the front: Lt side panel (kNB x lt_stride) + kDiagBuf
-__host__ __device__ __forceinline__ int group_elems(const int f) { return front_elems(f) + kNB * lt_stride(f) + kDiagBuf; }
+constexpr int kDiagBuf = kNB * kNB;   // explicit inverse of the current diagonal block
+// per-group scratch behind the front: -Lt side panel (kNB x lt_stride) + kDiagBuf
+__host__ __device__ __forceinline__ int group_elems(const int f) { return front_elems_blk(f) + kNB * lt_stride(f) + kDiagBuf; }
 
 __device__ __forceinline__ void check_pivot(const double piv, int* flag) {
   if (!(fabs(piv) > 0.0) || isinf(piv)) *flag = 2;
@@ -269,253 +281,167 @@ __device__ __forceinline__ void eliminate_warp(double* __restrict__ Fm, const in
   }
 }
 
-// ---- several warps: blocked right-looking elimination, NB = 4 pivots per panel, with the panel
-// factorisation reduced to a 4x4 problem on the critical path.
+// ---- several warps: blocked right-looking elimination, NB = 4 pivots per panel; everything that is a
+// product of matrices runs on the fp64 tensor-core path (mma.sync.m8n8k4.f64: the rank-4 update of an
+// 8x8 tile is ONE warp instruction instead of eight; tools/lu_micro.cu: phase B of a 128-front runs
+// at the fp64 peak of the SM).
 //
-//   panel t = pivots [p0, p0+nb), r0 = p0+nb.  With D = L11 U11 the diagonal block,
-//       L21 = A21 U11^{-1},   Lt = L21 L11^{-1} (= A21 D^{-1}),   A22 -= Lt A12
+//   panel t = pivots [p0, p0+nb), r0 = p0+nb.  With D = L11 U11 the 4x4 diagonal block,
+//       Lt = A21 D^{-1} (= L21 L11^{-1}),   A22 -= Lt A12,   L21 = Lt L11
 //   so the trailing update only reads the *unsolved* top rows A12 and the Lt side panel: nothing
 //   in the front is rewritten before the update starts.  Per panel:
-//     phase A  one warp per 32-row chunk derives the L / Lt rows from the published 4x4 factors
-//              (16 flops a row), puts Lt into the side panel and streams L21 straight to the factor
-//              storage when it is wanted;
-//     phase B  all worker warps update the trailing block, two 32-row chunks x strided columns
-//              per warp, multipliers in registers;
-//   meanwhile warp 0 (the diagonal warp) prepares the NEXT diagonal block: it alone owns those
-//   nb1 x nb1 entries, applies panel t to them and factors them in registers, so the serial chain
-//   per panel is load -> 4x4 update -> 4x4 LU (4 dependent reciprocals) -> publish, off the
-//   workers' path (it only *arrives* at the barrier between the phases).  The U rows are solved
-//   once at the end (finalize_u), and L21 never goes back to shared memory.
-struct Tri {   // factors of a 4x4 diagonal block, identity-padded when the panel has nb < 4 pivots
-  double l10, l20, l21, l30, l31, l32, u01, u02, u03, u12, u13, u23, r0, r1, r2, r3;
-};
-
-__device__ __forceinline__ Tri load_tri(const double* __restrict__ Fm, const double* __restrict__ rd,
-                                        const int p0, const int nb, const int ld) {
-  const double* __restrict__ b = Fm + p0 + p0 * ld;
-  Tri T;
-  T.l10 = nb > 1 ? b[1] : 0.0;
-  T.u01 = nb > 1 ? b[ld] : 0.0;
-  T.l20 = nb > 2 ? b[2] : 0.0;
-  T.l21 = nb > 2 ? b[2 + ld] : 0.0;
-  T.u02 = nb > 2 ? b[2 * ld] : 0.0;
-  T.u12 = nb > 2 ? b[1 + 2 * ld] : 0.0;
-  T.l30 = nb > 3 ? b[3] : 0.0;
-  T.l31 = nb > 3 ? b[3 + ld] : 0.0;
-  T.l32 = nb > 3 ? b[3 + 2 * ld] : 0.0;
-  T.u03 = nb > 3 ? b[3 * ld] : 0.0;
-  T.u13 = nb > 3 ? b[1 + 3 * ld] : 0.0;
-  T.u23 = nb > 3 ? b[2 + 3 * ld] : 0.0;
-  T.r0 = rd[0]; T.r1 = rd[1]; T.r2 = rd[2]; T.r3 = rd[3];
-  return T;
+//     phase A  (all warps, one 8-row tile at a time) -Lt = -(A21 D^{-1}) as one DMMA against the
+//              explicit 4x4 inverse published by the diagonal warp, into the side panel; when L is
+//              wanted, L21 = Lt L11 (one more DMMA) goes straight to the factor storage;
+//     phase B  (worker warps) the trailing block is cut into strips of 32 rows x 8 columns = four
+//              8x8 accumulator tiles; a warp keeps the four A fragments (-Lt) of its 32 rows in
+//              registers, and per strip loads one B fragment (top rows) and the accumulators,
+//              issues 4 DMMAs and stores.  The front's leading dimension is 2 (mod 4), which makes the
+//              accumulator loads / stores conflict-free (ld_blk); the side panel's stride is 4 (mod 16)
+//              for the A fragments;
+//   meanwhile warp 0 (the diagonal warp) prepares the NEXT diagonal block: it alone owns the 8x8 tile
+//   around it, applies panel t to that tile (one DMMA), then factors and inverts the 4x4 block
+//   redundantly in registers (no shuffles): the only serial chain per panel is 4 dependent reciprocals
+//   (`rcp.approx` + 2 Newton steps, 56 instead of 80 cycles) plus two short triangular solves, off the
+//   workers' path.  The U rows are solved once at the end (finalize_u), and L21 never goes back to
+//   shared memory.
+__device__ __forceinline__ void dmma(double& c0, double& c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
 }
 
-// one row of A21 (zero-padded to 4) -> its row of L21 (l) and of Lt (x)
-__device__ __forceinline__ void row_solve(const Tri& T, const double a0, const double a1, const double a2,
-                                          const double a3, double (&l)[4], double (&x)[4]) {
-  l[0] = a0 * T.r0;
-  l[1] = fma(-l[0], T.u01, a1) * T.r1;
-  l[2] = fma(-l[1], T.u12, fma(-l[0], T.u02, a2)) * T.r2;
-  l[3] = fma(-l[2], T.u23, fma(-l[1], T.u13, fma(-l[0], T.u03, a3))) * T.r3;
-  x[3] = l[3];
-  x[2] = fma(-x[3], T.l32, l[2]);
-  x[1] = fma(-x[2], T.l21, fma(-x[3], T.l31, l[1]));
-  x[0] = fma(-x[1], T.l10, fma(-x[2], T.l20, fma(-x[3], T.l30, l[0])));
-}
-
-// LU of the nb x nb block at (q0, q0) by one warp, in place; reciprocal pivots to rd[0..3]
-// (1.0 beyond nb).  All lanes compute redundantly in registers (no shuffles), lane 0 writes.
-__device__ __forceinline__ void diag_factor(double* __restrict__ Fm, double* __restrict__ rd, const int q0,
-                                            const int nb, const int ld, const int lane, int* flag) {
-  double a[4][4];
+// LU of the nb x nb block at (q0, q0) by one warp, in place (identity-padded to 4x4, all lanes compute
+// redundantly in registers, lane 0 writes), and its explicit inverse D^{-1} (column-major 4x4) to dinv
+// (lane c < 4 owns column c: L y = e_c, U x = y).
+__device__ __forceinline__ void diag_block(double* __restrict__ Fm, double* __restrict__ dinv, const int q0,
+                                           const int nb, const int ld, const int lane, int* flag) {
+  double a[kNB][kNB];
   double* __restrict__ b = Fm + q0 + q0 * ld;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < kNB; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i][j] = (i < nb && j < nb) ? b[i + j * ld] : (i == j ? 1.0 : 0.0);
-  double r[4];
+    for (int i = 0; i < kNB; ++i) a[i][j] = (i < nb && j < nb) ? b[i + j * ld] : (i == j ? 1.0 : 0.0);
+  double r[kNB];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < kNB; ++k) {
     if (lane == 0 && k < nb) check_pivot(a[k][k], flag);
     r[k] = fast_rcp(a[k][k]);
 #pragma unroll
-    for (int i = k + 1; i < 4; ++i) {
+    for (int i = k + 1; i < kNB; ++i) {
       a[i][k] *= r[k];
 #pragma unroll
-      for (int j = k + 1; j < 4; ++j) a[i][j] = fma(-a[i][k], a[k][j], a[i][j]);
+      for (int j = k + 1; j < kNB; ++j) a[i][j] = fma(-a[i][k], a[k][j], a[i][j]);
     }
   }
   if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < kNB; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < kNB; ++i)
         if (i < nb && j < nb) b[i + j * ld] = a[i][j];
+  }
+  const int c = lane & (kNB - 1);
+  double y[kNB], x[kNB];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) rd[k] = r[k];
+  for (int k = 0; k < kNB; ++k) {
+    double v = (k == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int q = 0; q < k; ++q) v = fma(-a[k][q], y[q], v);
+    y[k] = v;
+  }
+#pragma unroll
+  for (int k = kNB - 1; k >= 0; --k) {
+    double v = y[k];
+#pragma unroll
+    for (int q = k + 1; q < kNB; ++q) v = fma(-a[k][q], x[q], v);
+    x[k] = v * r[k];
+  }
+  if (lane < kNB) {
+#pragma unroll
+    for (int k = 0; k < kNB; ++k) dinv[k + kNB * lane] = x[k];
   }
 }
 
-// diagonal warp, iteration t: apply panel t (factors at (p0,p0), reciprocals rd_cur) to the next
-// diagonal block at (r0,r0), factor it, publish its reciprocals in rd_next.  Lane i < nb1 owns row i
-// of the update; the 4x4 LU is then done redundantly by all lanes.
-__device__ __forceinline__ void diag_next(double* __restrict__ Fm, const double* __restrict__ rd_cur,
-                                          double* __restrict__ rd_next, const int p0, const int nb,
-                                          const int nb1, const int ld, const int lane, int* flag) {
-  const int r0 = p0 + nb;
-  const Tri T = load_tri(Fm, rd_cur, p0, nb, ld);
-  const int i = min(lane, nb1 - 1);                    // idle lanes mirror a valid row, never store
-  const double* __restrict__ arow = Fm + (r0 + i) + p0 * ld;
-  const double a0 = arow[0];
-  const double a1 = nb > 1 ? arow[ld] : 0.0;
-  const double a2 = nb > 2 ? arow[2 * ld] : 0.0;
-  const double a3 = nb > 3 ? arow[3 * ld] : 0.0;
-  double l[4], x[4];
-  row_solve(T, a0, a1, a2, a3, l, x);
-  const int k1 = nb > 1 ? 1 : 0, k2 = nb > 2 ? 2 : 0, k3 = nb > 3 ? 3 : 0;   // stay inside the panel rows
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (j < nb1) {
-      double* __restrict__ col = Fm + (r0 + j) * ld;
-      double v = col[r0 + i];
-      v = fma(-x[0], col[p0], v);
-      v = fma(-x[1], col[p0 + k1], v);
-      v = fma(-x[2], col[p0 + k2], v);
-      v = fma(-x[3], col[p0 + k3], v);
-      if (lane < nb1) col[r0 + i] = v;
-    }
+// phase A, one 8-row tile (rows r0 + 8*rt .. +7 of the panel columns): -Lt into the side panel, L21 to
+// the factor storage when Lg != null.  bd: B fragment of D^{-1}, bl: B fragment of L11 (columns >= 4: 0).
+__device__ __forceinline__ void lt_tile(const double* __restrict__ Fm, double* __restrict__ lt, const int lts,
+                                        double* __restrict__ Lg, const int p0, const int nb, const int f,
+                                        const int ld, const int rt, const double bd, const double bl,
+                                        const int lane) {
+  const int r0 = p0 + nb, m = f - r0;
+  const int q = lane & 3, g8 = lane >> 2;
+  const int row = 8 * rt + g8;                           // relative to r0; a live tile has 8*rt < m
+  const double a0 = q < nb ? Fm[r0 + row + (p0 + q) * ld] : 0.0;   // rows beyond the front: zero padding
+  double c0 = 0.0, c1 = 0.0;
+  dmma(c0, c1, a0, bd);
+  if (q < 2) {                                           // columns 2q, 2q+1 < 4 of the 8-wide accumulator
+    lt[(2 * q) * lts + row] = -c0;
+    lt[(2 * q + 1) * lts + row] = -c1;
   }
-  __syncwarp();
-  diag_factor(Fm, rd_next, r0, nb1, ld, lane, flag);
-}
-
-// phase A: rows r0 + 32c + lane of panel t -> Lt side panel (and L21 to the factor storage)
-__device__ __forceinline__ void lt_chunk(const double* __restrict__ Fm, const double* __restrict__ rd,
-                                         double* __restrict__ lt, const int lts, double* __restrict__ Lg,
-                                         const int p0, const int nb, const int f, const int ld, const int c,
-                                         const int lane) {
-  const int r0 = p0 + nb;
-  const int i = lane + 32 * c;                         // row relative to r0
-  const bool ok = r0 + i < f;
-  const Tri T = load_tri(Fm, rd, p0, nb, ld);
-  const double* __restrict__ arow = Fm + (r0 + i) + p0 * ld;
-  const double a0 = ok ? arow[0] : 0.0;
-  const double a1 = (ok && nb > 1) ? arow[ld] : 0.0;
-  const double a2 = (ok && nb > 2) ? arow[2 * ld] : 0.0;
-  const double a3 = (ok && nb > 3) ? arow[3 * ld] : 0.0;
-  double l[4], x[4];
-  row_solve(T, a0, a1, a2, a3, l, x);
-  if (ok) {
-    lt[i] = x[0];
-    lt[lts + i] = x[1];
-    lt[2 * lts + i] = x[2];
-    lt[3 * lts + i] = x[3];
-    if (Lg != nullptr) {                               // L21 rows go straight to the factor storage
-      double* __restrict__ dst = Lg + (r0 + i) + p0 * f;
-      dst[0] = l[0];
-      if (nb > 1) dst[f] = l[1];
-      if (nb > 2) dst[2 * f] = l[2];
-      if (nb > 3) dst[3 * f] = l[3];
+  if (Lg != nullptr) {
+    __syncwarp();
+    const double x0 = lt[q * lts + row];
+    double d0 = 0.0, d1 = 0.0;
+    dmma(d0, d1, x0, bl);
+    if (row < m && q < 2) {
+      double* __restrict__ dst = Lg + (r0 + row) + (p0 + 2 * q) * f;
+      if (2 * q < nb) dst[0] = -d0;
+      if (2 * q + 1 < nb) dst[f] = -d1;
     }
   }
 }
 
-// phase B: R 32-row chunks (rows r0 + row0 + lane + 32 r) of the columns r0 + cg, r0 + cg + CW, ... < ncol.
-// The 4 R multipliers of a lane stay in registers; a column costs 4 broadcast loads of the unsolved top
-// values, R loads, 4 R fused multiply-adds and R stores; two columns are in flight per trip.
-// FULL: the panel has 4 pivots (immediate offsets for the top rows).
-template <int R, bool FULL>
-__device__ __forceinline__ void trailing_update(double* __restrict__ Fm, const double* __restrict__ lt,
-                                                const int lts, const int p0, const int nb, const int nb1,
-                                                const int m, const int ld, const int ncol, const int row0,
-                                                const int cg, const int CW, const int lane) {
-  const int r0 = p0 + nb;
-  const int i0 = row0 + lane;
-  double x[R][4];
-  bool ok[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    ok[r] = i0 + 32 * r < m;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) x[r][k] = ok[r] ? lt[k * lts + i0 + 32 * r] : 0.0;
-  }
-  const int k1 = FULL ? 1 : (nb > 1 ? 1 : 0), k2 = FULL ? 2 : (nb > 2 ? 2 : 0), k3 = FULL ? 3 : (nb > 3 ? 3 : 0);
-  int j = r0 + cg;
-  double* __restrict__ tp = Fm + p0 + j * ld;            // top rows of column j
-  double* __restrict__ vp = Fm + r0 + i0 + j * ld;       // this lane's rows of column j
-  const int step = CW * ld;
-  // the first nb1 columns: rows < nb1 are the next diagonal block, owned by warp 0
-  for (; j < r0 + nb1 && j < ncol; j += CW, tp += step, vp += step) {
-    const double t0 = tp[0], t1 = tp[k1], t2 = tp[k2], t3 = tp[k3];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (ok[r] && (r > 0 || i0 >= nb1)) {
-        double v = vp[32 * r];
-        v = fma(-x[r][0], t0, v); v = fma(-x[r][1], t1, v); v = fma(-x[r][2], t2, v); v = fma(-x[r][3], t3, v);
-        vp[32 * r] = v;
-      }
-    }
-  }
-  // two columns per trip (independent chains), no trip-count arithmetic
-  for (; j + CW < ncol; j += 2 * CW, tp += 2 * step, vp += 2 * step) {
-    const double* __restrict__ tq = tp + step;
-    double* __restrict__ vq = vp + step;
-    const double t0 = tp[0], t1 = tp[k1], t2 = tp[k2], t3 = tp[k3];
-    const double s0 = tq[0], s1 = tq[k1], s2 = tq[k2], s3 = tq[k3];
-    double v[R], w[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      v[r] = ok[r] ? vp[32 * r] : 0.0;
-      w[r] = ok[r] ? vq[32 * r] : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      v[r] = fma(-x[r][0], t0, v[r]); w[r] = fma(-x[r][0], s0, w[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      v[r] = fma(-x[r][1], t1, v[r]); w[r] = fma(-x[r][1], s1, w[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      v[r] = fma(-x[r][2], t2, v[r]); w[r] = fma(-x[r][2], s2, w[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      v[r] = fma(-x[r][3], t3, v[r]); w[r] = fma(-x[r][3], s3, w[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (ok[r]) { vp[32 * r] = v[r]; vq[32 * r] = w[r]; }
-    }
-  }
-  if (j < ncol) {
-    const double t0 = tp[0], t1 = tp[k1], t2 = tp[k2], t3 = tp[k3];
-    double v[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = ok[r] ? vp[32 * r] : 0.0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      v[r] = fma(-x[r][0], t0, v[r]); v[r] = fma(-x[r][1], t1, v[r]);
-      v[r] = fma(-x[r][2], t2, v[r]); v[r] = fma(-x[r][3], t3, v[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (ok[r]) vp[32 * r] = v[r];
-  }
-}
-
+// phase B, one warp: R row tiles (rows r0 + row0 .. + 8R-1, all of them holding rows of the front) x the
+// column tiles cg, cg + CW, ... < ct_end of the 8-column tiles right of the panel.  No masks and no
+// predicates (a predicated variant costs spills): tiles that overhang the front live in its zero padding
+// (kPad).  Per strip: 1 + 2R loads, R DMMAs, 2R stores, all with immediate offsets from two running pointers.
 template <int R>
-__device__ __forceinline__ void trailing_tile(double* __restrict__ Fm, const double* __restrict__ lt,
-                                              const int lts, const int p0, const int nb, const int nb1,
-                                              const int m, const int ld, const int ncol, const int row0,
-                                              const int cg, const int CW, const int lane) {
-  if (nb == kNB) trailing_update<R, true>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, row0, cg, CW, lane);
-  else trailing_update<R, false>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, row0, cg, CW, lane);
+__device__ __forceinline__ void trailing_strips(double* __restrict__ Fm, const double* __restrict__ lt,
+                                                const int lts, const int p0, const int nb, const int ld,
+                                                const int row0, const int cg, const int CW, const int ct_end,
+                                                const int lane) {
+  const int r0 = p0 + nb;
+  const int q = lane & 3, g8 = lane >> 2;
+  double xa[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) xa[r] = lt[q * lts + row0 + 8 * r + g8];
+  const int cstep = 8 * CW * ld;
+  const double* __restrict__ bp = Fm + p0 + (q < nb ? q : 0) + (r0 + 8 * cg + g8) * ld;   // stays inside the panel rows
+  double* __restrict__ cp = Fm + r0 + row0 + g8 + (r0 + 8 * cg + 2 * q) * ld;
+  for (int ct = cg; ct < ct_end; ct += CW, bp += cstep, cp += cstep) {
+    const double b0 = bp[0];
+    double c0[R], c1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      c0[r] = cp[8 * r];
+      c1[r] = cp[ld + 8 * r];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      dmma(c0[r], c1[r], xa[r], b0);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cp[8 * r] = c0[r];
+      cp[ld + 8 * r] = c1[r];
+    }
+  }
+}
+
+// up to four row tiles from row0: as many as hold rows of the trailing block (m rows)
+__device__ __forceinline__ void trailing_rows(double* __restrict__ Fm, const double* __restrict__ lt, const int lts,
+                                              const int p0, const int nb, const int m, const int ld, const int row0,
+                                              const int cg, const int CW, const int ct_end, const int lane) {
+  const int nt = (m - row0 + 7) >> 3;
+  if (nt >= 4) trailing_strips<4>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
+  else if (nt == 3) trailing_strips<3>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
+  else if (nt == 2) trailing_strips<2>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
+  else if (nt == 1) trailing_strips<1>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
 }
 
 // deferred triangular solves of the U rows: for every panel and every column right of it
-//   u = L11^{-1} a   (4 values per column, lanes over columns, warps over panels)
+//   u = L11^{-1} a   (up to 4 values per column, lanes over columns, warps over panels)
 __device__ __forceinline__ void finalize_u(double* __restrict__ Fm, const int s, const int ncol, const int ld,
                                            const int lane, const int w, const int nw) {
   const int npan = (s + kNB - 1) / kNB;
@@ -524,25 +450,24 @@ __device__ __forceinline__ void finalize_u(double* __restrict__ Fm, const int s,
     const int nb = min(kNB, s - p0);
     if (nb < 2) continue;
     const double* __restrict__ blk = Fm + p0 + p0 * ld;
-    const double L10 = blk[1];
-    const double L20 = nb > 2 ? blk[2] : 0.0, L21 = nb > 2 ? blk[2 + ld] : 0.0;
-    const double L30 = nb > 3 ? blk[3] : 0.0, L31 = nb > 3 ? blk[3 + ld] : 0.0, L32 = nb > 3 ? blk[3 + 2 * ld] : 0.0;
     for (int j = p0 + nb + lane; j < ncol; j += kWarp) {
       double* __restrict__ col = Fm + p0 + j * ld;
-      const double u0 = col[0];
-      const double u1 = fma(-L10, u0, col[1]);
-      col[1] = u1;
-      if (nb > 2) {
-        const double u2 = fma(-L21, u1, fma(-L20, u0, col[2]));
-        col[2] = u2;
-        if (nb > 3) col[3] = fma(-L32, u2, fma(-L31, u1, fma(-L30, u0, col[3])));
+      double u[kNB];
+#pragma unroll
+      for (int k = 0; k < kNB; ++k) {
+        if (k < nb) {
+          double v = col[k];
+#pragma unroll
+          for (int q2 = 0; q2 < k; ++q2) v = fma(-blk[k + q2 * ld], u[q2], v);
+          u[k] = v;
+          if (k > 0) col[k] = v;
+        }
       }
     }
   }
 }
 
-// a group of `nw` consecutive warps with two hardware named barriers: `id` for the whole group,
-// `id + 8` between the worker phases (the diagonal warp only arrives there)
+// a group of `nw` consecutive warps with one hardware named barrier
 struct PanelGrp {
   int id, nw, w0;
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
@@ -552,12 +477,6 @@ struct PanelGrp {
   __device__ __forceinline__ void sync() const {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nw << 5) : "memory");
   }
-  __device__ __forceinline__ void phase_sync() const {
-    asm volatile("bar.sync %0, %1;" ::"r"(id + 8), "r"(nw << 5) : "memory");
-  }
-  __device__ __forceinline__ void phase_arrive() const {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id + 8), "r"(nw << 5) : "memory");
-  }
 };
 
 #ifdef SZB_PHASE_TIMING
@@ -566,18 +485,27 @@ __device__ long long g_el[8 * 8];
 #else
 #define SZB_E(i)
 #endif
-__device__ __forceinline__ void eliminate_blocked(const PanelGrp g, double* __restrict__ Fm, double* __restrict__ lt,
-                                                  const int lts, double* __restrict__ rdbuf,
-                                                  double* __restrict__ Lg, const int s, const int f,
-                                                  const int ncol, const int ld, int* flag) {
+// Not inlined on purpose: the elimination gets the full register budget to itself (the caller's
+// prefetched assembly state is saved once per front).  The buffers are passed as offsets into the
+// dynamic shared memory so that the compiler keeps the LDS / STS forms; SM_FRONT = false: the front
+// itself lives in a global workspace (FmG), only the side panel and the inverse are on chip.
+template <bool SM_FRONT>
+__device__ __forceinline__ void eliminate_blocked(const PanelGrp g, double* FmG, const int fm_off, const int lt_off,
+                                               const int lts, double* __restrict__ Lg, const int s, const int f,
+                                               const int ncol, const int ld, int* flag) {
+  extern __shared__ double sm[];
+  double* __restrict__ Fm = SM_FRONT ? sm + fm_off : FmG;
+  double* __restrict__ lt = sm + lt_off;
+  double* __restrict__ dinv = lt + kNB * lts;
   const int lane = g.lane(), w = g.warp(), nw = g.nw;
+  const int q = lane & 3, g8 = lane >> 2;
   const int npan = (s + kNB - 1) / kNB;
 #ifdef SZB_PHASE_TIMING
   const bool dbg_ = blockIdx.x == 0 && g.id == 0 && (threadIdx.x & 127) == 0;
   long long el_[7] = {0, 0, 0, 0, 0, 0, 0};
   long long te_ = clock64();
 #endif
-  if (w == 0) diag_factor(Fm, rdbuf, 0, min(kNB, s), ld, lane, flag);
+  if (w == 0) diag_block(Fm, dinv, 0, min(kNB, s), ld, lane, flag);
   g.sync();
   SZB_E(0)
   for (int t = 0; t < npan; ++t) {
@@ -585,34 +513,45 @@ __device__ __forceinline__ void eliminate_blocked(const PanelGrp g, double* __re
     const int nb = min(kNB, s - p0);
     const int r0 = p0 + nb;
     const bool has_next = t + 1 < npan;
-    const int nb1 = has_next ? min(kNB, s - r0) : 0;
-    const double* rd_cur = rdbuf + (t & 1) * kNB;
+    const int m = f - r0;
+    // ---- phase A
+    const int nrt = (m + 7) >> 3;
+    if (w < nrt) {
+      const double bd = g8 < kNB ? dinv[q + kNB * g8] : 0.0;               // B[k][col] = Dinv[k][col]
+      double bl = 0.0;
+      if (Lg != nullptr)                                 // B[k][col] = L11[k][col] (unit lower, identity-padded)
+        bl = q == g8 ? 1.0 : ((q > g8 && q < nb) ? Fm[(p0 + q) + (p0 + g8) * ld] : 0.0);
+      for (int rt = w; rt < nrt; rt += nw) lt_tile(Fm, lt, lts, Lg, p0, nb, f, ld, rt, bd, bl, lane);
+    }
+    SZB_E(2)
+    g.sync();
+    SZB_E(3)
+    // ---- phase B
     if (has_next && w == 0) {
-      g.phase_arrive();
-      diag_next(Fm, rd_cur, rdbuf + ((t + 1) & 1) * kNB, p0, nb, nb1, ld, lane, flag);
+      // the diagonal warp: panel t applied to the 8x8 tile around the next diagonal block, then LU + inverse
+      trailing_strips<1>(Fm, lt, lts, p0, nb, ld, 0, 0, 1, 1, lane);
+      __syncwarp();
+      diag_block(Fm, dinv, r0, min(kNB, s - r0), ld, lane, flag);
       SZB_E(1)
-    } else {
+    } else if (m > 0) {
       const int W = has_next ? nw - 1 : nw;            // worker warps
       const int ww = has_next ? w - 1 : w;
-      const int m = f - r0;
-      const int nch = (m + 31) >> 5;                   // 32-row chunks of the trailing block
-      for (int c = ww; c < nch; c += W) lt_chunk(Fm, rd_cur, lt, lts, Lg, p0, nb, f, ld, c, lane);
-      SZB_E(2)
-      g.phase_sync();
-      SZB_E(3)
-      if (nch > 0) {
-        // every worker takes all row chunks (up to four per tile row) of its own strided columns, but at
-        // least kMinCols columns each: a tile's set-up (multipliers, addresses) costs as much as a few
-        // columns of updates
-        const int nt = (nch + 3) >> 2;                 // tile rows of four chunks (1 unless f > 128)
-        const int CW = max(1, min(nt == 1 ? W : W / nt, (ncol - r0) / kMinCols));   // no division on the common path
-        for (int tile = ww; tile < nt * CW; tile += W) {
-          const int tr = nt == 1 ? 0 : tile / CW;
-          const int cg = tile - tr * CW;
-          const int rem = nch - 4 * tr;                // chunks in this tile row
-          if (rem >= 3) trailing_tile<4>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, tr << 7, cg, CW, lane);
-          else if (rem == 2) trailing_tile<2>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, tr << 7, cg, CW, lane);
-          else trailing_tile<1>(Fm, lt, lts, p0, nb, nb1, m, ld, ncol, tr << 7, cg, CW, lane);
+      const int nch = (m + 31) >> 5;                   // row groups of 32 rows
+      const int nct = (ncol - r0 + 7) >> 3;            // column tiles
+      const int CW = max(1, min(W / nch, nct));        // warps that share a row group, striding over the column tiles
+      const int ntile = nch * CW;
+      const float inv_cw = 1.0f / static_cast<float>(CW);
+      for (int tile = ww; tile < ntile; tile += W) {
+        const int tr = nch == 1 ? 0 : fdiv(tile, inv_cw);
+        const int cg = tile - tr * CW;
+        if (tile == 0 && has_next) {                   // tile (0, 0) belongs to the diagonal warp
+          const int n3 = min(3, (m - 1) >> 3);          // rows 8.. of the first column tile
+          if (n3 == 3) trailing_strips<3>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane);
+          else if (n3 == 2) trailing_strips<2>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane);
+          else if (n3 == 1) trailing_strips<1>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane);
+          trailing_rows(Fm, lt, lts, p0, nb, m, ld, 0, CW, CW, nct, lane);
+        } else {
+          trailing_rows(Fm, lt, lts, p0, nb, m, ld, tr << 5, cg, CW, nct, lane);
         }
       }
     }
@@ -627,6 +566,7 @@ __device__ __forceinline__ void eliminate_blocked(const PanelGrp g, double* __re
   if (dbg_) for (int i = 0; i < 7; ++i) g_el[8 * (threadIdx.x >> 7 & 7) + i] += el_[i];
 #endif
 }
+
 
 #ifdef SZB_PHASE_TIMING
 #define SZB_T(i) { const long long now_ = clock64(); tacc_[(i) + 4 * lvl_] += now_ - tprev_; tprev_ = now_; }
@@ -646,13 +586,13 @@ __device__ __forceinline__ void clear_front(double* __restrict__ Fm, const int n
 
 // ---------------------------------------------------------------------------------------
 // numeric factorisation of one front; the front is column-major with leading dimension
-// ld = f | 1 and has f + 1 columns (the last one carries the right-hand side when one rides along).
+// ld = ld_warp(f) / ld_blk(f) and has f + 1 columns (the last one carries the right-hand side when one rides along).
 // ---------------------------------------------------------------------------------------
 // one warp, front of at most 32 rows
 __device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre& P, const int2* __restrict__ ga,
                                   double* __restrict__ Fm, const FactorArgs& A SZB_TPARAM) {
   SZB_TSTART
-  const int s = H.s, f = H.f, u = f - s, ld = f | 1;
+  const int s = H.s, f = H.f, u = f - s, ld = ld_warp(f);
   const int lane = threadIdx.x & 31;
   const int with_rhs = A.rhs != nullptr;
   const int ncol = f + with_rhs;
@@ -698,23 +638,29 @@ __device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre
 }
 
 // a group of warps
-__device__ void factor_front_group(const PanelGrp g, const FrontHdr H, const FrontHdr Hnext, AsmPre& P,
-                                   const int2* __restrict__ ga, double* __restrict__ Fm, double* __restrict__ lt,
-                                   const int lts, double* __restrict__ rdbuf, const FactorArgs& A SZB_TPARAM) {
+// Fm: the front (shared memory at offset fm_off of the dynamic array when SM_FRONT, else the global
+// workspace); lt_off: offset of the side panel + inverse scratch in shared memory
+template <bool SM_FRONT>
+__device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const int4* __restrict__ fh,
+                                       const int q_next, AsmPre& P, const int2* __restrict__ ga,
+                                       double* __restrict__ Fm, const int fm_off, const int lt_off, const int lts,
+                                       const FactorArgs& A SZB_TPARAM) {
   SZB_TSTART
-  const int s = H.s, f = H.f, u = f - s, ld = f | 1;
+  const int s = H.s, f = H.f, u = f - s, ld = ld_blk(f);
   const int lane = g.lane(), w = g.warp(), nw = g.nw, r = g.rank(), G_ = g.size();
   const int with_rhs = A.rhs != nullptr;
   const int ncol = f + with_rhs;
-  clear_front(Fm, ld * (f + 1), r, G_);
+  clear_front(Fm, ld * cols_blk(f), r, G_);
   g.sync();
   assemble_front(P, r, G_, H, ga, Fm, A);
-  asm_prefetch(P, Hnext, ga, r, G_, with_rhs != 0);         // in flight during the elimination
   g.sync();
   SZB_T(0)
   double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
-  eliminate_blocked(g, Fm, lt, lts, rdbuf, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
-  asm_prefetch_values(P, Hnext, A);                       // entries have landed; values fly during the write-out
+  eliminate_blocked<SM_FRONT>(g, Fm, fm_off, lt_off, lts, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
+  // the next front's descriptor and first gather entries fly during the write-out (nothing of them is
+  // kept across the elimination: it has the register file to itself)
+  const FrontHdr Hnext = load_hdr(fh, q_next);
+  asm_prefetch(P, Hnext, ga, r, G_, with_rhs != 0);
   SZB_T(1)
   // rows below a column's own panel were streamed by the workers (or are not wanted)
   for (int p = w; p < s; p += nw) {
@@ -746,6 +692,7 @@ __device__ void factor_front_group(const PanelGrp g, const FrontHdr H, const Fro
     for (int t = r; t < s; t += G_) A.yout[H.piv0 + t] = Fm[t + f * ld];
   g.sync();
   SZB_T(2)
+  return Hnext;
 }
 
 __global__ void __launch_bounds__(SZB_FACTOR_THREADS, 1)
@@ -757,10 +704,10 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
                  const int* __restrict__ active, int* __restrict__ flags, int B) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5;
-  const int wstride = front_elems(S.f_warp_max);
-  const int gfront = front_elems(S.f_group_max), glts = lt_stride(S.f_group_max);
+  const int wstride = front_elems_warp(S.f_warp_max);
+  const int gfront = front_elems_blk(S.f_group_max), glts = lt_stride(S.f_group_max);
   const int gstride = group_elems(S.f_group_max);
-  const int tfront = front_elems(S.f_top_max), tlts = lt_stride(S.f_top_max);
+  const int tfront = front_elems_blk(S.f_top_max), tlts = lt_stride(S.f_top_max);
   const int wpg = S.wpg;
   // the work lists are the same for every scenario: fetch their bounds once
   int wq0 = 0, wq1 = 0, gq0 = 0, gq1 = 0;
@@ -822,9 +769,8 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
         AsmPre P;
         asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
         for (int q = gq0; q < gq1; ++q) {
-          const FrontHdr Hn = load_hdr(S.fh, min(q + 1, gq1 - 1));
-          factor_front_group(g, H, Hn, P, S.ga, Fm, Fm + gfront, glts, Fm + gfront + kNB * glts, A SZB_TARG(1));
-          H = Hn;
+          H = factor_front_group<true>(g, H, S.fh, min(q + 1, gq1 - 1), P, S.ga, Fm, gi * gstride,
+                                       gi * gstride + gfront, glts, A SZB_TARG(1));
         }
       }
       __syncthreads();
@@ -845,16 +791,14 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
       asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
       if (FBW == nullptr) {
         for (int q = 0; q < S.n_top; ++q) {
-          const FrontHdr Hn = load_hdr(S.fh, tq0 + min(q + 1, S.n_top - 1));
-          factor_front_group(g, H, Hn, P, S.ga, sm, sm + tfront, tlts, sm + tfront + kNB * tlts, A SZB_TARG(2));
-          H = Hn;
+          H = factor_front_group<true>(g, H, S.fh, tq0 + min(q + 1, S.n_top - 1), P, S.ga, sm, 0, tfront, tlts,
+                                       A SZB_TARG(2));
         }
       } else {
         double* Ft = FBW + static_cast<size_t>(blockIdx.x) * tfront;
         for (int q = 0; q < S.n_top; ++q) {
-          const FrontHdr Hn = load_hdr(S.fh, tq0 + min(q + 1, S.n_top - 1));
-          factor_front_group(g, H, Hn, P, S.ga, Ft, sm, tlts, sm + kNB * tlts, A SZB_TARG(2));
-          H = Hn;
+          H = factor_front_group<false>(g, H, S.fh, tq0 + min(q + 1, S.n_top - 1), P, S.ga, Ft, 0, 0, tlts,
+                                        A SZB_TARG(2));
         }
       }
     }
@@ -1169,7 +1113,7 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   if (S.f_warp_max > 32) return cudaErrorInvalidConfiguration;   // lane = row
   if (S.n_group_lists > 7) return cudaErrorInvalidConfiguration;   // named barriers 1..7 (+8 for the phase barrier)
   if (S.threads > SZB_FACTOR_THREADS) return cudaErrorInvalidConfiguration;
-  size_t fsm = static_cast<size_t>(S.n_warp_lists) * front_elems(S.f_warp_max);
+  size_t fsm = static_cast<size_t>(S.n_warp_lists) * front_elems_warp(S.f_warp_max);
   fsm = smax(fsm, static_cast<size_t>(S.n_group_lists) * group_elems(S.f_group_max));
   if (fsm * sizeof(double) > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
   cfg->top_in_global = 0;
@@ -1180,7 +1124,7 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
       fsm = smax(fsm, top_sm);
     } else {   // CTA-level fronts in a global workspace, side panels in shared memory
       cfg->top_in_global = 1;
-      cfg->big_elems = static_cast<size_t>(front_elems(S.f_top_max));
+      cfg->big_elems = static_cast<size_t>(front_elems_blk(S.f_top_max));
       fsm = smax(fsm, static_cast<size_t>(kNB * lt_stride(S.f_top_max) + kDiagBuf));
     }
   }

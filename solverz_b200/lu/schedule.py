@@ -66,7 +66,7 @@ def plan_threads(sym) -> Dict[str, int]:
 def _front_sources(sym, k: int):
     """Sources of front k in assembly order: (dst, src, kind) with kind 0 = O, 1 = C, 2 = R."""
     s, f = int(sym.sn_s[k]), int(sym.sn_f[k])
-    ld = f | 1
+    ld = int(sym.sn_ld[k])
     a0, a1 = int(sym.a_ptr[k]), int(sym.a_ptr[k + 1])
     dst = [np.asarray(sym.a_dst[a0:a1], dtype=np.int64)]
     src = [np.asarray(sym.a_src[a0:a1], dtype=np.int64) | (TAG_J << 30)]
@@ -150,4 +150,5 @@ def build_tables(sym, threads: int, wpg: int) -> Dict[str, np.ndarray]:
     if len(ga) == 0:
         ga = np.full((1, 2), NOOP, dtype=np.uint32)
     return dict(fh=fh, ga=np.ascontiguousarray(ga).view(np.int32), n_sched=len(seqs), n_entries=int(cursor),
-                G_of=np.array([g for _, g in seqs], dtype=np.int64))
+                G_of=np.array([g for _, g in seqs], dtype=np.int64),
+                ld_of=np.array([int(sym.sn_ld[k]) for k, _ in seqs], dtype=np.int64))

@@ -344,6 +344,14 @@ def _postorder(parent: np.ndarray, children: List[List[int]], key) -> np.ndarray
     return np.array(post, dtype=np.int64)
 
 
+def front_ld(f, level):
+    """Leading dimension of a front of order ``f`` scheduled at ``level`` (0 = warp, else multi-warp);
+    mirrors ld_warp / ld_blk of csrc/szb_lu.cu."""
+    f = np.asarray(f)
+    fp = f + 7      # multi-warp fronts carry 7 rows of zero padding (kPad): unmasked 8x8 tensor-core tiles
+    return np.where(np.asarray(level) == 0, f | 1, fp + ((2 - fp) & 3))
+
+
 @dataclasses.dataclass
 class LUSymbolic:
     """Frozen result of the analysis; the integer arrays are uploaded to the device once."""
@@ -355,6 +363,7 @@ class LUSymbolic:
     sn_piv0: np.ndarray       # first pivot of supernode
     sn_s: np.ndarray          # pivots in supernode
     sn_f: np.ndarray          # front order (s + u)
+    sn_ld: np.ndarray         # leading dimension of the front buffer (front_ld)
     sn_parent: np.ndarray     # parent supernode or -1
     idx_ptr: np.ndarray       # front index lists (permuted indices; first s are the pivots)
     idx: np.ndarray
@@ -520,8 +529,6 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         loc_r[sel] = pr
         loc_c[sel] = pc
     a_src = by_owner.astype(np.int64)
-    sn_ld = sn_f | 1   # odd leading dimension: conflict-free shared-memory rows AND columns
-    a_dst = (loc_r[by_owner] + loc_c[by_owner] * sn_ld[owner[by_owner]]).astype(np.int64)
 
     # ---- factor storage
     lp_sz = sn_f * sn_s
@@ -549,6 +556,12 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
             sub_fmax[p] = max(sub_fmax[p], sub_fmax[k])
             sub_cost[p] += sub_cost[k]
     level = np.where(sub_fmax <= warp_front_max, 0, np.where(sub_fmax <= group_front_max, 1, 2))
+    # leading dimension of the column-major front in shared memory (csrc/szb_lu.cu: ld_warp / ld_blk):
+    # warp-level fronts (lane = row, rank-1 steps): odd, so rows AND columns are conflict-free;
+    # multi-warp fronts (8x8 tensor-core tiles): ld >= f + 7 and ld = 2 (mod 4), which puts the four column
+    # pairs of an mma.m8n8k4 accumulator fragment on disjoint banks.
+    sn_ld = front_ld(sn_f, level)
+    a_dst = (loc_r[by_owner] + loc_c[by_owner] * sn_ld[owner[by_owner]]).astype(np.int64)
     # (measured: lists balanced on s * f^2 finish within 5 % of each other; cost models with a per-front fixed
     # part or per-panel barrier costs did not do better, profiles/r1_v6_factor_ncu.md)
 
@@ -643,7 +656,7 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
 
     return LUSymbolic(
         n=n, nnzA=int(Ac.nnz), rowp=rowp, colp=colp, ns=ns, sn_piv0=sn_piv0, sn_s=sn_s,
-        sn_f=sn_f, sn_parent=sn_parent, idx_ptr=idx_ptr, idx=idx, rel_ptr=rel_ptr, rel=rel,
+        sn_f=sn_f, sn_ld=sn_ld, sn_parent=sn_parent, idx_ptr=idx_ptr, idx=idx, rel_ptr=rel_ptr, rel=rel,
         child_ptr=child_ptr, child=child, a_ptr=a_ptr, a_src=a_src, a_dst=a_dst, lp_off=lp_off,
         up_off=up_off, lu_size=lu_size, cb_off=cb_off, ea_ptr=ea_ptr, ea_dst=ea_dst, cb_size=cb_size,
         nnz_lu=nnz_lu,

@@ -17,7 +17,7 @@ def factor(sym, jv, mvals=None, scale=1.0):
     for k in order:
         s, f = int(sym.sn_s[k]), int(sym.sn_f[k])
         u = f - s
-        ld = f | 1
+        ld = int(sym.sn_ld[k])
         F = np.zeros(ld * f)
         a0, a1 = sym.a_ptr[k], sym.a_ptr[k + 1]
         v = scale * jv[sym.a_src[a0:a1]]
@@ -151,7 +151,7 @@ def factor_tables(sym, tabs, jv, rhs=None, mvals=None, scale=1.0, store_l=True):
         s, f, p0, lp_off, up_off, cb_off = (int(v) for v in fh[q, :6])
         G = int(G_of[q])
         u = f - s
-        ld = f | 1
+        ld = int(tabs["ld_of"][q])
         ncol = f + 1
         Fm = np.zeros(ld * ncol)
         owner = {}

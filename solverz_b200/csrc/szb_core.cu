@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "szb.h"
@@ -571,12 +572,20 @@ int szb_newton_host(szb_handle* h, double tol, int32_t max_it, double* y_host,
   SZB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t B = h->B, n = h->n;
-  SZB_CUDA(h, cudaMemcpyAsync(h->Y, y_host, B * n * sizeof(double), cudaMemcpyHostToDevice, st));
-  for (int i = 0; i < n_params; ++i) {
-    if (!params_host || !params_host[i]) continue;
-    const auto& pi = h->params[i];
-    const size_t bytes = (pi.dtype == SZB_DTYPE_F64 ? 8 : 4) * static_cast<size_t>(pi.len) * (pi.per_scenario ? B : 1);
-    SZB_CUDA(h, cudaMemcpyAsync(h->param_ptr[i], params_host[i], bytes, cudaMemcpyHostToDevice, st));
+  {
+    // Upload turnstile: handles driven concurrently from several host threads share one PCIe link, so
+    // their uploads are taken one at a time; the handle that has its inputs starts iterating while the
+    // next one uploads (copies of one handle overlap the kernels of the others).
+    static std::mutex upload_turn;
+    std::lock_guard<std::mutex> turn(upload_turn);
+    SZB_CUDA(h, cudaMemcpyAsync(h->Y, y_host, B * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < n_params; ++i) {
+      if (!params_host || !params_host[i]) continue;
+      const auto& pi = h->params[i];
+      const size_t bytes = (pi.dtype == SZB_DTYPE_F64 ? 8 : 4) * static_cast<size_t>(pi.len) * (pi.per_scenario ? B : 1);
+      SZB_CUDA(h, cudaMemcpyAsync(h->param_ptr[i], params_host[i], bytes, cudaMemcpyHostToDevice, st));
+    }
+    SZB_CUDA(h, cudaStreamSynchronize(st));
   }
   if ((rc = szb_newton(h, tol, max_it, nullptr, nullptr, stream)) != SZB_OK) return rc;
   SZB_CUDA(h, cudaMemcpyAsync(y_host, h->Y, B * n * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -479,8 +479,13 @@ struct PanelGrp {
   }
 };
 
+#if defined(SZB_PHASE_TIMING) && !defined(SZB_LEVEL_ONLY)
+#define SZB_FINE_TIMING
+#endif
 #ifdef SZB_PHASE_TIMING
 __device__ long long g_el[8 * 8];
+#endif
+#ifdef SZB_FINE_TIMING
 #define SZB_E(i) { const long long now_ = clock64(); el_[i] += now_ - te_; te_ = now_; }
 #else
 #define SZB_E(i)
@@ -490,7 +495,7 @@ __device__ long long g_el[8 * 8];
 // dynamic shared memory so that the compiler keeps the LDS / STS forms; SM_FRONT = false: the front
 // itself lives in a global workspace (FmG), only the side panel and the inverse are on chip.
 template <bool SM_FRONT>
-__device__ __forceinline__ void eliminate_blocked(const PanelGrp g, double* FmG, const int fm_off, const int lt_off,
+__device__ __noinline__ void eliminate_blocked(const PanelGrp g, double* FmG, const int fm_off, const int lt_off,
                                                const int lts, double* __restrict__ Lg, const int s, const int f,
                                                const int ncol, const int ld, int* flag) {
   extern __shared__ double sm[];
@@ -500,7 +505,7 @@ __device__ __forceinline__ void eliminate_blocked(const PanelGrp g, double* FmG,
   const int lane = g.lane(), w = g.warp(), nw = g.nw;
   const int q = lane & 3, g8 = lane >> 2;
   const int npan = (s + kNB - 1) / kNB;
-#ifdef SZB_PHASE_TIMING
+#ifdef SZB_FINE_TIMING
   const bool dbg_ = blockIdx.x == 0 && g.id == 0 && (threadIdx.x & 127) == 0;
   long long el_[7] = {0, 0, 0, 0, 0, 0, 0};
   long long te_ = clock64();
@@ -562,13 +567,13 @@ __device__ __forceinline__ void eliminate_blocked(const PanelGrp g, double* FmG,
   finalize_u(Fm, s, ncol, ld, lane, w, nw);
   g.sync();
   SZB_E(6)
-#ifdef SZB_PHASE_TIMING
+#ifdef SZB_FINE_TIMING
   if (dbg_) for (int i = 0; i < 7; ++i) g_el[8 * (threadIdx.x >> 7 & 7) + i] += el_[i];
 #endif
 }
 
 
-#ifdef SZB_PHASE_TIMING
+#ifdef SZB_FINE_TIMING
 #define SZB_T(i) { const long long now_ = clock64(); tacc_[(i) + 4 * lvl_] += now_ - tprev_; tprev_ = now_; }
 #define SZB_TPARAM , long long* tacc_, const int lvl_
 #define SZB_TSTART long long tprev_ = clock64();
@@ -720,11 +725,14 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
   long long tacc_[16];
   for (int i = 0; i < 16; ++i) tacc_[i] = 0;
   long long nscen_ = 0;
-#define SZB_TARG(l) , tacc_, l
 #define SZB_LVL(i) { const long long now_ = clock64(); tacc_[12 + (i)] += now_ - tlev_; tlev_ = now_; }
 #else
-#define SZB_TARG(l)
 #define SZB_LVL(i)
+#endif
+#ifdef SZB_FINE_TIMING
+#define SZB_TARG(l) , tacc_, l
+#else
+#define SZB_TARG(l)
 #endif
   FactorArgs A;
   A.mvals = mvals;

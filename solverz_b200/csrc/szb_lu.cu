@@ -1030,6 +1030,99 @@ __device__ void backward_front(const SolveHdr H, const double* __restrict__ lu, 
   }
 }
 
+// ---- a CTA-level front of the backward sweep, all warps of the CTA together.  The top of the tree is a
+// chain that holds almost half of U: walked by one warp it would leave the others idle with a few
+// kilobytes of loads in flight.  Here
+//   (a) the columns of U12 are dealt to the warps in chunks of 8 (lanes = rows): partial sums to red[w][i];
+//   (b) accs[i] = x_piv[i] - sum_w red[w][i];
+//   (c) the 32-row blocks of the triangle U11 are solved last block first by warp 0 (shuffles), and after
+//       each block every other row block above it takes that block's 32 new x (one warp per row block).
+// red: nwarps x s doubles, accs: s doubles of shared memory.
+__device__ void backward_front_cta(const SolveHdr H, const double* __restrict__ lu, const int* __restrict__ idx,
+                                   double* xb, double* __restrict__ red, double* __restrict__ accs, const int warp,
+                                   const int lane, const int nwarps) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0;
+  const double* __restrict__ Lp = lu + H.lp_off;       // f x s panel; rows <= column hold U11
+  const double* __restrict__ Up = lu + H.up_off;       // U12, s x u column-major
+  const int* __restrict__ ids = idx + H.idx_off + s;   // pivot-order indices of the update rows
+  const int nblk = (s + 31) >> 5;
+  for (int blk = 0; blk < nblk; ++blk) {               // (a)
+    const int i = 32 * blk + lane;
+    const int io = i < s ? i : 0;
+    const double* __restrict__ up = Up + io;
+    double acc = 0.0;
+    for (int c = 8 * warp; c < u; c += 8 * nwarps) {
+      int j[8];
+      double uv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const bool in = c + q < u;
+        j[q] = in ? __ldg(ids + c + q) : 0;
+        uv[q] = in ? up[(c + q) * s] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fma(uv[q], xb[j[q]], acc);
+    }
+    if (i < s) red[warp * s + i] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < s; i += blockDim.x) {  // (b)
+    double a = xb[p0 + i];
+    for (int w = 0; w < nwarps; ++w) a -= red[w * s + i];
+    accs[i] = a;
+  }
+  __syncthreads();
+  for (int blk = nblk - 1; blk >= 0; --blk) {          // (c)
+    const int bbeg = 32 * blk, bend = min(s, bbeg + 32);
+    if (warp == 0) {
+      const int i = bbeg + lane;
+      const bool ok = i < s;
+      const int io = ok ? i : 0;
+      double tv[kTri];
+      load_tri_cols(Lp, f, io, bend - 1, bbeg, tv);
+      double acc = accs[io];
+      for (int p = bend - 1; p >= bbeg; p -= kTri) {
+        double tn[kTri];
+        load_tri_cols(Lp, f, io, p - kTri, bbeg, tn);
+        double rinv[kTri];
+#pragma unroll
+        for (int q = 0; q < kTri; ++q) rinv[q] = 1.0 / __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);
+#pragma unroll
+        for (int q = 0; q < kTri; ++q) {
+          const int pq = p - q;
+          if (pq >= bbeg) {
+            const double xp = __shfl_sync(0xffffffffu, acc, pq & 31) * rinv[q];
+            if (i == pq) acc = xp;
+            else if (i < pq) acc = fma(-tv[q], xp, acc);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kTri; ++q) tv[q] = tn[q];
+      }
+      if (ok) xb[p0 + i] = acc;
+    }
+    if (blk == 0) break;
+    __syncthreads();
+    for (int b = warp; b < blk; b += nwarps) {         // rows of block b take the x of block blk
+      const int i = 32 * b + lane;                     // < bbeg <= s: always a row of the front
+      const double* __restrict__ lp = Lp + i + bbeg * f;
+      double acc = accs[i];
+      int p = bbeg;
+      for (; p + 8 <= bend; p += 8, lp += 8 * f) {
+        double uv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) uv[q] = lp[q * f];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fma(-uv[q], xb[p0 + p + q], acc);
+      }
+      for (; p < bend; ++p, lp += f) acc = fma(-lp[0], xb[p0 + p], acc);
+      accs[i] = acc;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(128, 6)
 lu_backward_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ YP,
                    double* __restrict__ X, double* __restrict__ XW, int x_in_smem, int mode,
@@ -1047,17 +1140,16 @@ lu_backward_kernel(const LuDev S, const double* __restrict__ LU, const double* _
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = yp[t];
     __syncthreads();
-    // the top of the tree is a chain: one warp walks it, root first
-    if (warp == 0 && S.n_top > 0) {
+    // the top of the tree is a chain, root first: every front by the whole CTA
+    if (S.n_top > 0) {
+      double* red = sm + (x_in_smem ? n : 0);
+      double* accs = red + nwarps * S.s_top_max;
       SolveHdr H = load_solve_hdr(S.fh, tq0 + S.n_top - 1);
-      SolveHdr Hn = load_solve_hdr(S.fh, tq0 + max(S.n_top - 2, 0));
-      prefetch_front(Hn, lu, lane);
       for (int q = S.n_top - 1; q >= 0; --q) {
-        const SolveHdr Hnn = load_solve_hdr(S.fh, tq0 + max(q - 2, 0));
-        if (q >= 2) prefetch_front(Hnn, lu, lane);
-        backward_front(H, lu, S.idx, xb, lane);
+        const SolveHdr Hn = load_solve_hdr(S.fh, tq0 + max(q - 1, 0));
+        if (q >= 1 && warp == nwarps - 1) prefetch_front(Hn, lu, lane);
+        backward_front_cta(H, lu, S.idx, xb, red, accs, warp, lane, nwarps);
         H = Hn;
-        Hn = Hnn;
       }
     }
     __syncthreads();
@@ -1151,7 +1243,8 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   // backward sweep: small CTAs, the permuted vector in shared memory when at least two CTAs fit an SM
   cfg->threads_bwd = 128;
   cfg->bwd_x_in_smem = static_cast<size_t>(S.n) * sizeof(double) * 2 <= static_cast<size_t>(smem_max) ? 1 : 0;
-  cfg->smem_bwd = cfg->bwd_x_in_smem ? static_cast<size_t>(S.n) * sizeof(double) : 0;
+  cfg->smem_bwd = (cfg->bwd_x_in_smem ? static_cast<size_t>(S.n) * sizeof(double) : 0) +
+                  (S.n_top > 0 ? static_cast<size_t>(cfg->threads_bwd / 32 + 1) * S.s_top_max * sizeof(double) : 0);
   e = cudaFuncSetAttribute(lu_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(cfg->smem_factor));
   if (e != cudaSuccess) return e;

@@ -275,9 +275,21 @@ def _gen_J(ir: ModelIR, k: int, jt: JacTemplate, tabs: _Tables) -> str:
     all_exprs += [eq.walkers[wi].expr for wi in walkers_needed]
     g.emit_loads(em, g.used_loads(all_exprs), inner=False)
     otab = [tabs.add(f"szbm_ot{k}_{ei}", sl) for ei, sl in enumerate(jt.outer_slots)]
-    itab = [tabs.add(f"szbm_it{k}_{ei}", sl) for ei, sl in enumerate(jt.inner_slots)]
+    # Inner entries that hit the same CSC slot at every position of the same walk (e.g. the G-walk and the
+    # B-walk terms of dP/dVa) are summed in registers and emitted ONCE: emitted separately the second one is
+    # a global read-modify-write of the value the same thread stored an instruction earlier (an L2 round
+    # trip on the dependent chain per term).  leader[ei] = the entry whose slot table the sum goes through.
+    group_of_w = {wi: gi for gi, g in enumerate(jt.groups) for wi in g}
+    leader: Dict[int, int] = {}
+    seen: Dict[Tuple, int] = {}
+    for ei, e in enumerate(jt.inner):
+        sl = np.asarray(jt.inner_slots[ei])
+        key = (group_of_w[e.walker], np.where(sl >= 0, sl, ~sl).tobytes(),
+               np.asarray(jt.inner_off[e.walker]).tobytes())
+        leader[ei] = seen.setdefault(key, ei)
+    itab = {ei: tabs.add(f"szbm_it{k}_{ei}", jt.inner_slots[ei]) for ei in sorted(set(leader.values()))}
     woff = {wi: tabs.add(f"szbm_wo{k}_{wi}", off) for wi, off in jt.inner_off.items()
-            if any(e.walker == wi for e in jt.inner)}
+            if any(e.walker == wi and leader[ei] == ei for ei, e in enumerate(jt.inner))}
 
     def sums_loop(gi, group, do_sums: bool, do_emit: bool):
         canon_ = self_canon[gi]
@@ -300,7 +312,10 @@ def _gen_J(ir: ModelIR, k: int, jt: JacTemplate, tabs: _Tables) -> str:
         g.emit_exprs(em, targets)
         if do_emit:
             for ei, e in ents:
-                em.w(f"szb_emit(JV, {itab[ei]}[{woff[e.walker]}[i] + (kk - kb{gi})], v{ei});")
+                if leader[ei] != ei:
+                    continue
+                total = " + ".join(f"v{ej}" for ej, _ in ents if leader[ej] == ei)
+                em.w(f"szb_emit(JV, {itab[ei]}[{woff[e.walker]}[i] + (kk - kb{gi})], {total});")
         em.ind -= 1
         em.w("}")
 

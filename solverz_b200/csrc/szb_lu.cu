@@ -1030,6 +1030,55 @@ __device__ void backward_front(const SolveHdr H, const double* __restrict__ lu, 
   }
 }
 
+// ---- a warp-level front (f <= 32: one row block, at most 31 update rows).  The indices of the update
+// rows were loaded a front ahead, one per lane (id_c); lane c gathers x[id_c] once and the dot products
+// take it by shuffles, so no global load sits between the parent's x and this front's arithmetic.
+__device__ __forceinline__ void backward_front_small(const SolveHdr H, const double* __restrict__ lu, const int id_c,
+                                                     double* xb, const int lane) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0;
+  const double* __restrict__ Lp = lu + H.lp_off;       // f x s panel; rows <= column hold U11
+  const double* __restrict__ Up = lu + H.up_off;       // U12, s x u column-major
+  const bool ok = lane < s;
+  const int io = ok ? lane : 0;                          // idle lanes mirror row 0 (finite data), never store
+  double tv[kTri];
+  load_tri_cols(Lp, f, io, s - 1, 0, tv);
+  const double xg = lane < u ? xb[id_c] : 0.0;
+  double acc = xb[p0 + io];
+  const double* __restrict__ up = Up + io;
+  for (int c = 0; c < u; c += 8, up += 8 * s) {
+    double uv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) uv[q] = c + q < u ? up[q * s] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc = fma(-uv[q], __shfl_sync(0xffffffffu, xg, (c + q) & 31), acc);
+  }
+  for (int p = s - 1; p >= 0; p -= kTri) {
+    double tn[kTri];
+    load_tri_cols(Lp, f, io, p - kTri, 0, tn);
+    double rinv[kTri];
+#pragma unroll
+    for (int q = 0; q < kTri; ++q) rinv[q] = 1.0 / __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);
+#pragma unroll
+    for (int q = 0; q < kTri; ++q) {
+      const int pq = p - q;
+      if (pq >= 0) {
+        const double xp = __shfl_sync(0xffffffffu, acc, pq & 31) * rinv[q];
+        if (lane == pq) acc = xp;
+        else if (lane < pq) acc = fma(-tv[q], xp, acc);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kTri; ++q) tv[q] = tn[q];
+  }
+  if (ok) xb[p0 + lane] = acc;
+  __syncwarp();
+}
+
+// index of lane's update row of front H (pivot order), 0 beyond the update rows
+__device__ __forceinline__ int load_update_id(const SolveHdr H, const int* __restrict__ idx, const int lane) {
+  return lane < H.f - H.s ? __ldg(idx + H.idx_off + H.s + lane) : 0;
+}
+
 // ---- a CTA-level front of the backward sweep, all warps of the CTA together.  The top of the tree is a
 // chain that holds almost half of U: walked by one warp it would leave the others idle with a few
 // kilobytes of loads in flight.  Here
@@ -1174,13 +1223,16 @@ lu_backward_kernel(const LuDev S, const double* __restrict__ LU, const double* _
       if (q0 < q1) {
         SolveHdr H = load_solve_hdr(S.fh, q1 - 1);
         SolveHdr Hn = load_solve_hdr(S.fh, max(q1 - 2, q0));
+        int id_c = load_update_id(H, S.idx, lane);
         prefetch_front(Hn, lu, lane);
         for (int q = q1 - 1; q >= q0; --q) {
           const SolveHdr Hnn = load_solve_hdr(S.fh, max(q - 2, q0));
+          const int id_n = load_update_id(Hn, S.idx, lane);      // lands while this front is solved
           if (q - 2 >= q0) prefetch_front(Hnn, lu, lane);
-          backward_front(H, lu, S.idx, xb, lane);
+          backward_front_small(H, lu, id_c, xb, lane);
           H = Hn;
           Hn = Hnn;
+          id_c = id_n;
         }
       }
     }

@@ -617,7 +617,8 @@ __device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre
     for (int t = lane; t < rows * s; t += kWarp) {
       const int p = fdiv(t, invr);
       const int i = t - p * rows;
-      Lp[i + p * f] = Fm[i + p * ld];
+      const double v = Fm[i + p * ld];
+      Lp[i + p * f] = i == p ? fast_rcp(v) : v;         // the diagonal of U is stored as its reciprocal
     }
   }
   if (u > 0) {
@@ -672,7 +673,7 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
     const int pend = min(s, (p & ~(kNB - 1)) + kNB);
     const double* __restrict__ src = Fm + p * ld;
     double* __restrict__ dst = Lp + p * f;
-    for (int i = lane; i < pend; i += kWarp) dst[i] = src[i];
+    for (int i = lane; i < pend; i += kWarp) dst[i] = i == p ? fast_rcp(src[i]) : src[i];   // 1 / u_pp on the diagonal
   }
   if (u > 0) {
     // lanes over the long dimension, pointer walks over the short one: no index arithmetic inside
@@ -1012,7 +1013,7 @@ __device__ void backward_front(const SolveHdr H, const double* __restrict__ lu, 
       load_tri_cols(Lp, f, io, p - kTri, bbeg, tn);
       double rinv[kTri];
 #pragma unroll
-      for (int q = 0; q < kTri; ++q) rinv[q] = 1.0 / __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);
+      for (int q = 0; q < kTri; ++q) rinv[q] = __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);   // the factor stores 1 / u_pp
 #pragma unroll
       for (int q = 0; q < kTri; ++q) {
         const int pq = p - q;
@@ -1057,7 +1058,7 @@ __device__ __forceinline__ void backward_front_small(const SolveHdr H, const dou
     load_tri_cols(Lp, f, io, p - kTri, 0, tn);
     double rinv[kTri];
 #pragma unroll
-    for (int q = 0; q < kTri; ++q) rinv[q] = 1.0 / __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);
+    for (int q = 0; q < kTri; ++q) rinv[q] = __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);   // the factor stores 1 / u_pp
 #pragma unroll
     for (int q = 0; q < kTri; ++q) {
       const int pq = p - q;
@@ -1135,7 +1136,7 @@ __device__ void backward_front_cta(const SolveHdr H, const double* __restrict__ 
         load_tri_cols(Lp, f, io, p - kTri, bbeg, tn);
         double rinv[kTri];
 #pragma unroll
-        for (int q = 0; q < kTri; ++q) rinv[q] = 1.0 / __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);
+        for (int q = 0; q < kTri; ++q) rinv[q] = __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);   // the factor stores 1 / u_pp
 #pragma unroll
         for (int q = 0; q < kTri; ++q) {
           const int pq = p - q;

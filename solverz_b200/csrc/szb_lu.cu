@@ -198,6 +198,10 @@ __device__ __forceinline__ void assemble_stream(const AsmPre& P, const int rank,
   auto live = [=](const int2 en) {
     return en.x != -1 && (with_rhs || (static_cast<unsigned>(en.x) >> 30) != 2u);
   };
+  // software pipeline: the entries of batch k+1 are in flight while the values of batch k are fetched
+  int2 en[kAsm];
+#pragma unroll
+  for (int q = 0; q < kAsm; ++q) en[q] = kAsm + q < iters ? __ldg(e + (kAsm + q) * G_) : make_int2(-1, 0);
   {
     double v[kAsm];
 #pragma unroll
@@ -209,16 +213,19 @@ __device__ __forceinline__ void assemble_stream(const AsmPre& P, const int rank,
     for (int q = 0; q < kAsm; ++q)
       if (live(P.en[q])) Fm[P.en[q].y] += v[q];
   }
+  if (iters <= kAsm) return;
   for (int it = kAsm; it < iters; it += kAsm) {
-    int2 en[kAsm];
+    int2 nx[kAsm];
     double v[kAsm];
 #pragma unroll
-    for (int q = 0; q < kAsm; ++q) en[q] = it + q < iters ? __ldg(e + (it + q) * G_) : make_int2(-1, 0);
+    for (int q = 0; q < kAsm; ++q) nx[q] = it + kAsm + q < iters ? __ldg(e + (it + kAsm + q) * G_) : make_int2(-1, 0);
 #pragma unroll
     for (int q = 0; q < kAsm; ++q) v[q] = live(en[q]) ? asm_fetch<PLAIN>(static_cast<unsigned>(en[q].x), A) : 0.0;
 #pragma unroll
     for (int q = 0; q < kAsm; ++q)
       if (live(en[q])) Fm[en[q].y] += v[q];
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q) en[q] = nx[q];
   }
 }
 

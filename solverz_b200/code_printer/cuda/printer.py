@@ -174,6 +174,61 @@ class _RowGen:
                 continue
             em.w(f"const double {self.names[s]} = {self.load_text(ld)};")
 
+    def open_walk(self, em: _Emitter, gi: int, canon: str, syms: Sequence[sp.Symbol],
+                  extra: Sequence[Tuple[str, str, str]] = (), pipelined: bool = True):
+        """Opens the CSR row walk ``for kk in [kb, ke)`` software-pipelined by one iteration: the column
+        index, the inner loads (matrix values, gathered variables / parameters) and ``extra`` per-position
+        loads ``(ctype, name, text in kk)`` of iteration kk + 1 are issued before iteration kk computes, so
+        that the two dependent round trips of a gather (index, then value) overlap the arithmetic (fp64
+        ``sincos`` is ~100 instructions) instead of sitting in front of it."""
+        import re
+        loads: List[Tuple[str, str, str]] = []
+        for s_ in sorted(syms, key=lambda x: int(x.name[2:])):
+            ld = self.eq.loads[s_]
+            if ld.index.kind == "inner" or ld.kind == "mat":
+                loads.append(("double", self.names[s_], self.load_text(ld)))
+        loads += list(extra)
+        if not pipelined:        # plain walk (the F kernel is issue-bound: the extra moves cost more than they hide)
+            em.w("{")
+            em.w(f"for (int kk = kb{gi}; kk < ke{gi}; ++kk) {{")
+            em.ind += 1
+            em.w(f"const int j = c.p_{canon}__indices[kk];")
+            for cty, nm, tx in loads:
+                em.w(f"const {cty} {nm} = {tx};")
+            em.w("(void)j;")
+            return
+        jn = f"jn{gi}"
+
+        def at(text: str, kk_expr: str) -> str:
+            return re.sub(r"\bj\b", jn, re.sub(r"\bkk\b", kk_expr, text))
+
+        em.w("{")                                      # own scope: a two-pass template walks the same row twice
+        em.w(f"int {jn} = 0;")
+        for cty, nm, _ in loads:
+            em.w(f"{cty} {nm}_n = 0;")
+        em.w(f"if (kb{gi} < ke{gi}) {{")
+        em.w(f"  {jn} = c.p_{canon}__indices[kb{gi}];")
+        for _, nm, tx in loads:
+            em.w(f"  {nm}_n = {at(tx, f'kb{gi}')};")
+        em.w("}")
+        em.w(f"for (int kk = kb{gi}; kk < ke{gi}; ++kk) {{")
+        em.ind += 1
+        em.w(f"const int j = {jn};")
+        for cty, nm, _ in loads:
+            em.w(f"const {cty} {nm} = {nm}_n;")
+        em.w(f"if (kk + 1 < ke{gi}) {{")
+        em.w(f"  {jn} = c.p_{canon}__indices[kk + 1];")
+        for _, nm, tx in loads:
+            em.w(f"  {nm}_n = {at(tx, '(kk + 1)')};")
+        em.w("}")
+        em.w("(void)j;")
+
+    @staticmethod
+    def close_walk(em: _Emitter):
+        em.ind -= 1
+        em.w("}")
+        em.w("}")
+
     def emit_exprs(self, em: _Emitter, targets: List[Tuple[str, sp.Expr]]):
         """targets: (statement prefix e.g. 'S0 +=' or 'const double v3 =', expr)."""
         exprs = [self.canon(e) for _, e in targets]
@@ -246,14 +301,10 @@ def _gen_F(ir: ModelIR, k: int, eq: EqTemplate, jt: JacTemplate, tabs: _Tables) 
         canon = g.walk_header(em, gi, group)
         for wi in group:
             em.w(f"double {g.names[eq.walkers[wi].sym]} = 0.0;")
-        em.w(f"for (int kk = kb{gi}; kk < ke{gi}; ++kk) {{")
-        em.ind += 1
-        em.w(f"const int j = c.p_{_ident(canon)}__indices[kk];")
         ex = [eq.walkers[wi].expr for wi in group]
-        g.emit_loads(em, g.used_loads(ex), inner=True)
+        g.open_walk(em, gi, _ident(canon), g.used_loads(ex), pipelined=False)
         g.emit_exprs(em, [(f"{g.names[eq.walkers[wi].sym]} +=", eq.walkers[wi].expr) for wi in group])
-        em.ind -= 1
-        em.w("}")
+        g.close_walk(em)
     g.emit_exprs(em, [("return", eq.expr)])
     head = f"SZB_HD static inline double szbm_F{k}(const int i, const szbm_ctx& c) {{  // {eq.name}\n"
     return head + em.text() + "\n}\n"
@@ -298,26 +349,25 @@ def _gen_J(ir: ModelIR, k: int, jt: JacTemplate, tabs: _Tables) -> str:
         ents = [(ei, e) for ei, e in enumerate(jt.inner) if e.walker in group]
         if not ((do_sums and (accs_here or s_here)) or (do_emit and ents)):
             return
-        em.w(f"for (int kk = kb{gi}; kk < ke{gi}; ++kk) {{")
-        em.ind += 1
-        em.w(f"const int j = c.p_{_ident(canon_)}__indices[kk];")
         targets: List[Tuple[str, sp.Expr]] = []
         if do_sums:
             targets += [(f"{g.names[eq.walkers[wi].sym]} +=", eq.walkers[wi].expr) for wi in s_here]
             targets += [(f"{g.names[a]} +=", x) for _, a, x in accs_here]
+        slot_loads: List[Tuple[str, str, str]] = []
         if do_emit:
             for ei, e in ents:
                 targets.append((f"const double v{ei} =", sp.Symbol(f"cf{ei}", real=True) * e.term))
-        g.emit_loads(em, g.used_loads([x for _, x in targets]), inner=True)
+                if leader[ei] == ei:                   # the CSC slot of this position, fetched an iteration ahead
+                    slot_loads.append(("int", f"sl{ei}", f"{itab[ei]}[{woff[e.walker]}[i] + (kk - kb{gi})]"))
+        g.open_walk(em, gi, _ident(canon_), g.used_loads([x for _, x in targets]), slot_loads)
         g.emit_exprs(em, targets)
         if do_emit:
             for ei, e in ents:
                 if leader[ei] != ei:
                     continue
                 total = " + ".join(f"v{ej}" for ej, _ in ents if leader[ej] == ei)
-                em.w(f"szb_emit(JV, {itab[ei]}[{woff[e.walker]}[i] + (kk - kb{gi})], {total});")
-        em.ind -= 1
-        em.w("}")
+                em.w(f"szb_emit(JV, sl{ei}, {total});")
+        g.close_walk(em)
 
     self_canon = {}
     for gi, group in enumerate(jt.groups):

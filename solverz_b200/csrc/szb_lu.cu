@@ -663,13 +663,30 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
   const int lane = g.lane(), w = g.warp(), nw = g.nw, r = g.rank(), G_ = g.size();
   const int with_rhs = A.rhs != nullptr;
   const int ncol = f + with_rhs;
+#ifdef SZB_PHASE_TIMING
+  const long long tfg0_ = clock64();
+#endif
   clear_front(Fm, ld * cols_blk(f), r, G_);
   g.sync();
+#ifdef SZB_PHASE_TIMING
+  const long long tfg1_ = clock64();
+#endif
   assemble_front(P, r, G_, H, ga, Fm, A);
   g.sync();
   SZB_T(0)
   double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
+#ifdef SZB_PHASE_TIMING
+  const long long tel0_ = clock64();
+#endif
   eliminate_blocked<SM_FRONT>(g, Fm, fm_off, lt_off, lts, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
+#ifdef SZB_PHASE_TIMING
+  const long long tel1_ = clock64();
+  if (blockIdx.x == 0 && g.rank() == 0 && g.id <= 1) {
+    g_el[56 + g.id] += tel1_ - tel0_;                  // [56] CTA level, [57] group 0: elimination
+    g_el[58 + g.id] += tfg1_ - tfg0_;                  // clear
+    g_el[60 + g.id] += tel0_ - tfg1_;                  // assembly (incl. its barrier)
+  }
+#endif
   // the next front's descriptor and first gather entries fly during the write-out (nothing of them is
   // kept across the elimination: it has the register file to itself)
   const FrontHdr Hnext = load_hdr(fh, q_next);
@@ -704,6 +721,9 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
   if (with_rhs)
     for (int t = r; t < s; t += G_) A.yout[H.piv0 + t] = Fm[t + f * ld];
   g.sync();
+#ifdef SZB_PHASE_TIMING
+  if (blockIdx.x == 0 && g.rank() == 0 && g.id <= 1) g_el[62 + g.id] += clock64() - tel1_;   // write-out
+#endif
   SZB_T(2)
   return Hnext;
 }
@@ -829,6 +849,10 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
     for (int l = 0; l < 3; ++l)
       printf("  %s level %8lld : clear+assemble %8lld  eliminate %8lld  write-out %8lld\n", nm[l], tacc_[12 + l] / n_,
              tacc_[4 * l] / n_, tacc_[4 * l + 1] / n_, tacc_[4 * l + 2] / n_);
+    for (int l = 0; l < 2; ++l)
+      printf("  %s fronts: clear %lld assemble %lld eliminate %lld write-out %lld cycles/scenario\n", l ? "group-0" : "CTA-level",
+             g_el[58 + l] / n_, g_el[60 + l] / n_, g_el[56 + l] / n_, g_el[62 + l] / n_);
+    for (int l = 56; l < 64; ++l) g_el[l] = 0;
     for (int wq = 0; wq < 8; ++wq) {
       printf("  top elimination, warp %2d: first-diag %lld diag_next %lld phaseA %lld wait-phase %lld phaseB %lld wait-main %lld finalize %lld\n",
              4 * wq, g_el[8 * wq] / n_, g_el[8 * wq + 1] / n_, g_el[8 * wq + 2] / n_, g_el[8 * wq + 3] / n_,

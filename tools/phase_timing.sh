@@ -9,5 +9,5 @@ nvcc $F $SZB_EXTRA -DSZB_PHASE_TIMING -c szb_lu.cu -o ../../build/timing/szb_lu.
 cp libszb.so ../../build/timing/libszb.keep.so
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o libszb.so szb_core.o ../../build/timing/szb_lu.o szb_rodas.o -lcudart -ldl
 cd ../..
-python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e "$@" 2>&1 | grep -A11 "lu_factor phases" | tail -12
+python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e "$@" 2>&1 | grep -A13 "lu_factor phases" | tail -14
 cp build/timing/libszb.keep.so solverz_b200/csrc/libszb.so

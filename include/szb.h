@@ -189,6 +189,15 @@ SZB_API int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters
 /* time t at which szb_newton evaluates F(t,y,p) and J(t,y,p) (0 by default); fdae_solver sets t0 + dt
  * before each step (fdesolver.py:104-108) */
 SZB_API int szb_set_time(szb_handle* h, double t);
+/* Implicit one-step mode of szb_newton: the residual and matrix of the algebraic system that
+ * backward_euler (beuler.py:66-72) and implicit_trapezoid (trapezoidal.py:65-73) hand to nr_method,
+ *     G(y) = M (y - y_prev) - c (F(t, y, p) + kappa F_prev),      A = M - c J(t, y, p),
+ * mode 1: backward Euler (c = dt, kappa = 0, f_prev_dev may be NULL), mode 2: trapezoid (c = dt/2, kappa = 1;
+ * the reference's residual is -G and its matrix -A: same iterates), mode 0: back to F(y) = 0.
+ * y_prev_dev / f_prev_dev: caller-owned device double[B][n], read during szb_newton; t comes from
+ * szb_set_time; needs szb_set_mass_rows. */
+SZB_API int szb_set_implicit(szb_handle* h, int32_t mode, double c, const double* y_prev_dev,
+                     const double* f_prev_dev);
 /* same with HOST buffers: copies y0 and the per-scenario parameters in, solves, copies y,
  * iters and flags out.  params_host[i] may be NULL to keep what is already on the device. */
 SZB_API int szb_newton_host(szb_handle* h, double tol, int32_t max_it, double* y_host,

@@ -171,6 +171,37 @@ int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b,
   return SZB_OK;
 }
 
+// G = M (y - y_prev) - c (F + kappa F_prev) and max|G| per scenario (NaN-propagating); one CTA per scenario
+__global__ void __launch_bounds__(256)
+implicit_residual_kernel(const double* __restrict__ F, const double* __restrict__ Y, const double* __restrict__ Y0,
+                         const double* __restrict__ F0, const int* __restrict__ mcol, double c, double kappa,
+                         double* __restrict__ G, double* __restrict__ fnorm, const int* __restrict__ active, int n) {
+  __shared__ double red[8];
+  const int b = blockIdx.x;
+  if (active && !active[b]) return;
+  const size_t o = static_cast<size_t>(b) * n;
+  double m = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int col = mcol[i];
+    double f = F[o + i];
+    if (F0) f += kappa * F0[o + i];
+    const double g = (col >= 0 ? Y[o + col] - Y0[o + col] : 0.0) - c * f;
+    G[o + i] = g;
+    const double a = fabs(g);
+    m = (a > m || a != a) ? a : m;
+  }
+  for (int s = 16; s > 0; s >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, m, s);
+    m = (t > m || t != t) ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = (red[w] > m || red[w] != red[w]) ? red[w] : m;
+    fnorm[b] = m;
+  }
+}
+
 // =========================================================================================
 extern "C" {
 
@@ -310,6 +341,7 @@ int szb_set_batch(szb_handle* h, int32_t B) {
   SZB_CUDA(h, cudaSetDevice(h->device));
   free_bag(h->batch_owned);
   free_bag(h->rodas_owned);
+  h->imp_G = nullptr; h->imp_G_B = 0;
   h->rodas_B = 0; h->rodas_stages = 0; h->rd_tout_cap = 0; h->rd_mcol_ready = false;
   h->ws_bytes = 0;
   h->B = 0;
@@ -504,8 +536,37 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
   newton_init_kernel<<<gb, tb, 0, st>>>(h->nstep, h->active, h->flags, B);
   h->launches[4]++;
   toc(4);
+  const bool implicit_step = h->imp_mode != 0;
+  if (implicit_step) {
+    if (!h->mass_vals || h->mass_row_col.size() != static_cast<size_t>(h->n) || !h->imp_y0) {
+      szb_set_error(h, "szb_newton (implicit step): needs a mass matrix, szb_set_mass_rows and y_prev");
+      return SZB_ESTATE;
+    }
+    if (!h->imp_mcol) {
+      void* p = nullptr;
+      SZB_CUDA(h, cudaMalloc(&p, sizeof(int) * h->n));
+      h->owned.push_back(p);
+      h->imp_mcol = static_cast<int*>(p);
+    }
+    SZB_CUDA(h, cudaMemcpyAsync(h->imp_mcol, h->mass_row_col.data(), sizeof(int) * h->n, cudaMemcpyHostToDevice, st));
+    if (!h->imp_G || h->imp_G_B != B) {
+      void* p = nullptr;
+      SZB_CUDA(h, cudaMalloc(&p, sizeof(double) * static_cast<size_t>(B) * h->n));
+      h->batch_owned.push_back(p);
+      h->imp_G = static_cast<double*>(p);
+      h->imp_G_B = B;
+    }
+  }
+  auto step_residual = [&]() {   // F -> G of the step equation (and its max-norm) when a one-step method drives Newton
+    if (!implicit_step) return;
+    implicit_residual_kernel<<<B, 256, 0, st>>>(h->F, h->Y, h->imp_y0, h->imp_mode == 2 ? h->imp_f0 : nullptr, h->imp_mcol,
+                                                h->imp_c, 1.0, h->imp_G, h->fnorm, h->active, h->n);
+    h->launches[4]++;
+  };
+  const double* resid = implicit_step ? h->imp_G : h->F;
   tic();
   if ((rc = szb_eval_F_masked(h, h->time, h->active, st)) != SZB_OK) return rc;
+  step_residual();
   toc(0);
   h->prof_units[0] += B;
   int sweeps = 0;
@@ -526,7 +587,8 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
     toc(1);
     tic();
     // factorisation with the residual riding along as an extra column: y = L^{-1} P F
-    if ((rc = szb_lu_refactor_masked(h, 0.0, nullptr, h->active, h->F, h->ybuf, 0, st)) != SZB_OK) return rc;
+    if ((rc = szb_lu_refactor_masked(h, implicit_step ? h->imp_c : 0.0, nullptr, h->active, resid, h->ybuf, 0, st)) != SZB_OK)
+      return rc;
     toc(2);
     tic();
     {
@@ -539,6 +601,7 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
     toc(3);
     tic();
     if ((rc = szb_eval_F_masked(h, h->time, h->active, st)) != SZB_OK) return rc;
+    step_residual();
     toc(0);
     if (++sweeps > max_it + 2) {  // cannot happen: every scenario stops after max_it+1 sweeps
       szb_set_error(h, "szb_newton: internal sweep bound exceeded");
@@ -612,6 +675,18 @@ int szb_query(const szb_handle* h, int32_t what, int64_t* out) {
     case SZB_Q_WORKSPACE_BYTES: *out = h->ws_bytes; return SZB_OK;
     default: return SZB_EINVAL;
   }
+}
+
+int szb_set_implicit(szb_handle* h, int32_t mode, double c, const double* y_prev_dev, const double* f_prev_dev) {
+  if (!h) return SZB_EINVAL;
+  if (mode < 0 || mode > 2) { szb_set_error(h, "szb_set_implicit: mode %d (0 off, 1 backward Euler, 2 trapezoid)", mode); return SZB_EINVAL; }
+  if (mode != 0 && !y_prev_dev) { szb_set_error(h, "szb_set_implicit: y_prev_dev is null"); return SZB_EINVAL; }
+  if (mode == 2 && !f_prev_dev) { szb_set_error(h, "szb_set_implicit: the trapezoid needs f_prev_dev"); return SZB_EINVAL; }
+  h->imp_mode = mode;
+  h->imp_c = c;
+  h->imp_y0 = y_prev_dev;
+  h->imp_f0 = f_prev_dev;
+  return SZB_OK;
 }
 
 int szb_set_time(szb_handle* h, double t) {

@@ -59,6 +59,13 @@ struct szb_handle {
   int rd_tout_cap = 0;
   bool rd_mcol_ready = false;
   std::vector<int> mass_row_col;   // row -> column of the unit mass entry, -1 for algebraic rows
+  // implicit one-step mode of szb_newton (szb_set_implicit)
+  int imp_mode = 0;
+  double imp_c = 0.0;
+  const double *imp_y0 = nullptr, *imp_f0 = nullptr;
+  double* imp_G = nullptr;         // [B][n] residual of the step equation (batch-owned)
+  int* imp_mcol = nullptr;         // device copy of mass_row_col (owned)
+  int imp_G_B = 0;
 };
 
 void szb_set_error(szb_handle* h, const char* fmt, ...);

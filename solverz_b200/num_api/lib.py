@@ -91,6 +91,7 @@ def load():
     lib.szb_lu_refactor_masked_rows.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.szb_query.argtypes = [H, C.c_int32, C.POINTER(C.c_int64)]
     lib.szb_set_time.argtypes = [H, C.c_double]
+    lib.szb_set_implicit.argtypes = [H, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
     lib.szb_set_profile.argtypes = [H, C.c_int32]
     lib.szb_get_profile.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     if lib.szb_abi_version() != SZB_ABI_VERSION:

@@ -5,3 +5,4 @@ from .nr import nr_method
 from .rodas import Rodas
 from .rodas_param import Rodas_param
 from .fdae import fdae_solver
+from .implicit import backward_euler, implicit_trapezoid

@@ -198,3 +198,110 @@ def swing_fault_scenarios(nb: int, B: int):
         tst[b] = [0.0, t0, t0 + 1e-3, t1, t1 + 1e-3, 10.0]
         tsv[b] = [0.0, 0.0, g, g, 0.0, 0.0]
     return fmask, tst, tsv
+
+
+# ------------------------------------------------------------------------------------------------
+# config #5: district-heating hydraulic-thermal FDAE -- supply network on a lattice, hydraulics by mass
+# continuity + loop pressure drops (mutable-matrix Jacobian), upwind pipe-outlet temperatures with an
+# AliasVar history node, time-stepped load profiles
+# ------------------------------------------------------------------------------------------------
+def dhs_fdae_model(nx: int, ny: int, ns=None, seed: int = 0, dt: float = 60.0):
+    """Builds the model with the DSL in namespace ``ns`` (this package by default; the golden generator
+    passes the reference's ``Solverz`` module).  Nodes on an nx x ny lattice, the source at node 0, pipes
+    oriented away from it (+x, +y); with loads at every other node all flows stay positive, which is what
+    the fixed upwind direction of the thermal part assumes.
+
+        0 = V_ns m - sc(t) m_inj                                  mass continuity at the non-source nodes
+        0 = L (K m |m|)                                           pressure drop around every lattice cell
+        0 = Tin - Vf Tn                                           pipe inlet = temperature of the node it leaves
+        0 = Tout - Tout_prev - cth m (Tin - Tout) + lam (Tout - Ta)        pipe outlet, one history node
+        0 = Vin (m Tout) - Tn[1:] (Vin m)                         mixing at the non-source nodes
+        0 = Tn[0] - Ts                                            supply temperature at the source
+
+    (Tin is a variable of its own: the reference's matrix calculus cannot differentiate ``m * (Vf Tn - Tout)``,
+    an element-wise product around a Mat_Mul -- found while generating the goldens.)
+    ``sc`` (a TimeSeriesParam) scales the loads over time and is the per-scenario input.  Returns
+    (model, info); the model starts from the steady state of the nominal load (sc = 1)."""
+    if ns is None:
+        import solverz_b200 as ns
+    own = ns.__name__ == "solverz_b200"
+    rng = np.random.default_rng(seed + 11)
+    n_node = nx * ny
+    node = lambda ix, iy: ix * ny + iy
+    pipes = []
+    for ix in range(nx):
+        for iy in range(ny):
+            if ix + 1 < nx:
+                pipes.append((node(ix, iy), node(ix + 1, iy)))
+            if iy + 1 < ny:
+                pipes.append((node(ix, iy), node(ix, iy + 1)))
+    n_pipe = len(pipes)
+    pidx = {p: k for k, p in enumerate(pipes)}
+    V = np.zeros((n_node, n_pipe))
+    for k, (a, b) in enumerate(pipes):
+        V[a, k] = -1.0
+        V[b, k] = 1.0
+    loops = []
+    for ix in range(nx - 1):
+        for iy in range(ny - 1):
+            row = np.zeros(n_pipe)                       # around the cell: +x, +y, -x, -y
+            row[pidx[(node(ix, iy), node(ix + 1, iy))]] = 1.0
+            row[pidx[(node(ix + 1, iy), node(ix + 1, iy + 1))]] = 1.0
+            row[pidx[(node(ix, iy + 1), node(ix + 1, iy + 1))]] = -1.0
+            row[pidx[(node(ix, iy), node(ix, iy + 1))]] = -1.0
+            loops.append(row)
+    Lm = np.array(loops)
+    K = rng.uniform(0.5, 2.0, n_pipe)
+    load = rng.uniform(0.5, 1.5, n_node - 1)            # withdrawals at the non-source nodes (flow into the node)
+    V_ns = V[1:, :]
+    Vin = np.maximum(V_ns, 0.0)                         # pipes that end at the node
+    Vf = np.zeros((n_pipe, n_node))                     # the node a pipe starts from
+    for k, (a, b) in enumerate(pipes):
+        Vf[k, a] = 1.0
+    # steady state of the nominal load: hydraulic Newton, then temperatures node by node (lattice order is topological)
+    mflow = np.linalg.lstsq(np.vstack([V_ns, Lm]), np.concatenate([load, np.zeros(len(loops))]), rcond=None)[0]
+    for _ in range(50):
+        res = np.concatenate([V_ns @ mflow - load, Lm @ (K * mflow * np.abs(mflow))])
+        Jh = np.vstack([V_ns, Lm * (2 * K * np.abs(mflow))[None, :]])
+        mflow = mflow - np.linalg.solve(Jh, res)
+    cth, lam, Ta, Ts = 0.08 * dt / 60.0, 0.01 * dt / 60.0, 10.0, 90.0
+    Tn = np.full(n_node, Ts)
+    Tout = np.full(n_pipe, Ts)
+    for _ in range(200):                                  # fixed point of the steady thermal equations
+        Tin = Vf @ Tn
+        Tout = (cth * mflow * Tin + lam * Ta) / (cth * mflow + lam)
+        Tn[1:] = (Vin @ (mflow * Tout)) / (Vin @ mflow)
+    kw = dict(per_scenario=True) if own else {}
+    m = ns.Model()
+    m.m = ns.Var('m', mflow)
+    m.Tout = ns.Var('Tout', Tout)
+    m.Tn = ns.Var('Tn', Tn)
+    m.Tin = ns.Var('Tin', Vf @ Tn)
+    m.Tout0 = ns.AliasVar('Tout', value=Tout, step=1) if own else ns.AliasVar('Tout', step=1, value=Tout)
+    for nm, A in (("V_ns", V_ns), ("L", Lm), ("Vin", Vin), ("Vf", Vf)):
+        setattr(m, nm, ns.Param(nm, sps.csc_array(A), dim=2, sparse=True))
+    m.K = ns.Param('K', K)
+    m.m_inj = ns.Param('m_inj', load)
+    m.sc = ns.TimeSeriesParam('sc', v_series=[1.0, 1.0, 1.2, 1.2], time_series=[0.0, dt, 3 * dt, 1e6], **kw)
+    Mat_Mul, Abs = ns.Mat_Mul, ns.Abs
+    m.mass = ns.Eqn('mass', Mat_Mul(m.V_ns, m.m) - m.sc * m.m_inj)
+    m.loop = ns.Eqn('loop', Mat_Mul(m.L, m.K * m.m * Abs(m.m)))
+    m.inlet = ns.Eqn('inlet', m.Tin - Mat_Mul(m.Vf, m.Tn))
+    m.pipe = ns.Eqn('pipe', m.Tout - m.Tout0 - cth * m.m * (m.Tin - m.Tout) + lam * (m.Tout - Ta))
+    m.mix = ns.Eqn('mix', Mat_Mul(m.Vin, m.m * m.Tout) - m.Tn[1:n_node] * Mat_Mul(m.Vin, m.m))
+    m.src = ns.Eqn('src', m.Tn[0] - Ts)
+    info = dict(n_node=n_node, n_pipe=n_pipe, n=3 * n_pipe + n_node, dt=dt)
+    return m, info
+
+
+def dhs_load_profiles(B: int, dt: float = 60.0):
+    """Scenario b: the loads ramp from 1 to 1 + 0.05 (b mod 7 + 1) between t = dt (1 + b mod 3) and two steps
+    later, then stay.  Returns (ts_t[B, 4], ts_v[B, 4])."""
+    tst = np.zeros((B, 4))
+    tsv = np.zeros((B, 4))
+    for b in range(B):
+        t0 = dt * (1 + b % 3)
+        a = 1.0 + 0.05 * (b % 7 + 1)
+        tst[b] = [0.0, t0, t0 + 2 * dt, 1e6]
+        tsv[b] = [1.0, 1.0, a, a]
+    return tst, tsv

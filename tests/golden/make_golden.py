@@ -269,6 +269,42 @@ def golden_events():
     print("orbit te", out["orbit_rodas4_te"], out["orbit_rodas3_te"])
 
 
+def golden_dhs(nx=3, B=6):
+    """Config #5 in miniature: the district-heating hydraulic-thermal FDAE of
+    ``solverz_b200.synthetic.dhs_fdae_model`` written with the REFERENCE's DSL (same builder, other namespace:
+    Mat_Mul hydraulics with the mutable-matrix Jacobian of L (K m |m|), AliasVar history of the pipe outlet
+    temperatures, a TimeSeriesParam load profile), integrated by the reference's fdae_solver, one scenario at
+    a time (the load profile is mutated in ``mdl.p`` between runs)."""
+    import Solverz as ns
+    from solverz_b200.synthetic import dhs_fdae_model, dhs_load_profiles
+    m, info = dhs_fdae_model(nx, nx, ns=ns)
+    fdae, y0 = m.create_instance()
+    mdl = ns.made_numerical(fdae, y0, sparse=True)
+    dt = info["dt"]
+    tst, tsv = dhs_load_profiles(B, dt)
+    F0 = np.array(mdl.F(0.0, y0.array, mdl.p, y0.array)).copy()
+    J0 = sps.csc_matrix(mdl.J(0.0, y0.array, mdl.p, y0.array))
+    J0.sort_indices()
+    yp = y0.array * (1 + 0.01 * np.cos(np.arange(len(y0.array))))
+    mdl.p["sc"] = ns.TimeSeriesParam('sc', v_series=tsv[1], time_series=tst[1])
+    Fp = np.array(mdl.F(2.5 * dt, yp, mdl.p, y0.array)).copy()
+    Jp = sps.csc_matrix(mdl.J(2.5 * dt, yp, mdl.p, y0.array))
+    Jp.sort_indices()
+    nt = 10
+    Y = np.zeros((B, nt + 1, len(y0.array)))
+    stats = np.zeros((B, 6), dtype=np.int64)
+    for b in range(B):
+        mdl.p["sc"] = ns.TimeSeriesParam('sc', v_series=tsv[b], time_series=tst[b])
+        sol = ns.fdae_solver(mdl, [0, nt * dt], y0, ns.Opt(step_size=dt, ite_tol=1e-8))
+        Y[b] = sol.Y.array
+        st = sol.stats
+        stats[b] = [st.nstep, st.nfeval, st.nJeval, st.ndecomp, st.nreject, st.nsolve]
+        print("dhs scenario", b, "stats", stats[b], "T", sol.T[-1])
+    np.savez_compressed(HERE / "dhs_ref_3x3.npz", Y=Y, stats=stats, y0=y0.array, yp=yp, F0=F0, Fp=Fp,
+                        J0_data=J0.data, J_indices=J0.indices, J_indptr=J0.indptr,
+                        Jp_dense=Jp.toarray(), T=sol.T)
+
+
 def Rodas_bench():
     """sol_bench of the reference's tests/test_dae.py:36-40."""
     from Solverz import Eqn, Model, Ode, Opt, Rodas, Var, made_numerical
@@ -318,7 +354,7 @@ def golden_implicit():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dae", "pf", "known", "swing", "events", "implicit"]
+    which = sys.argv[1:] or ["dae", "pf", "known", "swing", "events", "implicit", "dhs"]
     if "dae" in which:
         golden_dae_test()
     if "pf" in which:
@@ -331,4 +367,6 @@ if __name__ == "__main__":
         golden_events()
     if "implicit" in which:
         golden_implicit()
+    if "dhs" in which:
+        golden_dhs()
     print("golden fixtures written to", HERE)

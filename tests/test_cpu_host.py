@@ -288,6 +288,34 @@ def test_printer_swing_dae_matches_reference_golden(tmp_path):
     assert J[8 * 9 + 1, 4 * 9 + 1] != 0.0       # d(Fx - gf fmask Ux)/dUx at the faulted bus
 
 
+def test_printer_dhs_fdae_matches_reference_golden(tmp_path):
+    """Config #5 in miniature (Mat_Mul hydraulics with the mutable-matrix Jacobian of L (K m |m|), node
+    mixing Vin (m Tout) - Tn[1:] (Vin m), AliasVar history, TimeSeriesParam load profile): generated F and J
+    against the reference's own evaluation of the same model (tests/golden/make_golden.py::golden_dhs)."""
+    from solverz_b200.synthetic import dhs_fdae_model, dhs_load_profiles
+    g = np.load(GOLD / "dhs_ref_3x3.npz")
+    m, info = dhs_fdae_model(3, 3)
+    eqs, y0 = m.create_instance()
+    assert eqs.kind == "FDAE"
+    ir, pat, lib, _ = _host_lib(eqs, "dhs3", tmp_path)
+    assert ir.nstep == 1 and ir.n == info["n"]
+    np.testing.assert_allclose(y0.array, g["y0"], rtol=0, atol=1e-13)
+    tst, tsv = dhs_load_profiles(6, info["dt"])
+    tout = slice(*ir.var_off["Tout"][:1], ir.var_off["Tout"][0] + ir.var_off["Tout"][1])
+    hist = {"Tout_tag_0": np.atleast_2d(g["y0"][tout])}
+    F, JV = _eval(lib, ir, pat, g["y0"], hist, 0.0)
+    assert np.abs(F[0] - g["F0"]).max() <= 1e-12
+    J = sps.csc_matrix((JV[0], pat.indices, pat.indptr), shape=(ir.n, ir.n))
+    Jr = sps.csc_matrix((g["J0_data"], g["J_indices"], g["J_indptr"]), shape=(ir.n, ir.n))
+    assert abs(J - Jr).max() <= 1e-12 * abs(Jr).max()
+    par = dict(hist)
+    par["sc__ts_t"], par["sc__ts_v"] = np.atleast_2d(tst[1]), np.atleast_2d(tsv[1])
+    F, JV = _eval(lib, ir, pat, g["yp"], par, 2.5 * info["dt"])
+    assert np.abs(F[0] - g["Fp"]).max() <= 1e-11 * max(1.0, np.abs(g["Fp"]).max())
+    J = sps.csc_matrix((JV[0], pat.indices, pat.indptr), shape=(ir.n, ir.n)).toarray()
+    assert np.abs(J - g["Jp_dense"]).max() <= 1e-12 * np.abs(g["Jp_dense"]).max()
+
+
 def test_front_end_errors():
     from solverz_b200 import Eqn, LoopEqn, Model, Param, Set, Sum, Var
     m = Model()

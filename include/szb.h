@@ -50,7 +50,7 @@ extern "C" {
 #define SZB_API
 #endif
 
-#define SZB_ABI_VERSION 2
+#define SZB_ABI_VERSION 3
 
 /* error codes */
 #define SZB_OK 0
@@ -69,6 +69,8 @@ extern "C" {
 #define SZB_FLAG_NAN 5        /* NaN/Inf residual                              */
 #define SZB_FLAG_RUNNING 6    /* not finished (internal)                       */
 #define SZB_FLAG_NOTCONV 7    /* loop left with max|F| == tol (not < tol)      */
+#define SZB_FLAG_EVENT 8      /* Rodas stopped by a terminal event, rodas.py:267-271 (a success) */
+#define SZB_MAX_EVENTS 8
 
 /* szb_bind slots */
 #define SZB_SLOT_Y 0        /* double[B][n]     unknowns, updated in place               */
@@ -156,6 +158,17 @@ typedef struct szb_rodas_opt {
   double gamma;
   const double *alpha, *gammatilde; /* host [s*s] */
   const double *a, *g, *b, *bd, *c, *d, *e; /* host [s] */
+  /* Device-side events: the reference's events(t, y) callback (rodas.py:99-107,
+   * 200-271) restricted to component thresholds, value_i = y[ev_idx[i]] - ev_thr[i], so that detection,
+   * the secant start + bisection on the dense output ntrp1 and the roll-back to the event time run per
+   * scenario inside the step kernel.  n_events == 0: none.  Needs a scheme with ntrp1 (c, d, e given). */
+  int32_t n_events;          /* <= SZB_MAX_EVENTS */
+  const int32_t* ev_idx;     /* host [n_events] */
+  const double* ev_thr;      /* host [n_events] */
+  const int32_t* ev_dir;     /* host [n_events]: -1 falling, +1 rising, 0 both */
+  const int32_t* ev_term;    /* host [n_events]: 1 = the scenario stops at this event */
+  double event_duration;     /* events closer than this to the step start are dropped (rodas.py:257-259) */
+  int32_t ev_cap;            /* events recorded per scenario (rows of ev_t / ev_i / ev_y) */
 } szb_rodas_opt;
 
 typedef struct szb_rodas_out {
@@ -164,6 +177,11 @@ typedef struct szb_rodas_out {
   int32_t* stats;    /* device [B][8]: nstep, nfeval, nJeval, ndecomp, nreject, nsolve, flag, n_recorded */
   double* y_steps;   /* device [record_cap][B][n] or NULL */
   double* t_steps;   /* device [record_cap][B] or NULL */
+  int32_t* ev_count; /* device [B]: events located (may exceed ev_cap; only the first ev_cap are stored) */
+  double* ev_t;      /* device [B][ev_cap] */
+  int32_t* ev_i;     /* device [B][ev_cap] */
+  double* ev_y;      /* device [B][ev_cap][n] or NULL */
+  int32_t* n_rows;   /* device [B] or NULL: rows of y_out filled (< n_out after a terminal event) */
 } szb_rodas_out;
 
 SZB_API int szb_abi_version(void);

@@ -54,7 +54,7 @@ struct szb_handle {
   std::vector<void*> rodas_owned;
   int rodas_B = 0, rodas_stages = 0;
   double *rd_K = nullptr, *rd_y1 = nullptr, *rd_sum2 = nullptr, *rd_dfdt = nullptr, *rd_F1 = nullptr;
-  double *rd_dbl = nullptr, *rd_tout = nullptr;
+  double *rd_dbl = nullptr, *rd_tout = nullptr, *rd_ev = nullptr;
   int *rd_int = nullptr, *rd_mcol = nullptr;
   int rd_tout_cap = 0;
   bool rd_mcol_ready = false;

@@ -28,12 +28,18 @@ struct Tableau {
 struct Ctl {  // scalars of the step controller
   double tend, rtol, atol, f_savety, fac1, fac2, hmax, hmin, uround, hinit;
   int fix_h, n_out, record_cap, max_steps;
+  // component-threshold events (szb.h): value_i = y[ev_idx[i]] - ev_thr[i]
+  int n_events, ev_cap;
+  double event_duration;
+  int ev_idx[SZB_MAX_EVENTS], ev_dir[SZB_MAX_EVENTS], ev_term[SZB_MAX_EVENTS];
+  double ev_thr[SZB_MAX_EVENTS];
 };
 
 // per-scenario state, struct of arrays
 struct State {
   double *t, *dt, *told, *facmax, *scale, *tstage, *ddt;
   int *reject, *active, *jmask, *inext, *nrec, *stats;  // stats: [B][8]
+  double* ev_val;   // [B][SZB_MAX_EVENTS] event values at the end of the last accepted step (rodas.py:203)
 };
 
 // rodas.py:127-146 -- failure exits, end stretch, fixed step; prepares LU scale and the J mask
@@ -135,6 +141,12 @@ __global__ void stage_post_kernel(double* __restrict__ Kj, const double* __restr
 
 __device__ __forceinline__ double nanmax(double a, double b) { return (a > b || a != a) ? a : b; }
 
+// np.spacing(x): distance to the next double away from zero
+__device__ __forceinline__ double spacing(const double x) {
+  const double a = fabs(x);
+  return __longlong_as_double(__double_as_longlong(a) + 1) - a;
+}
+
 // error estimate, step-size controller, accept / reject, dense output (:176-327); one CTA per scenario
 __global__ void __launch_bounds__(256)
 step_finish_kernel(const double* __restrict__ K, double* __restrict__ Y, Tableau T, Ctl C, State S,
@@ -143,6 +155,8 @@ step_finish_kernel(const double* __restrict__ K, double* __restrict__ Y, Tableau
   __shared__ int s_bad;
   __shared__ int s_accept;
   __shared__ double s_told, s_tnew, s_dt;
+  __shared__ int s_nev, s_ev_i[SZB_MAX_EVENTS];
+  __shared__ double s_tau, s_ev_tau[SZB_MAX_EVENTS], s_ev_t[SZB_MAX_EVENTS];
   const int b = blockIdx.x;
   if (!S.active[b]) return;
   const size_t stride = static_cast<size_t>(B) * n;
@@ -208,9 +222,97 @@ step_finish_kernel(const double* __restrict__ K, double* __restrict__ Y, Tableau
     }
     s_tnew = S.t[b];
     S.dt[b] = fmin(C.hmax, fmax(C.hmin, dtnew));    // :327
+    s_nev = 0;
+    s_tau = 1.0;
+    // ---- events (:200-271), component thresholds; the dense output of ONE component is a scalar formula
+    // in tau, so the whole secant + bisection search runs on this thread
+    if (accept && C.n_events > 0) {
+      const double told = s_told;
+      double tcur = s_tnew;                           // `t` of the reference: rolls back to the event time
+      double* vold = S.ev_val + static_cast<size_t>(b) * SZB_MAX_EVENTS;
+      double vsave[SZB_MAX_EVENTS];
+      for (int i = 0; i < C.n_events; ++i) {          // value = events(t, ynew), ynew = y0 + K (dt b)  (:175-176, :203)
+        const int c = C.ev_idx[i];
+        double s1 = 0.0;
+        for (int l = 0; l < T.s; ++l) s1 = fma(K[l * stride + static_cast<size_t>(b) * n + c], dt * T.b[l], s1);
+        vsave[i] = (y[c] + s1) - C.ev_thr[i];
+      }
+      int stop = 0;
+      for (int i = 0; i < C.n_events && !stop; ++i) {
+        double v0 = vold[i], v1 = vsave[i];
+        if (!(v1 * v0 < 0.0)) continue;               // ff = where(value * valueold < 0)
+        if (C.ev_dir[i] < 0 && v0 <= v1) continue;
+        if (C.ev_dir[i] > 0 && v0 >= v1) continue;
+        const int c = C.ev_idx[i];
+        const size_t qc = static_cast<size_t>(b) * n + c;
+        auto comp = [&](const double tau) {           // ntrp1 of component c (:383-386)
+          double acc = 0.0;
+          for (int l = 0; l < T.s; ++l)
+            acc += K[l * stride + qc] * (T.b[l] + (tau - 1.0) * (T.c[l] + tau * (T.d[l] + tau * T.e[l])));
+          return y[c] + tau * dt * acc;
+        };
+        int iterate = 1;
+        double tL = told, tR = tcur, tevent;
+        if (fabs(v1 - v0) > C.uround) tevent = told - v0 * dt / (v1 - v0);     // :222-223
+        else { iterate = 0; tevent = tcur; }
+        double tol = 128.0 * fmax(spacing(told), spacing(tcur));                 // np.spacing, :228
+        tol = fmin(tol, fabs(tcur - told));
+        while (iterate > 0) {                          // :231-254
+          ++iterate;
+          const double vi = comp((tevent - told) / dt) - C.ev_thr[i];
+          if (v1 * vi < 0.0) { tL = tevent; tevent = 0.5 * (tevent + tR); v0 = vi; }
+          else if (v0 * vi < 0.0) { tR = tevent; tevent = 0.5 * (tL + tevent); v1 = vi; }
+          else iterate = 0;
+          if ((tR - tL) < tol) iterate = 0;
+          if (iterate > 100) break;                    // "Lost Event"
+        }
+        if (fabs(tevent - told) < C.event_duration) break;                      // :257-259
+        tcur = tevent;
+        s_ev_tau[s_nev] = (tevent - told) / dt;
+        s_ev_t[s_nev] = tevent;
+        s_ev_i[s_nev] = i;
+        ++s_nev;
+        if (C.ev_term[i]) stop = 1;                    // :267-271
+      }
+      for (int i = 0; i < C.n_events; ++i) vold[i] = vsave[i];                  // value = value_save (:266)
+      if (s_nev > 0) {
+        s_tau = s_ev_tau[s_nev - 1];
+        s_tnew = tcur;
+        S.t[b] = tcur;
+        if (stop) { S.active[b] = 0; st[6] = SZB_FLAG_EVENT; }
+        else if (st[6] == SZB_FLAG_CONVERGED && fabs(C.tend - tcur) >= C.uround) { S.active[b] = 1; st[6] = SZB_FLAG_RUNNING; }
+      }
+    }
   }
   __syncthreads();
   if (!s_accept) return;
+  // states at the located events (ye) and their bookkeeping (:262-265)
+  if (s_nev > 0) {
+    const int base = O.ev_count[b];
+    for (int k = 0; k < s_nev; ++k) {
+      const int slot = base + k;
+      if (slot >= C.ev_cap) break;
+      const double tau = s_ev_tau[k];
+      double w[kMaxStages];
+      for (int l = 0; l < T.s; ++l)
+        w[l] = tau * s_dt * (T.b[l] + (tau - 1.0) * (T.c[l] + tau * (T.d[l] + tau * T.e[l])));
+      if (O.ev_y) {
+        double* dst = O.ev_y + (static_cast<size_t>(b) * C.ev_cap + slot) * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const size_t q = static_cast<size_t>(b) * n + i;
+          double acc = 0.0;
+          for (int l = 0; l < T.s; ++l) acc += K[l * stride + q] * w[l];
+          dst[i] = y[i] + acc;
+        }
+      }
+      if (threadIdx.x == 0) {
+        O.ev_t[static_cast<size_t>(b) * C.ev_cap + slot] = s_ev_t[k];
+        O.ev_i[static_cast<size_t>(b) * C.ev_cap + slot] = s_ev_i[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) O.ev_count[b] = base + s_nev;
+  }
   // dense output at the requested times inside (told, t]   (:273-303, ntrp1 :383-386)
   if (C.n_out > 0) {
     int inext = S.inext[b];
@@ -231,14 +333,30 @@ step_finish_kernel(const double* __restrict__ K, double* __restrict__ Y, Tableau
       ++inext;
     }
     __syncthreads();
-    if (threadIdx.x == 0) S.inext[b] = inext;
+    if (threadIdx.x == 0) {
+      S.inext[b] = inext;
+      if (O.n_rows) O.n_rows[b] = inext;
+    }
   }
-  // y0 = ynew (:320)
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const size_t q = static_cast<size_t>(b) * n + i;
-    double s1 = 0.0;
-    for (int l = 0; l < T.s; ++l) s1 = fma(K[l * stride + q], s_dt * T.b[l], s1);
-    y[i] += s1;
+  // y0 = ynew (:320); after an event ynew = ynext = ntrp1 at the event time (:261)
+  if (s_nev > 0) {
+    const double tau = s_tau;
+    double w[kMaxStages];
+    for (int l = 0; l < T.s; ++l)
+      w[l] = tau * s_dt * (T.b[l] + (tau - 1.0) * (T.c[l] + tau * (T.d[l] + tau * T.e[l])));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const size_t q = static_cast<size_t>(b) * n + i;
+      double acc = 0.0;
+      for (int l = 0; l < T.s; ++l) acc += K[l * stride + q] * w[l];
+      y[i] += acc;
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const size_t q = static_cast<size_t>(b) * n + i;
+      double s1 = 0.0;
+      for (int l = 0; l < T.s; ++l) s1 = fma(K[l * stride + q], s_dt * T.b[l], s1);
+      y[i] += s1;
+    }
   }
   // record the accepted step (two-point tspan behaviour of the reference, :305-309)
   if (C.record_cap > 0) {
@@ -257,9 +375,15 @@ step_finish_kernel(const double* __restrict__ K, double* __restrict__ Y, Tableau
 }
 
 __global__ void rodas_init_kernel(State S, szb_rodas_out O, const double* __restrict__ Y, double t0,
-                                  double dt0, double facmax, int n_out, int record_cap, int n, int B) {
+                                  double dt0, double facmax, int n_out, int record_cap, Ctl C, int n, int B) {
   const int b = blockIdx.x;
   if (threadIdx.x == 0) {
+    if (C.n_events > 0) {                              // value = events(t0, y0), rodas.py:102-103
+      for (int i = 0; i < C.n_events; ++i)
+        S.ev_val[static_cast<size_t>(b) * SZB_MAX_EVENTS + i] = Y[static_cast<size_t>(b) * n + C.ev_idx[i]] - C.ev_thr[i];
+      O.ev_count[b] = 0;
+    }
+    if (O.n_rows) O.n_rows[b] = n_out > 0 ? 1 : 0;
     S.t[b] = t0; S.told[b] = t0; S.dt[b] = dt0; S.facmax[b] = facmax;
     S.reject[b] = 0; S.active[b] = 1; S.jmask[b] = 1; S.inext[b] = n_out > 0 ? 1 : 0;
     S.nrec[b] = record_cap > 0 ? 1 : 0;
@@ -323,8 +447,10 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
     h->rd_dbl = static_cast<double*>(alloc(sizeof(double) * 7 * B));
     h->rd_int = static_cast<int*>(alloc(sizeof(int) * (5 + 8) * B));
     h->rd_mcol = static_cast<int*>(alloc(sizeof(int) * n));
+    h->rd_ev = static_cast<double*>(alloc(sizeof(double) * SZB_MAX_EVENTS * B));
     h->rd_tout = nullptr;
-    if (!h->rd_K || !h->rd_y1 || !h->rd_sum2 || !h->rd_dfdt || !h->rd_F1 || !h->rd_dbl || !h->rd_int || !h->rd_mcol) {
+    if (!h->rd_K || !h->rd_y1 || !h->rd_sum2 || !h->rd_dfdt || !h->rd_F1 || !h->rd_dbl || !h->rd_int || !h->rd_mcol ||
+        !h->rd_ev) {
       szb_set_error(h, "szb_rodas: out of device memory for %d stages", s);
       return SZB_ENOMEM;
     }
@@ -365,6 +491,22 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
   C.uround = DBL_EPSILON;                                                // spacing(1.0), :81
   C.fix_h = o->fix_h; C.hinit = o->hinit; C.n_out = o->n_out; C.record_cap = o->record_cap;
   C.max_steps = o->max_steps > 0 ? o->max_steps : 1000000;
+  C.n_events = o->n_events;
+  C.ev_cap = o->ev_cap;
+  C.event_duration = o->event_duration;
+  if (o->n_events > 0) {
+    if (o->n_events > SZB_MAX_EVENTS || !o->ev_idx || !o->ev_thr || !o->ev_dir || !o->ev_term || o->ev_cap < 1 ||
+        !out->ev_count || !out->ev_t || !out->ev_i) {
+      szb_set_error(h, "szb_rodas: %d events need ev_idx/ev_thr/ev_dir/ev_term, ev_cap >= 1 and ev_count/ev_t/ev_i (max %d)",
+                    o->n_events, SZB_MAX_EVENTS);
+      return SZB_EINVAL;
+    }
+    if (!o->c || !o->d || !o->e) { szb_set_error(h, "szb_rodas: events need a scheme with dense output (ntrp1)"); return SZB_EINVAL; }
+    for (int i = 0; i < o->n_events; ++i) {
+      if (o->ev_idx[i] < 0 || o->ev_idx[i] >= n) { szb_set_error(h, "szb_rodas: event %d watches component %d of %d", i, o->ev_idx[i], n); return SZB_EINVAL; }
+      C.ev_idx[i] = o->ev_idx[i]; C.ev_thr[i] = o->ev_thr[i]; C.ev_dir[i] = o->ev_dir[i]; C.ev_term[i] = o->ev_term[i];
+    }
+  }
   double dt0 = o->hinit > 0 ? o->hinit : 1e-6 * (o->tend - o->t0);       // :110-114
   dt0 = fmax(dt0, C.hmin);                                               // :116
   dt0 = fmin(dt0, C.hmax);                                               // :117
@@ -374,9 +516,10 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
   S.tstage = S.scale + B; S.ddt = S.tstage + B;
   S.reject = h->rd_int; S.active = S.reject + B; S.jmask = S.active + B; S.inext = S.jmask + B;
   S.nrec = S.inext + B; S.stats = S.nrec + B;
+  S.ev_val = h->rd_ev;
 
   const dim3 eg((n + 255) / 256 > 64 ? 64 : (n + 255) / 256, B);
-  rodas_init_kernel<<<B, 128, 0, st>>>(S, *out, h->Y, o->t0, dt0, o->facmax, o->n_out, o->record_cap, n, B);
+  rodas_init_kernel<<<B, 128, 0, st>>>(S, *out, h->Y, o->t0, dt0, o->facmax, o->n_out, o->record_cap, C, n, B);
   h->launches[4]++;
   int rc;
   const bool use_dfdt = o->dfdt_mode != 0;

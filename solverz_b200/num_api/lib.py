@@ -11,7 +11,8 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE.parent / "csrc" / "libszb.so"
 
-SZB_ABI_VERSION = 2
+SZB_ABI_VERSION = 3
+SZB_FLAG_EVENT = 8
 SLOT_Y, SLOT_F, SLOT_JV, SLOT_RHS, SLOT_PARAM0 = 0, 1, 2, 3, 16
 DTYPE_F64, DTYPE_I32 = 0, 1
 FLAG_NAMES = {0: "converged", 1: "max_it", 2: "singular", 3: "dt_min", 4: "rejects", 5: "nan", 6: "running",
@@ -47,12 +48,15 @@ class RodasOptC(C.Structure):
                 ("max_steps", C.c_int32), ("n_out", C.c_int32), ("t_out", _dp), ("record_cap", C.c_int32),
                 ("s", C.c_int32), ("pord", C.c_int32), ("gamma", C.c_double), ("alpha", _dp),
                 ("gammatilde", _dp), ("a", _dp), ("g", _dp), ("b", _dp), ("bd", _dp), ("c", _dp), ("d", _dp),
-                ("e", _dp)]
+                ("e", _dp), ("n_events", C.c_int32), ("ev_idx", C.POINTER(C.c_int32)), ("ev_thr", _dp),
+                ("ev_dir", C.POINTER(C.c_int32)), ("ev_term", C.POINTER(C.c_int32)), ("event_duration", C.c_double),
+                ("ev_cap", C.c_int32)]
 
 
 class RodasOutC(C.Structure):
     _fields_ = [("y_out", C.c_void_p), ("t_end", C.c_void_p), ("stats", C.c_void_p), ("y_steps", C.c_void_p),
-                ("t_steps", C.c_void_p)]
+                ("t_steps", C.c_void_p), ("ev_count", C.c_void_p), ("ev_t", C.c_void_p), ("ev_i", C.c_void_p),
+                ("ev_y", C.c_void_p), ("n_rows", C.c_void_p)]
 
 
 _lib = None

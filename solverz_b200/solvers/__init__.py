@@ -6,3 +6,4 @@ from .rodas import Rodas
 from .rodas_param import Rodas_param
 from .fdae import fdae_solver
 from .implicit import backward_euler, implicit_trapezoid
+from .rodas_event import ComponentEvents

@@ -139,7 +139,9 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
     if t0 > tend:
         raise ValueError(f't0: {t0} > tend: {tend}')
     dense = len(tspan) > 2
-    if opt.event is not None:
+    from .rodas_event import ComponentEvents
+    dev_events = opt.event if isinstance(opt.event, ComponentEvents) and rp.has_dense_output else None
+    if opt.event is not None and dev_events is None:
         return _rodas_events(dae, tspan, y0, opt)
     if dense and not rp.has_dense_output:
         raise NotImplementedError(f"dense output of {opt.scheme} (ntrp2, rodas.py:389-393) is not built")
@@ -191,6 +193,24 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
         y_steps = torch.zeros((cap, B, n), dtype=torch.float64, device=dev)
         t_steps = torch.zeros((cap, B), dtype=torch.float64, device=dev)
         out.y_steps, out.t_steps = y_steps.data_ptr(), t_steps.data_ptr()
+    ev_count = ev_t = ev_i = ev_y = n_rows = None
+    if dev_events is not None:
+        ev = dev_events
+        if int(ev.index.max()) >= n or int(ev.index.min()) < 0:
+            raise IndexError(f"ComponentEvents: component index out of range for n = {n}")
+        cap = ev.max_events
+        keep += [np.ascontiguousarray(ev.index), np.ascontiguousarray(ev.threshold), np.ascontiguousarray(ev.direction),
+                 np.ascontiguousarray(ev.terminal)]
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        o.n_events, o.ev_idx, o.ev_thr, o.ev_dir, o.ev_term = len(ev.index), ip(keep[-4]), _dp(keep[-3]), ip(keep[-2]), ip(keep[-1])
+        o.event_duration, o.ev_cap = float(opt.event_duration), cap
+        ev_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        ev_t = torch.full((B, cap), float("nan"), dtype=torch.float64, device=dev)
+        ev_i = torch.full((B, cap), -1, dtype=torch.int32, device=dev)
+        ev_y = torch.zeros((B, cap, n), dtype=torch.float64, device=dev)
+        n_rows = torch.zeros(B, dtype=torch.int32, device=dev)
+        out.ev_count, out.ev_t, out.ev_i, out.ev_y = ev_count.data_ptr(), ev_t.data_ptr(), ev_i.data_ptr(), ev_y.data_ptr()
+        out.n_rows = n_rows.data_ptr()
     y_init = s.Y.clone()
     L.check(s.lib.szb_rodas(s.h, C.byref(o), C.byref(out), s._stream()), s.h, "szb_rodas")
     st = stats_d.cpu().numpy().astype(np.int64)
@@ -199,7 +219,7 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
     for i, k in enumerate(names):
         setattr(stats, k, int(st[0, i]) if single else st[:, i].copy())
     stats.flag = int(st[0, 6]) if single else st[:, 6].copy()
-    failed = st[:, 6] != 0
+    failed = (st[:, 6] != 0) & (st[:, 6] != L.SZB_FLAG_EVENT)   # a terminal event is a regular end (rodas.py:267-271)
     stats.ret = ("failed" if failed[0] else None) if single else np.where(failed, "failed", None)
     # the reference never sets succeed for Rodas (stats.py:11 stays False); keep that for B = 1
     stats.succeed = False if single else ~failed
@@ -219,6 +239,28 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
         T = np.stack([np.full(B, t0), t_end.cpu().numpy()], axis=1)
         Yh = torch.stack([y_init, s.Y], dim=1)             # [B, 2, n]
         Y = Yh.clone() if on_device else Yh.cpu().numpy()
+    te = ye = ie = None
+    if dev_events is not None:
+        cnt = ev_count.cpu().numpy().astype(np.int64)
+        stats.nevent = int(cnt[0]) if single else cnt.copy()
+        if single:
+            k = min(int(cnt[0]), dev_events.max_events)
+            if k > 0:
+                te, ie = ev_t[0, :k].cpu().numpy(), ev_i[0, :k].cpu().numpy().astype(float)
+                ye = ev_y[0, :k].cpu().numpy()
+            if dense:
+                # the reference's T ends at a terminal event (rodas.py:269-270, 291-299): grid nodes up to it, then the event
+                rows = int(n_rows[0])
+                T, Y = T[:rows], Y[:rows]
+                if int(st[0, 6]) == L.SZB_FLAG_EVENT and (rows == 0 or T[-1] < te[-1]):
+                    T = np.append(T, te[-1])
+                    Y = np.vstack([Y, ye[-1][None, :]])
+        else:                                             # [B, cap] padded with nan / -1; rows of Y past n_rows are zero
+            te, ie = ev_t.cpu().numpy(), ev_i.cpu().numpy()
+            ye = ev_y if on_device else ev_y.cpu().numpy()
+            stats.n_rows = n_rows.cpu().numpy().astype(np.int64) if dense else None
     if vars_in is not None and not isinstance(Y, torch.Tensor):
         Y = TimeVars(vars_in.a, Y)
-    return daesol(T, Y, stats=stats)
+        if ye is not None and single:
+            ye = TimeVars(vars_in.a, ye)
+    return daesol(T, Y, te, ye, ie, stats=stats)

@@ -19,7 +19,30 @@ from .rodas_param import Rodas_param
 from .solution import daesol
 from .stats import Stats
 
-__all__ = ["rodas_with_events", "DeviceOps"]
+__all__ = ["rodas_with_events", "DeviceOps", "ComponentEvents"]
+
+
+class ComponentEvents:
+    """Event functions of the form ``value_i = y[index_i] - threshold_i`` with the reference's
+    ``direction`` / ``isterminal`` semantics (rodas.py:99-107, 200-271).  The object is itself a valid
+    ``events(t, y)`` callback -- it can be handed to the reference's ``Rodas`` unchanged -- and, because the
+    forms are known, ``solverz_b200.Rodas`` runs the detection, the secant + bisection search on the dense
+    output and the roll-back to the event time per scenario inside the step kernel (any batch size; schemes
+    with ``ntrp1``).  At most 8 events (SZB_MAX_EVENTS)."""
+
+    def __init__(self, index, threshold=0.0, direction=0, terminal=1, max_events=16):
+        self.index = np.atleast_1d(np.asarray(index, dtype=np.int32))
+        ne = len(self.index)
+        self.threshold = np.broadcast_to(np.asarray(threshold, dtype=np.float64), (ne,)).copy()
+        self.direction = np.broadcast_to(np.asarray(direction, dtype=np.int32), (ne,)).copy()
+        self.terminal = np.broadcast_to(np.asarray(terminal, dtype=np.int32), (ne,)).copy()
+        self.max_events = int(max_events)       # events recorded per scenario
+        if ne < 1 or ne > 8:
+            raise ValueError("ComponentEvents: between 1 and 8 events")
+
+    def __call__(self, t, y):
+        y = np.asarray(y)
+        return y[self.index] - self.threshold, self.terminal, self.direction
 
 
 class DeviceOps:

@@ -263,6 +263,49 @@ def golden_events():
         out[f"orbit_{sch}_T"] = sol.T
         out[f"orbit_{sch}_Y"] = sol.Y.array
         out[f"orbit_{sch}_stats"] = np.array([st.nstep, st.nfeval, st.nJeval, st.ndecomp, st.nreject, st.nsolve])
+    # device-side events: component-threshold events handed to the REFERENCE as its
+    # callback (solverz_b200.ComponentEvents is a valid events(t, y)); a batch of bouncing balls with different
+    # launch speeds, and a linear oscillator with three non-terminal events and a terminal one
+    from solverz_b200 import ComponentEvents
+    v0s = np.array([10.0, 14.0, 20.0, 27.0, 33.0])
+    bt, bst, bT, bY = [], [], [], []
+    m = Model()
+    m.x = Var('x', [0, 20])
+    m.f1 = Ode('f1', m.x[1], m.x[0])
+    m.f2 = Ode('f2', -9.8, m.x[1])
+    bball, yb = m.create_instance()
+    nbball = made_numerical(bball, yb, sparse=True)
+    for v0 in v0s:
+        yb['x'][0] = 0
+        yb['x'][1] = v0
+        sol = Rodas(nbball, np.linspace(0, 8, 41), yb, Opt(event=ComponentEvents([0], 0.0, -1, 1)))
+        st = sol.stats
+        bt.append(sol.te[0] if sol.te is not None else np.nan)
+        bst.append([st.nstep, st.nfeval, st.nJeval, st.ndecomp, st.nreject, st.nsolve])
+        bT.append(len(sol.T))
+        Yp = np.zeros((41, 2))
+        Yp[:len(sol.T)] = sol.Y.array
+        bY.append(Yp)
+    out.update(batch_v0=v0s, batch_te=np.array(bt), batch_stats=np.array(bst), batch_nT=np.array(bT), batch_Y=np.array(bY))
+    m = Model()
+    m.x = Var('x', 1.0)
+    m.v = Var('v', 0.0)
+    m.f1 = Ode('f1', f=m.v, diff_var=m.x)
+    m.f2 = Ode('f2', f=-m.x - 0.1 * m.v, diff_var=m.v)
+    osc, yo = m.create_instance()
+    nosc = made_numerical(osc, yo, sparse=True)
+    for tag, term in (("nt", [0, 0, 0, 0]), ("term", [0, 0, 0, 1])):
+        ev = ComponentEvents([0, 0, 1, 0], [0.0, 0.0, 0.3, -0.5], [1, -1, 1, -1], term)
+        for kind, tsp in (("steps", [0, 12]), ("dense", np.linspace(0, 12, 61))):
+            sol = Rodas(nosc, tsp, yo, Opt(event=ev, rtol=1e-6, atol=1e-8))
+            st = sol.stats
+            out[f"osc_{tag}_{kind}_te"] = sol.te
+            out[f"osc_{tag}_{kind}_ie"] = sol.ie
+            out[f"osc_{tag}_{kind}_ye"] = sol.ye.array
+            out[f"osc_{tag}_{kind}_T"] = sol.T
+            out[f"osc_{tag}_{kind}_Y"] = sol.Y.array
+            out[f"osc_{tag}_{kind}_stats"] = np.array([st.nstep, st.nfeval, st.nJeval, st.ndecomp, st.nreject, st.nsolve])
+            print("osc", tag, kind, "te", np.round(sol.te, 4), "ie", sol.ie, "stats", out[f"osc_{tag}_{kind}_stats"], "nT", len(sol.T))
     np.savez_compressed(HERE / "events_ref.npz", **out)
     print("readme ball: T[-1] =", out["readme_T"][-1], "stats", out["readme_stats"])
     print("bounce te", out["bounce_te"])

@@ -108,3 +108,82 @@ def test_events_need_one_trajectory(libszb):
     nb = made_numerical(bball, y0, sparse=True)
     with pytest.raises(NotImplementedError):
         Rodas(nb, [0, 1], np.tile(y0.array, (3, 1)), Opt(event=ball_events))
+
+
+# ---------------------------------------------------------------------------- device-side events
+def test_device_events_readme_ball(libszb):
+    """The README case again, with the event given as a ComponentEvents object: detection, bisection and the
+    roll-back run inside the step kernel (szb_rodas) instead of the host loop; same fixture."""
+    from solverz_b200 import ComponentEvents, Model, Ode, Opt, Rodas, Var, made_numerical
+    g = np.load(GOLD / "events_ref.npz")
+    m = Model()
+    m.h = Var('h', 0)
+    m.v = Var('v', 20)
+    m.f1 = Ode('f1', f=m.v, diff_var=m.h)
+    m.f2 = Ode('f2', f=-9.8, diff_var=m.v)
+    bball, y0 = m.create_instance()
+    nbball = made_numerical(bball, y0, sparse=True)
+    sol = Rodas(nbball, np.linspace(0, 30, 100), y0, Opt(event=ComponentEvents([0], 0.0, direction=-1, terminal=1)))
+    assert _stats(sol.stats) == g["readme_stats"].tolist()
+    np.testing.assert_allclose(sol.T, g["readme_T"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(sol.Y.array, g["readme_Y"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(sol.te, g["readme_te"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(sol.ye.array, g["readme_ye"], rtol=0, atol=1e-9)
+    assert sol.ie.tolist() == g["readme_ie"].tolist()
+
+
+def test_device_events_batch_of_balls(libszb):
+    """Five launch speeds as ONE batch: every scenario stops at its own impact time."""
+    from solverz_b200 import ComponentEvents, Model, Ode, Opt, Rodas, Var, made_numerical
+    g = np.load(GOLD / "events_ref.npz")
+    m = Model()
+    m.x = Var('x', [0, 20])
+    m.f1 = Ode('f1', m.x[1], m.x[0])
+    m.f2 = Ode('f2', -9.8, m.x[1])
+    bball, y0 = m.create_instance()
+    nb = made_numerical(bball, y0, sparse=True)
+    v0 = g["batch_v0"]
+    Y0 = np.stack([np.zeros_like(v0), v0], axis=1)
+    sol = Rodas(nb, np.linspace(0, 8, 41), Y0, Opt(event=ComponentEvents([0], 0.0, -1, 1)))
+    for b in range(len(v0)):
+        st = [int(getattr(sol.stats, k)[b]) for k in ("nstep", "nfeval", "nJeval", "ndecomp", "nreject", "nsolve")]
+        assert st == g["batch_stats"][b].tolist(), b
+        if np.isnan(g["batch_te"][b]):                  # the ball is still in the air at t = 8
+            assert sol.stats.nevent[b] == 0 and sol.stats.flag[b] == 0
+            rows = 41
+        else:
+            assert sol.stats.nevent[b] == 1 and sol.stats.flag[b] == 8
+            assert abs(sol.te[b, 0] - g["batch_te"][b]) < 1e-11 and abs(sol.te[b, 0] - 2 * v0[b] / 9.8) < 1e-9
+            rows = int(sol.stats.n_rows[b])
+            assert rows in (g["batch_nT"][b] - 1, g["batch_nT"][b])   # the reference appends the event row to T
+            np.testing.assert_allclose(sol.ye[b, 0], g["batch_Y"][b][g["batch_nT"][b] - 1], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(sol.Y[b, :rows], g["batch_Y"][b][:rows], rtol=0, atol=1e-9)
+    assert sol.stats.succeed.all()
+
+
+@pytest.mark.parametrize("tag", ["nt", "term"])
+@pytest.mark.parametrize("kind", ["steps", "dense"])
+def test_device_events_oscillator(libszb, tag, kind):
+    """Damped oscillator with four component events (rising / falling zero crossings of x, two thresholds),
+    all non-terminal or the last one terminal; two-point tspan (every step) and dense output."""
+    from solverz_b200 import ComponentEvents, Model, Ode, Opt, Rodas, Var, made_numerical
+    g = np.load(GOLD / "events_ref.npz")
+    m = Model()
+    m.x = Var('x', 1.0)
+    m.v = Var('v', 0.0)
+    m.f1 = Ode('f1', f=m.v, diff_var=m.x)
+    m.f2 = Ode('f2', f=-m.x - 0.1 * m.v, diff_var=m.v)
+    osc, yo = m.create_instance()
+    nosc = made_numerical(osc, yo, sparse=True)
+    ev = ComponentEvents([0, 0, 1, 0], [0.0, 0.0, 0.3, -0.5], [1, -1, 1, -1], [0, 0, 0, 1 if tag == "term" else 0])
+    tsp = [0, 12] if kind == "steps" else np.linspace(0, 12, 61)
+    sol = Rodas(nosc, tsp, yo, Opt(event=ev, rtol=1e-6, atol=1e-8))
+    k = f"osc_{tag}_{kind}"
+    assert _stats(sol.stats) == g[f"{k}_stats"].tolist()
+    assert sol.ie.tolist() == g[f"{k}_ie"].tolist()
+    np.testing.assert_allclose(sol.te, g[f"{k}_te"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(sol.ye.array, g[f"{k}_ye"], rtol=0, atol=1e-8)
+    assert len(sol.T) == len(g[f"{k}_T"])
+    # the step sizes after an event inherit its last-bit differences through the controller's err**(1/4)
+    np.testing.assert_allclose(sol.T, g[f"{k}_T"], rtol=0, atol=2e-8)
+    np.testing.assert_allclose(sol.Y.array, g[f"{k}_Y"], rtol=0, atol=2e-8)

@@ -7,3 +7,4 @@ from .rodas_param import Rodas_param
 from .fdae import fdae_solver
 from .implicit import backward_euler, implicit_trapezoid
 from .rodas_event import ComponentEvents
+from .laesolver import BatchedLU, lu_decomposition, solve

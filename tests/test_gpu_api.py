@@ -152,3 +152,43 @@ def test_time_series_dae_vs_oracle(libszb):
         assert int(sol.stats.nstep[b]) == ref["stats"]["nstep"]
         assert int(sol.stats.nreject[b]) == ref["stats"]["nreject"]
         assert np.max(np.abs(sol.Y[b] - ref["Y"])) < 1e-8
+
+
+def test_linear_solver_seam(libszb):
+    """reference Solverz/solvers/laesolver.py:11-45: solve / lu_decomposition on user matrices, one matrix and
+    a batch with one pattern, against SciPy's SuperLU (the reference's own solver)."""
+    import scipy.sparse.linalg as sla
+    from solverz_b200 import BatchedLU, lu_decomposition, solve
+    rng = np.random.default_rng(3)
+    n = 60
+    base = sps.random(n, n, density=0.08, random_state=5, format="csc") + sps.identity(n, format="csc") * 4.0
+    base = sps.csc_matrix(base)
+    base.sort_indices()
+    b1 = rng.standard_normal(n)
+    x = solve(base, b1)
+    np.testing.assert_allclose(x, sla.spsolve(base, b1), rtol=1e-10, atol=1e-12)
+    B = 7
+    mats = []
+    for k in range(B):
+        M = base.copy()
+        M.data = base.data * (1.0 + 0.2 * rng.standard_normal(base.nnz))
+        M.setdiag(M.diagonal() + 3.0)
+        mats.append(sps.csc_matrix(M))
+    rhs = rng.standard_normal((B, n))
+    lu = lu_decomposition(mats)
+    assert sorted(lu.perm_r.tolist()) == list(range(n)) and sorted(lu.perm_c.tolist()) == list(range(n))
+    assert lu.nnz >= base.nnz
+    X = lu.solve(rhs)
+    for k in range(B):
+        np.testing.assert_allclose(X[k], sla.spsolve(mats[k], rhs[k]), rtol=1e-10, atol=1e-12)
+    # a second right-hand side reuses the factors (the .solve(b) of the reference's sp_decomposition)
+    rhs2 = rng.standard_normal((B, n))
+    X2 = lu.solve(rhs2)
+    np.testing.assert_allclose(X2[3], sla.spsolve(mats[3], rhs2[3]), rtol=1e-10, atol=1e-12)
+    # refactor with new values on the same object, tensors in / tensors out
+    import torch
+    vals = torch.as_tensor(np.stack([m.data for m in mats])[::-1].copy(), device="cuda")
+    Xt = lu.refactor(vals).solve(torch.as_tensor(rhs, device="cuda"))
+    assert Xt.is_cuda
+    np.testing.assert_allclose(Xt[0].cpu().numpy(), sla.spsolve(mats[B - 1], rhs[0]), rtol=1e-10, atol=1e-12)
+    lu.close()

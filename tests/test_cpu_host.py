@@ -346,7 +346,7 @@ def test_c_abi_exports_every_declared_symbol(libszb):
     out = subprocess.run(["nm", "-D", "--defined-only", str(L.LIB_PATH)], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (szb_\w+)", out))
     assert declared <= exported, declared - exported
-    assert libszb.szb_abi_version() == L.SZB_ABI_VERSION == 2
+    assert libszb.szb_abi_version() == L.SZB_ABI_VERSION == 3
     # error convention: NULL handle -> negative code, never a crash
     assert libszb.szb_set_batch(None, 4) < 0
     assert libszb.szb_destroy(None) == 0

@@ -626,17 +626,61 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
             peak = max(peak, sp_)
         return peak
 
-    # persistent region for blocks that cross lists (warp subtree roots -> top, top roots: none)
+    # Blocks that cross lists go one level up or more (a list holds whole subtrees of its level), and the
+    # levels are separated by CTA-wide barriers in the factor kernel, so regions of different lifetimes
+    # share addresses.  The workspace of a resident CTA is what decides whether the contribution blocks
+    # stay in L2 (148 CTAs x cb_size: 114 MB without this sharing on the 1024-bus benchmark, 88 MB with it,
+    # against 126 MB of L2).
+    #   A  warp -> CTA level blocks      live: warp level .. CTA level
+    #   B  warp -> group level blocks    live: warp level .. group level
+    #   C  group -> CTA level blocks     live: group level .. CTA level
+    #   S0 / S1 / S2  stacks of the warp lists / group lists / CTA-level list, live within their level
+    # layout:  [A][B][S0 ...]            warp level
+    #          [A][B][S1][C]             group level  (S1 and C over S0)
+    #          [A][S2 ......][C]         CTA level    (S2 over B and S1 when it fits, else behind C)
     all_lists = [list(map(int, l)) for l in lists] + [list(map(int, l)) for l in glists] + \
                 [list(map(int, top))]
-    for seq in all_lists:
+    list_level = [0] * len(lists) + [1] * len(glists) + [2]
+    lvl_of = {}
+    for seq, lv in zip(all_lists, list_level):
+        for k in seq:
+            lvl_of[k] = lv
+    cross = {"A": [], "B": [], "C": []}
+    for seq, lv in zip(all_lists, list_level):
         inseq = set(seq)
         for k in seq:
-            if sn_parent[k] >= 0 and int(sn_parent[k]) not in inseq:
-                cb_off[k] = cursor
-                cursor += int(cb_need[k])
-    for seq in all_lists:
-        cursor += alloc_list(seq, cursor)
+            p = int(sn_parent[k])
+            if p >= 0 and p not in inseq:
+                kind = {(0, 2): "A", (0, 1): "B", (1, 2): "C"}.get((lv, lvl_of[p]))
+                if kind is None:
+                    raise AssertionError("a contribution block crosses lists of one level")
+                cross[kind].append(k)
+    size_of = lambda ks: int(sum(int(cb_need[k]) for k in ks))
+    a_sz, b_sz, c_sz = size_of(cross["A"]), size_of(cross["B"]), size_of(cross["C"])
+
+    def place(ks, base):
+        for k in ks:
+            cb_off[k] = base
+            base += int(cb_need[k])
+
+    def stacks(seqs, base):
+        top_ = base
+        for seq in seqs:
+            top_ += alloc_list(seq, top_)
+        return top_ - base
+
+    place(cross["A"], 0)
+    place(cross["B"], a_sz)
+    zone = a_sz + b_sz
+    s0_sz = stacks(all_lists[:len(lists)], zone)
+    s1_sz = stacks(all_lists[len(lists):len(lists) + len(glists)], zone)
+    place(cross["C"], zone + s1_sz)
+    c_end = zone + s1_sz + c_sz
+    # the CTA-level stack: measure, then put it over [B][S1] if it fits there
+    s2_sz = alloc_list(all_lists[-1], 0)
+    s2_base = a_sz if s2_sz <= b_sz + s1_sz else c_end
+    alloc_list(all_lists[-1], s2_base)
+    cursor = max(zone + s0_sz, c_end, s2_base + s2_sz)
     cb_size = int(cursor)
 
     # ---- extend-add destinations: element t = i + j*u of the u x (u+1) block of child c goes to

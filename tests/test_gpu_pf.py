@@ -140,3 +140,38 @@ def test_large_fronts_in_global_memory(libszb, tmp_path_factory):
         ref = oracle_nr(lambda y: orc.F(y, P[b], Q[b]), orc.J, y0.array, 1e-8, 100)
         assert np.abs(sol.y[b] - ref["y"]).max() <= 1e-10 * np.abs(ref["y"]).max()
         assert int(sol.stats.nstep[b]) == ref["nstep"]
+
+
+def test_full_size_config2_properties(libszb, tmp_path_factory):
+    """BASELINE.json configs[1] at full size (1024 buses, n = 2048, 4096 load scenarios) through properties
+    that do not need 4096 oracle solves: every scenario converges; the ORACLE's residual of every GPU
+    solution is below the tolerance; a sample agrees with the oracle's Newton (solution and counts); the
+    batch is order-independent bit for bit (scenario b of a permuted batch = scenario perm[b])."""
+    from oracle.nr import nr_method as oracle_nr
+    from solverz_b200 import Opt, module_printer, nr_method
+    from solverz_b200.synthetic import pf_scenarios, polar_pf_model
+    d = tmp_path_factory.mktemp("mods32")
+    eqs, y0, info = polar_pf_model(32, 32)
+    module_printer(eqs, y0, "pfn32", directory=str(d)).render()
+    sys.path.insert(0, str(d))
+    mdl = importlib.import_module("pfn32").mdl
+    assert mdl.n == 2048
+    orc = _oracle(info)
+    B = 4096
+    P, Q = pf_scenarios(info, B)
+    mdl.p["Pinj"], mdl.p["Qinj"] = P, Q
+    Y0 = np.tile(y0.array, (B, 1))
+    sol = nr_method(mdl, Y0, Opt(ite_tol=1e-8))
+    assert sol.stats.succeed.all() and (sol.stats.flag == 0).all()
+    assert sol.stats.nstep.min() >= 2 and sol.stats.nstep.max() <= 6
+    assert (sol.stats.nfeval == sol.stats.nstep + 1).all()
+    res = np.array([np.abs(orc.F(sol.y[b], P[b], Q[b])).max() for b in range(B)])
+    assert res.max() <= 1e-8
+    for b in range(0, B, 128):                          # 32 scenarios against the oracle's own Newton
+        ref = oracle_nr(lambda y: orc.F(y, P[b], Q[b]), orc.J, y0.array, 1e-8, 100)
+        assert np.abs(sol.y[b] - ref["y"]).max() <= 1e-10 * np.abs(ref["y"]).max()
+        assert int(sol.stats.nstep[b]) == ref["nstep"]
+    perm = np.random.default_rng(0).permutation(B)
+    mdl.p["Pinj"], mdl.p["Qinj"] = P[perm], Q[perm]
+    sol2 = nr_method(mdl, Y0, Opt(ite_tol=1e-8))
+    assert np.array_equal(sol2.y, sol.y[perm]) and np.array_equal(sol2.stats.nstep, sol.stats.nstep[perm])

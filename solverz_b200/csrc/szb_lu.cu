@@ -580,6 +580,194 @@ __device__ __noinline__ void eliminate_blocked(const PanelGrp g, double* FmG, co
 }
 
 
+// ---- fronts too large for shared memory: the front lives in the per-CTA global workspace (L2), and a
+// rank-4 pass over the whole trailing block per panel would stream it from L2 once per 4 pivots.  Here the
+// pivots are taken in OUTER blocks of NO (<= 32) = NO/4 inner panels:
+//   * an inner panel updates at once only what the rest of its outer block needs: the tiles whose row OR
+//     column tile index lies inside the block (an L-shaped band, ~8/(m/8) of the trailing block);
+//   * the -Lt columns of all inner panels stay in shared memory (NO x lts doubles -- that is what the
+//     shared memory of this mode is for), the unsolved top rows stay in the front;
+//   * after the last inner panel ONE pass over the far trailing block (row and column tile index behind the
+//     block) applies all NO pivots: per 8x8 accumulator tile one load, NO/4 DMMAs, one store.
+// Tiles are anchored at absolute multiples of 8 here; rows / columns of a tile that lie before the current
+// panel are masked through the operands (their -Lt rows are written as zeros, their top-row fragment is 0),
+// so straddling tiles need no predicates on the accumulators.  Same mathematics as eliminate_blocked:
+// the far block receives sum_t Lt(t) A12(t) with every A12(t) already updated by the panels before t.
+template <int R>
+__device__ __forceinline__ void strip_abs(double* __restrict__ Fm, const double* __restrict__ ltk, const int lts,
+                                          const int p0, const int nb, const int r0, const int ld, const int tr,
+                                          const int tc, const int lane) {
+  const int q = lane & 3, g8 = lane >> 2;
+  double xa[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) xa[r] = ltk[q * lts + 8 * (tr + r) + g8];
+  const int col = 8 * tc + g8;
+  const double b0 = (q < nb && col >= r0) ? Fm[p0 + q + col * ld] : 0.0;
+  double* __restrict__ cp = Fm + 8 * tr + g8 + (8 * tc + 2 * q) * ld;
+  double c0[R], c1[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    c0[r] = cp[8 * r];
+    c1[r] = cp[ld + 8 * r];
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) dmma(c0[r], c1[r], xa[r], b0);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    cp[8 * r] = c0[r];
+    cp[ld + 8 * r] = c1[r];
+  }
+}
+
+__device__ __forceinline__ void strip_abs_n(const int nt, double* __restrict__ Fm, const double* __restrict__ ltk,
+                                            const int lts, const int p0, const int nb, const int r0, const int ld,
+                                            const int tr, const int tc, const int lane) {
+  if (nt >= 4) strip_abs<4>(Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+  else if (nt == 3) strip_abs<3>(Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+  else if (nt == 2) strip_abs<2>(Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+  else if (nt == 1) strip_abs<1>(Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+}
+
+// far pass: R row tiles x one column tile, all npi inner panels of the outer block [c0, cend)
+template <int R>
+__device__ __forceinline__ void strip_far(double* __restrict__ Fm, const double* __restrict__ lt, const int lts,
+                                          const int c0, const int cend, const int npi, const int ld, const int tr,
+                                          const int tc, const int lane) {
+  const int q = lane & 3, g8 = lane >> 2;
+  double* __restrict__ cp = Fm + 8 * tr + g8 + (8 * tc + 2 * q) * ld;
+  const double* __restrict__ bp = Fm + (8 * tc + g8) * ld;
+  double c0v[R], c1v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    c0v[r] = cp[8 * r];
+    c1v[r] = cp[ld + 8 * r];
+  }
+  const double* __restrict__ la = lt + q * lts + 8 * tr + g8;
+  for (int kb = 0; kb < npi; ++kb, la += 4 * lts) {
+    const int row = c0 + 4 * kb + q;
+    const double b0 = row < cend ? bp[row] : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dmma(c0v[r], c1v[r], la[8 * r], b0);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    cp[8 * r] = c0v[r];
+    cp[ld + 8 * r] = c1v[r];
+  }
+}
+
+__device__ __noinline__ void eliminate_global(const PanelGrp g, double* __restrict__ Fm, const int lt_off,
+                                              const int lts, const int NO, double* __restrict__ Lg, const int s,
+                                              const int f, const int ncol, const int ld, int* flag) {
+  extern __shared__ double sm[];
+  double* __restrict__ lt = sm + lt_off;               // NO columns of -Lt, rows indexed absolutely
+  double* __restrict__ dinv = lt + NO * lts;
+  const int lane = g.lane(), w = g.warp(), nw = g.nw;
+  const int q = lane & 3, g8 = lane >> 2;
+  const int trmax = (f - 1) >> 3, tcmax = (ncol - 1) >> 3;
+  if (w == 0) diag_block(Fm, dinv, 0, min(kNB, s), ld, lane, flag);
+  g.sync();
+  for (int c0 = 0; c0 < s; c0 += NO) {
+    const int cend = min(s, c0 + NO);
+    const int npi = (cend - c0 + kNB - 1) / kNB;
+    const int tb = (cend + 7) >> 3;                    // first tile index behind the block
+    bool next_done = false;                            // the diagonal block at cend is already factored
+    for (int ti = 0; ti < npi; ++ti) {
+      const int p0 = c0 + kNB * ti;
+      const int nb = min(kNB, cend - p0);
+      const int r0 = p0 + nb;
+      const bool has_next = r0 < s;
+      const int tr0 = r0 >> 3;
+      double* __restrict__ ltk = lt + kNB * ti * lts;
+      // ---- phase A: -Lt of this inner panel for every row tile from the one that holds r0
+      {
+        const double bd = g8 < kNB ? dinv[q + kNB * g8] : 0.0;
+        double bl = 0.0;
+        if (Lg != nullptr) bl = q == g8 ? 1.0 : ((q > g8 && q < nb) ? Fm[(p0 + q) + (p0 + g8) * ld] : 0.0);
+        for (int tr = tr0 + w; tr <= trmax; tr += nw) {
+          const int row = 8 * tr + g8;
+          const double a0 = (q < nb && row >= r0) ? Fm[row + (p0 + q) * ld] : 0.0;
+          double c0v = 0.0, c1v = 0.0;
+          dmma(c0v, c1v, a0, bd);
+          if (q < 2) {
+            ltk[(2 * q) * lts + row] = -c0v;
+            ltk[(2 * q + 1) * lts + row] = -c1v;
+          }
+          if (Lg != nullptr) {
+            __syncwarp();
+            double d0 = 0.0, d1 = 0.0;
+            dmma(d0, d1, ltk[q * lts + row], bl);
+            if (row >= r0 && row < f && q < 2) {
+              double* __restrict__ dst = Lg + row + (p0 + 2 * q) * f;
+              if (2 * q < nb) dst[0] = -d0;
+              if (2 * q + 1 < nb) dst[f] = -d1;
+            }
+          }
+        }
+      }
+      g.sync();
+      // ---- phase B, the L-shaped band: tiles (tr, tc) with tr0 <= tr, tc and (tr < tb or tc < tb)
+      const bool look = has_next && tr0 < tb;          // the next diagonal block lies inside the band
+      if (look && w == 0) {
+        strip_abs<1>(Fm, ltk, lts, p0, nb, r0, ld, tr0, tr0, lane);
+        __syncwarp();
+        diag_block(Fm, dinv, r0, min(kNB, s - r0), ld, lane, flag);
+        if (r0 == cend) next_done = true;
+      } else {
+        const int W = look ? nw - 1 : nw, ww = look ? w - 1 : w;
+        const int ncC = max(0, min(tb, tcmax + 1) - tr0);               // column tiles inside the block
+        const int nchC = (trmax - tr0 + 4) >> 2;                        // chunks of 4 row tiles, all rows
+        const int nrR = max(0, min(tb, trmax + 1) - tr0);               // row tiles inside the block
+        const int nchR = (nrR + 3) >> 2;
+        const int ncR = max(0, tcmax - tb + 1);                         // column tiles behind the block
+        const int JC = ncC * nchC, J = JC + ncR * nchR;
+        const float inv_c = 1.0f / static_cast<float>(max(nchC, 1)), inv_r = 1.0f / static_cast<float>(max(nchR, 1));
+        for (int j = ww; j < J; j += W) {
+          int tc, tr, nt;
+          if (j < JC) {
+            const int a = fdiv(j, inv_c);
+            tc = tr0 + a;
+            tr = tr0 + 4 * (j - a * nchC);
+            nt = min(4, trmax - tr + 1);
+          } else {
+            const int jr = j - JC, a = fdiv(jr, inv_r);
+            tc = tb + a;
+            tr = tr0 + 4 * (jr - a * nchR);
+            nt = min(4, tr0 + nrR - tr);
+          }
+          if (look && tr == tr0 && tc == tr0) { ++tr; --nt; }          // that tile belongs to the diagonal warp
+          strip_abs_n(nt, Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+        }
+      }
+      g.sync();
+    }
+    // ---- far pass: everything behind the block takes all its pivots in one sweep
+    {
+      const int ntr = trmax - tb + 1, ntc = tcmax - tb + 1;
+      if (ntr > 0 && ntc > 0) {
+        const int nch = (ntr + 3) >> 2;
+        const float inv = 1.0f / static_cast<float>(nch);
+        for (int j = w; j < nch * ntc; j += nw) {
+          const int a = fdiv(j, inv);
+          const int tc = tb + a, tr = tb + 4 * (j - a * nch);
+          const int nt = min(4, trmax - tr + 1);
+          if (nt >= 4) strip_far<4>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+          else if (nt == 3) strip_far<3>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+          else if (nt == 2) strip_far<2>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+          else strip_far<1>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+        }
+      }
+      g.sync();
+    }
+    if (cend < s && !next_done) {                       // the next block starts on a tile boundary: factor it now
+      if (w == 0) diag_block(Fm, dinv, cend, min(kNB, s - cend), ld, lane, flag);
+      g.sync();
+    }
+  }
+  finalize_u(Fm, s, ncol, ld, lane, w, nw);
+  g.sync();
+}
+
 #ifdef SZB_FINE_TIMING
 #define SZB_T(i) { const long long now_ = clock64(); tacc_[(i) + 4 * lvl_] += now_ - tprev_; tprev_ = now_; }
 #define SZB_TPARAM , long long* tacc_, const int lvl_
@@ -657,7 +845,7 @@ template <bool SM_FRONT>
 __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const int4* __restrict__ fh,
                                        const int q_next, AsmPre& P, const int2* __restrict__ ga,
                                        double* __restrict__ Fm, const int fm_off, const int lt_off, const int lts,
-                                       const FactorArgs& A SZB_TPARAM) {
+                                       const int outer_nb, const FactorArgs& A SZB_TPARAM) {
   SZB_TSTART
   const int s = H.s, f = H.f, u = f - s, ld = ld_blk(f);
   const int lane = g.lane(), w = g.warp(), nw = g.nw, r = g.rank(), G_ = g.size();
@@ -678,7 +866,8 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
 #ifdef SZB_PHASE_TIMING
   const long long tel0_ = clock64();
 #endif
-  eliminate_blocked<SM_FRONT>(g, Fm, fm_off, lt_off, lts, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
+  if (SM_FRONT) eliminate_blocked<true>(g, Fm, fm_off, lt_off, lts, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
+  else eliminate_global(g, Fm, lt_off, lts, outer_nb, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
 #ifdef SZB_PHASE_TIMING
   const long long tel1_ = clock64();
   if (blockIdx.x == 0 && g.rank() == 0 && g.id <= 1) {
@@ -734,7 +923,7 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
                  const double* __restrict__ slot_mask,
                  const double* __restrict__ scale_b, double scale_const,
                  const double* __restrict__ RHS, double* __restrict__ YOUT, int store_l,
-                 const int* __restrict__ active, int* __restrict__ flags, int B) {
+                 const int* __restrict__ active, int* __restrict__ flags, int B, int outer_nb, int smem_elems) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5;
   const int wstride = front_elems_warp(S.f_warp_max);
@@ -806,7 +995,7 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
         asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
         for (int q = gq0; q < gq1; ++q) {
           H = factor_front_group<true>(g, H, S.fh, min(q + 1, gq1 - 1), P, S.ga, Fm, gi * gstride,
-                                       gi * gstride + gfront, glts, A SZB_TARG(1));
+                                       gi * gstride + gfront, glts, 0, A SZB_TARG(1));
         }
       }
       __syncthreads();
@@ -827,14 +1016,20 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
       asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
       if (FBW == nullptr) {
         for (int q = 0; q < S.n_top; ++q) {
-          H = factor_front_group<true>(g, H, S.fh, tq0 + min(q + 1, S.n_top - 1), P, S.ga, sm, 0, tfront, tlts,
+          H = factor_front_group<true>(g, H, S.fh, tq0 + min(q + 1, S.n_top - 1), P, S.ga, sm, 0, tfront, tlts, 0,
                                        A SZB_TARG(2));
         }
       } else {
+        // per front: shared memory when the front fits next to its 4-column side panel, else the global
+        // workspace with the outer-blocked elimination (its NO-column side panel fills the shared memory)
         double* Ft = FBW + static_cast<size_t>(blockIdx.x) * tfront;
         for (int q = 0; q < S.n_top; ++q) {
-          H = factor_front_group<false>(g, H, S.fh, tq0 + min(q + 1, S.n_top - 1), P, S.ga, Ft, 0, 0, tlts,
-                                        A SZB_TARG(2));
+          const int qn = tq0 + min(q + 1, S.n_top - 1);
+          if (group_elems(H.f) <= smem_elems)
+            H = factor_front_group<true>(g, H, S.fh, qn, P, S.ga, sm, 0, front_elems_blk(H.f), lt_stride(H.f), 0,
+                                         A SZB_TARG(2));
+          else
+            H = factor_front_group<false>(g, H, S.fh, qn, P, S.ga, Ft, 0, 0, tlts, outer_nb, A SZB_TARG(2));
         }
       }
     }
@@ -1302,14 +1497,22 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   if (fsm * sizeof(double) > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
   cfg->top_in_global = 0;
   cfg->big_elems = 0;
+  cfg->outer_nb = 0;
   if (S.n_top > 0) {
     const size_t top_sm = static_cast<size_t>(group_elems(S.f_top_max));
     if (top_sm * sizeof(double) <= static_cast<size_t>(smem_max)) {
       fsm = smax(fsm, top_sm);
     } else {   // CTA-level fronts in a global workspace, side panels in shared memory
+      // CTA-level fronts that do not fit: global workspace + outer-blocked elimination whose side panel
+      // (outer_nb columns of -Lt) takes what shared memory there is
       cfg->top_in_global = 1;
       cfg->big_elems = static_cast<size_t>(front_elems_blk(S.f_top_max));
-      fsm = smax(fsm, static_cast<size_t>(kNB * lt_stride(S.f_top_max) + kDiagBuf));
+      const size_t lts = static_cast<size_t>(lt_stride(S.f_top_max));
+      size_t nbo = (static_cast<size_t>(smem_max) / sizeof(double) - kDiagBuf) / lts;
+      nbo = nbo > 32 ? 32 : (nbo & ~static_cast<size_t>(3));
+      if (nbo < 4) return cudaErrorInvalidConfiguration;
+      cfg->outer_nb = static_cast<int>(nbo);
+      fsm = smax(fsm, nbo * lts + kDiagBuf);
     }
   }
   cfg->smem_factor = fsm * sizeof(double);
@@ -1361,7 +1564,7 @@ cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const doubl
   if (B <= 0) return cudaSuccess;
   lu_factor_kernel<<<cfg.grid_factor, cfg.threads, cfg.smem_factor, st>>>(
       S, JV, LU, CBW, cfg.top_in_global ? FBW : nullptr, mvals, slot_mask, scale_b, scale_const, RHS, YOUT, store_l,
-      active, flags, B);
+      active, flags, B, cfg.outer_nb, static_cast<int>(cfg.smem_factor / sizeof(double)));
   return cudaGetLastError();
 }
 

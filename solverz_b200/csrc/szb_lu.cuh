@@ -33,6 +33,7 @@ struct LuLaunchCfg {
   size_t smem_solve;
   int top_in_global;  // CTA-level fronts do not fit shared memory: they live in a per-CTA global workspace
   size_t big_elems;   // doubles of that workspace per resident block
+  int outer_nb;       // pivots per outer block of the global-front elimination (side panel columns in shared memory)
   int threads_fwd;    // forward sweep: threads per block
   int x_in_smem;      // forward kernel keeps the permuted vector in shared memory
   int threads_bwd;    // backward sweep: threads per block, resident blocks, dynamic shared memory

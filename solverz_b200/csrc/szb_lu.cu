@@ -628,32 +628,62 @@ __device__ __forceinline__ void strip_abs_n(const int nt, double* __restrict__ F
   else if (nt == 1) strip_abs<1>(Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
 }
 
-// far pass: R row tiles x one column tile, all npi inner panels of the outer block [c0, cend)
-template <int R>
+// far pass: R row tiles x NC (1 or 2) adjacent column tiles, all npi inner panels of the outer block
+// [c0, cend).  Two column tiles share the -Lt fragments and put twice the loads in flight per warp (the
+// pass is bound by L2 latency at 16 warps per SM).
+template <int R, int NC>
 __device__ __forceinline__ void strip_far(double* __restrict__ Fm, const double* __restrict__ lt, const int lts,
                                           const int c0, const int cend, const int npi, const int ld, const int tr,
                                           const int tc, const int lane) {
   const int q = lane & 3, g8 = lane >> 2;
   double* __restrict__ cp = Fm + 8 * tr + g8 + (8 * tc + 2 * q) * ld;
   const double* __restrict__ bp = Fm + (8 * tc + g8) * ld;
-  double c0v[R], c1v[R];
+  double c0v[NC][R], c1v[NC][R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    c0v[r] = cp[8 * r];
-    c1v[r] = cp[ld + 8 * r];
-  }
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      c0v[c][r] = cp[c * 8 * ld + 8 * r];
+      c1v[c][r] = cp[c * 8 * ld + ld + 8 * r];
+    }
+  // all top-row fragments of the strip first (one L2 round trip instead of one per inner panel)
+  double bv[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      const int row = c0 + 4 * kb + q;
+      bv[c][kb] = (kb < npi && row < cend) ? bp[c * 8 * ld + row] : 0.0;
+    }
   const double* __restrict__ la = lt + q * lts + 8 * tr + g8;
-  for (int kb = 0; kb < npi; ++kb, la += 4 * lts) {
-    const int row = c0 + 4 * kb + q;
-    const double b0 = row < cend ? bp[row] : 0.0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) dmma(c0v[r], c1v[r], la[8 * r], b0);
+  for (int kb = 0; kb < 8; ++kb) {
+    if (kb < npi) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double xa = la[kb * 4 * lts + 8 * r];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dmma(c0v[c][r], c1v[c][r], xa, bv[c][kb]);
+      }
+    }
   }
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    cp[8 * r] = c0v[r];
-    cp[ld + 8 * r] = c1v[r];
-  }
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cp[c * 8 * ld + 8 * r] = c0v[c][r];
+      cp[c * 8 * ld + ld + 8 * r] = c1v[c][r];
+    }
+}
+
+template <int NC>
+__device__ __forceinline__ void strip_far_n(const int nt, double* __restrict__ Fm, const double* __restrict__ lt,
+                                            const int lts, const int c0, const int cend, const int npi, const int ld,
+                                            const int tr, const int tc, const int lane) {
+  if (nt >= 4) strip_far<4, NC>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+  else if (nt == 3) strip_far<3, NC>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+  else if (nt == 2) strip_far<2, NC>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+  else strip_far<1, NC>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
 }
 
 __device__ __noinline__ void eliminate_global(const PanelGrp g, double* __restrict__ Fm, const int lt_off,
@@ -745,16 +775,15 @@ __device__ __noinline__ void eliminate_global(const PanelGrp g, double* __restri
     {
       const int ntr = trmax - tb + 1, ntc = tcmax - tb + 1;
       if (ntr > 0 && ntc > 0) {
-        const int nch = (ntr + 3) >> 2;
+        const int nch = (ntr + 3) >> 2;                // chunks of 4 row tiles
+        const int npair = (ntc + 1) >> 1;              // pairs of column tiles
         const float inv = 1.0f / static_cast<float>(nch);
-        for (int j = w; j < nch * ntc; j += nw) {
+        for (int j = w; j < nch * npair; j += nw) {
           const int a = fdiv(j, inv);
-          const int tc = tb + a, tr = tb + 4 * (j - a * nch);
+          const int tc = tb + 2 * a, tr = tb + 4 * (j - a * nch);
           const int nt = min(4, trmax - tr + 1);
-          if (nt >= 4) strip_far<4>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
-          else if (nt == 3) strip_far<3>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
-          else if (nt == 2) strip_far<2>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
-          else strip_far<1>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+          if (tc + 1 <= tcmax) strip_far_n<2>(nt, Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+          else strip_far_n<1>(nt, Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
         }
       }
       g.sync();
@@ -917,6 +946,9 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
   return Hnext;
 }
 
+// GLOBAL_TOP: some CTA-level fronts live in the global workspace FBW (a separate instantiation, so that the
+// register allocation of the all-in-shared-memory kernel does not pay for the call into eliminate_global)
+template <bool GLOBAL_TOP>
 __global__ void __launch_bounds__(SZB_FACTOR_THREADS, 1)
 lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restrict__ LU,
                  double* CBW, double* FBW, const double* __restrict__ mvals,
@@ -1014,7 +1046,7 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restric
       FrontHdr H = load_hdr(S.fh, tq0);
       AsmPre P;
       asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
-      if (FBW == nullptr) {
+      if (!GLOBAL_TOP) {
         for (int q = 0; q < S.n_top; ++q) {
           H = factor_front_group<true>(g, H, S.fh, tq0 + min(q + 1, S.n_top - 1), P, S.ga, sm, 0, tfront, tlts, 0,
                                        A SZB_TARG(2));
@@ -1532,8 +1564,11 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   cfg->bwd_x_in_smem = static_cast<size_t>(S.n) * sizeof(double) * 2 <= static_cast<size_t>(smem_max) ? 1 : 0;
   cfg->smem_bwd = (cfg->bwd_x_in_smem ? static_cast<size_t>(S.n) * sizeof(double) : 0) +
                   (S.n_top > 0 ? static_cast<size_t>(cfg->threads_bwd / 32 + 1) * S.s_top_max * sizeof(double) : 0);
-  e = cudaFuncSetAttribute(lu_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(cfg->smem_factor));
+  e = cfg->top_in_global
+          ? cudaFuncSetAttribute(lu_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(cfg->smem_factor))
+          : cudaFuncSetAttribute(lu_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(cfg->smem_factor));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(lu_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(cfg->smem_solve));
@@ -1542,7 +1577,8 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
                            static_cast<int>(cfg->smem_bwd));
   if (e != cudaSuccess) return e;
   int occ_f = 1, occ_s = 1, occ_b = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lu_factor_kernel, cfg->threads, cfg->smem_factor);
+  if (cfg->top_in_global) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lu_factor_kernel<true>, cfg->threads, cfg->smem_factor);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lu_factor_kernel<false>, cfg->threads, cfg->smem_factor);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, lu_forward_kernel, cfg->threads_fwd, cfg->smem_solve);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, lu_backward_kernel, cfg->threads_bwd, cfg->smem_bwd);
   if (occ_f < 1) occ_f = 1;
@@ -1562,9 +1598,13 @@ cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const doubl
                              const double* scale_b, double scale_const, const double* RHS, double* YOUT,
                              int store_l, const int* active, int* flags, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  lu_factor_kernel<<<cfg.grid_factor, cfg.threads, cfg.smem_factor, st>>>(
-      S, JV, LU, CBW, cfg.top_in_global ? FBW : nullptr, mvals, slot_mask, scale_b, scale_const, RHS, YOUT, store_l,
-      active, flags, B, cfg.outer_nb, static_cast<int>(cfg.smem_factor / sizeof(double)));
+  if (cfg.top_in_global)
+    lu_factor_kernel<true><<<cfg.grid_factor, cfg.threads, cfg.smem_factor, st>>>(
+        S, JV, LU, CBW, FBW, mvals, slot_mask, scale_b, scale_const, RHS, YOUT, store_l, active, flags, B, cfg.outer_nb,
+        static_cast<int>(cfg.smem_factor / sizeof(double)));
+  else
+    lu_factor_kernel<false><<<cfg.grid_factor, cfg.threads, cfg.smem_factor, st>>>(
+        S, JV, LU, CBW, nullptr, mvals, slot_mask, scale_b, scale_const, RHS, YOUT, store_l, active, flags, B, 0, 0);
   return cudaGetLastError();
 }
 

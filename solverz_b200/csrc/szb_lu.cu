@@ -714,23 +714,36 @@ __device__ __noinline__ void eliminate_global(const PanelGrp g, double* __restri
         const double bd = g8 < kNB ? dinv[q + kNB * g8] : 0.0;
         double bl = 0.0;
         if (Lg != nullptr) bl = q == g8 ? 1.0 : ((q > g8 && q < nb) ? Fm[(p0 + q) + (p0 + g8) * ld] : 0.0);
-        for (int tr = tr0 + w; tr <= trmax; tr += nw) {
-          const int row = 8 * tr + g8;
-          const double a0 = (q < nb && row >= r0) ? Fm[row + (p0 + q) * ld] : 0.0;
-          double c0v = 0.0, c1v = 0.0;
-          dmma(c0v, c1v, a0, bd);
-          if (q < 2) {
-            ltk[(2 * q) * lts + row] = -c0v;
-            ltk[(2 * q + 1) * lts + row] = -c1v;
+        // the A21 values of up to eight row tiles of this warp are fetched first: one L2 round trip per
+        // batch instead of one per tile
+        for (int trb = tr0 + w; trb <= trmax; trb += 8 * nw) {
+          double av[8];
+#pragma unroll
+          for (int u8 = 0; u8 < 8; ++u8) {
+            const int row = 8 * (trb + u8 * nw) + g8;
+            av[u8] = (trb + u8 * nw <= trmax && q < nb && row >= r0) ? Fm[row + (p0 + q) * ld] : 0.0;
           }
-          if (Lg != nullptr) {
-            __syncwarp();
-            double d0 = 0.0, d1 = 0.0;
-            dmma(d0, d1, ltk[q * lts + row], bl);
-            if (row >= r0 && row < f && q < 2) {
-              double* __restrict__ dst = Lg + row + (p0 + 2 * q) * f;
-              if (2 * q < nb) dst[0] = -d0;
-              if (2 * q + 1 < nb) dst[f] = -d1;
+#pragma unroll
+          for (int u8 = 0; u8 < 8; ++u8) {
+            const int tr = trb + u8 * nw;
+            if (tr <= trmax) {
+              const int row = 8 * tr + g8;
+              double c0v = 0.0, c1v = 0.0;
+              dmma(c0v, c1v, av[u8], bd);
+              if (q < 2) {
+                ltk[(2 * q) * lts + row] = -c0v;
+                ltk[(2 * q + 1) * lts + row] = -c1v;
+              }
+              if (Lg != nullptr) {
+                __syncwarp();
+                double d0 = 0.0, d1 = 0.0;
+                dmma(d0, d1, ltk[q * lts + row], bl);
+                if (row >= r0 && row < f && q < 2) {
+                  double* __restrict__ dst = Lg + row + (p0 + 2 * q) * f;
+                  if (2 * q < nb) dst[0] = -d0;
+                  if (2 * q + 1 < nb) dst[f] = -d1;
+                }
+              }
             }
           }
         }

@@ -1444,7 +1444,7 @@ __device__ void backward_front_cta(const SolveHdr H, const double* __restrict__ 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, 8)
 lu_backward_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ YP,
                    double* __restrict__ X, double* __restrict__ XW, int x_in_smem, int mode,
                    const int* __restrict__ active, int B) {

@@ -34,6 +34,7 @@
 #include "szb_lu.cuh"
 
 #include <cstdio>
+#include <type_traits>
 
 namespace szb {
 
@@ -198,21 +199,28 @@ __device__ __forceinline__ void assemble_stream(const AsmPre& P, const int rank,
   auto live = [=](const int2 en) {
     return en.x != -1 && (with_rhs || (static_cast<unsigned>(en.x) >> 30) != 2u);
   };
-  // software pipeline: the entries of batch k+1 are in flight while the values of batch k are fetched
-  int2 en[kAsm];
+  // Most fronts of the tree are tiny: their whole stream is one or two entries per thread.  The first
+  // batch is therefore specialised on its length (2, 4 or 8 slots) -- an unrolled 8-slot batch executes
+  // its ~30 instructions per slot whether the slot is live or not.
+  auto first_batch = [&](auto nslots) {
+    constexpr int N = decltype(nslots)::value;
+    double v[N];
 #pragma unroll
-  for (int q = 0; q < kAsm; ++q) en[q] = kAsm + q < iters ? __ldg(e + (kAsm + q) * G_) : make_int2(-1, 0);
-  {
-    double v[kAsm];
-#pragma unroll
-    for (int q = 0; q < kAsm; ++q) {
+    for (int q = 0; q < N; ++q) {
       if (q < kAsmO && q < P.n_ov) v[q] = P.ov[q];
       else v[q] = live(P.en[q]) ? asm_fetch<PLAIN>(static_cast<unsigned>(P.en[q].x), A) : 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < kAsm; ++q)
+    for (int q = 0; q < N; ++q)
       if (live(P.en[q])) Fm[P.en[q].y] += v[q];
-  }
+  };
+  if (iters <= 2) { first_batch(std::integral_constant<int, 2>{}); return; }
+  if (iters <= 4) { first_batch(std::integral_constant<int, 4>{}); return; }
+  // software pipeline: the entries of batch k+1 are in flight while the values of batch k are fetched
+  int2 en[kAsm];
+#pragma unroll
+  for (int q = 0; q < kAsm; ++q) en[q] = kAsm + q < iters ? __ldg(e + (kAsm + q) * G_) : make_int2(-1, 0);
+  first_batch(std::integral_constant<int, kAsm>{});
   if (iters <= kAsm) return;
   for (int it = kAsm; it < iters; it += kAsm) {
     int2 nx[kAsm];

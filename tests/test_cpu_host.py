@@ -382,6 +382,36 @@ def test_no_cpu_fallback():
     mdl = made_numerical(g, y0, sparse=True)      # printing + nvcc work without a GPU
     with pytest.raises(SzbError, match="no CPU fallback"):
         nr_method(mdl, y0)
+    # the other product entry points: time steppers, events, the linear-solver seam
+    from solverz_b200 import (BatchedLU, ComponentEvents, Ode, Opt, Rodas, backward_euler, implicit_trapezoid,
+                              lu_decomposition, solve)
+    m = Model()
+    m.x = Var('x', [0.0, 20.0])
+    m.f1 = Ode('f1', m.x[1], m.x[0])
+    m.f2 = Ode('f2', -9.8, m.x[1])
+    dae, yd = m.create_instance()
+    nd = made_numerical(dae, yd, sparse=True)
+    for call in (lambda: Rodas(nd, [0, 1], yd),
+                 lambda: Rodas(nd, [0, 1], yd, Opt(event=ComponentEvents([0], 0.0, -1, 1))),
+                 lambda: Rodas(nd, [0, 1], yd, Opt(event=lambda t, y: (np.array([y[0]]), np.array([1]), np.array([-1])))),
+                 lambda: backward_euler(nd, [0, 1], yd, Opt(step_size=0.1)),
+                 lambda: implicit_trapezoid(nd, [0, 1], yd, Opt(step_size=0.1)),
+                 lambda: BatchedLU(sps.identity(4, format="csc")),
+                 lambda: lu_decomposition(sps.identity(4, format="csc")),
+                 lambda: solve(sps.identity(4, format="csc"), np.ones(4))):
+        with pytest.raises(SzbError, match="no CPU fallback"):
+            call()
+
+
+def test_component_events_is_a_reference_style_callback():
+    """ComponentEvents doubles as the reference's events(t, y) callback (rodas.py:102-103, 203)."""
+    from solverz_b200 import ComponentEvents
+    ev = ComponentEvents([0, 2, 2], [0.0, 1.5, -1.0], [1, -1, 0], [0, 0, 1])
+    value, isterminal, direction = ev(0.3, np.array([0.25, 9.0, 1.0]))
+    np.testing.assert_allclose(value, [0.25, -0.5, 2.0])
+    assert isterminal.tolist() == [0, 0, 1] and direction.tolist() == [1, -1, 0]
+    with pytest.raises(ValueError):
+        ComponentEvents(list(range(9)))
 
 
 # ----------------------------------------------------------------------------- multi-rank plan

@@ -1162,6 +1162,72 @@ __device__ void forward_front(const LuDev& S, const SolveHdr H, const double* __
   __syncwarp();
 }
 
+// ---- a CTA-level front of the forward sweep, all warps of the CTA together (the mirror image of
+// backward_front_cta; walked by one warp, a 779-row separator front costs one L2 round trip per pivot and
+// chunk).  r lives in shared memory (rv, f doubles):
+//   (a) r = [b_piv ; 0] + children's contribution vectors (all threads, a barrier per child);
+//   (b) per 32-pivot block: warp 0 solves the unit-lower 32 x 32 triangle by shuffles, then every row below
+//       the block takes the block's 32 values, rows dealt to all threads (coalesced column loads, 8 in flight).
+__device__ void forward_front_cta(const LuDev& S, const SolveHdr H, const double* __restrict__ lu, double* xb,
+                                  double* cv, double* __restrict__ rv, const int warp, const int lane) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0, k = H.k;
+  const double* __restrict__ Lp = lu + H.lp_off;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int t = tid; t < f; t += nthr) rv[t] = t < s ? xb[p0 + t] : 0.0;
+  __syncthreads();
+  for (int ci = S.child_ptr[k]; ci < S.child_ptr[k + 1]; ++ci) {
+    const int c = S.child[ci];
+    const int c0 = S.rel_ptr[c], uc = S.rel_ptr[c + 1] - c0;
+    for (int t = tid; t < uc; t += nthr) rv[S.rel[c0 + t]] += cv[c0 + t];
+    __syncthreads();
+  }
+  const int nblk = (s + 31) >> 5;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int bbeg = 32 * blk, bend = min(s, bbeg + 32), nbk = bend - bbeg;
+    if (warp == 0) {
+      const int i = bbeg + lane;
+      const int io = i < bend ? i : bbeg;             // idle lanes mirror the first row, never store
+      double acc = rv[io];
+      const double* __restrict__ row = Lp + io + bbeg * f;
+      for (int pb = 0; pb < nbk; pb += 8) {
+        double lv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) lv[q] = (pb + q < nbk && io > bbeg + pb + q) ? row[(pb + q) * f] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (pb + q < nbk) {
+            const double xp = __shfl_sync(0xffffffffu, acc, pb + q);
+            acc = fma(-lv[q], xp, acc);                // lv = 0 on and above the diagonal
+          }
+        }
+      }
+      if (i < bend) rv[i] = acc;
+    }
+    __syncthreads();
+    for (int i = bend + tid; i < f; i += nthr) {
+      const double* __restrict__ row = Lp + i + bbeg * f;
+      double acc = rv[i];
+      int p = 0;
+      for (; p + 8 <= nbk; p += 8) {
+        double lv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) lv[q] = row[(p + q) * f];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fma(-lv[q], rv[bbeg + p + q], acc);
+      }
+      for (; p < nbk; ++p) acc = fma(-row[p * f], rv[bbeg + p], acc);
+      rv[i] = acc;
+    }
+    __syncthreads();
+  }
+  for (int t = tid; t < s; t += nthr) xb[p0 + t] = rv[t];
+  if (u > 0) {
+    const int c0 = S.rel_ptr[k];
+    for (int i = tid; i < u; i += nthr) cv[c0 + i] = rv[s + i];
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(128, 6)
 lu_forward_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ RHS,
                   double* __restrict__ YP, double* CVW, double* __restrict__ XW,
@@ -1188,9 +1254,7 @@ lu_forward_kernel(const LuDev S, const double* __restrict__ LU, const double* __
       for (int q = gq_base + S.gl_ptr[g]; q < gq_base + S.gl_ptr[g + 1]; ++q)
         forward_front(S, load_solve_hdr(S.fh, q), lu, xb, cv, rv, lane);
     __syncthreads();
-    if (warp == 0)
-      for (int q = 0; q < S.n_top; ++q) forward_front(S, load_solve_hdr(S.fh, tq0 + q), lu, xb, cv, rv, lane);
-    __syncthreads();
+    for (int q = 0; q < S.n_top; ++q) forward_front_cta(S, load_solve_hdr(S.fh, tq0 + q), lu, xb, cv, sm, warp, lane);
     double* __restrict__ yp = YP + static_cast<size_t>(b) * n;
     for (int t = threadIdx.x; t < n; t += blockDim.x) yp[t] = xb[t];
   }

@@ -17,20 +17,26 @@
 //       group : a few warps (named barrier) share one medium front; groups run independent
 //               subtrees concurrently;
 //       CTA   : the few big fronts at the top use all threads.
-//     Inside a front: lane = row (conflict-free column-major shared memory with an odd leading
-//     dimension); multi-warp fronts run a blocked (NB = 4) elimination whose only serial chain is
-//     a 4x4 diagonal-block problem on one warp, one barrier per panel;
+//     Warp-level fronts: lane = row, rank-1 steps (column-major shared memory, odd leading dimension).
+//     Multi-warp fronts: blocked (NB = 4) elimination whose trailing update runs on the fp64 tensor-core
+//     path (mma.sync.m8n8k4.f64 over zero-padded 8x8 tiles, leading dimension 2 mod 4), with a 4x4
+//     diagonal-block LU + inverse in registers on one warp as the only serial chain; fronts too large
+//     for shared memory live in a per-CTA global workspace and are eliminated in outer blocks of 32
+//     pivots (eliminate_global);
 //   * a front is described by ONE 64-byte descriptor (prefetched a front ahead) and assembled in
 //     ONE pass over a host-built gather table (lu/schedule.py): matrix entries, right-hand side and
 //     all children's contribution blocks, every destination owned by one thread (no barriers
 //     between children, no atomics);
 //   * the right-hand side can ride along as an extra front column, which fuses the forward
 //     substitution L y = b into the factorisation (Newton never needs L again);
-//   * contribution blocks travel through a per-CTA stack in global memory (L2 resident, reused
-//     across scenarios by the persistent CTA); factors are written exactly once;
+//   * contribution blocks travel through a per-CTA workspace in global memory (L2 resident, reused
+//     across scenarios by the persistent CTA, regions of different lifetimes sharing addresses);
+//     factors are written exactly once (the diagonal of U as its reciprocal);
 //   * triangular solves follow the same tree; the forward sweep passes contribution vectors up
-//     the tree (no atomics => bitwise reproducible), the backward sweep only reads ancestors.
-//   No tensor cores: fp64 FMA fed from shared memory; nothing here is a large dense contraction.
+//     the tree (no atomics => bitwise reproducible), the backward sweep only reads ancestors; the
+//     CTA-level chain at the top of the tree is walked by all warps of the CTA in both sweeps.
+//   The sparse structure is never reshaped into a dense contraction; the frontal matrices of the
+//   multifrontal method ARE dense, and their rank-4 updates are what the DMMA path is used for.
 #include "szb_lu.cuh"
 
 #include <cstdio>

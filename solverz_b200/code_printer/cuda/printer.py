@@ -108,10 +108,11 @@ class _Emitter:
 class _RowGen:
     """Shared code generation for one equation template."""
 
-    def __init__(self, ir: ModelIR, eq: EqTemplate, tabs: "_Tables"):
+    def __init__(self, ir: ModelIR, eq: EqTemplate, tabs: "_Tables", hoist_trig: bool = True):
         self.ir = ir
         self.eq = eq
         self.tabs = tabs
+        self.hoist_trig = hoist_trig
         self.names: Dict[sp.Symbol, str] = {}
         for s, ld in eq.loads.items():
             self.names[s] = s.name.lstrip("_")
@@ -119,6 +120,8 @@ class _RowGen:
             self.names[w.sym] = w.sym.name.lstrip("_")
         self.cse_count = 0
         self.alias: Dict[sp.Symbol, sp.Symbol] = {}
+        self.trig_outer: Dict[sp.Symbol, Tuple[sp.Symbol, sp.Symbol]] = {}
+        self.trig_inner: Dict[sp.Symbol, Tuple[sp.Symbol, sp.Symbol]] = {}
 
     def set_groups(self, groups: List[List[int]]):
         """Inner loads of walkers that share one CSR walk read the same address: merge them so
@@ -135,6 +138,71 @@ class _RowGen:
 
     def canon(self, e: sp.Expr) -> sp.Expr:
         return e.xreplace(self.alias) if self.alias else e
+
+    # ---- trig hoisting: sin / cos of (outer-indexed V) - (walk-indexed V) by the angle-difference
+    # identities from one sincos per ROW (outer value) and a per-scenario table of sin V, cos V that the
+    # kernel fills once (one sincos per variable entry instead of one per walked position and equation).
+    def hoist(self, e: sp.Expr) -> sp.Expr:
+        e = self.canon(e)
+        if not (self.tabs.trig_ok and self.hoist_trig):
+            return e
+
+        def split(arg):
+            """arg = a*Lo + b*Li with a = -b = +-1, Lo outer / Li inner loads of one variable -> (a, Lo, Li)."""
+            if not (arg.is_Add and len(arg.args) == 2):
+                return None
+            terms = []
+            for t in arg.args:
+                c, sym = t.as_coeff_Mul()
+                if sym not in self.eq.loads or c not in (1, -1):
+                    return None
+                terms.append((int(c), sym))
+            (c1, s1), (c2, s2) = terms
+            if c1 != -c2:
+                return None
+            l1, l2 = self.eq.loads[s1], self.eq.loads[s2]
+            if l1.kind != "var" or l2.kind != "var" or l1.base != l2.base:
+                return None
+            in1, in2 = l1.index.kind == "inner", l2.index.kind == "inner"
+            if in1 == in2:
+                return None
+            return (c2, s2, s1) if in1 else (c1, s1, s2)
+
+        def fix(node):
+            sp_ = split(node.args[0])
+            if sp_ is None:
+                return node
+            a, lo, li = sp_
+            base = self.eq.loads[lo].base
+            self.tabs.trig_table(self.ir, base)
+            so, co = self.trig_outer.setdefault(lo, (sp.Symbol(f"so{lo.name[2:]}", real=True),
+                                                     sp.Symbol(f"co{lo.name[2:]}", real=True)))
+            si, ci = self.trig_inner.setdefault(li, (sp.Symbol(f"si{li.name[2:]}", real=True),
+                                                     sp.Symbol(f"ci{li.name[2:]}", real=True)))
+            for x in (so, co, si, ci):
+                self.names[x] = x.name
+            if isinstance(node, sp.sin):                  # sin(a (Lo - Li)) = a (sin Lo cos Li - cos Lo sin Li)
+                return a * (so * ci - co * si)
+            return co * ci + so * si                      # cos is even
+        return e.replace(lambda x: isinstance(x, (sp.sin, sp.cos)), fix)
+
+    def emit_outer_trig(self, em: _Emitter):
+        for lo, (so, co) in sorted(self.trig_outer.items(), key=lambda kv: int(kv[0].name[2:])):
+            em.w(f"double {so.name}, {co.name};")
+            em.w(f"sincos({self.names[lo]}, &{so.name}, &{co.name});")
+
+    def trig_loads(self, exprs: Sequence[sp.Expr]) -> List[Tuple[str, str, str]]:
+        """(ctype, name, text) of the table reads the walk body needs."""
+        free = set().union(*[e.free_symbols for e in exprs]) if exprs else set()
+        out = []
+        for li, (si, ci) in sorted(self.trig_inner.items(), key=lambda kv: int(kv[0].name[2:])):
+            ld = self.eq.loads[li]
+            ix = self.idx_text(ld.index)
+            if si in free:
+                out.append(("double", si.name, f"c.ts_{_ident(ld.base)}[{ix}]"))
+            if ci in free:
+                out.append(("double", ci.name, f"c.tc_{_ident(ld.base)}[{ix}]"))
+        return out
 
     # ---- index / load text
     def idx_text(self, ix: Index) -> str:
@@ -275,8 +343,16 @@ class _RowGen:
 class _Tables:
     """int32 tables printed as static arrays."""
 
-    def __init__(self):
+    def __init__(self, trig_ok: bool = True):
         self.items: List[Tuple[str, np.ndarray]] = []
+        # variables whose sin / cos are tabulated per scenario (trig hoisting): base -> (table offset, length)
+        self.trig: Dict[str, Tuple[int, int]] = {}
+        self.trig_ok = trig_ok
+
+    def trig_table(self, ir: ModelIR, base: str) -> None:
+        if base not in self.trig:
+            off = sum(ln for _, ln in self.trig.values())
+            self.trig[base] = (off, int(ir.var_off[base][1]))
 
     def add(self, name: str, arr: np.ndarray) -> str:
         self.items.append((name, np.asarray(arr, dtype=np.int32)))
@@ -294,16 +370,17 @@ def _gen_F(ir: ModelIR, k: int, eq: EqTemplate, jt: JacTemplate, tabs: _Tables) 
     g = _RowGen(ir, eq, tabs)
     g.set_groups(jt.groups)
     em = _Emitter()
-    inner_exprs = [w.expr for w in eq.walkers]
-    outer_syms = g.used_loads([eq.expr] + inner_exprs)
+    wexpr = [g.hoist(w.expr) for w in eq.walkers]
+    outer_syms = g.used_loads([eq.expr] + wexpr) | set(g.trig_outer)
     g.emit_loads(em, outer_syms, inner=False)
+    g.emit_outer_trig(em)
     for gi, group in enumerate(jt.groups):
         canon = g.walk_header(em, gi, group)
         for wi in group:
             em.w(f"double {g.names[eq.walkers[wi].sym]} = 0.0;")
-        ex = [eq.walkers[wi].expr for wi in group]
-        g.open_walk(em, gi, _ident(canon), g.used_loads(ex), pipelined=False)
-        g.emit_exprs(em, [(f"{g.names[eq.walkers[wi].sym]} +=", eq.walkers[wi].expr) for wi in group])
+        ex = [wexpr[wi] for wi in group]
+        g.open_walk(em, gi, _ident(canon), g.used_loads(ex), g.trig_loads(ex), pipelined=False)
+        g.emit_exprs(em, [(f"{g.names[eq.walkers[wi].sym]} +=", wexpr[wi]) for wi in group])
         g.close_walk(em)
     g.emit_exprs(em, [("return", eq.expr)])
     head = f"SZB_HD static inline double szbm_F{k}(const int i, const szbm_ctx& c) {{  // {eq.name}\n"
@@ -312,19 +389,24 @@ def _gen_F(ir: ModelIR, k: int, eq: EqTemplate, jt: JacTemplate, tabs: _Tables) 
 
 def _gen_J(ir: ModelIR, k: int, jt: JacTemplate, tabs: _Tables) -> str:
     eq = jt.eq
-    g = _RowGen(ir, eq, tabs)
+    # no trig hoisting in the Jacobian rows: measured on B200, the J kernel is bound by the latency of its
+    # scattered CSC stores, not by sincos, and the two extra table reads per position cost 9 %
+    g = _RowGen(ir, eq, tabs, hoist_trig=False)
     g.set_groups(jt.groups)
     for _, a, _ in jt.accs:
         g.names[a] = a.name.lstrip("_")
     em = _Emitter()
     if not jt.outer and not jt.inner:
         return f"SZB_HD static inline void szbm_J{k}(const int, const szbm_ctx&, double* __restrict__) {{}}  // {eq.name}\n"
-    all_exprs = [e.expr for e in jt.outer] + [e.coef for e in jt.inner] + [e.term for e in jt.inner] + \
-                [x for _, _, x in jt.accs]
+    wexpr = [g.hoist(w.expr) for w in eq.walkers]                  # walk bodies with the trig hoisted
+    terms = [g.hoist(e.term) for e in jt.inner]
+    accs_h = [(wi, a, g.hoist(x)) for wi, a, x in jt.accs]
+    all_exprs = [e.expr for e in jt.outer] + [e.coef for e in jt.inner] + terms + [x for _, _, x in accs_h]
     need_syms = set().union(*[e.free_symbols for e in all_exprs]) if all_exprs else set()
     walkers_needed = [wi for wi, w in enumerate(eq.walkers) if w.sym in need_syms]
-    all_exprs += [eq.walkers[wi].expr for wi in walkers_needed]
-    g.emit_loads(em, g.used_loads(all_exprs), inner=False)
+    all_exprs += [wexpr[wi] for wi in walkers_needed]
+    g.emit_loads(em, g.used_loads(all_exprs) | set(g.trig_outer), inner=False)
+    g.emit_outer_trig(em)
     otab = [tabs.add(f"szbm_ot{k}_{ei}", sl) for ei, sl in enumerate(jt.outer_slots)]
     # Inner entries that hit the same CSC slot at every position of the same walk (e.g. the G-walk and the
     # B-walk terms of dP/dVa) are summed in registers and emitted ONCE: emitted separately the second one is
@@ -344,22 +426,23 @@ def _gen_J(ir: ModelIR, k: int, jt: JacTemplate, tabs: _Tables) -> str:
 
     def sums_loop(gi, group, do_sums: bool, do_emit: bool):
         canon_ = self_canon[gi]
-        accs_here = [(wi, a, x) for wi, a, x in jt.accs if wi in group]
+        accs_here = [(wi, a, x) for wi, a, x in accs_h if wi in group]
         s_here = [wi for wi in group if wi in walkers_needed]
         ents = [(ei, e) for ei, e in enumerate(jt.inner) if e.walker in group]
         if not ((do_sums and (accs_here or s_here)) or (do_emit and ents)):
             return
         targets: List[Tuple[str, sp.Expr]] = []
         if do_sums:
-            targets += [(f"{g.names[eq.walkers[wi].sym]} +=", eq.walkers[wi].expr) for wi in s_here]
+            targets += [(f"{g.names[eq.walkers[wi].sym]} +=", wexpr[wi]) for wi in s_here]
             targets += [(f"{g.names[a]} +=", x) for _, a, x in accs_here]
         slot_loads: List[Tuple[str, str, str]] = []
         if do_emit:
             for ei, e in ents:
-                targets.append((f"const double v{ei} =", sp.Symbol(f"cf{ei}", real=True) * e.term))
+                targets.append((f"const double v{ei} =", sp.Symbol(f"cf{ei}", real=True) * terms[ei]))
                 if leader[ei] == ei:                   # the CSC slot of this position, fetched an iteration ahead
                     slot_loads.append(("int", f"sl{ei}", f"{itab[ei]}[{woff[e.walker]}[i] + (kk - kb{gi})]"))
-        g.open_walk(em, gi, _ident(canon_), g.used_loads([x for _, x in targets]), slot_loads)
+        g.open_walk(em, gi, _ident(canon_), g.used_loads([x for _, x in targets]),
+                    g.trig_loads([x for _, x in targets]) + slot_loads)
         g.emit_exprs(em, targets)
         if do_emit:
             for ei, e in ents:
@@ -458,9 +541,17 @@ __device__ __forceinline__ double szbm_nanmax(double a, double b) { return (a > 
 
 __global__ void __launch_bounds__(SZBM_THREADS) szbm_F_kernel(const szbm_kargs a) {
   __shared__ double red[SZBM_THREADS / 32];
+#if SZBM_TRIG_N > 0
+  __shared__ double szbm_ts[SZBM_TRIG_N], szbm_tc[SZBM_TRIG_N];
+#endif
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     if (a.active && !a.active[b]) continue;
-    const szbm_ctx c = szbm_make_ctx(a, b);
+    szbm_ctx c = szbm_make_ctx(a, b);
+#if SZBM_TRIG_N > 0
+    __syncthreads();                      // the rows of the previous scenario are done with the tables
+    szbm_fill_trig(c, szbm_ts, szbm_tc, threadIdx.x, SZBM_THREADS);
+    __syncthreads();
+#endif
     double* __restrict__ F = a.F + (size_t)b * SZBM_N;
     double m = 0.0;
     for (int row = threadIdx.x; row < SZBM_N; row += SZBM_THREADS) {
@@ -482,7 +573,7 @@ __global__ void __launch_bounds__(SZBM_THREADS) szbm_F_kernel(const szbm_kargs a
 __global__ void __launch_bounds__(SZBM_THREADS) szbm_J_kernel(const szbm_kargs a) {
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     if (a.active && !a.active[b]) continue;
-    const szbm_ctx c = szbm_make_ctx(a, b);
+    const szbm_ctx c = szbm_make_ctx(a, b);     // the Jacobian rows read no trig tables (see _gen_J)
     double* __restrict__ JV = a.JV + (size_t)b * SZBM_NNZ;
     for (int row = threadIdx.x; row < SZBM_N; row += SZBM_THREADS) szbm_row_J(row, c, JV);
   }
@@ -515,6 +606,8 @@ SZBM_API void szbm_host_F(int B, double t, const double* Y, const void* const* p
   for (int b = 0; b < B; ++b) {
     szbm_ctx c; c.t = t; c.Y = Y + (size_t)b * SZBM_N;
 %(host_ctx_fill)s
+    static double ts_[SZBM_TRIG_N > 0 ? SZBM_TRIG_N : 1], tc_[SZBM_TRIG_N > 0 ? SZBM_TRIG_N : 1];
+    szbm_fill_trig(c, ts_, tc_, 0, 1);
     for (int row = 0; row < SZBM_N; ++row) F[(size_t)b * SZBM_N + row] = szbm_row_F(row, c);
   }
 }
@@ -522,6 +615,8 @@ SZBM_API void szbm_host_J(int B, double t, const double* Y, const void* const* p
   for (int b = 0; b < B; ++b) {
     szbm_ctx c; c.t = t; c.Y = Y + (size_t)b * SZBM_N;
 %(host_ctx_fill)s
+    static double ts_[SZBM_TRIG_N > 0 ? SZBM_TRIG_N : 1], tc_[SZBM_TRIG_N > 0 ? SZBM_TRIG_N : 1];
+    szbm_fill_trig(c, ts_, tc_, 0, 1);
     for (int row = 0; row < SZBM_N; ++row) szbm_row_J(row, c, JV + (size_t)b * SZBM_NNZ);
   }
 }
@@ -532,14 +627,30 @@ SZBM_API void szbm_host_J(int B, double t, const double* Y, const void* const* p
 
 def print_model(ir: ModelIR, pat: JacPattern, name: str = "model", threads: int = 256) -> str:
     """Return the CUDA source of the model library."""
-    tabs = _Tables()
-    _CPrinter.snippets = {}
-    f_funcs, j_funcs = [], []
-    for k, (eq, jt) in enumerate(zip(ir.eqs, pat.templates)):
-        f_funcs.append(_gen_F(ir, k, eq, jt, tabs))
-        j_funcs.append(_gen_J(ir, k, jt, tabs))
+    # Trig hoisting needs 16 bytes of static shared memory per tabulated variable entry (48 kB limit):
+    # generate with it, and again without it when the tables would not fit.
+    for trig_ok in (True, False):
+        tabs = _Tables(trig_ok)
+        _CPrinter.snippets = {}
+        f_funcs, j_funcs = [], []
+        for k, (eq, jt) in enumerate(zip(ir.eqs, pat.templates)):
+            f_funcs.append(_gen_F(ir, k, eq, jt, tabs))
+            j_funcs.append(_gen_J(ir, k, jt, tabs))
+        trig_n = sum(ln for _, ln in tabs.trig.values())
+        if trig_n <= 3072:
+            break
     pnames = list(ir.params)
     ctx_fields = ["  double t;", "  const double* Y;"]
+    for base in tabs.trig:
+        ctx_fields.append(f"  const double* ts_{_ident(base)};")
+        ctx_fields.append(f"  const double* tc_{_ident(base)};")
+    fill = ["SZB_HD static inline void szbm_fill_trig(szbm_ctx& c, double* ts, double* tc, const int tid, const int nthr) {",
+            "  (void)ts; (void)tc; (void)tid; (void)nthr; (void)c;"]
+    for base, (toff, ln) in tabs.trig.items():
+        voff = ir.var_off[base][0]
+        fill.append(f"  for (int k = tid; k < {ln}; k += nthr) sincos(c.Y[{voff} + k], ts + {toff} + k, tc + {toff} + k);")
+        fill.append(f"  c.ts_{_ident(base)} = ts + {toff}; c.tc_{_ident(base)} = tc + {toff};")
+    fill.append("}")
     karg_fields, ctx_fill, karg_fill, host_fill, ptable = [], [], [], [], []
     for pi, pn in enumerate(pnames):
         p = ir.params[pn]
@@ -561,11 +672,11 @@ def print_model(ir: ModelIR, pat: JacPattern, name: str = "model", threads: int 
         disp_J.append(f"  {els}{cond} szbm_J{k}(row - {eq.row0}, c, JV);")
     src = _PRELUDE % dict(name=name, kind=ir.kind, n=ir.n, nnz=pat.nnz, neq=len(ir.eqs))
     src += f"\n#define SZBM_N {ir.n}\n#define SZBM_NNZ {pat.nnz}\n#define SZBM_NPARAMS {len(pnames)}\n"
-    src += f"#define SZBM_THREADS {threads}\n\n"
+    src += f"#define SZBM_THREADS {threads}\n#define SZBM_TRIG_N {trig_n}\n\n"
     src += "struct szbm_ctx {\n" + "\n".join(ctx_fields) + "\n};\n\n"
     src += "static const szbm_param_info szbm_param_table[] = {\n" + "\n".join(ptable) + \
            ("\n" if ptable else "") + '  {0, 0, 0, 0}\n};\n\n'
-    src += tabs.text() + "\n\n"
+    src += "\n".join(fill) + "\n\n" + tabs.text() + "\n\n"
     if _CPrinter.snippets:
         src += "// device code of custom functions (_cuda_device_code)\n" + "\n".join(_CPrinter.snippets.values()) + "\n\n"
     src += "\n".join(f_funcs) + "\n" + "\n".join(j_funcs) + "\n"

@@ -127,6 +127,12 @@ def test_printer_pf_matches_reference_golden(tmp_path):
         assert np.abs(Fh[0] - F).max() <= 1e-13
         assert np.abs(JVh[0] - Jd).max() <= 1e-12 * np.abs(Jd).max()
     assert "sincos(" in src and "szbm_launch_F" in src
+    # trig hoisting: the F rows read the per-scenario sin / cos table of Va, the Jacobian rows do not
+    f0 = src[src.index("szbm_F0(const int i"):src.index("szbm_F1(const int i")]
+    j0 = src[src.index("szbm_J0(const int i"):src.index("szbm_J1(const int i")]
+    assert "c.ts_Va[j]" in f0 and "c.tc_Va[j]" in f0 and f0.count("sincos(") == 1
+    assert "c.ts_Va" not in j0 and "sincos(" in j0
+    assert "#define SZBM_TRIG_N 64" in src
 
 
 def test_printer_vector_eqn_matmul_and_known_values(tmp_path):

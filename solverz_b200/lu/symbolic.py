@@ -417,7 +417,7 @@ def _flops_of(struct_sizes: np.ndarray) -> float:
 
 def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.ndarray,
            relax_frac: float, relax_small: int, warp_front_max: int, n_warps: int,
-           group_front_max: int, n_groups: int, name: str) -> LUSymbolic:
+           group_front_max: int, n_groups: int, name: str, warp_fixed: float = 3000.0) -> LUSymbolic:
     n = A.shape[0]
     parent, children, struct = _symbolic_structs(S, order)
     size = np.array([len(s) for s in struct], dtype=np.int64)
@@ -550,6 +550,10 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
     sub_fmax = sn_f.copy()
     sub_cost = (sn_s * sn_f * sn_f).astype(np.float64)
     own_cost = sub_cost.copy()
+    # warp level: a front costs a few thousand cycles of latency (descriptor, gather, write-out) whatever its
+    # size; with s f^2 alone the lists held 25 to 44 fronts and the longest set the level's time (measured:
+    # factor 11.25 -> 11.13 ms, sweeps 2.18 -> 2.14 ms with 3000 per front)
+    warp_cost = own_cost + warp_fixed
     for k in range(ns):  # postorder: children before parents
         p = sn_parent[k]
         if p >= 0:
@@ -574,9 +578,10 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
             if mine[k]:
                 p = sn_parent[k]
                 root_of[k] = k if (p < 0 or not mine[p]) else root_of[p]
+        per_front = warp_cost if lv == 0 else own_cost
         for k in range(ns):
             if mine[k]:
-                cost[root_of[k]] += own_cost[k]
+                cost[root_of[k]] += per_front[k]
         n_lists = max(1, min(n_max, len(roots))) if roots else 0
         loads = np.zeros(max(n_lists, 1))
         assign = {}
@@ -713,7 +718,7 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
 
 def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
             warp_front_max: int = 32, n_warps: int = 16, group_front_max: int = 72, n_groups: int = 4,
-            orderings: Sequence[str] = ("nd", "mmd")) -> LUSymbolic:
+            orderings: Sequence[str] = ("nd", "mmd"), warp_fixed: float = 3000.0) -> LUSymbolic:
     """Analyse the pattern (and representative values) of ``A``; see the module docstring."""
     A = sp.csc_matrix(A)
     A.sort_indices()
@@ -761,4 +766,4 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
     assert best is not None
     _, name, order = best
     return _build(A, rowperm, S, order, relax_frac, relax_small, warp_front_max, n_warps,
-                  group_front_max, n_groups, name)
+                  group_front_max, n_groups, name, float(warp_fixed))

@@ -417,7 +417,8 @@ def _flops_of(struct_sizes: np.ndarray) -> float:
 
 def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.ndarray,
            relax_frac: float, relax_small: int, warp_front_max: int, n_warps: int,
-           group_front_max: int, n_groups: int, name: str, warp_fixed: float = 3000.0) -> LUSymbolic:
+           group_front_max: int, n_groups: int, name: str, warp_fixed: float = 3000.0,
+           group_fixed: float = 60000.0) -> LUSymbolic:
     n = A.shape[0]
     parent, children, struct = _symbolic_structs(S, order)
     size = np.array([len(s) for s in struct], dtype=np.int64)
@@ -578,7 +579,8 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
             if mine[k]:
                 p = sn_parent[k]
                 root_of[k] = k if (p < 0 or not mine[p]) else root_of[p]
-        per_front = warp_cost if lv == 0 else own_cost
+        # (group level: 60000 per front on the same scale, measured 11.13 -> 11.06 ms)
+        per_front = warp_cost if lv == 0 else (own_cost + group_fixed if lv == 1 else own_cost)
         for k in range(ns):
             if mine[k]:
                 cost[root_of[k]] += per_front[k]
@@ -718,7 +720,7 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
 
 def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
             warp_front_max: int = 32, n_warps: int = 16, group_front_max: int = 72, n_groups: int = 4,
-            orderings: Sequence[str] = ("nd", "mmd"), warp_fixed: float = 3000.0) -> LUSymbolic:
+            orderings: Sequence[str] = ("nd", "mmd"), warp_fixed: float = 3000.0, group_fixed: float = 60000.0) -> LUSymbolic:
     """Analyse the pattern (and representative values) of ``A``; see the module docstring."""
     A = sp.csc_matrix(A)
     A.sort_indices()
@@ -766,4 +768,4 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
     assert best is not None
     _, name, order = best
     return _build(A, rowperm, S, order, relax_frac, relax_small, warp_front_max, n_warps,
-                  group_front_max, n_groups, name, float(warp_fixed))
+                  group_front_max, n_groups, name, float(warp_fixed), float(group_fixed))

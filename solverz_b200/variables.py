@@ -53,6 +53,10 @@ class Vars:
         return self.a.names
 
     @property
+    def var_size(self):
+        return {k: self.a[k].stop - self.a[k].start for k in self.a.names}
+
+    @property
     def total_size(self):
         return self.a.total_size
 
@@ -89,6 +93,14 @@ class TimeVars:
             if isinstance(item, slice):
                 return TimeVars(self.a, self.array[item])
         return self.array[item]
+
+    @property
+    def var_list(self):
+        return self.a.names
+
+    @property
+    def var_size(self):
+        return {k: self.a[k].stop - self.a[k].start for k in self.a.names}
 
     def __len__(self):
         return self.array.shape[-2]

@@ -7,5 +7,5 @@ from .variables import Vars, TimeVars, Address
 
 __version__ = "0.1.0"
 from .code_printer import module_printer, made_numerical
-from .solvers import Opt, Stats, aesol, daesol, nr_method, Rodas, fdae_solver, backward_euler, implicit_trapezoid, ComponentEvents, BatchedLU, lu_decomposition, solve
+from .solvers import sicnm, Opt, Stats, aesol, daesol, nr_method, Rodas, fdae_solver, backward_euler, implicit_trapezoid, ComponentEvents, BatchedLU, lu_decomposition, solve
 from .io import save, load, save_result, load_result

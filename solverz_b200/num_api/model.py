@@ -199,8 +199,10 @@ class CudaModel:
 
     def __init__(self, name: str, kind: str, so_path, n: int, nnz_j: int, indptr, indices, params_meta,
                  y0: np.ndarray, var_slices: Dict[str, slice], mass=None, mass_slots=None, nstep: int = 0,
-                 symbolic=None, pkl_path=None, lu_options: Optional[dict] = None):
+                 symbolic=None, pkl_path=None, lu_options: Optional[dict] = None, hvp_dir=None):
         self.name = name
+        self._hvp_dir = hvp_dir
+        self._hvp_model = None
         self.kind = kind
         self.so_path = Path(so_path)
         self.n = int(n)
@@ -273,6 +275,31 @@ class CudaModel:
         jv = s.eval_J(t)[0].cpu().numpy()
         return sps.csc_array((jv, self.indices, self.indptr), shape=(self.n, self.n))
 
+    @property
+    def hvp_model(self) -> "CudaModel":
+        """The twin model whose Jacobian is ``d(J(y) v)/dy`` (rendered by ``make_hvp=True``); its per-scenario
+        parameters ``v__<var>`` carry the vector."""
+        if self._hvp_model is None:
+            if self._hvp_dir is None:
+                raise AttributeError("this module was rendered without make_hvp=True: no HVP (module_printer(..., "
+                                     "make_hvp=True) / made_numerical(..., make_hvp=True))")
+            self._hvp_model = load_rendered(str(Path(self._hvp_dir) / "__init__.py"))[0]
+        return self._hvp_model
+
+    def HVP(self, y, p, v):
+        """``HVP(y_, p_, v_)`` of the reference's rendered module (module_printer.py, `make_hvp`): sparse
+        ``d(J(y) v)/dy`` of one scenario."""
+        hm = self.hvp_model
+        s = hm.session(1, with_lu=False)
+        v = np.asarray(v.array if isinstance(v, Vars) else v, dtype=float)
+        pv = {k: val for k, val in p.items() if k in hm.p}
+        for k in self.a.names:
+            pv["v__" + k] = v[self.a[k]]
+        s.set_params(pv)
+        s.set_y(y)
+        hv = s.eval_J(0.0)[0].cpu().numpy()
+        return sps.csc_array((hv, hm.indices, hm.indptr), shape=(self.n, self.n))
+
     # -- batched access --------------------------------------------------------------------
     def session(self, B: int, device: Optional[int] = None, with_lu: bool = True) -> BatchSession:
         torch = _torch()
@@ -320,6 +347,8 @@ class CudaModel:
         for s in self._sessions.values():
             s.close()
         self._sessions.clear()
+        if self._hvp_model is not None:
+            self._hvp_model.close()
 
 
 def load_rendered(init_file: str):
@@ -329,7 +358,8 @@ def load_rendered(init_file: str):
         st = pickle.load(f)
     mdl = CudaModel(st["name"], st["kind"], d / st["so"], st["n"], st["nnz_j"], st["indptr"], st["indices"],
                     st["params_meta"], st["y0"], st["var_slices"], st["mass"], st["mass_slots"], st["nstep"],
-                    st.get("symbolic"), d / "param_and_setting.pkl", st.get("lu_options"))
+                    st.get("symbolic"), d / "param_and_setting.pkl", st.get("lu_options"),
+                    d / st["hvp"] if st.get("hvp") else None)
     a = Address()
     for k, s in st["var_slices"].items():
         a.add(k, s.stop - s.start)

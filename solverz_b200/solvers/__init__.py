@@ -8,3 +8,4 @@ from .fdae import fdae_solver
 from .implicit import backward_euler, implicit_trapezoid
 from .rodas_event import ComponentEvents
 from .laesolver import BatchedLU, lu_decomposition, solve
+from .sicnm import sicnm

@@ -396,8 +396,54 @@ def golden_implicit():
     np.savez_compressed(HERE / "implicit_ref.npz", **out)
 
 
+def sicnm_model(lib):
+    """Element-wise algebraic model the reference's Hvp supports (vector / scalar derivative blocks only,
+    equation/hvp.py:19-53): 0 = exp(u) + sin(w) - a,  0 = u w + w^2 - b  with u = x[0:3], w = x[3:6]."""
+    kw = dict(per_scenario=True) if lib.__name__ == "solverz_b200" else {}
+    m = lib.Model()
+    m.x = lib.Var('x', [0.2, 0.1, 0.3, 0.5, 0.4, 0.6])
+    m.a = lib.Param('a', [2.0, 1.8, 2.2], **kw)
+    m.b = lib.Param('b', [1.5, 1.2, 1.9], **kw)
+    m.f = lib.Eqn('f', lib.exp(m.x[0:3]) + lib.sin(m.x[3:6]) - m.a)
+    m.g = lib.Eqn('g', m.x[0:3] * m.x[3:6] + m.x[3:6] ** 2 - m.b)
+    return m.create_instance()
+
+
+def golden_sicnm():
+    """the reference's HVP matrix and `sicnm` runs (solution, Stats, accepted iterates) on
+    `sicnm_model`, for rodas4 / rodas3d and a few per-scenario parameter sets."""
+    import Solverz
+    from Solverz import Opt, module_printer, nr_method, sicnm
+    ae, y0 = sicnm_model(Solverz)
+    d = tempfile.mkdtemp()
+    module_printer(ae, y0, "gold_sicnm", directory=d, jit=True, make_hvp=True).render()
+    sys.path.insert(0, d)
+    mod = importlib.import_module("gold_sicnm")
+    mdl = mod.mdl
+    rng = np.random.default_rng(3)
+    yp = y0.array + 0.1 * rng.standard_normal(6)
+    v = rng.standard_normal(6)
+    out = dict(y0=y0.array, yp=yp, v=v, H=sps.csc_matrix(mdl.HVP(yp, mdl.p, v)).toarray(),
+               J=sps.csc_matrix(mdl.J(yp, mdl.p)).toarray())
+    A = np.array([[2.0, 1.8, 2.2], [2.6, 1.1, 2.9], [1.4, 2.4, 1.7], [3.0, 3.0, 3.0]])
+    Bp = np.array([[1.5, 1.2, 1.9], [2.5, 0.6, 3.1], [0.8, 2.0, 1.0], [4.0, 0.3, 2.0]])
+    out["A"], out["B"] = A, Bp
+    for scheme in ("rodas4", "rodas3d"):
+        ys, sts, Ts = [], [], []
+        for a, b in zip(A, Bp):
+            mdl.p["a"], mdl.p["b"] = a, b
+            s = sicnm(mdl, mod.y, Opt(ite_tol=1e-8, scheme=scheme))
+            st = s.stats
+            ys.append(s.y.array.copy())
+            sts.append([st.nstep, st.nfeval, st.ndecomp, st.nreject])
+            Ts.append(st.T[-1])
+            print(scheme, a, b, sts[-1], "t_end", st.T[-1], "max|F|", np.abs(mdl.F(s.y.array, mdl.p)).max())
+        out[f"{scheme}_y"], out[f"{scheme}_stats"], out[f"{scheme}_tend"] = np.array(ys), np.array(sts), np.array(Ts)
+    np.savez_compressed(HERE / "sicnm_ref.npz", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dae", "pf", "known", "swing", "events", "implicit", "dhs"]
+    which = sys.argv[1:] or ["dae", "pf", "known", "swing", "events", "implicit", "dhs", "sicnm"]
     if "dae" in which:
         golden_dae_test()
     if "pf" in which:
@@ -412,4 +458,6 @@ if __name__ == "__main__":
         golden_implicit()
     if "dhs" in which:
         golden_dhs()
+    if "sicnm" in which:
+        golden_sicnm()
     print("golden fixtures written to", HERE)

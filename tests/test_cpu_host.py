@@ -446,3 +446,52 @@ sys.stdout.write("rank " + str(r) + " ok " + str(lo) + " " + str(hi) + chr(10));
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 ok 0 6" in r.stdout and "rank 1 ok 6 11" in r.stdout
+
+
+def test_hvp_twin_model_matches_reference_golden(tmp_path):
+    """SURVEY.md §8f item 3 on the host: the twin model of solverz_b200/hvp.py evaluates ``J(y) v`` as its residual
+    and the reference's ``HVP(y, p, v)`` matrix (equation/hvp.py:12-74, golden from the reference's rendered
+    module) as its Jacobian; on the LoopEqn power-flow model (which the reference's Hvp rejects) the same
+    Jacobian agrees with a central difference of ``J v`` and stays inside the pattern of ``J``."""
+    import scipy.sparse as sps
+    import solverz_b200 as szb
+    from solverz_b200.hvp import HvpEquations
+    from solverz_b200.synthetic import polar_pf_model
+    sys.path.insert(0, str(GOLD))
+    from make_golden import sicnm_model
+    g = np.load(GOLD / "sicnm_ref.npz")
+    ae, y0 = sicnm_model(szb)
+    ir, pat, lib, _ = _host_lib(ae, "sic", tmp_path)
+    hir, hpat, hlib, _ = _host_lib(HvpEquations(ir), "sich", tmp_path)
+    vp = {f"v__{k}": g["v"][o:o + s] for k, (o, s) in ir.var_off.items()}
+    G, HV = _eval(hlib, hir, hpat, g["yp"], vp)
+    H = sps.csc_matrix((HV[0], hpat.indices, hpat.indptr), shape=(ir.n, ir.n)).toarray()
+    np.testing.assert_allclose(H, g["H"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(G[0], g["J"] @ g["v"], rtol=0, atol=1e-13)
+
+    eqs, y0, info = polar_pf_model(4, 4)
+    ir, pat, lib, _ = _host_lib(eqs, "pf4", tmp_path)
+    hir, hpat, hlib, _ = _host_lib(HvpEquations(ir), "pf4h", tmp_path)
+    rng = np.random.default_rng(0)
+    y = y0.array + 0.05 * rng.normal(size=ir.n)
+    v = rng.normal(size=ir.n)
+    vp = {f"v__{k}": v[o:o + s] for k, (o, s) in ir.var_off.items()}
+
+    def Jv(yy):
+        return sps.csc_matrix((_eval(lib, ir, pat, yy, {})[1][0], pat.indices, pat.indptr), shape=(ir.n, ir.n)) @ v
+    G, HV = _eval(hlib, hir, hpat, y, vp)
+    assert np.abs(G[0] - Jv(y)).max() < 1e-12
+    H = sps.csc_matrix((HV[0], hpat.indices, hpat.indptr), shape=(ir.n, ir.n)).toarray()
+    e = 1e-6
+    for k in range(ir.n):
+        d = np.zeros(ir.n)
+        d[k] = e
+        assert np.abs(H[:, k] - (Jv(y + d) - Jv(y - d)) / (2 * e)).max() < 1e-6
+    hp = sps.csc_matrix((np.ones(hpat.nnz), hpat.indices, hpat.indptr), shape=(ir.n, ir.n))
+    jp = sps.csc_matrix((np.ones(pat.nnz), pat.indices, pat.indptr), shape=(ir.n, ir.n))
+    assert (hp - hp.multiply(jp)).nnz == 0
+    m = szb.Model()
+    m.h = szb.Var('h', 0)
+    m.f1 = szb.Ode('f1', f=-m.h, diff_var=m.h)
+    with pytest.raises(NotImplementedError):
+        HvpEquations(m.create_instance()[0].to_ir())

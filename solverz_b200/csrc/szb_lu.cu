@@ -869,7 +869,7 @@ __device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre
       const int p = fdiv(t, invr);
       const int i = t - p * rows;
       const double v = Fm[i + p * ld];
-      Lp[i + p * f] = i == p ? fast_rcp(v) : v;         // the diagonal of U is stored as its reciprocal
+      __stcs(Lp + i + p * f, i == p ? fast_rcp(v) : v);  // the diagonal of U is stored as its reciprocal
     }
   }
   if (u > 0) {
@@ -881,7 +881,7 @@ __device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre
     for (int t = lane; t < u * s; t += kWarp) {
       const int c = fdiv(t, invs);
       const int rr = t - c * s;
-      Up[t] = Fm[rr + (s + c) * ld];
+      __stcs(Up + t, Fm[rr + (s + c) * ld]);             // factors stream out: evict-first, the L2 is for the contribution blocks
     }
     for (int t = lane; t < u * nc; t += kWarp) {
       const int j = fdiv(t, invu);
@@ -942,7 +942,7 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
     const int pend = min(s, (p & ~(kNB - 1)) + kNB);
     const double* __restrict__ src = Fm + p * ld;
     double* __restrict__ dst = Lp + p * f;
-    for (int i = lane; i < pend; i += kWarp) dst[i] = i == p ? fast_rcp(src[i]) : src[i];   // 1 / u_pp on the diagonal
+    for (int i = lane; i < pend; i += kWarp) __stcs(dst + i, i == p ? fast_rcp(src[i]) : src[i]);   // 1 / u_pp on the diagonal
   }
   if (u > 0) {
     // lanes over the long dimension, pointer walks over the short one: no index arithmetic inside
@@ -952,7 +952,7 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
       for (int t = r; t < u * s; t += G_) {
         const int c = fdiv(t, invs);
         const int rr = t - c * s;
-        Up[t] = Fm[rr + (s + c) * ld];
+        __stcs(Up + t, Fm[rr + (s + c) * ld]);
       }
     }
     double* C = A.cb + H.cb_off;                         // u x (u+1), column-major

@@ -407,6 +407,12 @@ def test_no_cpu_fallback():
                  lambda: solve(sps.identity(4, format="csc"), np.ones(4))):
         with pytest.raises(SzbError, match="no CPU fallback"):
             call()
+    # the Hessian-vector product and sicnm
+    from solverz_b200 import sicnm
+    mh = made_numerical(g, y0, sparse=True, make_hvp=True)
+    for call in (lambda: sicnm(mh, y0), lambda: mh.HVP(y0.array, mh.p, np.ones(1))):
+        with pytest.raises(SzbError, match="no CPU fallback"):
+            call()
 
 
 def test_component_events_is_a_reference_style_callback():

@@ -922,6 +922,7 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
 #ifdef SZB_PHASE_TIMING
   const long long tel0_ = clock64();
 #endif
+  const FrontHdr Hnext = load_hdr(fh, q_next);          // lands during the elimination
   if (SM_FRONT) eliminate_blocked<true>(g, Fm, fm_off, lt_off, lts, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
   else eliminate_global(g, Fm, lt_off, lts, outer_nb, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
 #ifdef SZB_PHASE_TIMING
@@ -934,7 +935,6 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
 #endif
   // the next front's descriptor and first gather entries fly during the write-out (nothing of them is
   // kept across the elimination: it has the register file to itself)
-  const FrontHdr Hnext = load_hdr(fh, q_next);
   asm_prefetch(P, Hnext, ga, r, G_, with_rhs != 0);
   SZB_T(1)
   // rows below a column's own panel were streamed by the workers (or are not wanted)

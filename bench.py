@@ -80,9 +80,12 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0: float = None, t1: float = None):
+        """Samples that arrived inside [t0, t1] (the timed region); when the region was shorter than the sampling
+        period, every sample since start() -- the sampler is started before the warm-up steps, so those are
+        under the same load."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -93,7 +96,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = [ln for ts, ln in self.lines if t0 is None or t0 <= ts <= t1 + 0.05]
+        if len(lines) < 2:
+            lines = [ln for _, ln in self.lines]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -268,17 +274,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs ~0.2 s to deliver its first line: start before the warm-up
     for _ in range(max(args.warmup, 3)):
         it, fl = step()
     sync_all()
     launches0 = sess.query(5)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     prof = {k: dict(ms=0.0, units=0) for k in ("F", "J", "lu_refactor", "lu_solve", "bookkeeping")}
     pr0 = sess.get_profile()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_region0 = time.perf_counter()
     e0.record()
     iters_total = 0
     its_steps = []
@@ -291,7 +298,7 @@ def main():
             prof[k]["units"] += pr[k]["units"]
     e1.record()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
     pr1 = sess.get_profile()
     for k in prof:
         prof[k]["launches"] = pr1[k]["launches"] - pr0[k]["launches"]

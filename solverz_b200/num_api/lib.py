@@ -11,7 +11,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE.parent / "csrc" / "libszb.so"
 
-SZB_ABI_VERSION = 3
+SZB_ABI_VERSION = 4
 SZB_FLAG_EVENT = 8
 SLOT_Y, SLOT_F, SLOT_JV, SLOT_RHS, SLOT_PARAM0 = 0, 1, 2, 3, 16
 DTYPE_F64, DTYPE_I32 = 0, 1
@@ -24,13 +24,8 @@ _i32p = C.POINTER(C.c_int32)
 
 class LuSymbolicC(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n", "nnz_a", "ns", "lu_size", "cb_size", "cv_size", "n_warp_lists",
-                                         "n_group_lists", "n_top", "f_warp_max", "f_group_max", "f_top_max",
-                                         "s_warp_max", "s_group_max", "s_top_max", "threads", "wpg",
-                                         "n_sched", "n_ga")] + \
-               [(k, _i32p) for k in ("rowp", "colp", "sn_piv0", "sn_s", "sn_f", "idx_ptr", "idx", "rel_ptr",
-                                     "rel", "child_ptr", "child", "a_ptr", "a_src", "a_dst", "lp_off",
-                                     "up_off", "cb_off", "ea_ptr", "ea_dst", "wl_ptr", "wl", "gl_ptr", "gl", "top",
-                                     "fh", "ga")]
+                                         "n_warp_sn", "n_sched", "n_child", "n_idx", "n_rel", "f_max")] + \
+               [(k, _i32p) for k in ("rowp", "colp", "idx", "rel", "a_src", "a_dst", "wl_ptr", "fh", "ct")]
 
 
 class DescC(C.Structure):
@@ -87,6 +82,8 @@ def load():
     lib.szb_eval_J.argtypes = [H, C.c_double, C.c_void_p]
     lib.szb_lu_refactor.argtypes = [H, C.c_double, C.c_void_p]
     lib.szb_lu_solve.argtypes = [H, C.c_int32, C.c_void_p]
+    lib.szb_lu_status.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.szb_set_growth_tol.argtypes = [H, C.c_double]
     lib.szb_newton.argtypes = [H, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.szb_newton_host.argtypes = [H, C.c_double, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
@@ -111,38 +108,27 @@ def check(rc: int, handle=None, what: str = ""):
 
 
 def lu_symbolic_c(sym, keep: list) -> LuSymbolicC:
-    """Convert solverz_b200.lu.symbolic.LUSymbolic into the C struct (int32 arrays kept alive in `keep`)."""
+    """Lower solverz_b200.lu.symbolic.LUSymbolic to the device schedule (lu/schedule.py) and wrap it in the C
+    struct (int32 arrays kept alive in `keep`)."""
     s = LuSymbolicC()
     if sym is None:
         return s
-    ns = sym.ns
-    s.n, s.nnz_a, s.ns = sym.n, sym.nnzA, ns
-    s.lu_size, s.cb_size, s.cv_size = sym.lu_size, sym.cb_size, int(sym.rel_ptr[-1])
-    s.n_warp_lists, s.n_group_lists, s.n_top = sym.n_warp_lists, sym.n_group_lists, len(sym.top)
-    s.f_warp_max, s.f_group_max, s.f_top_max = sym.f_warp_max, sym.f_group_max, sym.f_top_max
-
-    def smax(ids):
-        ids = np.asarray(ids, dtype=np.int64)
-        return int(sym.sn_s[ids].max()) if len(ids) else 0
-    s.s_warp_max, s.s_group_max, s.s_top_max = smax(sym.wl), smax(sym.gl), smax(sym.top)
-    if max(sym.lu_size, sym.cb_size, int(sym.a_dst.max(initial=0))) >= 2 ** 31:
+    from ..lu.schedule import build_tables
+    tabs = build_tables(sym)
+    if max(int(sym.lu_size), int(sym.cb_size)) * 32 >= 2 ** 31 * 32:
         raise SzbError("LU schedule exceeds int32 offsets")
-    for name in ("rowp", "colp", "sn_piv0", "sn_s", "sn_f", "idx_ptr", "idx", "rel_ptr", "rel", "child_ptr",
-                 "child", "a_ptr", "a_src", "a_dst", "lp_off", "up_off", "cb_off", "ea_ptr", "ea_dst", "wl_ptr",
-                 "wl", "gl_ptr", "gl", "top"):
-        arr = np.ascontiguousarray(np.asarray(getattr(sym, name)), dtype=np.int32)
+    s.n, s.nnz_a, s.ns = sym.n, sym.nnzA, sym.ns
+    s.lu_size, s.cb_size, s.cv_size = sym.lu_size, sym.cb_size, int(sym.rel_ptr[-1])
+    s.n_warp_lists, s.n_warp_sn = sym.n_warp_lists, tabs["n_warp_sn"]
+    s.n_sched, s.n_child = tabs["n_sched"], len(tabs["ct"])
+    s.n_idx, s.n_rel = len(sym.idx), len(sym.rel)
+    s.f_max = sym.f_max
+    arrays = dict(rowp=sym.rowp, colp=sym.colp, idx=sym.idx, rel=sym.rel, a_src=sym.a_src, a_dst=sym.a_dst,
+                  wl_ptr=sym.wl_ptr, fh=tabs["fh"], ct=tabs["ct"])
+    for name, a in arrays.items():
+        arr = np.ascontiguousarray(np.asarray(a), dtype=np.int32).reshape(-1)
         if arr.size == 0:
             arr = np.zeros(1, dtype=np.int32)
-        keep.append(arr)
-        setattr(s, name, arr.ctypes.data_as(_i32p))
-    # device schedule: front descriptors + gather tables for exactly this thread layout
-    from ..lu.schedule import build_tables, plan_threads
-    plan = plan_threads(sym)
-    tabs = build_tables(sym, plan["threads"], plan["wpg"])
-    s.threads, s.wpg = plan["threads"], plan["wpg"]
-    s.n_sched, s.n_ga = tabs["n_sched"], len(tabs["ga"])
-    for name in ("fh", "ga"):
-        arr = np.ascontiguousarray(tabs[name], dtype=np.int32)
         keep.append(arr)
         setattr(s, name, arr.ctypes.data_as(_i32p))
     return s

@@ -93,21 +93,30 @@ typedef void* szb_stream; /* cudaStream_t */
 typedef struct szb_lu_symbolic {
   int32_t n, nnz_a, ns;
   int32_t lu_size, cb_size, cv_size; /* lines per group: factors, contribution ws, forward-sweep ws */
-  int32_t n_warp_lists;     /* warp-level work lists (<= warps per CTA) */
-  int32_t n_warp_sn;        /* fronts in the warp lists (they come first in schedule order) */
+  int32_t n_warp_lists;     /* level-0 work lists: on-chip fronts, one warp each (<= warps per CTA) */
+  int32_t n_warp_sn;        /* fronts in the level-0 lists (they come first in schedule order) */
+  int32_t n_mid_lists;      /* level-1 work lists: tiled fronts, one warp each */
+  int32_t n_mid_sn;         /* fronts in the level-1 lists (they follow the level-0 fronts; the rest is level 2) */
   int32_t n_sched, n_child; /* fronts in schedule order; rows of the child table */
   int32_t n_idx, n_rel;     /* lengths of idx / rel */
-  int32_t f_max;
+  int32_t n_atp, n_tcp, n_tce; /* lengths of atp / tcp, rows of tce */
+  int32_t warp_lines;       /* shared-memory lines per warp the level-0 fronts were sized for (must equal the kernels') */
+  int32_t f_max, f_warp_max; /* largest front; largest front of the level-0 lists */
   const int32_t* rowp;      /* [n]   pivot k <- original row     */
   const int32_t* colp;      /* [n]   pivot k <- original column  */
   const int32_t* idx;       /* [n_idx] front index lists (pivot order) */
   const int32_t* rel;       /* [n_rel] positions of a child's update rows in its parent's front */
-  const int32_t* a_src;     /* [nnz_a] Jacobian slot of a matrix entry, grouped by front */
-  const int32_t* a_dst;     /* [nnz_a] its offset in the factor storage */
-  const int32_t* wl_ptr;    /* [n_warp_lists+1] runs of the warp lists in schedule order */
+  const int32_t* a_src;     /* [nnz_a] Jacobian slot of a matrix entry, grouped by front (tiled fronts: by tile) */
+  const int32_t* a_dst;     /* [nnz_a] its offset in the factor storage (tiled fronts: r + 8 c inside its tile) */
+  const int32_t* wl_ptr;    /* [n_warp_lists+1] runs of the level-0 lists in schedule order */
+  const int32_t* ml_ptr;    /* [n_mid_lists+1] runs of the level-1 lists, relative to n_warp_sn */
   const int32_t* fh;        /* [n_sched][16] front descriptors: s, f, piv0, lp_off, up_off, cb_off, a0, a1,
-                               c0, c1, idx_ptr, cv_off, k, 0, 0, 0 */
-  const int32_t* ct;        /* [n_child][4] child table: cb_off, u, rel_ptr, cv_off of the child */
+                               c0, c1, idx_ptr, cv_off, atp0, tcp0 (-1: not tiled), k, 0 */
+  const int32_t* ct;        /* [n_child][8] child table: cb_off, u, rel_ptr, cv_off of the child, 0, 0, 0, 0 */
+  const int32_t* atp;       /* [n_atp] tiled fronts: first matrix entry of every 8 x 8 tile */
+  const int32_t* tcp;       /* [n_tcp] tiled fronts: first contributor of every tile (incl. the rhs column) */
+  const int32_t* tce;       /* [n_tce][4] contributors: workspace offset of the piece of a child's block that lands
+                               in the tile, u of the child, row nibbles, column nibbles (lu/schedule.py) */
 } szb_lu_symbolic;
 
 typedef struct szb_desc {

@@ -167,7 +167,7 @@ int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b,
   cudaError_t e = szb::lu_map_launch(active, h->B, h->lu_map, h->lu_npos, st);
   if (e == cudaSuccess)
     e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, mv, slot_mask, scale_b, scale, rhs, yout, h->lu_map,
-                              h->lu_npos, h->flags, h->growth_tol, st);
+                              h->lu_npos, h->lu_mon, h->flags, h->growth_tol, st);
   if (e != cudaSuccess) { szb_set_error(h, "LU factor launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
   h->launches[4]++;
   h->launches[2]++;
@@ -260,9 +260,12 @@ int szb_create(const szb_desc* d, szb_handle** out) {
     S.n = L.n; S.nnz_a = L.nnz_a; S.ns = L.ns;
     S.lu_size = L.lu_size; S.cb_size = L.cb_size; S.cv_size = L.cv_size;
     S.n_warp_lists = L.n_warp_lists; S.n_warp_sn = L.n_warp_sn; S.n_sched = L.n_sched;
-    S.f_max = L.f_max;
-    if (L.n_sched <= 0 || L.n_warp_sn < 0 || L.n_warp_sn > L.n_sched || L.n_warp_lists < 0 || !L.fh || !L.ct ||
-        !L.wl_ptr || (L.n_warp_lists > 0 && L.wl_ptr[L.n_warp_lists] != L.n_warp_sn)) {
+    S.n_mid_lists = L.n_mid_lists; S.n_mid_sn = L.n_mid_sn;
+    S.f_max = L.f_max; S.f_warp_max = L.f_warp_max; S.warp_lines = L.warp_lines;
+    if (L.n_sched <= 0 || L.n_warp_sn < 0 || L.n_mid_sn < 0 || L.n_warp_sn + L.n_mid_sn > L.n_sched ||
+        L.n_warp_lists < 0 || L.n_mid_lists < 0 || !L.fh || !L.ct || !L.wl_ptr || !L.ml_ptr ||
+        (L.n_warp_lists > 0 && L.wl_ptr[L.n_warp_lists] != L.n_warp_sn) ||
+        (L.n_mid_lists > 0 && L.ml_ptr[L.n_mid_lists] != L.n_mid_sn)) {
       szb_set_error(h, "szb_create: LU schedule tables missing or inconsistent (n_sched=%d, n_warp_sn=%d)",
                     L.n_sched, L.n_warp_sn);
       return fail(SZB_EINVAL);
@@ -274,14 +277,16 @@ int szb_create(const szb_desc* d, szb_handle** out) {
     S.field = p_;                                                                    \
   } while (0)
     UP(rowp, L.n); UP(colp, L.n); UP(idx, L.n_idx); UP(rel, L.n_rel);
-    UP(a_src, L.nnz_a); UP(a_dst, L.nnz_a); UP(wl_ptr, L.n_warp_lists + 1);
+    UP(a_src, L.nnz_a); UP(a_dst, L.nnz_a); UP(wl_ptr, L.n_warp_lists + 1); UP(ml_ptr, L.n_mid_lists + 1); UP(atp, L.n_atp); UP(tcp, L.n_tcp);
 #undef UP
     {
       int* p_ = nullptr;
       if ((rc = upload<int>(h, L.fh, static_cast<size_t>(L.n_sched) * 16, &p_)) != SZB_OK) return fail(rc);
       S.fh = reinterpret_cast<const int4*>(p_);
-      if ((rc = upload<int>(h, L.ct, static_cast<size_t>(L.n_child) * 4, &p_)) != SZB_OK) return fail(rc);
+      if ((rc = upload<int>(h, L.ct, static_cast<size_t>(L.n_child) * 8, &p_)) != SZB_OK) return fail(rc);
       S.ct = reinterpret_cast<const int4*>(p_);
+      if ((rc = upload<int>(h, L.tce, static_cast<size_t>(L.n_tce) * 4, &p_)) != SZB_OK) return fail(rc);
+      S.tce = reinterpret_cast<const int4*>(p_);
     }
   }
   if (d->mass_vals) {
@@ -364,7 +369,8 @@ int szb_set_batch(szb_handle* h, int32_t B) {
     const size_t G = static_cast<size_t>(h->cfg.groups), K = szb::kGroup, R = static_cast<size_t>(h->cfg.grid);
     ALLOC(h->LU, double, G * K * h->S.lu_size);
     ALLOC(h->ybuf, double, G * K * n);
-    ALLOC(h->CBW, double, R * K * (h->S.cb_size > 0 ? h->S.cb_size : 1));
+    ALLOC(h->CBW, double, G * K * (h->S.cb_size > 0 ? h->S.cb_size : 1));   // per group: blocks cross kernel launches
+    ALLOC(h->lu_mon, double, G * K * 3);
     ALLOC(h->CVW, double, R * K * (h->S.cv_size > 0 ? h->S.cv_size : 1));
     ALLOC(h->lu_map, int, G * K);
     ALLOC(h->lu_npos, int, 1);

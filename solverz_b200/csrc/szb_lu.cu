@@ -34,11 +34,16 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
+// shared memory of the factor kernels in lines of 32 doubles: a level-0 front (front_lines(f) <= kWarpLines;
+// lu/symbolic.py cuts those subtrees at warp_front_max = 10: 10 * 11 = 110 lines) is assembled and eliminated
+// in its warp's buffer; the tiled levels use kTileScratch lines per warp (+ one shared diagonal tile)
+constexpr int kWarpLines = 110;
+constexpr int kSmemLines = kWarps * kWarpLines;   // 880 lines = 225 280 bytes >= kNB * kNB + kWarps * kTileScratch
 
 __device__ __forceinline__ Tabs make_tabs(const LuDev& S) {
   Tabs T;
   T.fh = S.fh; T.ct = S.ct; T.a_src = S.a_src; T.a_dst = S.a_dst; T.rel = S.rel; T.idx = S.idx;
-  T.rowp = S.rowp; T.colp = S.colp;
+  T.rowp = S.rowp; T.colp = S.colp; T.atp = S.atp; T.tcp = S.tcp; T.tce = S.tce;
   return T;
 }
 
@@ -73,26 +78,39 @@ __global__ void __launch_bounds__(1024) lu_map_kernel(const int* __restrict__ ac
   if (threadIdx.x == 0) *npos = n;
 }
 
-// ---- factorisation ---------------------------------------------------------------------------------
+#ifdef SZB_LU_TIMING
+__device__ unsigned long long g_lu_cycles[24];
+#endif
+
+// ---- factorisation: one kernel per level of the schedule --------------------------------------------
+//   LEVEL 0: each warp walks its list of small subtrees, a front is assembled and eliminated in the warp's
+//            shared-memory buffer and written out once;
+//   LEVEL 1: each warp walks its list of medium subtrees by register tiles (operands from L2 through the
+//            warp's asynchronous-copy ring);
+//   LEVEL 2: the top of the tree, all warps of the CTA share a front (same tiles, dealt to the warps).
+// Separate launches: each body gets the whole register file for its inner loop (merged into one kernel ptxas
+// spilled 6 kB), and contribution blocks that cross levels live in the per-group workspace.
+template <int LEVEL>
 __global__ void __launch_bounds__(kThreads, 1)
 lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* LU, double* CBW,
                  const double* __restrict__ mvals, const double* __restrict__ slot_mask,
                  const double* __restrict__ scale_b, double scale_const, const double* __restrict__ RHS,
-                 double* YI, const int* __restrict__ map, const int* __restrict__ npos, int* __restrict__ flags,
-                 double growth_tol) {
-  __shared__ double red_a[kWarps][32], red_u[kWarps][32];
-  __shared__ int red_b[kWarps][32];
+                 double* YI, const int* __restrict__ map, const int* __restrict__ npos, double* MON,
+                 int* __restrict__ flags, double growth_tol) {
+  extern __shared__ double sm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n_groups = (*npos + kGroup - 1) / kGroup;
   const Tabs T = make_tabs(S);
   int wq0 = 0, wq1 = 0;
-  if (w < S.n_warp_lists) { wq0 = S.wl_ptr[w]; wq1 = S.wl_ptr[w + 1]; }
+  if (LEVEL == 0 && w < S.n_warp_lists) { wq0 = S.wl_ptr[w]; wq1 = S.wl_ptr[w + 1]; }
+  if (LEVEL == 1 && w < S.n_mid_lists) { wq0 = S.n_warp_sn + S.ml_ptr[w]; wq1 = S.n_warp_sn + S.ml_ptr[w + 1]; }
   for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
     const int b = map[g * kGroup + lane];
     Lane L;
     L.valid = b >= 0;
     L.lu = LU + static_cast<size_t>(g) * S.lu_size * kGroup + lane;
-    L.cb = CBW + static_cast<size_t>(blockIdx.x) * S.cb_size * kGroup + lane;
+    L.cb = CBW + static_cast<size_t>(g) * S.cb_size * kGroup + lane;
+    L.cbsrc = L.cb;
     L.y = YI + static_cast<size_t>(g) * S.n * kGroup + lane;
     L.jv = L.valid ? JV + static_cast<size_t>(b) * S.nnz_a : nullptr;
     L.with_rhs = RHS != nullptr;
@@ -102,35 +120,53 @@ lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* LU, doubl
     L.scale = (L.valid && scale_b) ? scale_b[b] : scale_const;
     L.plain = mvals == nullptr && slot_mask == nullptr && scale_b == nullptr && scale_const == 1.0;
     L.amax = 0.0; L.umax = 0.0; L.bad = 0;
-    // level 0: every warp walks its own subtrees
-    {
+#ifdef SZB_LU_TIMING
+    long long tacc[8];
+    for (int i = 0; i < 8; ++i) tacc[i] = 0;
+    L.tacc = tacc; L.tbase = 0;
+    const long long tl0 = clock64();
+#endif
+    if (LEVEL == 0) {
       const Coop C{0, 1, false};
-      for (int q = wq0; q < wq1; ++q) {
-        const Front F = load_front(T.fh, q);
-        factor_front(L, F, T, C);
-      }
-    }
-    __syncthreads();
-    // level 1: the top of the tree, all warps per front
-    {
+      double* buf = sm + static_cast<size_t>(w) * kWarpLines * kGroup + lane;
+      for (int q = wq0; q < wq1; ++q) factor_front_buffered(L, load_front(T.fh, q), T, C, buf);
+    } else if (LEVEL == 1) {
+      const Coop C{0, 1, false};
+      double* tbuf = sm + static_cast<size_t>(w) * kTileScratch * kGroup + lane;
+      for (int q = wq0; q < wq1; ++q) factor_front_tiled(L, load_front(T.fh, q), T, C, tbuf, nullptr);
+    } else {
       const Coop C{w, kWarps, true};
-      for (int q = S.n_warp_sn; q < S.n_sched; ++q) {
-        const Front F = load_front(T.fh, q);
-        factor_front(L, F, T, C);
-      }
+      double* tbuf = sm + static_cast<size_t>(kNB * kNB + w * kTileScratch) * kGroup + lane;
+      for (int q = S.n_warp_sn + S.n_mid_sn; q < S.n_sched; ++q)
+        factor_front_tiled(L, load_front(T.fh, q), T, C, tbuf, sm + lane);
     }
-    // pivot / growth monitor of the scenario = reduction over the warps of the lane's values
-    red_a[w][lane] = L.amax; red_u[w][lane] = L.umax; red_b[w][lane] = L.bad;
     __syncthreads();
-    if (w == 0 && L.valid) {
-      double am = 0.0, um = 0.0;
-      int bad = 0;
+#ifdef SZB_LU_TIMING
+    tacc[7] = clock64() - tl0;
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_lu_cycles[8 * LEVEL + i], static_cast<unsigned long long>(tacc[i]));
+#endif
+    // pivot / growth monitor of the scenario: reduction over the warps, carried across the level kernels in MON
+    sm[(3 * w + 0) * kGroup + lane] = L.amax;
+    sm[(3 * w + 1) * kGroup + lane] = L.umax;
+    sm[(3 * w + 2) * kGroup + lane] = L.bad ? 1.0 : 0.0;
+    __syncthreads();
+    if (w == 0) {
+      double am = 0.0, um = 0.0, bad = 0.0;
       for (int i = 0; i < kWarps; ++i) {
-        am = red_a[i][lane] > am ? red_a[i][lane] : am;
-        um = red_u[i][lane] > um ? red_u[i][lane] : um;
-        bad |= red_b[i][lane];
+        const double a_ = sm[(3 * i + 0) * kGroup + lane], u_ = sm[(3 * i + 1) * kGroup + lane];
+        am = a_ > am ? a_ : am;
+        um = u_ > um ? u_ : um;
+        bad += sm[(3 * i + 2) * kGroup + lane];
       }
-      if (bad || !(um <= growth_tol * am)) flags[b] = 2;
+      double* mon = MON + (static_cast<size_t>(g) * kGroup + lane) * 3;
+      if (LEVEL > 0) {
+        am = mon[0] > am ? mon[0] : am;
+        um = mon[1] > um ? mon[1] : um;
+        bad += mon[2];
+      }
+      if (LEVEL < 2) { mon[0] = am; mon[1] = um; mon[2] = bad; }
+      else if (L.valid && (bad > 0.0 || !(um <= growth_tol * am))) flags[b] = 2;
     }
     __syncthreads();
   }
@@ -143,8 +179,9 @@ lu_forward_kernel(const LuDev S, const double* LU, const double* __restrict__ RH
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n_groups = (*npos + kGroup - 1) / kGroup;
   const Tabs T = make_tabs(S);
-  int wq0 = 0, wq1 = 0;
+  int wq0 = 0, wq1 = 0, mq0 = 0, mq1 = 0;
   if (w < S.n_warp_lists) { wq0 = S.wl_ptr[w]; wq1 = S.wl_ptr[w + 1]; }
+  if (w < S.n_mid_lists) { mq0 = S.n_warp_sn + S.ml_ptr[w]; mq1 = S.n_warp_sn + S.ml_ptr[w + 1]; }
   for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
     const int b = map[g * kGroup + lane];
     Lane L;
@@ -159,11 +196,13 @@ lu_forward_kernel(const LuDev S, const double* LU, const double* __restrict__ RH
     {
       const Coop C{0, 1, false};
       for (int q = wq0; q < wq1; ++q) forward_front(L, cv, load_front(T.fh, q), T, C);
+      __syncthreads();
+      for (int q = mq0; q < mq1; ++q) forward_front(L, cv, load_front(T.fh, q), T, C);
     }
     __syncthreads();
     {
       const Coop C{w, kWarps, true};
-      for (int q = S.n_warp_sn; q < S.n_sched; ++q) forward_front(L, cv, load_front(T.fh, q), T, C);
+      for (int q = S.n_warp_sn + S.n_mid_sn; q < S.n_sched; ++q) forward_front(L, cv, load_front(T.fh, q), T, C);
     }
     __syncthreads();
   }
@@ -173,11 +212,13 @@ lu_forward_kernel(const LuDev S, const double* LU, const double* __restrict__ RH
 __global__ void __launch_bounds__(kThreads, 1)
 lu_backward_kernel(const LuDev S, const double* LU, double* YI, double* __restrict__ X, int mode,
                    const int* __restrict__ map, const int* __restrict__ npos, const int* __restrict__ active) {
+  __shared__ double red[kWarps * kNB * kGroup];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n_groups = (*npos + kGroup - 1) / kGroup;
   const Tabs T = make_tabs(S);
-  int wq0 = 0, wq1 = 0;
+  int wq0 = 0, wq1 = 0, mq0 = 0, mq1 = 0;
   if (w < S.n_warp_lists) { wq0 = S.wl_ptr[w]; wq1 = S.wl_ptr[w + 1]; }
+  if (w < S.n_mid_lists) { mq0 = S.n_warp_sn + S.ml_ptr[w]; mq1 = S.n_warp_sn + S.ml_ptr[w + 1]; }
   for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
     const int b = map[g * kGroup + lane];
     Lane L;
@@ -187,12 +228,15 @@ lu_backward_kernel(const LuDev S, const double* LU, double* YI, double* __restri
     L.y = YI + static_cast<size_t>(g) * S.n * kGroup + lane;
     {
       const Coop C{w, kWarps, true};
-      for (int q = S.n_sched - 1; q >= S.n_warp_sn; --q) backward_front(L, load_front(T.fh, q), T, C);
+      for (int q = S.n_sched - 1; q >= S.n_warp_sn + S.n_mid_sn; --q)
+        backward_front(L, load_front(T.fh, q), T, C, red + lane);
     }
     __syncthreads();
     {
       const Coop C{0, 1, false};
-      for (int q = wq1 - 1; q >= wq0; --q) backward_front(L, load_front(T.fh, q), T, C);
+      for (int q = mq1 - 1; q >= mq0; --q) backward_front(L, load_front(T.fh, q), T, C, red + lane);
+      __syncthreads();
+      for (int q = wq1 - 1; q >= wq0; --q) backward_front(L, load_front(T.fh, q), T, C, red + lane);
     }
     __syncthreads();
     if (L.valid) {
@@ -214,17 +258,32 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (S.n_warp_lists > kWarps) return cudaErrorInvalidConfiguration;
+  if (S.n_warp_lists > kWarps || S.n_mid_lists > kWarps || S.warp_lines != kWarpLines ||
+      S.f_warp_max * (S.f_warp_max + 1) > kWarpLines)
+    return cudaErrorInvalidConfiguration;
   cfg->threads = kThreads;
-  cfg->smem = 0;
+  cfg->smem = static_cast<size_t>(kSmemLines) * kGroup * sizeof(double);
+  const int sm_bytes = static_cast<int>(cfg->smem);
+  if ((e = cudaFuncSetAttribute(lu_factor_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lu_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(lu_factor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes)) != cudaSuccess) return e;
   cfg->groups = (B + kGroup - 1) / kGroup;
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lu_factor_kernel, kThreads, cfg->smem);
-  if (occ < 1) occ = 1;
-  cfg->grid = sms * occ;
+  cfg->grid = sms;                       // one CTA per SM (register file and shared memory are both full)
   if (cfg->grid > cfg->groups) cfg->grid = cfg->groups > 0 ? cfg->groups : 1;
   return cudaSuccess;
 }
+
+#ifdef SZB_LU_TIMING
+extern "C" __attribute__((visibility("default"))) int szb_debug_lu_cycles(unsigned long long* out24, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out24, g_lu_cycles, sizeof(unsigned long long) * 24);
+  if (reset) {
+    unsigned long long z[24] = {0};
+    cudaMemcpyToSymbol(g_lu_cycles, z, sizeof z);
+  }
+  return 0;
+}
+#endif
 
 cudaError_t lu_map_launch(const int* active, int B, int* map, int* npos, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
@@ -235,9 +294,13 @@ cudaError_t lu_map_launch(const int* active, int B, int* map, int* npos, cudaStr
 cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV, double* LU, double* CBW,
                              const double* mvals, const double* slot_mask, const double* scale_b,
                              double scale_const, const double* RHS, double* YI, const int* map, const int* npos,
-                             int* flags, double growth_tol, cudaStream_t st) {
-  lu_factor_kernel<<<cfg.grid, cfg.threads, cfg.smem, st>>>(S, JV, LU, CBW, mvals, slot_mask, scale_b, scale_const,
-                                                            RHS, YI, map, npos, flags, growth_tol);
+                             double* MON, int* flags, double growth_tol, cudaStream_t st) {
+  lu_factor_kernel<0><<<cfg.grid, cfg.threads, cfg.smem, st>>>(S, JV, LU, CBW, mvals, slot_mask, scale_b, scale_const,
+                                                               RHS, YI, map, npos, MON, flags, growth_tol);
+  lu_factor_kernel<1><<<cfg.grid, cfg.threads, cfg.smem, st>>>(S, JV, LU, CBW, mvals, slot_mask, scale_b, scale_const,
+                                                               RHS, YI, map, npos, MON, flags, growth_tol);
+  lu_factor_kernel<2><<<cfg.grid, cfg.threads, cfg.smem, st>>>(S, JV, LU, CBW, mvals, slot_mask, scale_b, scale_const,
+                                                               RHS, YI, map, npos, MON, flags, growth_tol);
   return cudaGetLastError();
 }
 

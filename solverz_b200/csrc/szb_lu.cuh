@@ -12,12 +12,14 @@ constexpr int kGroup = 32;   // scenarios per group = lanes of a warp
 struct LuDev {
   int n, nnz_a, ns;
   int lu_size, cb_size, cv_size;   // lines (of kGroup doubles) per group: factors, contribution ws, fwd ws
-  int n_warp_lists, n_warp_sn, n_sched;
-  int f_max;
+  int n_warp_lists, n_warp_sn, n_mid_lists, n_mid_sn, n_sched;
+  int f_max, f_warp_max, warp_lines;
   const int *rowp, *colp;
   const int *idx, *rel;
   const int *a_src, *a_dst;
-  const int *wl_ptr;
+  const int *wl_ptr, *ml_ptr;
+  const int *atp, *tcp;   // tile tables of the tiled fronts (levels 1 and 2)
+  const int4* tce;
   const int4* fh;   // front descriptors, 4 x int4 each, schedule order (lu/schedule.py)
   const int4* ct;   // child table
 };
@@ -40,11 +42,12 @@ cudaError_t lu_map_launch(const int* active, int B, int* map, int* npos, cudaStr
 // A(b) = scale(b) * slot_mask * JV[b] + mvals  ->  LU (interleaved by position, see lu_map_launch);
 // scale_b may be null (then scale_const).  RHS non-null: the right-hand side rides along (forward
 // substitution fused) and YI gets y = L^{-1} P b in pivot order (interleaved).  flags[b] = 2 for a zero /
-// non-finite pivot or an element growth max|u| / max|a| above growth_tol.
+// non-finite pivot or an element growth max|u| / max|a| above growth_tol (MON: 3 doubles per position of
+// scratch for the monitors, carried across the three level kernels).
 cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV, double* LU, double* CBW,
                              const double* mvals, const double* slot_mask, const double* scale_b,
                              double scale_const, const double* RHS, double* YI, const int* map, const int* npos,
-                             int* flags, double growth_tol, cudaStream_t st);
+                             double* MON, int* flags, double growth_tol, cudaStream_t st);
 
 // mode 0:  X[b] <- A^{-1} RHS[b]         (X may alias RHS)
 // mode 1:  X[b] <- X[b] - A^{-1} RHS[b]  (Newton update y -= dx; X is Y)

@@ -374,26 +374,30 @@ class LUSymbolic:
     nnz_lu: int               # true nnz(L+U) of the symbolic factor (no supernode padding)
     flops: float              # factor flops per scenario (2 per multiply-add)
     f_max: int
-    # schedule: warp-level subtrees, then the CTA-level top
+    # schedule: warp-level subtrees (on-chip fronts), warp-level subtrees (tiled fronts), the CTA-level top
     n_warp_lists: int
-    wl_ptr: np.ndarray        # warp work lists (supernode ids, each list in postorder)
+    wl_ptr: np.ndarray        # level-0 work lists (supernode ids, each list in postorder)
     wl: np.ndarray
-    top: np.ndarray           # CTA-level supernodes in postorder
+    n_mid_lists: int
+    ml_ptr: np.ndarray        # level-1 work lists
+    ml: np.ndarray
+    top: np.ndarray           # level-2 (CTA-level) supernodes in postorder
     f_warp_max: int
+    f_mid_max: int
     f_top_max: int
     ordering: str = ""
-    sched_version: int = 2    # layout of the schedule fields (rendered packages cache this object)
+    sched_version: int = 3    # layout of the schedule fields (rendered packages cache this object)
 
     @property
     def order(self) -> np.ndarray:
         """A valid sequential elimination order (children before parents)."""
-        return np.concatenate([self.wl, self.top]).astype(np.int64)
+        return np.concatenate([self.wl, self.ml, self.top]).astype(np.int64)
 
     def stats(self) -> Dict[str, float]:
         return dict(n=self.n, nnzA=self.nnzA, nnz_lu=self.nnz_lu, lu_size=self.lu_size,
                     cb_size=self.cb_size, flops=self.flops, ns=self.ns, f_max=self.f_max,
-                    f_warp_max=self.f_warp_max, f_top_max=self.f_top_max,
-                    n_warp_sn=len(self.wl), n_top=len(self.top),
+                    f_warp_max=self.f_warp_max, f_mid_max=self.f_mid_max, f_top_max=self.f_top_max,
+                    n_warp_sn=len(self.wl), n_mid_sn=len(self.ml), n_top=len(self.top),
                     ordering=self.ordering)
 
 
@@ -403,7 +407,7 @@ def _flops_of(struct_sizes: np.ndarray) -> float:
 
 
 def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.ndarray,
-           relax_frac: float, relax_small: int, warp_front_max: int, n_warps: int,
+           relax_frac: float, relax_small: int, warp_front_max: int, mid_front_max: int, n_warps: int,
            name: str, warp_fixed: float = 3000.0) -> LUSymbolic:
     n = A.shape[0]
     parent, children, struct = _symbolic_structs(S, order)
@@ -530,18 +534,21 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         off += up_sz[k]
     lu_size = int(off)
 
-    # ---- schedule: two levels of the tree (csrc/szb_lu.cu: one CTA works on a GROUP of 32 scenarios, lane =
-    # scenario).  A supernode is warp-level when every front of its subtree fits a warp-private shared-memory
-    # buffer (front_lines(f) <= warp_lines); the warp-level forest is split into independent subtrees that are
-    # dealt to the warps' work lists by longest-processing-time first.  Everything else is the CTA-level list,
-    # walked in postorder by all warps together.
+    # ---- schedule: three levels of the tree (csrc/szb_lu.cu: one CTA works on a GROUP of 32 scenarios,
+    # lane = scenario; one kernel per level).
+    #   level 0: every front of the subtree fits a warp-private shared-memory buffer (f <= warp_front_max): the
+    #            forest is split into independent subtrees dealt to the warps' work lists (longest processing
+    #            time first); a warp assembles and eliminates a front on chip, no synchronisation at all;
+    #   level 1: every front of the subtree has f <= mid_front_max: again independent subtrees dealt to the
+    #            warps, each front walked by ONE warp in register tiles (tiled path, operands from L2);
+    #   level 2: the top of the tree, one list in postorder, all warps of the CTA share a front (tiled path).
     sub_fmax = sn_f.copy()
     own_cost = (sn_s * sn_f * sn_f).astype(np.float64) + float(warp_fixed)
     for k in range(ns):  # postorder: children before parents
         p = sn_parent[k]
         if p >= 0:
             sub_fmax[p] = max(sub_fmax[p], sub_fmax[k])
-    level = np.where(sub_fmax <= warp_front_max, 0, 2)
+    level = np.where(sub_fmax <= warp_front_max, 0, np.where(sub_fmax <= mid_front_max, 1, 2))
     a_dst = np.where(loc_c[by_owner] < sn_s[owner[by_owner]],
                      lp_off[owner[by_owner]] + loc_r[by_owner] + loc_c[by_owner] * sn_f[owner[by_owner]],
                      up_off[owner[by_owner]] + loc_r[by_owner]
@@ -579,14 +586,15 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         return n_lists, lists, ptr, flat
 
     n_lists, lists, wl_ptr, wl = make_lists(0, n_warps)
+    n_mlists, mlists, ml_ptr, ml = make_lists(1, n_warps)
     top = np.array([k for k in range(ns) if level[k] == 2], dtype=np.int64)
 
-    # ---- contribution-block workspace (one per resident CTA, in lines of 32 scenarios).  Each work list
-    # is a sequential postorder walk, so the classic multifrontal stack is valid per list: when a supernode
+    # ---- contribution-block workspace (one per group, in lines of 32 scenarios).  Each work list is a
+    # sequential postorder walk, so the classic multifrontal stack is valid per list: when a supernode
     # starts, the blocks of its children (of the same list) are the top of the stack; they are absorbed and
-    # popped, and the supernode's own block is pushed in their place.  Blocks that cross from a warp list
-    # to the CTA-level list live in a persistent region A; the CTA-level stack shares addresses with the
-    # warp lists' stacks (the two levels are separated by a CTA-wide barrier).
+    # popped, and the supernode's own block is pushed in their place.  Blocks that cross from one list to a
+    # list of a higher level live in a persistent region A; the stacks of the three levels share addresses
+    # (the levels are separate kernel launches).
     cb_off = np.zeros(ns, dtype=np.int64)
     cb_need = sn_u * (sn_u + 1)   # u x u Schur block + one right-hand-side column
     # The fronts are assembled IN PLACE: a parent's block is being accumulated while its children's blocks
@@ -616,23 +624,25 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
             peak[par] = max(peak[par], sp_[par])
         return peak
 
-    all_lists = [list(map(int, l)) for l in lists] + [list(map(int, top))]
+    level_lists = [[list(map(int, l)) for l in lists], [list(map(int, l)) for l in mlists], [list(map(int, top))]]
     a_sz = 0
-    for seq in all_lists[:-1]:
-        inseq = set(seq)
-        for k in seq:
-            p = int(sn_parent[k])
-            if p >= 0 and p not in inseq:
-                cb_off[k] = a_sz
-                a_sz += int(cb_need[k])
-    cursor = a_sz
-    for seq in all_lists[:-1]:
-        pk = alloc_list(seq, (0, 0))
-        alloc_list(seq, (cursor, cursor + pk[0]))
-        cursor += pk[0] + pk[1]
-    pk = alloc_list(all_lists[-1], (0, 0))
-    alloc_list(all_lists[-1], (a_sz, a_sz + pk[0]))
-    cb_size = int(max(cursor, a_sz + pk[0] + pk[1]))
+    for lls in level_lists:
+        for seq in lls:
+            inseq = set(seq)
+            for k in seq:
+                p = int(sn_parent[k])
+                if p >= 0 and p not in inseq:
+                    cb_off[k] = a_sz
+                    a_sz += int(cb_need[k])
+    cb_size = a_sz
+    for lls in level_lists:
+        cursor = a_sz
+        for seq in lls:
+            pk = alloc_list(seq, (0, 0))
+            alloc_list(seq, (cursor, cursor + pk[0]))
+            cursor += pk[0] + pk[1]
+        cb_size = max(cb_size, cursor)
+    cb_size = int(cb_size)
 
     # rows of a child's update set that fall inside the pivot block of its parent (rel is ascending)
     sn_m = np.zeros(ns, dtype=np.int64)
@@ -647,13 +657,15 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         child_ptr=child_ptr, child=child, a_ptr=a_ptr, a_src=a_src, a_dst=a_dst, lp_off=lp_off,
         up_off=up_off, lu_size=lu_size, cb_off=cb_off, cb_size=cb_size, sn_m=sn_m,
         nnz_lu=nnz_lu,
-        flops=flops, f_max=int(sn_f.max()), n_warp_lists=n_lists, wl_ptr=wl_ptr, wl=wl, top=top,
+        flops=flops, f_max=int(sn_f.max()), n_warp_lists=n_lists, wl_ptr=wl_ptr, wl=wl,
+        n_mid_lists=n_mlists, ml_ptr=ml_ptr, ml=ml, top=top,
         f_warp_max=int(sn_f[level == 0].max()) if (level == 0).any() else 0,
+        f_mid_max=int(sn_f[level == 1].max()) if (level == 1).any() else 0,
         f_top_max=int(sn_f[level == 2].max()) if (level == 2).any() else 0, ordering=name)
 
 
 def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
-            warp_front_max: int = 10, n_warps: int = 8,
+            warp_front_max: int = 10, mid_front_max: int = 32, n_warps: int = 8,
             orderings: Sequence[str] = ("nd", "mmd"), warp_fixed: float = 3000.0) -> LUSymbolic:
     """Analyse the pattern (and representative values) of ``A``; see the module docstring."""
     A = sp.csc_matrix(A)
@@ -701,5 +713,5 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
             best = (fl, name, order)
     assert best is not None
     _, name, order = best
-    return _build(A, rowperm, S, order, relax_frac, relax_small, warp_front_max, n_warps,
-                  name, float(warp_fixed))
+    return _build(A, rowperm, S, order, relax_frac, relax_small, warp_front_max, max(mid_front_max, warp_front_max),
+                  n_warps, name, float(warp_fixed))

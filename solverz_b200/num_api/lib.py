@@ -9,7 +9,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE.parent / "csrc" / "libszb.so"
+LIB_PATH = Path(os.environ.get("SZB_LIB", str(_HERE.parent / "csrc" / "libszb.so")))   # SZB_LIB: instrumented builds of tools/
 
 SZB_ABI_VERSION = 4
 SZB_FLAG_EVENT = 8
@@ -24,8 +24,10 @@ _i32p = C.POINTER(C.c_int32)
 
 class LuSymbolicC(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n", "nnz_a", "ns", "lu_size", "cb_size", "cv_size", "n_warp_lists",
-                                         "n_warp_sn", "n_sched", "n_child", "n_idx", "n_rel", "f_max")] + \
-               [(k, _i32p) for k in ("rowp", "colp", "idx", "rel", "a_src", "a_dst", "wl_ptr", "fh", "ct")]
+                                         "n_warp_sn", "n_mid_lists", "n_mid_sn", "n_sched", "n_child", "n_idx",
+                                         "n_rel", "n_atp", "n_tcp", "n_tce", "warp_lines", "f_max", "f_warp_max")] + \
+               [(k, _i32p) for k in ("rowp", "colp", "idx", "rel", "a_src", "a_dst", "wl_ptr", "ml_ptr", "fh", "ct",
+                                     "atp", "tcp", "tce")]
 
 
 class DescC(C.Structure):
@@ -113,18 +115,20 @@ def lu_symbolic_c(sym, keep: list) -> LuSymbolicC:
     s = LuSymbolicC()
     if sym is None:
         return s
-    from ..lu.schedule import build_tables
+    from ..lu.schedule import WARP_LINES, build_tables
     tabs = build_tables(sym)
     if max(int(sym.lu_size), int(sym.cb_size)) * 32 >= 2 ** 31 * 32:
         raise SzbError("LU schedule exceeds int32 offsets")
     s.n, s.nnz_a, s.ns = sym.n, sym.nnzA, sym.ns
     s.lu_size, s.cb_size, s.cv_size = sym.lu_size, sym.cb_size, int(sym.rel_ptr[-1])
     s.n_warp_lists, s.n_warp_sn = sym.n_warp_lists, tabs["n_warp_sn"]
+    s.n_mid_lists, s.n_mid_sn = sym.n_mid_lists, tabs["n_mid_sn"]
     s.n_sched, s.n_child = tabs["n_sched"], len(tabs["ct"])
     s.n_idx, s.n_rel = len(sym.idx), len(sym.rel)
-    s.f_max = sym.f_max
-    arrays = dict(rowp=sym.rowp, colp=sym.colp, idx=sym.idx, rel=sym.rel, a_src=sym.a_src, a_dst=sym.a_dst,
-                  wl_ptr=sym.wl_ptr, fh=tabs["fh"], ct=tabs["ct"])
+    s.n_atp, s.n_tcp, s.n_tce, s.warp_lines = len(tabs["atp"]), len(tabs["tcp"]), len(tabs["tce"]), WARP_LINES
+    s.f_max, s.f_warp_max = sym.f_max, sym.f_warp_max
+    arrays = dict(rowp=sym.rowp, colp=sym.colp, idx=sym.idx, rel=sym.rel, a_src=tabs["a_src"], a_dst=tabs["a_dst"],
+                  wl_ptr=sym.wl_ptr, ml_ptr=sym.ml_ptr, fh=tabs["fh"], ct=tabs["ct"], atp=tabs["atp"], tcp=tabs["tcp"], tce=tabs["tce"])
     for name, a in arrays.items():
         arr = np.ascontiguousarray(np.asarray(a), dtype=np.int32).reshape(-1)
         if arr.size == 0:

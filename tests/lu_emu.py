@@ -40,18 +40,20 @@ def _p(a):
 
 class Tables:
     def __init__(self, sym):
-        from solverz_b200.lu.schedule import build_tables
+        from solverz_b200.lu.schedule import WARP_LINES, build_tables
         t = build_tables(sym)
         self.sym = sym
+        self.cta_lines = WARP_LINES
         self.fh, self.ct, self.n_sched = t["fh"], t["ct"], t["n_sched"]
-        self.a_src, self.a_dst = _i32(sym.a_src), _i32(sym.a_dst)
+        self.a_src, self.a_dst, self.atp, self.tcp, self.tce = t["a_src"], t["a_dst"], t["atp"], t["tcp"], t["tce"]
         self.rel, self.idx = _i32(sym.rel if len(sym.rel) else [0]), _i32(sym.idx)
         self.rowp, self.colp = _i32(sym.rowp), _i32(sym.colp)
 
 
-def factor(sym, jv, mvals=None, scale=1.0, smask=None, rhs=None, tabs=None):
+def factor(sym, jv, mvals=None, scale=1.0, smask=None, rhs=None, tabs=None, buf_lines=None):
     """Returns (lu, y, monitors) with y = L^{-1} P rhs in pivot order (None without rhs)."""
     T = tabs or Tables(sym)
+    buf_lines = T.cta_lines if buf_lines is None else buf_lines
     jv = np.ascontiguousarray(jv, dtype=float)
     mv = None if mvals is None else np.ascontiguousarray(mvals, dtype=float)
     sm = None if smask is None else np.ascontiguousarray(smask, dtype=float)
@@ -60,8 +62,8 @@ def factor(sym, jv, mvals=None, scale=1.0, smask=None, rhs=None, tabs=None):
     y = np.full(sym.n, np.nan)
     mon = np.zeros(3)
     lib().emu_factor(C.c_int(T.n_sched), _p(T.fh), _p(T.ct), _p(T.a_src), _p(T.a_dst), _p(T.rel), _p(T.idx),
-                     _p(T.rowp), _p(T.colp), C.c_int(int(sym.cb_size)), _p(jv), _p(mv), _p(sm), C.c_double(scale),
-                     _p(r), _p(lu), _p(y), _p(mon))
+                     _p(T.rowp), _p(T.colp), _p(T.atp), _p(T.tcp), _p(T.tce), C.c_int(int(sym.cb_size)), _p(jv), _p(mv), _p(sm), C.c_double(scale),
+                     _p(r), _p(lu), _p(y), _p(mon), C.c_int(int(buf_lines)))
     return lu, (y if rhs is not None else None), mon
 
 

@@ -31,8 +31,9 @@ def _pf_jacobian(nx, seed=0):
     return J, orc
 
 
-@pytest.mark.parametrize("nx,opts", [(6, {}), (12, {}), (12, dict(warp_front_max=20, n_warps=4)),
-                                     (12, dict(warp_front_max=0)), (16, dict(warp_front_max=64, n_warps=8)),
+@pytest.mark.parametrize("nx,opts", [(6, {}), (12, {}), (12, dict(warp_front_max=10, mid_front_max=20, n_warps=4)),
+                                     (12, dict(warp_front_max=0, mid_front_max=0)), (12, dict(warp_front_max=4, mid_front_max=12)),
+                                     (16, dict(warp_front_max=0, mid_front_max=64)),
                                      (10, dict(orderings=("nd",))), (10, dict(orderings=("natural",)))])
 def test_symbolic_schedule_solves(nx, opts):
     """The schedule of lu/symbolic.py + lu/schedule.py walked by the device code itself (csrc/szb_lu_front.cuh

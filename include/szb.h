@@ -50,7 +50,7 @@ extern "C" {
 #define SZB_API
 #endif
 
-#define SZB_ABI_VERSION 4
+#define SZB_ABI_VERSION 3
 
 /* error codes */
 #define SZB_OK 0
@@ -63,8 +63,7 @@ extern "C" {
 /* per-scenario status written to flags[] by szb_newton / szb_rodas */
 #define SZB_FLAG_CONVERGED 0
 #define SZB_FLAG_MAXIT 1      /* nr.py:50-52                                   */
-#define SZB_FLAG_SINGULAR 2   /* zero / non-finite static pivot, or element growth max|u| / max|a| of the
-                                 factorisation above the tolerance (szb_set_growth_tol) */
+#define SZB_FLAG_SINGULAR 2   /* zero / non-finite static pivot                */
 #define SZB_FLAG_DTMIN 3      /* rodas.py:127-130                              */
 #define SZB_FLAG_REJECTS 4    /* rodas.py:131-135                              */
 #define SZB_FLAG_NAN 5        /* NaN/Inf residual                              */
@@ -86,37 +85,44 @@ extern "C" {
 typedef struct szb_handle szb_handle;
 typedef void* szb_stream; /* cudaStream_t */
 
-/* Result of the host-side symbolic analysis (solverz_b200/lu/symbolic.py) lowered to the device schedule
- * (solverz_b200/lu/schedule.py).  All arrays are host pointers, copied to the device by szb_create.
- * Index arrays are int32.  Offsets into the factor storage / contribution workspace count LINES of 32
- * scenarios (the factor kernels work on groups of 32 scenarios, lane = scenario). */
+/* Result of the host-side symbolic analysis (solverz_b200/lu/symbolic.py).  All arrays are
+ * host pointers, copied to the device by szb_create.  Index arrays are int32. */
 typedef struct szb_lu_symbolic {
   int32_t n, nnz_a, ns;
-  int32_t lu_size, cb_size, cv_size; /* lines per group: factors, contribution ws, forward-sweep ws */
-  int32_t n_warp_lists;     /* level-0 work lists: on-chip fronts, one warp each (<= warps per CTA) */
-  int32_t n_warp_sn;        /* fronts in the level-0 lists (they come first in schedule order) */
-  int32_t n_mid_lists;      /* level-1 work lists: tiled fronts, one warp each */
-  int32_t n_mid_sn;         /* fronts in the level-1 lists (they follow the level-0 fronts; the rest is level 2) */
-  int32_t n_sched, n_child; /* fronts in schedule order; rows of the child table */
-  int32_t n_idx, n_rel;     /* lengths of idx / rel */
-  int32_t n_atp, n_tcp, n_tce; /* lengths of atp / tcp, rows of tce */
-  int32_t warp_lines;       /* shared-memory lines per warp the level-0 fronts were sized for (must equal the kernels') */
-  int32_t f_max, f_warp_max; /* largest front; largest front of the level-0 lists */
+  int32_t lu_size, cb_size, cv_size; /* doubles per scenario: factors, contribution ws, fwd ws */
+  int32_t n_warp_lists, n_group_lists, n_top;
+  int32_t f_warp_max, f_group_max, f_top_max, s_warp_max, s_group_max, s_top_max;
+  int32_t threads, wpg;     /* threads per CTA and warps per group the tables below were laid out for */
+  int32_t n_sched, n_ga;    /* fronts in schedule order; (src, dst) pairs in the gather table */
   const int32_t* rowp;      /* [n]   pivot k <- original row     */
   const int32_t* colp;      /* [n]   pivot k <- original column  */
-  const int32_t* idx;       /* [n_idx] front index lists (pivot order) */
-  const int32_t* rel;       /* [n_rel] positions of a child's update rows in its parent's front */
-  const int32_t* a_src;     /* [nnz_a] Jacobian slot of a matrix entry, grouped by front (tiled fronts: by tile) */
-  const int32_t* a_dst;     /* [nnz_a] its offset in the factor storage (tiled fronts: r + 8 c inside its tile) */
-  const int32_t* wl_ptr;    /* [n_warp_lists+1] runs of the level-0 lists in schedule order */
-  const int32_t* ml_ptr;    /* [n_mid_lists+1] runs of the level-1 lists, relative to n_warp_sn */
-  const int32_t* fh;        /* [n_sched][16] front descriptors: s, f, piv0, lp_off, up_off, cb_off, a0, a1,
-                               c0, c1, idx_ptr, cv_off, atp0, tcp0 (-1: not tiled), k, 0 */
-  const int32_t* ct;        /* [n_child][8] child table: cb_off, u, rel_ptr, cv_off of the child, 0, 0, 0, 0 */
-  const int32_t* atp;       /* [n_atp] tiled fronts: first matrix entry of every 8 x 8 tile */
-  const int32_t* tcp;       /* [n_tcp] tiled fronts: first contributor of every tile (incl. the rhs column) */
-  const int32_t* tce;       /* [n_tce][4] contributors: workspace offset of the piece of a child's block that lands
-                               in the tile, u of the child, row nibbles, column nibbles (lu/schedule.py) */
+  const int32_t* sn_piv0;   /* [ns]  */
+  const int32_t* sn_s;      /* [ns]  */
+  const int32_t* sn_f;      /* [ns]  */
+  const int32_t* idx_ptr;   /* [ns+1] */
+  const int32_t* idx;       /* front index lists */
+  const int32_t* rel_ptr;   /* [ns+1] */
+  const int32_t* rel;
+  const int32_t* child_ptr; /* [ns+1] */
+  const int32_t* child;
+  const int32_t* a_ptr;     /* [ns+1] */
+  const int32_t* a_src;     /* [nnz_a] */
+  const int32_t* a_dst;     /* [nnz_a] */
+  const int32_t* lp_off;    /* [ns] */
+  const int32_t* up_off;    /* [ns] */
+  const int32_t* cb_off;    /* [ns] */
+  const int32_t* ea_ptr;    /* [ns+1] extend-add tables: ea_dst[ea_ptr[c] + t] = position in the parent */
+  const int32_t* ea_dst;    /*        front of element t of the u_c x (u_c+1) contribution block of c   */
+  const int32_t* wl_ptr;    /* [n_warp_lists+1] */
+  const int32_t* wl;
+  const int32_t* gl_ptr;    /* [n_group_lists+1] */
+  const int32_t* gl;
+  const int32_t* top;       /* [n_top] */
+  const int32_t* fh;        /* [n_sched][16] front descriptors in schedule order (warp lists, group lists,
+                               top): s, f, piv0, lp_off, up_off, cb_off, gaJ, itJ, gaC, itC, gaR, itR, k, n_src,
+                               idx_ptr, 0 */
+  const int32_t* ga;        /* [n_ga][2] gather table: per front three [iterations][group threads] blocks
+                               (J slots, contribution offsets, right-hand side) of (source, front position); see solverz_b200/lu/schedule.py */
 } szb_lu_symbolic;
 
 typedef struct szb_desc {
@@ -195,14 +201,6 @@ SZB_API int szb_eval_J(szb_handle* h, double t, szb_stream stream);
 SZB_API int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream);
 /* SLOT_RHS <- A^{-1} SLOT_RHS for nrhs right-hand sides stored as [nrhs][B][n] */
 SZB_API int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream);
-/* status of the last szb_lu_refactor / szb_lu_refactor_masked_rows per scenario into the device array
- * flags_dev int32[B]: 0 fine, SZB_FLAG_SINGULAR for a zero / non-finite pivot or an element growth above
- * the tolerance -- what the reference's splu / spsolve report as RuntimeError / MatrixRankWarning
- * (laesolver.py:11-45) */
-SZB_API int szb_lu_status(szb_handle* h, int32_t* flags_dev, szb_stream stream);
-/* element-growth tolerance of the static-pivot factorisation (default 1e8): a scenario whose
- * max|u_ij| / max|a_ij| exceeds it is flagged SZB_FLAG_SINGULAR */
-SZB_API int szb_set_growth_tol(szb_handle* h, double tol);
 /* whole Newton solve, nr.py:45-64, on device buffers; iters/flags are device int32[B] */
 SZB_API int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, int32_t* flags_dev,
                szb_stream stream);

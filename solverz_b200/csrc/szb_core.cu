@@ -163,15 +163,11 @@ int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b,
     mv = h->mass_vals;
     scale = -h_gamma;
   }
-  (void)store_l;   // the factors are built in place: L is always there
-  cudaError_t e = szb::lu_map_launch(active, h->B, h->lu_map, h->lu_npos, st);
-  if (e == cudaSuccess)
-    e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, mv, slot_mask, scale_b, scale, rhs, yout, h->lu_map,
-                              h->lu_npos, h->lu_mon, h->flags, h->growth_tol, st);
+  cudaError_t e = szb::lu_factor_launch(h->S, h->cfg, h->JV, h->LU, h->CBW, h->FBW, mv, slot_mask, scale_b, scale, rhs,
+                                        yout, store_l, active, h->flags, h->B, st);
   if (e != cudaSuccess) { szb_set_error(h, "LU factor launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
-  h->launches[4]++;
   h->launches[2]++;
-  h->factored = true;
+  h->factored = store_l != 0;
   return SZB_OK;
 }
 
@@ -257,37 +253,42 @@ int szb_create(const szb_desc* d, szb_handle** out) {
   szb::LuDev& S = h->S;
   h->has_lu = L.ns > 0;
   if (h->has_lu) {
-    S.n = L.n; S.nnz_a = L.nnz_a; S.ns = L.ns;
-    S.lu_size = L.lu_size; S.cb_size = L.cb_size; S.cv_size = L.cv_size;
-    S.n_warp_lists = L.n_warp_lists; S.n_warp_sn = L.n_warp_sn; S.n_sched = L.n_sched;
-    S.n_mid_lists = L.n_mid_lists; S.n_mid_sn = L.n_mid_sn;
-    S.f_max = L.f_max; S.f_warp_max = L.f_warp_max; S.warp_lines = L.warp_lines;
-    if (L.n_sched <= 0 || L.n_warp_sn < 0 || L.n_mid_sn < 0 || L.n_warp_sn + L.n_mid_sn > L.n_sched ||
-        L.n_warp_lists < 0 || L.n_mid_lists < 0 || !L.fh || !L.ct || !L.wl_ptr || !L.ml_ptr ||
-        (L.n_warp_lists > 0 && L.wl_ptr[L.n_warp_lists] != L.n_warp_sn) ||
-        (L.n_mid_lists > 0 && L.ml_ptr[L.n_mid_lists] != L.n_mid_sn)) {
-      szb_set_error(h, "szb_create: LU schedule tables missing or inconsistent (n_sched=%d, n_warp_sn=%d)",
-                    L.n_sched, L.n_warp_sn);
-      return fail(SZB_EINVAL);
-    }
+  S.n = L.n; S.nnz_a = L.nnz_a; S.ns = L.ns;
+  S.lu_size = L.lu_size; S.cb_size = L.cb_size; S.cv_size = L.cv_size;
+  S.n_warp_lists = L.n_warp_lists; S.n_group_lists = L.n_group_lists; S.n_top = L.n_top;
+  S.f_warp_max = L.f_warp_max; S.f_group_max = L.f_group_max; S.f_top_max = L.f_top_max;
+  S.s_warp_max = L.s_warp_max; S.s_group_max = L.s_group_max; S.s_top_max = L.s_top_max;
+  S.threads = L.threads; S.wpg = L.wpg;
+  S.f_max = L.f_warp_max > L.f_group_max ? L.f_warp_max : L.f_group_max;
+  if (L.f_top_max > S.f_max) S.f_max = L.f_top_max;
+  S.n_warp_sn = L.wl_ptr[L.n_warp_lists];
+  S.n_group_sn = L.n_group_lists > 0 ? L.gl_ptr[L.n_group_lists] : 0;
+  if (L.n_sched != S.n_warp_sn + S.n_group_sn + L.n_top || L.n_ga <= 0 || !L.fh || !L.ga) {
+    szb_set_error(h, "szb_create: LU schedule tables missing or inconsistent (n_sched=%d)", L.n_sched);
+    return fail(SZB_EINVAL);
+  }
+  const int ns = L.ns;
 #define UP(field, cnt)                                                               \
   do {                                                                               \
     int* p_ = nullptr;                                                               \
     if ((rc = upload<int>(h, L.field, static_cast<size_t>(cnt), &p_)) != SZB_OK) return fail(rc); \
     S.field = p_;                                                                    \
   } while (0)
-    UP(rowp, L.n); UP(colp, L.n); UP(idx, L.n_idx); UP(rel, L.n_rel);
-    UP(a_src, L.nnz_a); UP(a_dst, L.nnz_a); UP(wl_ptr, L.n_warp_lists + 1); UP(ml_ptr, L.n_mid_lists + 1); UP(atp, L.n_atp); UP(tcp, L.n_tcp);
+  UP(rowp, L.n); UP(colp, L.n); UP(sn_piv0, ns); UP(sn_s, ns); UP(sn_f, ns);
+  UP(idx_ptr, ns + 1); UP(idx, L.idx_ptr[ns]); UP(rel_ptr, ns + 1); UP(rel, L.rel_ptr[ns]);
+  UP(child_ptr, ns + 1); UP(child, L.child_ptr[ns]);
+  UP(a_ptr, ns + 1); UP(a_src, L.nnz_a); UP(a_dst, L.nnz_a);
+  UP(lp_off, ns); UP(up_off, ns); UP(cb_off, ns); UP(ea_ptr, ns + 1); UP(ea_dst, L.ea_ptr[ns]);
+  UP(wl_ptr, L.n_warp_lists + 1); UP(wl, L.wl_ptr[L.n_warp_lists]);
+  UP(gl_ptr, L.n_group_lists + 1); UP(gl, L.n_group_lists > 0 ? L.gl_ptr[L.n_group_lists] : 0); UP(top, L.n_top);
 #undef UP
-    {
-      int* p_ = nullptr;
-      if ((rc = upload<int>(h, L.fh, static_cast<size_t>(L.n_sched) * 16, &p_)) != SZB_OK) return fail(rc);
-      S.fh = reinterpret_cast<const int4*>(p_);
-      if ((rc = upload<int>(h, L.ct, static_cast<size_t>(L.n_child) * 8, &p_)) != SZB_OK) return fail(rc);
-      S.ct = reinterpret_cast<const int4*>(p_);
-      if ((rc = upload<int>(h, L.tce, static_cast<size_t>(L.n_tce) * 4, &p_)) != SZB_OK) return fail(rc);
-      S.tce = reinterpret_cast<const int4*>(p_);
-    }
+  {
+    int* p_ = nullptr;
+    if ((rc = upload<int>(h, L.fh, static_cast<size_t>(L.n_sched) * 16, &p_)) != SZB_OK) return fail(rc);
+    S.fh = reinterpret_cast<const int4*>(p_);
+    if ((rc = upload<int>(h, L.ga, static_cast<size_t>(L.n_ga) * 2, &p_)) != SZB_OK) return fail(rc);
+    S.ga = reinterpret_cast<const int2*>(p_);
+  }
   }
   if (d->mass_vals) {
     double* p = nullptr;
@@ -348,7 +349,8 @@ int szb_set_batch(szb_handle* h, int32_t B) {
   if (h->has_lu) {
     cudaError_t e = szb::lu_plan(h->S, B, &h->cfg);
     if (e != cudaSuccess) {
-      szb_set_error(h, "LU launch plan failed (largest front %d): %s", h->S.f_max, cudaGetErrorString(e));
+      szb_set_error(h, "LU launch plan failed (front %d / %d too large for shared memory?): %s",
+                    h->S.f_warp_max, h->S.f_top_max, cudaGetErrorString(e));
       return SZB_ECUDA;
     }
   }
@@ -365,15 +367,14 @@ int szb_set_batch(szb_handle* h, int32_t B) {
   ALLOC(h->own_JV, double, B * nz);
   ALLOC(h->own_RHS, double, B * n);
   if (h->has_lu) {
-    // interleaved storage: whole groups of szb::kGroup scenarios; workspaces per resident CTA
-    const size_t G = static_cast<size_t>(h->cfg.groups), K = szb::kGroup, R = static_cast<size_t>(h->cfg.grid);
-    ALLOC(h->LU, double, G * K * h->S.lu_size);
-    ALLOC(h->ybuf, double, G * K * n);
-    ALLOC(h->CBW, double, G * K * (h->S.cb_size > 0 ? h->S.cb_size : 1));   // per group: blocks cross kernel launches
-    ALLOC(h->lu_mon, double, G * K * 3);
-    ALLOC(h->CVW, double, R * K * (h->S.cv_size > 0 ? h->S.cv_size : 1));
-    ALLOC(h->lu_map, int, G * K);
-    ALLOC(h->lu_npos, int, 1);
+    ALLOC(h->LU, double, static_cast<size_t>(B) * h->S.lu_size);
+    ALLOC(h->ybuf, double, B * n);
+    int gmax = h->cfg.grid_factor > h->cfg.grid_solve ? h->cfg.grid_factor : h->cfg.grid_solve;
+    if (h->cfg.grid_bwd > gmax) gmax = h->cfg.grid_bwd;
+    ALLOC(h->CBW, double, static_cast<size_t>(gmax) * (h->S.cb_size > 0 ? h->S.cb_size : 1));
+    ALLOC(h->FBW, double, h->cfg.top_in_global ? static_cast<size_t>(h->cfg.grid_factor) * h->cfg.big_elems : 1);
+    ALLOC(h->CVW, double, static_cast<size_t>(gmax) * (h->S.cv_size > 0 ? h->S.cv_size : 1));
+    ALLOC(h->XW, double, (h->cfg.x_in_smem && h->cfg.bwd_x_in_smem) ? 1 : static_cast<size_t>(gmax) * n);
   }
   ALLOC(h->fnorm, double, B);
   ALLOC(h->scale_b, double, B);
@@ -464,7 +465,6 @@ int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream) {
   if (!h) return SZB_EINVAL;
   if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
   SZB_CUDA(h, cudaSetDevice(h->device));
-  SZB_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * h->B, static_cast<cudaStream_t>(stream)));
   return szb_lu_refactor_masked(h, h_gamma, nullptr, nullptr, nullptr, nullptr, 1,
                                 static_cast<cudaStream_t>(stream));
 }
@@ -473,7 +473,6 @@ int szb_lu_refactor_masked_rows(szb_handle* h, const double* row_mask_dev, szb_s
   if (!h) return SZB_EINVAL;
   if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
   SZB_CUDA(h, cudaSetDevice(h->device));
-  SZB_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * h->B, static_cast<cudaStream_t>(stream)));
   return szb_lu_refactor_masked(h, -1.0, nullptr, nullptr, nullptr, nullptr, 1,
                                 static_cast<cudaStream_t>(stream), row_mask_dev);
 }
@@ -490,8 +489,8 @@ int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream) {
   SZB_CUDA(h, cudaSetDevice(h->device));
   for (int r = 0; r < nrhs; ++r) {
     double* x = h->RHS + r * per;
-    cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, x, x, h->CVW, h->ybuf, 1, 0, h->lu_map, h->lu_npos,
-                                         nullptr, static_cast<cudaStream_t>(stream));
+    cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, x, x, h->CVW, h->XW, h->ybuf, 1, 0, nullptr, h->B,
+                                         static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
     h->launches[3]++;
   }
@@ -594,8 +593,8 @@ int szb_newton(szb_handle* h, double tol, int32_t max_it, int32_t* iters_dev, in
     tic();
     {
       // backward substitution and Newton update  Y -= U^{-1} y
-      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, nullptr, h->Y, h->CVW, h->ybuf, 0, 1, h->lu_map,
-                                           h->lu_npos, h->active, st);
+      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->ybuf, h->Y, h->CVW, h->XW, nullptr, 0, 1,
+                                           h->active, B, st);
       if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
       h->launches[3]++;
     }
@@ -687,21 +686,6 @@ int szb_set_implicit(szb_handle* h, int32_t mode, double c, const double* y_prev
   h->imp_c = c;
   h->imp_y0 = y_prev_dev;
   h->imp_f0 = f_prev_dev;
-  return SZB_OK;
-}
-
-int szb_lu_status(szb_handle* h, int32_t* flags_dev, szb_stream stream) {
-  if (!h || !flags_dev) return SZB_EINVAL;
-  if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
-  SZB_CUDA(h, cudaSetDevice(h->device));
-  SZB_CUDA(h, cudaMemcpyAsync(flags_dev, h->flags, sizeof(int) * h->B, cudaMemcpyDeviceToDevice,
-                              static_cast<cudaStream_t>(stream)));
-  return SZB_OK;
-}
-
-int szb_set_growth_tol(szb_handle* h, double tol) {
-  if (!h || !(tol > 0.0)) return SZB_EINVAL;
-  h->growth_tol = tol;
   return SZB_OK;
 }
 

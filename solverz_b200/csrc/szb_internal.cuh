@@ -32,9 +32,7 @@ struct szb_handle {
   double *bound_Y = nullptr, *bound_F = nullptr, *bound_JV = nullptr, *bound_RHS = nullptr;
   double *Y = nullptr, *F = nullptr, *JV = nullptr, *RHS = nullptr;
   int64_t rhs_len = 0;
-  double *LU = nullptr, *CBW = nullptr, *CVW = nullptr, *ybuf = nullptr, *lu_mon = nullptr;   // interleaved by groups of 32
-  int *lu_map = nullptr, *lu_npos = nullptr;   // position -> scenario of the last factorisation (szb::lu_map_launch)
-  double growth_tol = 1e8;
+  double *LU = nullptr, *CBW = nullptr, *FBW = nullptr, *CVW = nullptr, *XW = nullptr, *ybuf = nullptr;
   double *fnorm = nullptr, *scale_b = nullptr;
   int *active = nullptr, *nstep = nullptr, *flags = nullptr, *counter = nullptr;
   int* pinned = nullptr;  // 16 ints of pinned host memory

@@ -1,318 +1,1718 @@
-// szb_lu.cu -- batched fixed-pattern multifrontal sparse LU for sm_100a, batch-interleaved.
+// szb_lu.cu -- batched fixed-pattern multifrontal sparse LU for sm_100a.
 //
 // Replaces, for a whole batch of scenarios that share one sparsity pattern, the per-call
 // SuperLU factorisation behind the reference's linear-solve seam
 //   solve(A,b) -> scipy.sparse.linalg.spsolve      (Solverz/solvers/laesolver.py:11-15)
 //   lu_decomposition(A) -> splu ; .solve(b)        (Solverz/solvers/laesolver.py:18-45)
 //
-// Design (DESIGN.md "LU"; the per-front arithmetic is csrc/szb_lu_front.cuh):
-//   * one CTA per GROUP of 32 scenarios, lane = scenario; factors, contribution blocks and the
-//     pivot-order vectors are stored interleaved (element e of a group at [e][lane]), so every warp
-//     access is one coalesced 256-byte line and every index of the host schedule is decoded once per
-//     32 scenarios; lanes never communicate (no shuffles, no atomics => bitwise reproducible and
-//     independent of a scenario's position in the batch);
-//   * the active scenarios of a call are compacted into dense groups first (lu_map_kernel), so a
-//     ragged active set (Newton stragglers, Rodas scenarios that finished) costs what is active;
-//   * the host analysis (lu/symbolic.py) fixes pivots, ordering, supernodes and the split of the
-//     elimination tree into warp-level subtrees (each warp of the CTA walks its own list of small
-//     fronts without any synchronisation) and the CTA-level top (all warps share a front, CTA
-//     barriers between the phases);
-//   * fronts are assembled and eliminated in place in the factor storage / contribution workspace;
-//     the right-hand side can ride along as an extra front column, which fuses the forward
-//     substitution L y = b into the factorisation (Newton);
-//   * the triangular sweeps follow the same tree with the same lane = scenario layout: the backward
-//     sweep streams U once, coalesced.
+// Design (see DESIGN.md "LU"):
+//   * one CTA per scenario (persistent grid, grid-stride over scenarios); values are
+//     scenario-major so every panel of the factors is one contiguous, coalesced stream;
+//   * the host analysis (lu/symbolic.py) fixes pivots, ordering, supernodes and all index
+//     maps once; the kernels below are pure value arithmetic driven by int32 tables that are
+//     identical for all scenarios (L1/L2 resident);
+//   * three levels of the elimination tree run with three kinds of thread groups:
+//       warp  : every warp walks its own list of small subtrees, front in a warp-private
+//               shared-memory buffer, __syncwarp only;
+//       group : a few warps (named barrier) share one medium front; groups run independent
+//               subtrees concurrently;
+//       CTA   : the few big fronts at the top use all threads.
+//     Warp-level fronts: lane = row, rank-1 steps (column-major shared memory, odd leading dimension).
+//     Multi-warp fronts: blocked (NB = 4) elimination whose trailing update runs on the fp64 tensor-core
+//     path (mma.sync.m8n8k4.f64 over zero-padded 8x8 tiles, leading dimension 2 mod 4), with a 4x4
+//     diagonal-block LU + inverse in registers on one warp as the only serial chain; fronts too large
+//     for shared memory live in a per-CTA global workspace and are eliminated in outer blocks of 32
+//     pivots (eliminate_global);
+//   * a front is described by ONE 64-byte descriptor (prefetched a front ahead) and assembled in
+//     ONE pass over a host-built gather table (lu/schedule.py): matrix entries, right-hand side and
+//     all children's contribution blocks, every destination owned by one thread (no barriers
+//     between children, no atomics);
+//   * the right-hand side can ride along as an extra front column, which fuses the forward
+//     substitution L y = b into the factorisation (Newton never needs L again);
+//   * contribution blocks travel through a per-CTA workspace in global memory (L2 resident, reused
+//     across scenarios by the persistent CTA, regions of different lifetimes sharing addresses);
+//     factors are written exactly once (the diagonal of U as its reciprocal);
+//   * triangular solves follow the same tree; the forward sweep passes contribution vectors up
+//     the tree (no atomics => bitwise reproducible), the backward sweep only reads ancestors; the
+//     CTA-level chain at the top of the tree is walked by all warps of the CTA in both sweeps.
+//   The sparse structure is never reshaped into a dense contraction; the frontal matrices of the
+//   multifrontal method ARE dense, and their rank-4 updates are what the DMMA path is used for.
 #include "szb_lu.cuh"
 
 #include <cstdio>
-
-#include "szb_lu_front.cuh"
+#include <type_traits>
 
 namespace szb {
 
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
-// shared memory of the factor kernels in lines of 32 doubles: a level-0 front (front_lines(f) <= kWarpLines;
-// lu/symbolic.py cuts those subtrees at warp_front_max = 10: 10 * 11 = 110 lines) is assembled and eliminated
-// in its warp's buffer; the tiled levels use kTileScratch lines per warp (+ one shared diagonal tile)
-constexpr int kWarpLines = 110;
-constexpr int kSmemLines = kWarps * kWarpLines;   // 880 lines = 225 280 bytes >= kNB * kNB + kWarps * kTileScratch
-
-__device__ __forceinline__ Tabs make_tabs(const LuDev& S) {
-  Tabs T;
-  T.fh = S.fh; T.ct = S.ct; T.a_src = S.a_src; T.a_dst = S.a_dst; T.rel = S.rel; T.idx = S.idx;
-  T.rowp = S.rowp; T.colp = S.colp; T.atp = S.atp; T.tcp = S.tcp; T.tce = S.tce;
-  return T;
-}
-
-// ---- compaction of the active scenarios into dense groups ---------------------------------------
-__global__ void __launch_bounds__(1024) lu_map_kernel(const int* __restrict__ active, int B, int* __restrict__ map,
-                                                      int* __restrict__ npos) {
-  __shared__ int wsum[32];
-  __shared__ int base;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base = 0;
-  __syncthreads();
-  for (int b0 = 0; b0 < B; b0 += 1024) {
-    const int b = b0 + threadIdx.x;
-    const int a = b < B && (!active || active[b]) ? 1 : 0;
-    const unsigned m = __ballot_sync(0xffffffffu, a);
-    if (lane == 0) wsum[w] = __popc(m);
-    __syncthreads();
-    int off = base;
-    for (int i = 0; i < w; ++i) off += wsum[i];
-    if (a) map[off + __popc(m & ((1u << lane) - 1u))] = b;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int t = 0;
-      for (int i = 0; i < 32; ++i) t += wsum[i];
-      base += t;
-    }
-    __syncthreads();
-  }
-  const int n = base;
-  const int end = (n + kGroup - 1) / kGroup * kGroup;
-  for (int p = n + threadIdx.x; p < end; p += 1024) map[p] = -1;
-  if (threadIdx.x == 0) *npos = n;
-}
-
-#ifdef SZB_LU_TIMING
-__device__ unsigned long long g_lu_cycles[24];
+constexpr int kWarp = 32;
+#ifndef SZB_FACTOR_THREADS
+#define SZB_FACTOR_THREADS 512
 #endif
 
-// ---- factorisation: one kernel per level of the schedule --------------------------------------------
-//   LEVEL 0: each warp walks its list of small subtrees, a front is assembled and eliminated in the warp's
-//            shared-memory buffer and written out once;
-//   LEVEL 1: each warp walks its list of medium subtrees by register tiles (operands from L2 through the
-//            warp's asynchronous-copy ring);
-//   LEVEL 2: the top of the tree, all warps of the CTA share a front (same tiles, dealt to the warps).
-// Separate launches: each body gets the whole register file for its inner loop (merged into one kernel ptxas
-// spilled 6 kB), and contribution blocks that cross levels live in the per-group workspace.
-template <int LEVEL>
-__global__ void __launch_bounds__(kThreads, 1)
-lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* LU, double* CBW,
-                 const double* __restrict__ mvals, const double* __restrict__ slot_mask,
-                 const double* __restrict__ scale_b, double scale_const, const double* __restrict__ RHS,
-                 double* YI, const int* __restrict__ map, const int* __restrict__ npos, double* MON,
-                 int* __restrict__ flags, double growth_tol) {
+// t / m for 0 <= t < 2^22 without an integer division: (t + 0.5)/m is never within 0.5/m of an
+// integer, far more than the 2^-23 relative rounding of the float product
+__device__ __forceinline__ int fdiv(int t, float invm) {
+  return __float2int_rz((static_cast<float>(t) + 0.5f) * invm);
+}
+
+struct FactorArgs {
+  const double* __restrict__ jv;     // matrix values of this scenario (CSC slots)
+  const double* __restrict__ mvals;  // optional mass values (shared)
+  const double* __restrict__ smask;  // optional 0/1 mask per slot applied to jv (shared)
+  double scale;
+  const double* __restrict__ rhs;    // optional right-hand side of this scenario (original order)
+  double* __restrict__ yout;         // forward-substituted rhs in pivot order (when rhs != null)
+  double* __restrict__ lu;           // factor storage of this scenario
+  double* cb;                        // contribution workspace of this CTA (written and re-read: no restrict)
+  int store_l;                       // write the L21 rows of the panels
+  int* flag;
+};
+
+// one front of the schedule (lu/schedule.py: 16 int32, 12 used on the device)
+struct FrontHdr {
+  int s, f, piv0, lp_off, up_off, cb_off;
+  int gaO, itO, gaC, itC, gaR, itR;
+};
+
+__device__ __forceinline__ FrontHdr load_hdr(const int4* __restrict__ fh, const int q) {
+  const int4 a = __ldg(fh + 4 * q), b = __ldg(fh + 4 * q + 1), c = __ldg(fh + 4 * q + 2);
+  FrontHdr H;
+  H.s = a.x; H.f = a.y; H.piv0 = a.z; H.lp_off = a.w;
+  H.up_off = b.x; H.cb_off = b.y; H.gaO = b.z; H.itO = b.w;
+  H.gaC = c.x; H.itC = c.y; H.gaR = c.z; H.itR = c.w;
+  return H;
+}
+
+// doubles of shared memory of a front of order f with its right-hand-side column (column-major,
+// odd leading dimension f|1), rounded to an even count so that buffers stay 16-byte aligned
+// Leading dimensions (lu/symbolic.py::front_ld builds the assembly tables with the same numbers):
+// warp-level fronts (lane = row, rank-1 steps) odd, so that rows AND columns are conflict-free;
+// multi-warp fronts ld = 2 (mod 4): the four column pairs of an mma.m8n8k4 accumulator fragment
+// (rows g, columns 2q and 2q+1) then fall on disjoint banks in each half-warp.  Multi-warp fronts also
+// carry 7 rows and 7 columns of zero padding, so that the 8x8 tiles of the tensor-core update never
+// need a mask: a tile that overhangs the front reads zeros and writes zeros.
+constexpr int kPad = 7;
+__host__ __device__ __forceinline__ int ld_warp(const int f) { return f | 1; }
+__host__ __device__ __forceinline__ int ld_blk(const int f) { return f + kPad + ((2 - (f + kPad)) & 3); }
+__host__ __device__ __forceinline__ int cols_blk(const int f) { return f + 1 + kPad; }
+__host__ __device__ __forceinline__ int front_elems_warp(const int f) { return ((ld_warp(f) * (f + 1)) + 1) & ~1; }
+__host__ __device__ __forceinline__ int front_elems_blk(const int f) { return ((ld_blk(f) * cols_blk(f)) + 1) & ~1; }
+// side-panel stride: covers the front rounded up to whole 8-row tiles, 4 (mod 16) so that the A
+// fragments (rows g, panel columns q) are conflict-free
+__host__ __device__ __forceinline__ int lt_stride(const int f) { return (((((f + 7) & ~7) + 11) >> 4) << 4) + 4; }
+constexpr int kNB = 4;
+constexpr int kDiagBuf = kNB * kNB;   // explicit inverse of the current diagonal block
+// per-group scratch behind the front: -Lt side panel (kNB x lt_stride) + kDiagBuf
+__host__ __device__ __forceinline__ int group_elems(const int f) { return front_elems_blk(f) + kNB * lt_stride(f) + kDiagBuf; }
+
+__device__ __forceinline__ void check_pivot(const double piv, int* flag) {
+  if (!(fabs(piv) > 0.0) || isinf(piv)) *flag = 2;
+}
+
+// 1/x to full double precision (not correctly rounded): 20-bit hardware seed + two Newton steps;
+// 56 cycles dependent instead of 80 for the IEEE division (tools/fp64_lat.cu)
+__device__ __forceinline__ double fast_rcp(const double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// ---- assembly: one pass over the front's stream of gather entries (lu/schedule.py).  A batch of
+// kAsm entries per thread is in flight: entries first, then the values they address, then the
+// shared-memory updates; a destination is only ever touched by one thread, so there is nothing to
+// synchronise.  The first batch of a front is fetched while the previous front is still being
+// eliminated (AsmPre), which takes the table round trip off the critical path.
+constexpr int kAsm = 8;
+
+constexpr int kAsmO = 2;   // leading entries per thread whose values (original data) are prefetched too
+
+struct AsmPre {
+  int2 en[kAsm];
+  double ov[kAsmO];
+  int n_ov;        // how many of ov[] are valid (0 unless the plain A = J path prefetched them)
+};
+
+// number of entries per thread: the right-hand-side block is skipped when no rhs rides along
+__device__ __forceinline__ int asm_iters(const FrontHdr& H, const bool with_rhs) {
+  return H.itO + H.itC + (with_rhs ? H.itR : 0);
+}
+
+__device__ __forceinline__ void asm_prefetch(AsmPre& P, const FrontHdr& H, const int2* __restrict__ ga,
+                                             const int rank, const int G_, const bool with_rhs) {
+  const int iters = asm_iters(H, with_rhs);
+  const int2* __restrict__ e = ga + H.gaO + rank;
+#pragma unroll
+  for (int q = 0; q < kAsm; ++q) P.en[q] = q < iters ? __ldg(e + q * G_) : make_int2(-1, 0);
+  P.n_ov = 0;
+}
+
+// second half of the prefetch, issued once the entries have landed (after the elimination of the
+// previous front): the values of the leading original-data entries (Jacobian slots and right-hand
+// side rows come from HBM; nothing in them depends on the children)
+__device__ __forceinline__ void asm_prefetch_values(AsmPre& P, const FrontHdr& H, const FactorArgs& A) {
+#ifndef SZB_VALUE_PREFETCH   // measured slower: the dependent value loads stall the warp before the write-out
+  return;
+#endif
+  if (A.mvals != nullptr || A.smask != nullptr || A.scale != 1.0) return;
+  const int n = min(H.itO, kAsmO);
+  const bool with_rhs = A.rhs != nullptr;
+#pragma unroll
+  for (int q = 0; q < kAsmO; ++q) {
+    double v = 0.0;
+    if (q < n) {
+      const unsigned sr = static_cast<unsigned>(P.en[q].x);
+      const unsigned tag = sr >> 30;
+      const int off = static_cast<int>(sr & 0x3fffffffu);
+      if (tag == 1u) v = A.jv[off];
+      else if (tag == 2u && with_rhs) v = A.rhs[off];
+    }
+    P.ov[q] = v;
+  }
+  P.n_ov = n;
+}
+
+template <bool PLAIN>
+__device__ __forceinline__ double asm_fetch(const unsigned sr, const FactorArgs& A) {
+  const unsigned tag = sr >> 30;
+  const int off = static_cast<int>(sr & 0x3fffffffu);
+  if (PLAIN) {   // A = J: the value fetch is a pointer select
+    const double* base = tag == 0u ? A.cb : (tag == 1u ? A.jv : A.rhs);
+    return base[off];
+  } else {
+    if (tag == 1u) {
+      const double mv = A.mvals ? A.mvals[off] : 0.0;
+      const double mk = A.smask ? A.smask[off] : 1.0;
+      return fma(A.scale * mk, A.jv[off], mv);
+    }
+    const double* base = tag == 0u ? A.cb : A.rhs;
+    return base[off];
+  }
+}
+
+template <bool PLAIN>
+__device__ __forceinline__ void assemble_stream(const AsmPre& P, const int rank, const int G_, const FrontHdr& H,
+                                                const int2* __restrict__ ga, double* __restrict__ Fm,
+                                                const FactorArgs& A) {
+  const bool with_rhs = A.rhs != nullptr;
+  const int iters = asm_iters(H, with_rhs);
+  const int2* __restrict__ e = ga + H.gaO + rank;
+  // an entry is dead when it is padding, or a right-hand-side row while no right-hand side rides along
+  auto live = [=](const int2 en) {
+    return en.x != -1 && (with_rhs || (static_cast<unsigned>(en.x) >> 30) != 2u);
+  };
+  // Most fronts of the tree are tiny: their whole stream is one or two entries per thread.  The first
+  // batch is therefore specialised on its length (2, 4 or 8 slots) -- an unrolled 8-slot batch executes
+  // its ~30 instructions per slot whether the slot is live or not.
+  auto first_batch = [&](auto nslots) {
+    constexpr int N = decltype(nslots)::value;
+    double v[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      if (q < kAsmO && q < P.n_ov) v[q] = P.ov[q];
+      else v[q] = live(P.en[q]) ? asm_fetch<PLAIN>(static_cast<unsigned>(P.en[q].x), A) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+      if (live(P.en[q])) Fm[P.en[q].y] += v[q];
+  };
+  if (iters <= 2) { first_batch(std::integral_constant<int, 2>{}); return; }
+  if (iters <= 4) { first_batch(std::integral_constant<int, 4>{}); return; }
+  // software pipeline: the entries of batch k+1 are in flight while the values of batch k are fetched
+  int2 en[kAsm];
+#pragma unroll
+  for (int q = 0; q < kAsm; ++q) en[q] = kAsm + q < iters ? __ldg(e + (kAsm + q) * G_) : make_int2(-1, 0);
+  first_batch(std::integral_constant<int, kAsm>{});
+  if (iters <= kAsm) return;
+  for (int it = kAsm; it < iters; it += kAsm) {
+    int2 nx[kAsm];
+    double v[kAsm];
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q) nx[q] = it + kAsm + q < iters ? __ldg(e + (it + kAsm + q) * G_) : make_int2(-1, 0);
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q) v[q] = live(en[q]) ? asm_fetch<PLAIN>(static_cast<unsigned>(en[q].x), A) : 0.0;
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q)
+      if (live(en[q])) Fm[en[q].y] += v[q];
+#pragma unroll
+    for (int q = 0; q < kAsm; ++q) en[q] = nx[q];
+  }
+}
+
+__device__ __forceinline__ void assemble_front(const AsmPre& P, const int rank, const int G_, const FrontHdr& H,
+                                               const int2* __restrict__ ga, double* __restrict__ Fm,
+                                               const FactorArgs& A) {
+  if (A.mvals == nullptr && A.smask == nullptr && A.scale == 1.0) assemble_stream<true>(P, rank, G_, H, ga, Fm, A);
+  else assemble_stream<false>(P, rank, G_, H, ga, Fm, A);
+}
+
+// ---- single warp, fronts with at most 32 rows: right-looking rank-1 steps, lane = row.  When the
+// trailing block has m <= 16 (<= 8) rows, two (four) columns are updated per warp instruction so that
+// all lanes stay busy on the tiny fronts that make up most of the tree.
+__device__ __forceinline__ void eliminate_warp(double* __restrict__ Fm, const int s, const int f,
+                                               const int ncol, const int ld, const int lane, int* flag) {
+  // The reciprocal of the NEXT pivot is computed by every lane from three broadcast values while the
+  // trailing update of the current pivot runs, so the dependent chain per pivot is one shuffle, one
+  // multiply-add and the update loop -- not load -> reciprocal -> scale -> update.
+  double piv = Fm[0];
+  double inv = fast_rcp(piv);
+  for (int p = 0; p < s; ++p) {
+    const int m = f - p - 1;
+    const int nc = ncol - p - 1;
+    double* __restrict__ colp = Fm + (p + 1) + p * ld;
+    if (lane == 0) check_pivot(piv, flag);
+    const bool more = p + 1 < s;                        // then m >= 1
+    const double a_next = more ? colp[ld] : 1.0;        // F[p+1][p+1] before this step's update
+    const double c_next = more ? colp[ld - 1] : 0.0;    // F[p][p+1]
+    const int sh = m <= 8 ? 3 : (m <= 16 ? 4 : 5);      // rows per column slot = 1 << sh
+    const int i = lane & ((1 << sh) - 1);
+    const int cj = lane >> sh;                          // column slot of this lane
+    const int cpw = 32 >> sh;                           // columns per warp instruction
+    const bool row_ok = i < m;
+    const double l = row_ok ? colp[i] * inv : 0.0;
+    const double l_next = __shfl_sync(0xffffffffu, l, 0);   // l of row p+1 (lane 0: i = 0, slot 0)
+    if (cj == 0 && row_ok) colp[i] = l;                 // L stored scaled (only its own lane reads colp[i])
+    piv = fma(-l_next, c_next, a_next);                 // exactly what the update below stores at (p+1, p+1)
+    const double inv_next = fast_rcp(piv);
+    double* __restrict__ col = Fm + (p + 1) + (p + 1 + cj) * ld;
+    const int step = cpw * ld;
+    for (int j = cj; j < nc; j += 4 * cpw, col += 4 * step) {
+      const bool k1 = j + cpw < nc, k2 = j + 2 * cpw < nc, k3 = j + 3 * cpw < nc;
+      const double u0 = col[-1];
+      const double u1 = k1 ? col[step - 1] : 0.0;
+      const double u2 = k2 ? col[2 * step - 1] : 0.0;
+      const double u3 = k3 ? col[3 * step - 1] : 0.0;
+      if (row_ok) {
+        const double v0 = col[i];
+        const double v1 = k1 ? col[step + i] : 0.0;
+        const double v2 = k2 ? col[2 * step + i] : 0.0;
+        const double v3 = k3 ? col[3 * step + i] : 0.0;
+        col[i] = fma(-l, u0, v0);
+        if (k1) col[step + i] = fma(-l, u1, v1);
+        if (k2) col[2 * step + i] = fma(-l, u2, v2);
+        if (k3) col[3 * step + i] = fma(-l, u3, v3);
+      }
+    }
+    __syncwarp();
+    inv = inv_next;
+  }
+}
+
+// ---- several warps: blocked right-looking elimination, NB = 4 pivots per panel; everything that is a
+// product of matrices runs on the fp64 tensor-core path (mma.sync.m8n8k4.f64: the rank-4 update of an
+// 8x8 tile is ONE warp instruction instead of eight; tools/lu_micro.cu: phase B of a 128-front runs
+// at the fp64 peak of the SM).
+//
+//   panel t = pivots [p0, p0+nb), r0 = p0+nb.  With D = L11 U11 the 4x4 diagonal block,
+//       Lt = A21 D^{-1} (= L21 L11^{-1}),   A22 -= Lt A12,   L21 = Lt L11
+//   so the trailing update only reads the *unsolved* top rows A12 and the Lt side panel: nothing
+//   in the front is rewritten before the update starts.  Per panel:
+//     phase A  (all warps, one 8-row tile at a time) -Lt = -(A21 D^{-1}) as one DMMA against the
+//              explicit 4x4 inverse published by the diagonal warp, into the side panel; when L is
+//              wanted, L21 = Lt L11 (one more DMMA) goes straight to the factor storage;
+//     phase B  (worker warps) the trailing block is cut into strips of 32 rows x 8 columns = four
+//              8x8 accumulator tiles; a warp keeps the four A fragments (-Lt) of its 32 rows in
+//              registers, and per strip loads one B fragment (top rows) and the accumulators,
+//              issues 4 DMMAs and stores.  The front's leading dimension is 2 (mod 4), which makes the
+//              accumulator loads / stores conflict-free (ld_blk); the side panel's stride is 4 (mod 16)
+//              for the A fragments;
+//   meanwhile warp 0 (the diagonal warp) prepares the NEXT diagonal block: it alone owns the 8x8 tile
+//   around it, applies panel t to that tile (one DMMA), then factors and inverts the 4x4 block
+//   redundantly in registers (no shuffles): the only serial chain per panel is 4 dependent reciprocals
+//   (`rcp.approx` + 2 Newton steps, 56 instead of 80 cycles) plus two short triangular solves, off the
+//   workers' path.  The U rows are solved once at the end (finalize_u), and L21 never goes back to
+//   shared memory.
+__device__ __forceinline__ void dmma(double& c0, double& c1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// LU of the nb x nb block at (q0, q0) by one warp, in place (identity-padded to 4x4, all lanes compute
+// redundantly in registers, lane 0 writes), and its explicit inverse D^{-1} (column-major 4x4) to dinv
+// (lane c < 4 owns column c: L y = e_c, U x = y).
+__device__ __forceinline__ void diag_block(double* __restrict__ Fm, double* __restrict__ dinv, const int q0,
+                                           const int nb, const int ld, const int lane, int* flag) {
+  double a[kNB][kNB];
+  double* __restrict__ b = Fm + q0 + q0 * ld;
+#pragma unroll
+  for (int j = 0; j < kNB; ++j)
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) a[i][j] = (i < nb && j < nb) ? b[i + j * ld] : (i == j ? 1.0 : 0.0);
+  double r[kNB];
+#pragma unroll
+  for (int k = 0; k < kNB; ++k) {
+    if (lane == 0 && k < nb) check_pivot(a[k][k], flag);
+    r[k] = fast_rcp(a[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < kNB; ++i) {
+      a[i][k] *= r[k];
+#pragma unroll
+      for (int j = k + 1; j < kNB; ++j) a[i][j] = fma(-a[i][k], a[k][j], a[i][j]);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kNB; ++j)
+#pragma unroll
+      for (int i = 0; i < kNB; ++i)
+        if (i < nb && j < nb) b[i + j * ld] = a[i][j];
+  }
+  const int c = lane & (kNB - 1);
+  double y[kNB], x[kNB];
+#pragma unroll
+  for (int k = 0; k < kNB; ++k) {
+    double v = (k == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int q = 0; q < k; ++q) v = fma(-a[k][q], y[q], v);
+    y[k] = v;
+  }
+#pragma unroll
+  for (int k = kNB - 1; k >= 0; --k) {
+    double v = y[k];
+#pragma unroll
+    for (int q = k + 1; q < kNB; ++q) v = fma(-a[k][q], x[q], v);
+    x[k] = v * r[k];
+  }
+  if (lane < kNB) {
+#pragma unroll
+    for (int k = 0; k < kNB; ++k) dinv[k + kNB * lane] = x[k];
+  }
+}
+
+// phase A, one 8-row tile (rows r0 + 8*rt .. +7 of the panel columns): -Lt into the side panel, L21 to
+// the factor storage when Lg != null.  bd: B fragment of D^{-1}, bl: B fragment of L11 (columns >= 4: 0).
+__device__ __forceinline__ void lt_tile(const double* __restrict__ Fm, double* __restrict__ lt, const int lts,
+                                        double* __restrict__ Lg, const int p0, const int nb, const int f,
+                                        const int ld, const int rt, const double bd, const double bl,
+                                        const int lane) {
+  const int r0 = p0 + nb, m = f - r0;
+  const int q = lane & 3, g8 = lane >> 2;
+  const int row = 8 * rt + g8;                           // relative to r0; a live tile has 8*rt < m
+  const double a0 = q < nb ? Fm[r0 + row + (p0 + q) * ld] : 0.0;   // rows beyond the front: zero padding
+  double c0 = 0.0, c1 = 0.0;
+  dmma(c0, c1, a0, bd);
+  if (q < 2) {                                           // columns 2q, 2q+1 < 4 of the 8-wide accumulator
+    lt[(2 * q) * lts + row] = -c0;
+    lt[(2 * q + 1) * lts + row] = -c1;
+  }
+  if (Lg != nullptr) {
+    __syncwarp();
+    const double x0 = lt[q * lts + row];
+    double d0 = 0.0, d1 = 0.0;
+    dmma(d0, d1, x0, bl);
+    if (row < m && q < 2) {
+      double* __restrict__ dst = Lg + (r0 + row) + (p0 + 2 * q) * f;
+      if (2 * q < nb) dst[0] = -d0;
+      if (2 * q + 1 < nb) dst[f] = -d1;
+    }
+  }
+}
+
+// phase B, one warp: R row tiles (rows r0 + row0 .. + 8R-1, all of them holding rows of the front) x the
+// column tiles cg, cg + CW, ... < ct_end of the 8-column tiles right of the panel.  No masks and no
+// predicates (a predicated variant costs spills): tiles that overhang the front live in its zero padding
+// (kPad).  Per strip: 1 + 2R loads, R DMMAs, 2R stores, all with immediate offsets from two running pointers.
+template <int R>
+__device__ __forceinline__ void trailing_strips(double* __restrict__ Fm, const double* __restrict__ lt,
+                                                const int lts, const int p0, const int nb, const int ld,
+                                                const int row0, const int cg, const int CW, const int ct_end,
+                                                const int lane) {
+  const int r0 = p0 + nb;
+  const int q = lane & 3, g8 = lane >> 2;
+  double xa[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) xa[r] = lt[q * lts + row0 + 8 * r + g8];
+  const int cstep = 8 * CW * ld;
+  const double* __restrict__ bp = Fm + p0 + (q < nb ? q : 0) + (r0 + 8 * cg + g8) * ld;   // stays inside the panel rows
+  double* __restrict__ cp = Fm + r0 + row0 + g8 + (r0 + 8 * cg + 2 * q) * ld;
+  for (int ct = cg; ct < ct_end; ct += CW, bp += cstep, cp += cstep) {
+    const double b0 = bp[0];
+    double c0[R], c1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      c0[r] = cp[8 * r];
+      c1[r] = cp[ld + 8 * r];
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      dmma(c0[r], c1[r], xa[r], b0);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cp[8 * r] = c0[r];
+      cp[ld + 8 * r] = c1[r];
+    }
+  }
+}
+
+// up to four row tiles from row0: as many as hold rows of the trailing block (m rows)
+__device__ __forceinline__ void trailing_rows(double* __restrict__ Fm, const double* __restrict__ lt, const int lts,
+                                              const int p0, const int nb, const int m, const int ld, const int row0,
+                                              const int cg, const int CW, const int ct_end, const int lane) {
+  const int nt = (m - row0 + 7) >> 3;
+  if (nt >= 4) trailing_strips<4>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
+  else if (nt == 3) trailing_strips<3>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
+  else if (nt == 2) trailing_strips<2>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
+  else if (nt == 1) trailing_strips<1>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
+}
+
+// deferred triangular solves of the U rows: for every panel and every column right of it
+//   u = L11^{-1} a   (up to 4 values per column, lanes over columns, warps over panels)
+__device__ __forceinline__ void finalize_u(double* __restrict__ Fm, const int s, const int ncol, const int ld,
+                                           const int lane, const int w, const int nw) {
+  const int npan = (s + kNB - 1) / kNB;
+  for (int t = w; t < npan; t += nw) {
+    const int p0 = t * kNB;
+    const int nb = min(kNB, s - p0);
+    if (nb < 2) continue;
+    const double* __restrict__ blk = Fm + p0 + p0 * ld;
+    for (int j = p0 + nb + lane; j < ncol; j += kWarp) {
+      double* __restrict__ col = Fm + p0 + j * ld;
+      double u[kNB];
+#pragma unroll
+      for (int k = 0; k < kNB; ++k) {
+        if (k < nb) {
+          double v = col[k];
+#pragma unroll
+          for (int q2 = 0; q2 < k; ++q2) v = fma(-blk[k + q2 * ld], u[q2], v);
+          u[k] = v;
+          if (k > 0) col[k] = v;
+        }
+      }
+    }
+  }
+}
+
+// a group of `nw` consecutive warps with one hardware named barrier
+struct PanelGrp {
+  int id, nw, w0;
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int warp() const { return (threadIdx.x >> 5) - w0; }
+  __device__ __forceinline__ int rank() const { return threadIdx.x - (w0 << 5); }
+  __device__ __forceinline__ int size() const { return nw << 5; }
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nw << 5) : "memory");
+  }
+};
+
+#if defined(SZB_PHASE_TIMING) && !defined(SZB_LEVEL_ONLY)
+#define SZB_FINE_TIMING
+#endif
+#ifdef SZB_PHASE_TIMING
+__device__ long long g_el[8 * 8];
+#endif
+#ifdef SZB_FINE_TIMING
+#define SZB_E(i) { const long long now_ = clock64(); el_[i] += now_ - te_; te_ = now_; }
+#else
+#define SZB_E(i)
+#endif
+// Not inlined on purpose: the elimination gets the full register budget to itself (the caller's
+// prefetched assembly state is saved once per front).  The buffers are passed as offsets into the
+// dynamic shared memory so that the compiler keeps the LDS / STS forms; SM_FRONT = false: the front
+// itself lives in a global workspace (FmG), only the side panel and the inverse are on chip.
+template <bool SM_FRONT>
+__device__ __noinline__ void eliminate_blocked(const PanelGrp g, double* FmG, const int fm_off, const int lt_off,
+                                               const int lts, double* __restrict__ Lg, const int s, const int f,
+                                               const int ncol, const int ld, int* flag) {
   extern __shared__ double sm[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n_groups = (*npos + kGroup - 1) / kGroup;
-  const Tabs T = make_tabs(S);
-  int wq0 = 0, wq1 = 0;
-  if (LEVEL == 0 && w < S.n_warp_lists) { wq0 = S.wl_ptr[w]; wq1 = S.wl_ptr[w + 1]; }
-  if (LEVEL == 1 && w < S.n_mid_lists) { wq0 = S.n_warp_sn + S.ml_ptr[w]; wq1 = S.n_warp_sn + S.ml_ptr[w + 1]; }
-  for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-    const int b = map[g * kGroup + lane];
-    Lane L;
-    L.valid = b >= 0;
-    L.lu = LU + static_cast<size_t>(g) * S.lu_size * kGroup + lane;
-    L.cb = CBW + static_cast<size_t>(g) * S.cb_size * kGroup + lane;
-    L.cbsrc = L.cb;
-    L.y = YI + static_cast<size_t>(g) * S.n * kGroup + lane;
-    L.jv = L.valid ? JV + static_cast<size_t>(b) * S.nnz_a : nullptr;
-    L.with_rhs = RHS != nullptr;
-    L.rhs = (L.valid && RHS) ? RHS + static_cast<size_t>(b) * S.n : nullptr;
-    L.mvals = mvals;
-    L.smask = slot_mask;
-    L.scale = (L.valid && scale_b) ? scale_b[b] : scale_const;
-    L.plain = mvals == nullptr && slot_mask == nullptr && scale_b == nullptr && scale_const == 1.0;
-    L.amax = 0.0; L.umax = 0.0; L.bad = 0;
-#ifdef SZB_LU_TIMING
-    long long tacc[8];
-    for (int i = 0; i < 8; ++i) tacc[i] = 0;
-    L.tacc = tacc; L.tbase = 0;
-    const long long tl0 = clock64();
+  double* __restrict__ Fm = SM_FRONT ? sm + fm_off : FmG;
+  double* __restrict__ lt = sm + lt_off;
+  double* __restrict__ dinv = lt + kNB * lts;
+  const int lane = g.lane(), w = g.warp(), nw = g.nw;
+  const int q = lane & 3, g8 = lane >> 2;
+  const int npan = (s + kNB - 1) / kNB;
+#ifdef SZB_FINE_TIMING
+  const bool dbg_ = blockIdx.x == 0 && g.id == 0 && (threadIdx.x & 127) == 0;
+  long long el_[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long te_ = clock64();
 #endif
-    if (LEVEL == 0) {
-      const Coop C{0, 1, false};
-      double* buf = sm + static_cast<size_t>(w) * kWarpLines * kGroup + lane;
-      for (int q = wq0; q < wq1; ++q) factor_front_buffered(L, load_front(T.fh, q), T, C, buf);
-    } else if (LEVEL == 1) {
-      const Coop C{0, 1, false};
-      double* tbuf = sm + static_cast<size_t>(w) * kTileScratch * kGroup + lane;
-      for (int q = wq0; q < wq1; ++q) factor_front_tiled(L, load_front(T.fh, q), T, C, tbuf, nullptr);
+  if (w == 0) diag_block(Fm, dinv, 0, min(kNB, s), ld, lane, flag);
+  g.sync();
+  SZB_E(0)
+  for (int t = 0; t < npan; ++t) {
+    const int p0 = t * kNB;
+    const int nb = min(kNB, s - p0);
+    const int r0 = p0 + nb;
+    const bool has_next = t + 1 < npan;
+    const int m = f - r0;
+    // ---- phase A
+    const int nrt = (m + 7) >> 3;
+    if (w < nrt) {
+      const double bd = g8 < kNB ? dinv[q + kNB * g8] : 0.0;               // B[k][col] = Dinv[k][col]
+      double bl = 0.0;
+      if (Lg != nullptr)                                 // B[k][col] = L11[k][col] (unit lower, identity-padded)
+        bl = q == g8 ? 1.0 : ((q > g8 && q < nb) ? Fm[(p0 + q) + (p0 + g8) * ld] : 0.0);
+      for (int rt = w; rt < nrt; rt += nw) lt_tile(Fm, lt, lts, Lg, p0, nb, f, ld, rt, bd, bl, lane);
+    }
+    SZB_E(2)
+    g.sync();
+    SZB_E(3)
+    // ---- phase B
+    if (has_next && w == 0) {
+      // the diagonal warp: panel t applied to the 8x8 tile around the next diagonal block, then LU + inverse
+      trailing_strips<1>(Fm, lt, lts, p0, nb, ld, 0, 0, 1, 1, lane);
+      __syncwarp();
+      diag_block(Fm, dinv, r0, min(kNB, s - r0), ld, lane, flag);
+      SZB_E(1)
+    } else if (m > 0) {
+      const int W = has_next ? nw - 1 : nw;            // worker warps
+      const int ww = has_next ? w - 1 : w;
+      const int nch = (m + 31) >> 5;                   // row groups of 32 rows
+      const int nct = (ncol - r0 + 7) >> 3;            // column tiles
+      const int CW = max(1, min(W / nch, nct));        // warps that share a row group, striding over the column tiles
+      const int ntile = nch * CW;
+      const float inv_cw = 1.0f / static_cast<float>(CW);
+      for (int tile = ww; tile < ntile; tile += W) {
+        const int tr = nch == 1 ? 0 : fdiv(tile, inv_cw);
+        const int cg = tile - tr * CW;
+        if (tile == 0 && has_next) {                   // tile (0, 0) belongs to the diagonal warp
+          const int n3 = min(3, (m - 1) >> 3);          // rows 8.. of the first column tile
+          if (n3 == 3) trailing_strips<3>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane);
+          else if (n3 == 2) trailing_strips<2>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane);
+          else if (n3 == 1) trailing_strips<1>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane);
+          trailing_rows(Fm, lt, lts, p0, nb, m, ld, 0, CW, CW, nct, lane);
+        } else {
+          trailing_rows(Fm, lt, lts, p0, nb, m, ld, tr << 5, cg, CW, nct, lane);
+        }
+      }
+    }
+    SZB_E(4)
+    g.sync();
+    SZB_E(5)
+  }
+  finalize_u(Fm, s, ncol, ld, lane, w, nw);
+  g.sync();
+  SZB_E(6)
+#ifdef SZB_FINE_TIMING
+  if (dbg_) for (int i = 0; i < 7; ++i) g_el[8 * (threadIdx.x >> 7 & 7) + i] += el_[i];
+#endif
+}
+
+
+// ---- fronts too large for shared memory: the front lives in the per-CTA global workspace (L2), and a
+// rank-4 pass over the whole trailing block per panel would stream it from L2 once per 4 pivots.  Here the
+// pivots are taken in OUTER blocks of NO (<= 32) = NO/4 inner panels:
+//   * an inner panel updates at once only what the rest of its outer block needs: the tiles whose row OR
+//     column tile index lies inside the block (an L-shaped band, ~8/(m/8) of the trailing block);
+//   * the -Lt columns of all inner panels stay in shared memory (NO x lts doubles -- that is what the
+//     shared memory of this mode is for), the unsolved top rows stay in the front;
+//   * after the last inner panel ONE pass over the far trailing block (row and column tile index behind the
+//     block) applies all NO pivots: per 8x8 accumulator tile one load, NO/4 DMMAs, one store.
+// Tiles are anchored at absolute multiples of 8 here; rows / columns of a tile that lie before the current
+// panel are masked through the operands (their -Lt rows are written as zeros, their top-row fragment is 0),
+// so straddling tiles need no predicates on the accumulators.  Same mathematics as eliminate_blocked:
+// the far block receives sum_t Lt(t) A12(t) with every A12(t) already updated by the panels before t.
+template <int R>
+__device__ __forceinline__ void strip_abs(double* __restrict__ Fm, const double* __restrict__ ltk, const int lts,
+                                          const int p0, const int nb, const int r0, const int ld, const int tr,
+                                          const int tc, const int lane) {
+  const int q = lane & 3, g8 = lane >> 2;
+  double xa[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) xa[r] = ltk[q * lts + 8 * (tr + r) + g8];
+  const int col = 8 * tc + g8;
+  const double b0 = (q < nb && col >= r0) ? Fm[p0 + q + col * ld] : 0.0;
+  double* __restrict__ cp = Fm + 8 * tr + g8 + (8 * tc + 2 * q) * ld;
+  double c0[R], c1[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    c0[r] = cp[8 * r];
+    c1[r] = cp[ld + 8 * r];
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) dmma(c0[r], c1[r], xa[r], b0);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    cp[8 * r] = c0[r];
+    cp[ld + 8 * r] = c1[r];
+  }
+}
+
+__device__ __forceinline__ void strip_abs_n(const int nt, double* __restrict__ Fm, const double* __restrict__ ltk,
+                                            const int lts, const int p0, const int nb, const int r0, const int ld,
+                                            const int tr, const int tc, const int lane) {
+  if (nt >= 4) strip_abs<4>(Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+  else if (nt == 3) strip_abs<3>(Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+  else if (nt == 2) strip_abs<2>(Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+  else if (nt == 1) strip_abs<1>(Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+}
+
+// far pass: R row tiles x NC (1 or 2) adjacent column tiles, all npi inner panels of the outer block
+// [c0, cend).  Two column tiles share the -Lt fragments and put twice the loads in flight per warp (the
+// pass is bound by L2 latency at 16 warps per SM).
+template <int R, int NC>
+__device__ __forceinline__ void strip_far(double* __restrict__ Fm, const double* __restrict__ lt, const int lts,
+                                          const int c0, const int cend, const int npi, const int ld, const int tr,
+                                          const int tc, const int lane) {
+  const int q = lane & 3, g8 = lane >> 2;
+  double* __restrict__ cp = Fm + 8 * tr + g8 + (8 * tc + 2 * q) * ld;
+  const double* __restrict__ bp = Fm + (8 * tc + g8) * ld;
+  double c0v[NC][R], c1v[NC][R];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      c0v[c][r] = cp[c * 8 * ld + 8 * r];
+      c1v[c][r] = cp[c * 8 * ld + ld + 8 * r];
+    }
+  // all top-row fragments of the strip first (one L2 round trip instead of one per inner panel)
+  double bv[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      const int row = c0 + 4 * kb + q;
+      bv[c][kb] = (kb < npi && row < cend) ? bp[c * 8 * ld + row] : 0.0;
+    }
+  const double* __restrict__ la = lt + q * lts + 8 * tr + g8;
+#pragma unroll
+  for (int kb = 0; kb < 8; ++kb) {
+    if (kb < npi) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double xa = la[kb * 4 * lts + 8 * r];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dmma(c0v[c][r], c1v[c][r], xa, bv[c][kb]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cp[c * 8 * ld + 8 * r] = c0v[c][r];
+      cp[c * 8 * ld + ld + 8 * r] = c1v[c][r];
+    }
+}
+
+template <int NC>
+__device__ __forceinline__ void strip_far_n(const int nt, double* __restrict__ Fm, const double* __restrict__ lt,
+                                            const int lts, const int c0, const int cend, const int npi, const int ld,
+                                            const int tr, const int tc, const int lane) {
+  if (nt >= 4) strip_far<4, NC>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+  else if (nt == 3) strip_far<3, NC>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+  else if (nt == 2) strip_far<2, NC>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+  else strip_far<1, NC>(Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+}
+
+__device__ __noinline__ void eliminate_global(const PanelGrp g, double* __restrict__ Fm, const int lt_off,
+                                              const int lts, const int NO, double* __restrict__ Lg, const int s,
+                                              const int f, const int ncol, const int ld, int* flag) {
+  extern __shared__ double sm[];
+  double* __restrict__ lt = sm + lt_off;               // NO columns of -Lt, rows indexed absolutely
+  double* __restrict__ dinv = lt + NO * lts;
+  const int lane = g.lane(), w = g.warp(), nw = g.nw;
+  const int q = lane & 3, g8 = lane >> 2;
+  const int trmax = (f - 1) >> 3, tcmax = (ncol - 1) >> 3;
+  if (w == 0) diag_block(Fm, dinv, 0, min(kNB, s), ld, lane, flag);
+  g.sync();
+  for (int c0 = 0; c0 < s; c0 += NO) {
+    const int cend = min(s, c0 + NO);
+    const int npi = (cend - c0 + kNB - 1) / kNB;
+    const int tb = (cend + 7) >> 3;                    // first tile index behind the block
+    bool next_done = false;                            // the diagonal block at cend is already factored
+    for (int ti = 0; ti < npi; ++ti) {
+      const int p0 = c0 + kNB * ti;
+      const int nb = min(kNB, cend - p0);
+      const int r0 = p0 + nb;
+      const bool has_next = r0 < s;
+      const int tr0 = r0 >> 3;
+      double* __restrict__ ltk = lt + kNB * ti * lts;
+      // ---- phase A: -Lt of this inner panel for every row tile from the one that holds r0
+      {
+        const double bd = g8 < kNB ? dinv[q + kNB * g8] : 0.0;
+        double bl = 0.0;
+        if (Lg != nullptr) bl = q == g8 ? 1.0 : ((q > g8 && q < nb) ? Fm[(p0 + q) + (p0 + g8) * ld] : 0.0);
+        // the A21 values of up to eight row tiles of this warp are fetched first: one L2 round trip per
+        // batch instead of one per tile
+        for (int trb = tr0 + w; trb <= trmax; trb += 8 * nw) {
+          double av[8];
+#pragma unroll
+          for (int u8 = 0; u8 < 8; ++u8) {
+            const int row = 8 * (trb + u8 * nw) + g8;
+            av[u8] = (trb + u8 * nw <= trmax && q < nb && row >= r0) ? Fm[row + (p0 + q) * ld] : 0.0;
+          }
+#pragma unroll
+          for (int u8 = 0; u8 < 8; ++u8) {
+            const int tr = trb + u8 * nw;
+            if (tr <= trmax) {
+              const int row = 8 * tr + g8;
+              double c0v = 0.0, c1v = 0.0;
+              dmma(c0v, c1v, av[u8], bd);
+              if (q < 2) {
+                ltk[(2 * q) * lts + row] = -c0v;
+                ltk[(2 * q + 1) * lts + row] = -c1v;
+              }
+              if (Lg != nullptr) {
+                __syncwarp();
+                double d0 = 0.0, d1 = 0.0;
+                dmma(d0, d1, ltk[q * lts + row], bl);
+                if (row >= r0 && row < f && q < 2) {
+                  double* __restrict__ dst = Lg + row + (p0 + 2 * q) * f;
+                  if (2 * q < nb) dst[0] = -d0;
+                  if (2 * q + 1 < nb) dst[f] = -d1;
+                }
+              }
+            }
+          }
+        }
+      }
+      g.sync();
+      // ---- phase B, the L-shaped band: tiles (tr, tc) with tr0 <= tr, tc and (tr < tb or tc < tb)
+      const bool look = has_next && tr0 < tb;          // the next diagonal block lies inside the band
+      if (look && w == 0) {
+        strip_abs<1>(Fm, ltk, lts, p0, nb, r0, ld, tr0, tr0, lane);
+        __syncwarp();
+        diag_block(Fm, dinv, r0, min(kNB, s - r0), ld, lane, flag);
+        if (r0 == cend) next_done = true;
+      } else {
+        const int W = look ? nw - 1 : nw, ww = look ? w - 1 : w;
+        const int ncC = max(0, min(tb, tcmax + 1) - tr0);               // column tiles inside the block
+        const int nchC = (trmax - tr0 + 4) >> 2;                        // chunks of 4 row tiles, all rows
+        const int nrR = max(0, min(tb, trmax + 1) - tr0);               // row tiles inside the block
+        const int nchR = (nrR + 3) >> 2;
+        const int ncR = max(0, tcmax - tb + 1);                         // column tiles behind the block
+        const int JC = ncC * nchC, J = JC + ncR * nchR;
+        const float inv_c = 1.0f / static_cast<float>(max(nchC, 1)), inv_r = 1.0f / static_cast<float>(max(nchR, 1));
+        for (int j = ww; j < J; j += W) {
+          int tc, tr, nt;
+          if (j < JC) {
+            const int a = fdiv(j, inv_c);
+            tc = tr0 + a;
+            tr = tr0 + 4 * (j - a * nchC);
+            nt = min(4, trmax - tr + 1);
+          } else {
+            const int jr = j - JC, a = fdiv(jr, inv_r);
+            tc = tb + a;
+            tr = tr0 + 4 * (jr - a * nchR);
+            nt = min(4, tr0 + nrR - tr);
+          }
+          if (look && tr == tr0 && tc == tr0) { ++tr; --nt; }          // that tile belongs to the diagonal warp
+          strip_abs_n(nt, Fm, ltk, lts, p0, nb, r0, ld, tr, tc, lane);
+        }
+      }
+      g.sync();
+    }
+    // ---- far pass: everything behind the block takes all its pivots in one sweep
+    {
+      const int ntr = trmax - tb + 1, ntc = tcmax - tb + 1;
+      if (ntr > 0 && ntc > 0) {
+        const int nch = (ntr + 3) >> 2;                // chunks of 4 row tiles
+        const int npair = (ntc + 1) >> 1;              // pairs of column tiles
+        const float inv = 1.0f / static_cast<float>(nch);
+        for (int j = w; j < nch * npair; j += nw) {
+          const int a = fdiv(j, inv);
+          const int tc = tb + 2 * a, tr = tb + 4 * (j - a * nch);
+          const int nt = min(4, trmax - tr + 1);
+          if (tc + 1 <= tcmax) strip_far_n<2>(nt, Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+          else strip_far_n<1>(nt, Fm, lt, lts, c0, cend, npi, ld, tr, tc, lane);
+        }
+      }
+      g.sync();
+    }
+    if (cend < s && !next_done) {                       // the next block starts on a tile boundary: factor it now
+      if (w == 0) diag_block(Fm, dinv, cend, min(kNB, s - cend), ld, lane, flag);
+      g.sync();
+    }
+  }
+  finalize_u(Fm, s, ncol, ld, lane, w, nw);
+  g.sync();
+}
+
+#ifdef SZB_FINE_TIMING
+#define SZB_T(i) { const long long now_ = clock64(); tacc_[(i) + 4 * lvl_] += now_ - tprev_; tprev_ = now_; }
+#define SZB_TPARAM , long long* tacc_, const int lvl_
+#define SZB_TSTART long long tprev_ = clock64();
+#else
+#define SZB_T(i)
+#define SZB_TPARAM
+#define SZB_TSTART
+#endif
+
+__device__ __forceinline__ void clear_front(double* __restrict__ Fm, const int n_el, const int rank, const int G_) {
+  double2* __restrict__ p = reinterpret_cast<double2*>(Fm);
+  const int n2 = (n_el + 1) >> 1;
+  for (int t = rank; t < n2; t += G_) p[t] = make_double2(0.0, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------
+// numeric factorisation of one front; the front is column-major with leading dimension
+// ld = ld_warp(f) / ld_blk(f) and has f + 1 columns (the last one carries the right-hand side when one rides along).
+// ---------------------------------------------------------------------------------------
+// one warp, front of at most 32 rows
+__device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre& P, const int2* __restrict__ ga,
+                                  double* __restrict__ Fm, const FactorArgs& A SZB_TPARAM) {
+  SZB_TSTART
+  const int s = H.s, f = H.f, u = f - s, ld = ld_warp(f);
+  const int lane = threadIdx.x & 31;
+  const int with_rhs = A.rhs != nullptr;
+  const int ncol = f + with_rhs;
+  clear_front(Fm, ld * (f + 1), lane, kWarp);
+  __syncwarp();
+  assemble_front(P, lane, kWarp, H, ga, Fm, A);
+  asm_prefetch(P, Hnext, ga, lane, kWarp, with_rhs != 0);   // in flight during the elimination
+  __syncwarp();
+  SZB_T(0)
+  eliminate_warp(Fm, s, f, ncol, ld, lane, A.flag);
+  asm_prefetch_values(P, Hnext, A);                       // entries have landed; values fly during the write-out
+  SZB_T(1)
+  double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
+  {
+    const int rows = A.store_l ? f : s;
+    const float invr = 1.0f / static_cast<float>(rows);
+    for (int t = lane; t < rows * s; t += kWarp) {
+      const int p = fdiv(t, invr);
+      const int i = t - p * rows;
+      const double v = Fm[i + p * ld];
+      __stcs(Lp + i + p * f, i == p ? fast_rcp(v) : v);  // the diagonal of U is stored as its reciprocal
+    }
+  }
+  if (u > 0) {
+    double* __restrict__ Up = A.lu + H.up_off;           // U12, s x u column-major: Up[r + c*s]
+    double* C = A.cb + H.cb_off;                         // u x (u+1), column-major
+    const int nc = u + with_rhs;
+    const float invu = 1.0f / static_cast<float>(u);
+    const float invs = 1.0f / static_cast<float>(s);
+    for (int t = lane; t < u * s; t += kWarp) {
+      const int c = fdiv(t, invs);
+      const int rr = t - c * s;
+      __stcs(Up + t, Fm[rr + (s + c) * ld]);             // factors stream out: evict-first, the L2 is for the contribution blocks
+    }
+    for (int t = lane; t < u * nc; t += kWarp) {
+      const int j = fdiv(t, invu);
+      const int i = t - j * u;
+      C[t] = Fm[(s + i) + (s + j) * ld];
+    }
+  }
+  if (with_rhs && lane < s) A.yout[H.piv0 + lane] = Fm[lane + f * ld];
+  __syncwarp();
+  SZB_T(2)
+}
+
+// a group of warps
+// Fm: the front (shared memory at offset fm_off of the dynamic array when SM_FRONT, else the global
+// workspace); lt_off: offset of the side panel + inverse scratch in shared memory
+template <bool SM_FRONT>
+__device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const int4* __restrict__ fh,
+                                       const int q_next, AsmPre& P, const int2* __restrict__ ga,
+                                       double* __restrict__ Fm, const int fm_off, const int lt_off, const int lts,
+                                       const int outer_nb, const FactorArgs& A SZB_TPARAM) {
+  SZB_TSTART
+  const int s = H.s, f = H.f, u = f - s, ld = ld_blk(f);
+  const int lane = g.lane(), w = g.warp(), nw = g.nw, r = g.rank(), G_ = g.size();
+  const int with_rhs = A.rhs != nullptr;
+  const int ncol = f + with_rhs;
+#ifdef SZB_PHASE_TIMING
+  const long long tfg0_ = clock64();
+#endif
+  clear_front(Fm, ld * cols_blk(f), r, G_);
+  g.sync();
+#ifdef SZB_PHASE_TIMING
+  const long long tfg1_ = clock64();
+#endif
+  assemble_front(P, r, G_, H, ga, Fm, A);
+  g.sync();
+  SZB_T(0)
+  double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
+#ifdef SZB_PHASE_TIMING
+  const long long tel0_ = clock64();
+#endif
+  const FrontHdr Hnext = load_hdr(fh, q_next);          // lands during the elimination
+  if (SM_FRONT) eliminate_blocked<true>(g, Fm, fm_off, lt_off, lts, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
+  else eliminate_global(g, Fm, lt_off, lts, outer_nb, A.store_l ? Lp : nullptr, s, f, ncol, ld, A.flag);
+#ifdef SZB_PHASE_TIMING
+  const long long tel1_ = clock64();
+  if (blockIdx.x == 0 && g.rank() == 0 && g.id <= 1) {
+    g_el[56 + g.id] += tel1_ - tel0_;                  // [56] CTA level, [57] group 0: elimination
+    g_el[58 + g.id] += tfg1_ - tfg0_;                  // clear
+    g_el[60 + g.id] += tel0_ - tfg1_;                  // assembly (incl. its barrier)
+  }
+#endif
+  // the next front's descriptor and first gather entries fly during the write-out (nothing of them is
+  // kept across the elimination: it has the register file to itself)
+  asm_prefetch(P, Hnext, ga, r, G_, with_rhs != 0);
+  SZB_T(1)
+  // rows below a column's own panel were streamed by the workers (or are not wanted)
+  for (int p = w; p < s; p += nw) {
+    const int pend = min(s, (p & ~(kNB - 1)) + kNB);
+    const double* __restrict__ src = Fm + p * ld;
+    double* __restrict__ dst = Lp + p * f;
+    for (int i = lane; i < pend; i += kWarp) __stcs(dst + i, i == p ? fast_rcp(src[i]) : src[i]);   // 1 / u_pp on the diagonal
+  }
+  if (u > 0) {
+    // lanes over the long dimension, pointer walks over the short one: no index arithmetic inside
+    double* __restrict__ Up = A.lu + H.up_off;           // U12, s x u column-major: Up[r + c*s]
+    {
+      const float invs = 1.0f / static_cast<float>(s);
+      for (int t = r; t < u * s; t += G_) {
+        const int c = fdiv(t, invs);
+        const int rr = t - c * s;
+        __stcs(Up + t, Fm[rr + (s + c) * ld]);
+      }
+    }
+    double* C = A.cb + H.cb_off;                         // u x (u+1), column-major
+    const int nc = u + with_rhs;
+    for (int i = lane; i < u; i += kWarp) {
+      const double* __restrict__ src = Fm + (s + i) + (s + w) * ld;
+      double* dst = C + i + w * u;
+      for (int j = w; j < nc; j += nw, src += nw * ld, dst += nw * u) *dst = *src;
+    }
+  }
+  if (with_rhs)
+    for (int t = r; t < s; t += G_) A.yout[H.piv0 + t] = Fm[t + f * ld];
+  g.sync();
+#ifdef SZB_PHASE_TIMING
+  if (blockIdx.x == 0 && g.rank() == 0 && g.id <= 1) g_el[62 + g.id] += clock64() - tel1_;   // write-out
+#endif
+  SZB_T(2)
+  return Hnext;
+}
+
+// GLOBAL_TOP: some CTA-level fronts live in the global workspace FBW (a separate instantiation, so that the
+// register allocation of the all-in-shared-memory kernel does not pay for the call into eliminate_global)
+template <bool GLOBAL_TOP>
+__global__ void __launch_bounds__(SZB_FACTOR_THREADS, 1)
+lu_factor_kernel(const LuDev S, const double* __restrict__ JV, double* __restrict__ LU,
+                 double* CBW, double* FBW, const double* __restrict__ mvals,
+                 const double* __restrict__ slot_mask,
+                 const double* __restrict__ scale_b, double scale_const,
+                 const double* __restrict__ RHS, double* __restrict__ YOUT, int store_l,
+                 const int* __restrict__ active, int* __restrict__ flags, int B, int outer_nb, int smem_elems) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5;
+  const int wstride = front_elems_warp(S.f_warp_max);
+  const int gfront = front_elems_blk(S.f_group_max), glts = lt_stride(S.f_group_max);
+  const int gstride = group_elems(S.f_group_max);
+  const int tfront = front_elems_blk(S.f_top_max), tlts = lt_stride(S.f_top_max);
+  const int wpg = S.wpg;
+  // the work lists are the same for every scenario: fetch their bounds once
+  int wq0 = 0, wq1 = 0, gq0 = 0, gq1 = 0;
+  if (warp < S.n_warp_lists) { wq0 = S.wl_ptr[warp]; wq1 = S.wl_ptr[warp + 1]; }
+  const int gi = wpg > 0 ? warp / wpg : 0;
+  const bool in_group = S.n_group_lists > 0 && gi < S.n_group_lists;
+  if (in_group) { gq0 = S.n_warp_sn + S.gl_ptr[gi]; gq1 = S.n_warp_sn + S.gl_ptr[gi + 1]; }
+  const int tq0 = S.n_warp_sn + S.n_group_sn;
+#ifdef SZB_PHASE_TIMING
+  long long tacc_[16];
+  for (int i = 0; i < 16; ++i) tacc_[i] = 0;
+  long long nscen_ = 0;
+#define SZB_LVL(i) { const long long now_ = clock64(); tacc_[12 + (i)] += now_ - tlev_; tlev_ = now_; }
+#else
+#define SZB_LVL(i)
+#endif
+#ifdef SZB_FINE_TIMING
+#define SZB_TARG(l) , tacc_, l
+#else
+#define SZB_TARG(l)
+#endif
+  FactorArgs A;
+  A.mvals = mvals;
+  A.smask = slot_mask;
+  A.store_l = store_l;
+  A.cb = CBW + static_cast<size_t>(blockIdx.x) * S.cb_size;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    if (active && !active[b]) continue;
+    A.jv = JV + static_cast<size_t>(b) * S.nnz_a;
+    A.lu = LU + static_cast<size_t>(b) * S.lu_size;
+    A.scale = scale_b ? scale_b[b] : scale_const;
+    A.rhs = RHS ? RHS + static_cast<size_t>(b) * S.n : nullptr;
+    A.yout = YOUT ? YOUT + static_cast<size_t>(b) * S.n : nullptr;
+    A.flag = flags + b;
+#ifdef SZB_PHASE_TIMING
+    long long tlev_ = clock64();
+    ++nscen_;
+#endif
+    // level 0: warps
+    if (wq0 < wq1) {
+      double* Fm = sm + warp * wstride;
+      FrontHdr H = load_hdr(S.fh, wq0);
+      AsmPre P;
+      asm_prefetch(P, H, S.ga, threadIdx.x & 31, kWarp, A.rhs != nullptr);
+      for (int q = wq0; q < wq1; ++q) {
+        const FrontHdr Hn = load_hdr(S.fh, min(q + 1, wq1 - 1));   // the next descriptor
+        factor_front_warp(H, Hn, P, S.ga, Fm, A SZB_TARG(0));
+        H = Hn;
+      }
+    }
+    __syncthreads();
+    SZB_LVL(0)
+    // level 1: groups of warps
+    if (S.n_group_lists > 0) {
+      if (in_group && gq0 < gq1) {
+        double* Fm = sm + gi * gstride;
+        PanelGrp g;
+        g.id = 1 + gi;
+        g.nw = wpg;
+        g.w0 = gi * wpg;
+        FrontHdr H = load_hdr(S.fh, gq0);
+        AsmPre P;
+        asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
+        for (int q = gq0; q < gq1; ++q) {
+          H = factor_front_group<true>(g, H, S.fh, min(q + 1, gq1 - 1), P, S.ga, Fm, gi * gstride,
+                                       gi * gstride + gfront, glts, 0, A SZB_TARG(1));
+        }
+      }
+      __syncthreads();
+    }
+    SZB_LVL(1)
+    // level 2: the whole CTA as one group (barrier 0)
+    if (S.n_top > 0) {
+      PanelGrp g;
+      g.id = 0;
+      g.nw = blockDim.x >> 5;
+      g.w0 = 0;
+      // fronts too large for shared memory live in a per-CTA global workspace (L2): same code, the
+      // barriers order global memory within the CTA as well; only the side panels stay on chip
+      // (two call sites on purpose: with a run-time select the compiler would have to treat the
+      // shared-memory front as a generic pointer and lose the LDS/STS forms)
+      FrontHdr H = load_hdr(S.fh, tq0);
+      AsmPre P;
+      asm_prefetch(P, H, S.ga, g.rank(), g.size(), A.rhs != nullptr);
+      if (!GLOBAL_TOP) {
+        for (int q = 0; q < S.n_top; ++q) {
+          H = factor_front_group<true>(g, H, S.fh, tq0 + min(q + 1, S.n_top - 1), P, S.ga, sm, 0, tfront, tlts, 0,
+                                       A SZB_TARG(2));
+        }
+      } else {
+        // per front: shared memory when the front fits next to its 4-column side panel, else the global
+        // workspace with the outer-blocked elimination (its NO-column side panel fills the shared memory)
+        double* Ft = FBW + static_cast<size_t>(blockIdx.x) * tfront;
+        for (int q = 0; q < S.n_top; ++q) {
+          const int qn = tq0 + min(q + 1, S.n_top - 1);
+          if (group_elems(H.f) <= smem_elems)
+            H = factor_front_group<true>(g, H, S.fh, qn, P, S.ga, sm, 0, front_elems_blk(H.f), lt_stride(H.f), 0,
+                                         A SZB_TARG(2));
+          else
+            H = factor_front_group<false>(g, H, S.fh, qn, P, S.ga, Ft, 0, 0, tlts, outer_nb, A SZB_TARG(2));
+        }
+      }
+    }
+    __syncthreads();   // the next scenario reuses the fronts and the contribution workspace
+    SZB_LVL(2)
+  }
+#ifdef SZB_PHASE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long n_ = nscen_ > 0 ? nscen_ : 1;
+    printf("[lu_factor phases, cycles/scenario over %lld scenarios, thread 0]\n", n_);
+    const char* nm[3] = {"warp ", "group", "top  "};
+    for (int l = 0; l < 3; ++l)
+      printf("  %s level %8lld : clear+assemble %8lld  eliminate %8lld  write-out %8lld\n", nm[l], tacc_[12 + l] / n_,
+             tacc_[4 * l] / n_, tacc_[4 * l + 1] / n_, tacc_[4 * l + 2] / n_);
+    for (int l = 0; l < 2; ++l)
+      printf("  %s fronts: clear %lld assemble %lld eliminate %lld write-out %lld cycles/scenario\n", l ? "group-0" : "CTA-level",
+             g_el[58 + l] / n_, g_el[60 + l] / n_, g_el[56 + l] / n_, g_el[62 + l] / n_);
+    for (int l = 56; l < 64; ++l) g_el[l] = 0;
+    for (int wq = 0; wq < 8; ++wq) {
+      printf("  top elimination, warp %2d: first-diag %lld diag_next %lld phaseA %lld wait-phase %lld phaseB %lld wait-main %lld finalize %lld\n",
+             4 * wq, g_el[8 * wq] / n_, g_el[8 * wq + 1] / n_, g_el[8 * wq + 2] / n_, g_el[8 * wq + 3] / n_,
+             g_el[8 * wq + 4] / n_, g_el[8 * wq + 5] / n_, g_el[8 * wq + 6] / n_);
+      for (int i = 0; i < 8; ++i) g_el[8 * wq + i] = 0;
+    }
+  }
+#endif
+}
+
+// ---------------------------------------------------------------------------------------
+// triangular solves
+// ---------------------------------------------------------------------------------------
+struct SolveHdr {
+  int s, f, piv0, lp_off, up_off, idx_off, k;
+};
+
+__device__ __forceinline__ SolveHdr load_solve_hdr(const int4* __restrict__ fh, const int q) {
+  const int4 a = __ldg(fh + 4 * q), b = __ldg(fh + 4 * q + 1), d = __ldg(fh + 4 * q + 3);
+  SolveHdr H;
+  H.s = a.x; H.f = a.y; H.piv0 = a.z; H.lp_off = a.w; H.up_off = b.x; H.k = d.x; H.idx_off = d.z;
+  return H;
+}
+
+// ---- forward sweep  y = L^{-1} P b  (Rodas' stage solves and szb_lu_solve come through here; Newton
+// gets y from the fused factorisation).  One warp per front, lane = row:
+//   r = [b_piv ; 0] + sum_children cv_c ;  for every pivot p: r_i -= L_ip r_p (i > p, both the L11 and
+//   the L21 rows in one sweep down the panel column) ;  y_piv = r_piv ; cv_k = r_upd.
+// rv: f doubles of per-warp scratch.  Contribution vectors travel through the per-CTA workspace cv.
+__device__ void forward_front(const LuDev& S, const SolveHdr H, const double* __restrict__ lu,
+                              double* xb, double* cv, double* rv, const int lane) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0, k = H.k;
+  const double* __restrict__ Lp = lu + H.lp_off;
+  for (int t = lane; t < f; t += kWarp) rv[t] = t < s ? xb[p0 + t] : 0.0;
+  __syncwarp();
+  for (int ci = S.child_ptr[k]; ci < S.child_ptr[k + 1]; ++ci) {
+    const int c = S.child[ci];
+    const int c0 = S.rel_ptr[c], uc = S.rel_ptr[c + 1] - c0;
+    for (int t = lane; t < uc; t += kWarp) rv[S.rel[c0 + t]] += cv[c0 + t];
+    __syncwarp();
+  }
+  for (int p = 0; p < s; ++p) {
+    const double xp = rv[p];
+    const double* __restrict__ col = Lp + p * f;
+    int i = p + 1 + lane;
+    for (; i + kWarp < f; i += 2 * kWarp) {             // two chunks in flight
+      const double l0 = col[i], l1 = col[i + kWarp];
+      rv[i] = fma(-l0, xp, rv[i]);
+      rv[i + kWarp] = fma(-l1, xp, rv[i + kWarp]);
+    }
+    if (i < f) rv[i] = fma(-col[i], xp, rv[i]);
+    __syncwarp();
+  }
+  for (int t = lane; t < s; t += kWarp) xb[p0 + t] = rv[t];
+  if (u > 0) {
+    const int c0 = S.rel_ptr[k];
+    for (int i = lane; i < u; i += kWarp) cv[c0 + i] = rv[s + i];
+  }
+  __syncwarp();
+}
+
+// ---- a CTA-level front of the forward sweep, all warps of the CTA together (the mirror image of
+// backward_front_cta; walked by one warp, a 779-row separator front costs one L2 round trip per pivot and
+// chunk).  r lives in shared memory (rv, f doubles):
+//   (a) r = [b_piv ; 0] + children's contribution vectors (all threads, a barrier per child);
+//   (b) per 32-pivot block: warp 0 solves the unit-lower 32 x 32 triangle by shuffles, then every row below
+//       the block takes the block's 32 values, rows dealt to all threads (coalesced column loads, 8 in flight).
+__device__ void forward_front_cta(const LuDev& S, const SolveHdr H, const double* __restrict__ lu, double* xb,
+                                  double* cv, double* __restrict__ rv, const int warp, const int lane) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0, k = H.k;
+  const double* __restrict__ Lp = lu + H.lp_off;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int t = tid; t < f; t += nthr) rv[t] = t < s ? xb[p0 + t] : 0.0;
+  __syncthreads();
+  for (int ci = S.child_ptr[k]; ci < S.child_ptr[k + 1]; ++ci) {
+    const int c = S.child[ci];
+    const int c0 = S.rel_ptr[c], uc = S.rel_ptr[c + 1] - c0;
+    for (int t = tid; t < uc; t += nthr) rv[S.rel[c0 + t]] += cv[c0 + t];
+    __syncthreads();
+  }
+  const int nblk = (s + 31) >> 5;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int bbeg = 32 * blk, bend = min(s, bbeg + 32), nbk = bend - bbeg;
+    if (warp == 0) {
+      const int i = bbeg + lane;
+      const int io = i < bend ? i : bbeg;             // idle lanes mirror the first row, never store
+      double acc = rv[io];
+      const double* __restrict__ row = Lp + io + bbeg * f;
+      for (int pb = 0; pb < nbk; pb += 8) {
+        double lv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) lv[q] = (pb + q < nbk && io > bbeg + pb + q) ? row[(pb + q) * f] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (pb + q < nbk) {
+            const double xp = __shfl_sync(0xffffffffu, acc, pb + q);
+            acc = fma(-lv[q], xp, acc);                // lv = 0 on and above the diagonal
+          }
+        }
+      }
+      if (i < bend) rv[i] = acc;
+    }
+    __syncthreads();
+    for (int i = bend + tid; i < f; i += nthr) {
+      const double* __restrict__ row = Lp + i + bbeg * f;
+      double acc = rv[i];
+      int p = 0;
+      for (; p + 8 <= nbk; p += 8) {
+        double lv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) lv[q] = row[(p + q) * f];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fma(-lv[q], rv[bbeg + p + q], acc);
+      }
+      for (; p < nbk; ++p) acc = fma(-row[p * f], rv[bbeg + p], acc);
+      rv[i] = acc;
+    }
+    __syncthreads();
+  }
+  for (int t = tid; t < s; t += nthr) xb[p0 + t] = rv[t];
+  if (u > 0) {
+    const int c0 = S.rel_ptr[k];
+    for (int i = tid; i < u; i += nthr) cv[c0 + i] = rv[s + i];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128, 6)
+lu_forward_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ RHS,
+                  double* __restrict__ YP, double* CVW, double* __restrict__ XW,
+                  int x_in_smem, const int* __restrict__ active, int B) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int n = S.n;
+  double* rv = sm + warp * S.f_max;
+  double* xb = x_in_smem ? sm + nwarps * S.f_max : XW + static_cast<size_t>(blockIdx.x) * n;
+  double* cv = CVW + static_cast<size_t>(blockIdx.x) * S.cv_size;
+  const int gq_base = S.n_warp_sn, tq0 = S.n_warp_sn + S.n_group_sn;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    if (active && !active[b]) continue;
+    const double* __restrict__ lu = LU + static_cast<size_t>(b) * S.lu_size;
+    const double* __restrict__ rhs = RHS + static_cast<size_t>(b) * n;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = rhs[S.rowp[t]];
+    __syncthreads();
+    for (int l = warp; l < S.n_warp_lists; l += nwarps)
+      for (int q = S.wl_ptr[l]; q < S.wl_ptr[l + 1]; ++q)
+        forward_front(S, load_solve_hdr(S.fh, q), lu, xb, cv, rv, lane);
+    __syncthreads();
+    for (int g = warp; g < S.n_group_lists; g += nwarps)
+      for (int q = gq_base + S.gl_ptr[g]; q < gq_base + S.gl_ptr[g + 1]; ++q)
+        forward_front(S, load_solve_hdr(S.fh, q), lu, xb, cv, rv, lane);
+    __syncthreads();
+    for (int q = 0; q < S.n_top; ++q) forward_front_cta(S, load_solve_hdr(S.fh, tq0 + q), lu, xb, cv, sm, warp, lane);
+    double* __restrict__ yp = YP + static_cast<size_t>(b) * n;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) yp[t] = xb[t];
+  }
+}
+
+// ---- backward sweep  x = U^{-1} y.  One WARP per front, lane = pivot row (blocks of 32 rows), no
+// barriers and no reductions: row i accumulates  y_i - sum_{j > i} U_ij x_j  over the U12 columns
+// (stored s x u column-major, so a column is one coalesced load), then over the later pivots of the
+// front, and the 32 x 32 triangle is finished with shuffles.  Everything read from the factors is
+// independent of x, so the loads of one front overlap the dependent chain; many small CTAs per SM
+// (several scenarios in flight) hide the rest of the latency.
+constexpr int kTri = 4;   // pivots of the triangle whose columns are fetched together
+
+// pull the factor data of a front that comes up two fronts from now into L1: nothing the backward
+// sweep reads from the factors depends on x, so the only dependent chain left is arithmetic
+__device__ __forceinline__ void prefetch_front(const SolveHdr H, const double* __restrict__ lu, const int lane) {
+  const int s = H.s, f = H.f, u = f - s;
+  const char* up = reinterpret_cast<const char*>(lu + H.up_off);
+  const int nb = s * u * 8;
+  for (int o = lane * 128; o < nb; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(up + o));
+  const double* Lp = lu + H.lp_off;
+  for (int p = lane; p < s; p += 32) {
+    const char* c0 = reinterpret_cast<const char*>(Lp + p * f);
+    for (int o = 0; o <= p * 8; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(c0 + o));
+  }
+}
+
+// columns p, p-1, ..., p-kTri+1 (down to pmin) of the panel, row min(io, column): one batch of loads
+__device__ __forceinline__ void load_tri_cols(const double* __restrict__ Lp, const int f, const int io,
+                                              const int p, const int pmin, double (&tv)[kTri]) {
+#pragma unroll
+  for (int q = 0; q < kTri; ++q) {
+    const int pq = p - q;
+    tv[q] = pq >= pmin ? Lp[min(io, pq) + pq * f] : 1.0;
+  }
+}
+
+__device__ void backward_front(const SolveHdr H, const double* __restrict__ lu, const int* __restrict__ idx,
+                               double* xb, const int lane) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0;
+  const double* __restrict__ Lp = lu + H.lp_off;       // f x s panel; rows <= column hold U11
+  const double* __restrict__ Up = lu + H.up_off;       // U12, s x u column-major
+  const int* __restrict__ ids = idx + H.idx_off + s;   // pivot-order indices of the update rows
+  for (int blk = (s - 1) >> 5; blk >= 0; --blk) {
+    const int i = 32 * blk + lane;
+    const bool ok = i < s;
+    const int bend = min(s, 32 * blk + 32), bbeg = 32 * blk;
+    const int io = ok ? i : 0;                          // idle lanes mirror row 0 (finite data), never store
+    // nothing read from the factors depends on x: fetch the first batch of triangle columns now so that
+    // its latency overlaps the accumulation below
+    double tv[kTri];
+    load_tri_cols(Lp, f, io, bend - 1, bbeg, tv);
+    double acc = xb[p0 + io];
+    // columns of U12, eight in flight
+    {
+      const double* __restrict__ up = Up + io;
+      int c = 0;
+      for (; c + 8 <= u; c += 8, up += 8 * s) {
+        int j[8];
+        double uv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { j[q] = __ldg(ids + c + q); uv[q] = up[q * s]; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fma(-uv[q], xb[j[q]], acc);
+      }
+      if (c < u) {
+        int j[8];
+        double uv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const bool in = c + q < u;
+          j[q] = in ? __ldg(ids + c + q) : 0;
+          uv[q] = in ? up[q * s] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double xv = (c + q < u) ? xb[j[q]] : 0.0;
+          acc = fma(-uv[q], xv, acc);
+        }
+      }
+    }
+    // pivots of this front behind the block (already solved)
+    {
+      const double* __restrict__ lp = Lp + io + bend * f;
+      int p = bend;
+      for (; p + 4 <= s; p += 4, lp += 4 * f) {
+        const double u0 = lp[0], u1 = lp[f], u2 = lp[2 * f], u3 = lp[3 * f];
+        acc = fma(-u0, xb[p0 + p], acc);
+        acc = fma(-u1, xb[p0 + p + 1], acc);
+        acc = fma(-u2, xb[p0 + p + 2], acc);
+        acc = fma(-u3, xb[p0 + p + 3], acc);
+      }
+      for (; p < s; ++p, lp += f) acc = fma(-lp[0], xb[p0 + p], acc);
+    }
+    // the triangle of the block, last pivot first, kTri pivots per batch: the next batch of columns is in
+    // flight while this one is solved, and the reciprocals of the diagonal are off the dependent chain
+    for (int p = bend - 1; p >= bbeg; p -= kTri) {
+      double tn[kTri];
+      load_tri_cols(Lp, f, io, p - kTri, bbeg, tn);
+      double rinv[kTri];
+#pragma unroll
+      for (int q = 0; q < kTri; ++q) rinv[q] = __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);   // the factor stores 1 / u_pp
+#pragma unroll
+      for (int q = 0; q < kTri; ++q) {
+        const int pq = p - q;
+        if (pq >= bbeg) {
+          const double xp = __shfl_sync(0xffffffffu, acc, pq & 31) * rinv[q];
+          if (i == pq) acc = xp;
+          else if (i < pq) acc = fma(-tv[q], xp, acc);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kTri; ++q) tv[q] = tn[q];
+    }
+    if (ok) xb[p0 + i] = acc;
+    __syncwarp();
+  }
+}
+
+// ---- a warp-level front (f <= 32: one row block, at most 31 update rows).  The indices of the update
+// rows were loaded a front ahead, one per lane (id_c); lane c gathers x[id_c] once and the dot products
+// take it by shuffles, so no global load sits between the parent's x and this front's arithmetic.
+__device__ __forceinline__ void backward_front_small(const SolveHdr H, const double* __restrict__ lu, const int id_c,
+                                                     double* xb, const int lane) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0;
+  const double* __restrict__ Lp = lu + H.lp_off;       // f x s panel; rows <= column hold U11
+  const double* __restrict__ Up = lu + H.up_off;       // U12, s x u column-major
+  const bool ok = lane < s;
+  const int io = ok ? lane : 0;                          // idle lanes mirror row 0 (finite data), never store
+  double tv[kTri];
+  load_tri_cols(Lp, f, io, s - 1, 0, tv);
+  const double xg = lane < u ? xb[id_c] : 0.0;
+  double acc = xb[p0 + io];
+  const double* __restrict__ up = Up + io;
+  for (int c = 0; c < u; c += 8, up += 8 * s) {
+    double uv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) uv[q] = c + q < u ? up[q * s] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc = fma(-uv[q], __shfl_sync(0xffffffffu, xg, (c + q) & 31), acc);
+  }
+  for (int p = s - 1; p >= 0; p -= kTri) {
+    double tn[kTri];
+    load_tri_cols(Lp, f, io, p - kTri, 0, tn);
+    double rinv[kTri];
+#pragma unroll
+    for (int q = 0; q < kTri; ++q) rinv[q] = __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);   // the factor stores 1 / u_pp
+#pragma unroll
+    for (int q = 0; q < kTri; ++q) {
+      const int pq = p - q;
+      if (pq >= 0) {
+        const double xp = __shfl_sync(0xffffffffu, acc, pq & 31) * rinv[q];
+        if (lane == pq) acc = xp;
+        else if (lane < pq) acc = fma(-tv[q], xp, acc);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kTri; ++q) tv[q] = tn[q];
+  }
+  if (ok) xb[p0 + lane] = acc;
+  __syncwarp();
+}
+
+// index of lane's update row of front H (pivot order), 0 beyond the update rows
+__device__ __forceinline__ int load_update_id(const SolveHdr H, const int* __restrict__ idx, const int lane) {
+  return lane < H.f - H.s ? __ldg(idx + H.idx_off + H.s + lane) : 0;
+}
+
+// ---- a CTA-level front of the backward sweep, all warps of the CTA together.  The top of the tree is a
+// chain that holds almost half of U: walked by one warp it would leave the others idle with a few
+// kilobytes of loads in flight.  Here
+//   (a) the columns of U12 are dealt to the warps in chunks of 8 (lanes = rows): partial sums to red[w][i];
+//   (b) accs[i] = x_piv[i] - sum_w red[w][i];
+//   (c) the 32-row blocks of the triangle U11 are solved last block first by warp 0 (shuffles), and after
+//       each block every other row block above it takes that block's 32 new x (one warp per row block).
+// red: nwarps x s doubles, accs: s doubles of shared memory.
+__device__ void backward_front_cta(const SolveHdr H, const double* __restrict__ lu, const int* __restrict__ idx,
+                                   double* xb, double* __restrict__ red, double* __restrict__ accs, const int warp,
+                                   const int lane, const int nwarps) {
+  const int s = H.s, f = H.f, u = f - s, p0 = H.piv0;
+  const double* __restrict__ Lp = lu + H.lp_off;       // f x s panel; rows <= column hold U11
+  const double* __restrict__ Up = lu + H.up_off;       // U12, s x u column-major
+  const int* __restrict__ ids = idx + H.idx_off + s;   // pivot-order indices of the update rows
+  const int nblk = (s + 31) >> 5;
+  for (int blk = 0; blk < nblk; ++blk) {               // (a)
+    const int i = 32 * blk + lane;
+    const int io = i < s ? i : 0;
+    const double* __restrict__ up = Up + io;
+    double acc = 0.0;
+    for (int c = 8 * warp; c < u; c += 8 * nwarps) {
+      int j[8];
+      double uv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const bool in = c + q < u;
+        j[q] = in ? __ldg(ids + c + q) : 0;
+        uv[q] = in ? up[(c + q) * s] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fma(uv[q], xb[j[q]], acc);
+    }
+    if (i < s) red[warp * s + i] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < s; i += blockDim.x) {  // (b)
+    double a = xb[p0 + i];
+    for (int w = 0; w < nwarps; ++w) a -= red[w * s + i];
+    accs[i] = a;
+  }
+  __syncthreads();
+  for (int blk = nblk - 1; blk >= 0; --blk) {          // (c)
+    const int bbeg = 32 * blk, bend = min(s, bbeg + 32);
+    if (warp == 0) {
+      const int i = bbeg + lane;
+      const bool ok = i < s;
+      const int io = ok ? i : 0;
+      double tv[kTri];
+      load_tri_cols(Lp, f, io, bend - 1, bbeg, tv);
+      double acc = accs[io];
+      for (int p = bend - 1; p >= bbeg; p -= kTri) {
+        double tn[kTri];
+        load_tri_cols(Lp, f, io, p - kTri, bbeg, tn);
+        double rinv[kTri];
+#pragma unroll
+        for (int q = 0; q < kTri; ++q) rinv[q] = __shfl_sync(0xffffffffu, tv[q], (p - q) & 31);   // the factor stores 1 / u_pp
+#pragma unroll
+        for (int q = 0; q < kTri; ++q) {
+          const int pq = p - q;
+          if (pq >= bbeg) {
+            const double xp = __shfl_sync(0xffffffffu, acc, pq & 31) * rinv[q];
+            if (i == pq) acc = xp;
+            else if (i < pq) acc = fma(-tv[q], xp, acc);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kTri; ++q) tv[q] = tn[q];
+      }
+      if (ok) xb[p0 + i] = acc;
+    }
+    if (blk == 0) break;
+    __syncthreads();
+    for (int b = warp; b < blk; b += nwarps) {         // rows of block b take the x of block blk
+      const int i = 32 * b + lane;                     // < bbeg <= s: always a row of the front
+      const double* __restrict__ lp = Lp + i + bbeg * f;
+      double acc = accs[i];
+      int p = bbeg;
+      for (; p + 8 <= bend; p += 8, lp += 8 * f) {
+        double uv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) uv[q] = lp[q * f];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fma(-uv[q], xb[p0 + p + q], acc);
+      }
+      for (; p < bend; ++p, lp += f) acc = fma(-lp[0], xb[p0 + p], acc);
+      accs[i] = acc;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128, 8)
+lu_backward_kernel(const LuDev S, const double* __restrict__ LU, const double* __restrict__ YP,
+                   double* __restrict__ X, double* __restrict__ XW, int x_in_smem, int mode,
+                   const int* __restrict__ active, int B) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int n = S.n;
+  double* xb = x_in_smem ? sm : XW + static_cast<size_t>(blockIdx.x) * n;
+  const int gq_base = S.n_warp_sn, tq0 = S.n_warp_sn + S.n_group_sn;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    if (active && !active[b]) continue;
+    const double* __restrict__ lu = LU + static_cast<size_t>(b) * S.lu_size;
+    const double* __restrict__ yp = YP + static_cast<size_t>(b) * n;
+    double* __restrict__ x = X + static_cast<size_t>(b) * n;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) xb[t] = yp[t];
+    __syncthreads();
+    // the top of the tree is a chain, root first: every front by the whole CTA
+    if (S.n_top > 0) {
+      double* red = sm + (x_in_smem ? n : 0);
+      double* accs = red + nwarps * S.s_top_max;
+      SolveHdr H = load_solve_hdr(S.fh, tq0 + S.n_top - 1);
+      for (int q = S.n_top - 1; q >= 0; --q) {
+        const SolveHdr Hn = load_solve_hdr(S.fh, tq0 + max(q - 1, 0));
+        if (q >= 1 && warp == nwarps - 1) prefetch_front(Hn, lu, lane);
+        backward_front_cta(H, lu, S.idx, xb, red, accs, warp, lane, nwarps);
+        H = Hn;
+      }
+    }
+    __syncthreads();
+    for (int g = warp; g < S.n_group_lists; g += nwarps) {
+      const int q0 = gq_base + S.gl_ptr[g], q1 = gq_base + S.gl_ptr[g + 1];
+      if (q0 < q1) {
+        SolveHdr H = load_solve_hdr(S.fh, q1 - 1);
+        SolveHdr Hn = load_solve_hdr(S.fh, max(q1 - 2, q0));
+        prefetch_front(Hn, lu, lane);
+        for (int q = q1 - 1; q >= q0; --q) {
+          const SolveHdr Hnn = load_solve_hdr(S.fh, max(q - 2, q0));
+          if (q - 2 >= q0) prefetch_front(Hnn, lu, lane);
+          backward_front(H, lu, S.idx, xb, lane);
+          H = Hn;
+          Hn = Hnn;
+        }
+      }
+    }
+    __syncthreads();
+    for (int l = warp; l < S.n_warp_lists; l += nwarps) {
+      const int q0 = S.wl_ptr[l], q1 = S.wl_ptr[l + 1];
+      if (q0 < q1) {
+        SolveHdr H = load_solve_hdr(S.fh, q1 - 1);
+        SolveHdr Hn = load_solve_hdr(S.fh, max(q1 - 2, q0));
+        int id_c = load_update_id(H, S.idx, lane);
+        prefetch_front(Hn, lu, lane);
+        for (int q = q1 - 1; q >= q0; --q) {
+          const SolveHdr Hnn = load_solve_hdr(S.fh, max(q - 2, q0));
+          const int id_n = load_update_id(Hn, S.idx, lane);      // lands while this front is solved
+          if (q - 2 >= q0) prefetch_front(Hnn, lu, lane);
+          backward_front_small(H, lu, id_c, xb, lane);
+          H = Hn;
+          Hn = Hnn;
+          id_c = id_n;
+        }
+      }
+    }
+    __syncthreads();
+    if (mode == 0) {
+      for (int t = threadIdx.x; t < n; t += blockDim.x) x[S.colp[t]] = xb[t];
     } else {
-      const Coop C{w, kWarps, true};
-      double* tbuf = sm + static_cast<size_t>(kNB * kNB + w * kTileScratch) * kGroup + lane;
-      for (int q = S.n_warp_sn + S.n_mid_sn; q < S.n_sched; ++q)
-        factor_front_tiled(L, load_front(T.fh, q), T, C, tbuf, sm + lane);
+      for (int t = threadIdx.x; t < n; t += blockDim.x) x[S.colp[t]] -= xb[t];
     }
-    __syncthreads();
-#ifdef SZB_LU_TIMING
-    tacc[7] = clock64() - tl0;
-    if (threadIdx.x == 0)
-      for (int i = 0; i < 8; ++i) atomicAdd(&g_lu_cycles[8 * LEVEL + i], static_cast<unsigned long long>(tacc[i]));
-#endif
-    // pivot / growth monitor of the scenario: reduction over the warps, carried across the level kernels in MON
-    sm[(3 * w + 0) * kGroup + lane] = L.amax;
-    sm[(3 * w + 1) * kGroup + lane] = L.umax;
-    sm[(3 * w + 2) * kGroup + lane] = L.bad ? 1.0 : 0.0;
-    __syncthreads();
-    if (w == 0) {
-      double am = 0.0, um = 0.0, bad = 0.0;
-      for (int i = 0; i < kWarps; ++i) {
-        const double a_ = sm[(3 * i + 0) * kGroup + lane], u_ = sm[(3 * i + 1) * kGroup + lane];
-        am = a_ > am ? a_ : am;
-        um = u_ > um ? u_ : um;
-        bad += sm[(3 * i + 2) * kGroup + lane];
-      }
-      double* mon = MON + (static_cast<size_t>(g) * kGroup + lane) * 3;
-      if (LEVEL > 0) {
-        am = mon[0] > am ? mon[0] : am;
-        um = mon[1] > um ? mon[1] : um;
-        bad += mon[2];
-      }
-      if (LEVEL < 2) { mon[0] = am; mon[1] = um; mon[2] = bad; }
-      else if (L.valid && (bad > 0.0 || !(um <= growth_tol * am))) flags[b] = 2;
-    }
-    __syncthreads();
   }
 }
 
-// ---- forward sweep with stored factors --------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
-lu_forward_kernel(const LuDev S, const double* LU, const double* __restrict__ RHS, double* YI, double* CVW,
-                  const int* __restrict__ map, const int* __restrict__ npos, const int* __restrict__ active) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n_groups = (*npos + kGroup - 1) / kGroup;
-  const Tabs T = make_tabs(S);
-  int wq0 = 0, wq1 = 0, mq0 = 0, mq1 = 0;
-  if (w < S.n_warp_lists) { wq0 = S.wl_ptr[w]; wq1 = S.wl_ptr[w + 1]; }
-  if (w < S.n_mid_lists) { mq0 = S.n_warp_sn + S.ml_ptr[w]; mq1 = S.n_warp_sn + S.ml_ptr[w + 1]; }
-  for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-    const int b = map[g * kGroup + lane];
-    Lane L;
-    L.valid = b >= 0 && (!active || active[b]);
-    L.lu = const_cast<double*>(LU) + static_cast<size_t>(g) * S.lu_size * kGroup + lane;
-    L.cb = nullptr;
-    L.y = YI + static_cast<size_t>(g) * S.n * kGroup + lane;
-    L.jv = nullptr;
-    L.rhs = L.valid ? RHS + static_cast<size_t>(b) * S.n : nullptr;
-    L.with_rhs = true;
-    double* cv = CVW + static_cast<size_t>(blockIdx.x) * S.cv_size * kGroup + lane;
-    {
-      const Coop C{0, 1, false};
-      for (int q = wq0; q < wq1; ++q) forward_front(L, cv, load_front(T.fh, q), T, C);
-      __syncthreads();
-      for (int q = mq0; q < mq1; ++q) forward_front(L, cv, load_front(T.fh, q), T, C);
-    }
-    __syncthreads();
-    {
-      const Coop C{w, kWarps, true};
-      for (int q = S.n_warp_sn + S.n_mid_sn; q < S.n_sched; ++q) forward_front(L, cv, load_front(T.fh, q), T, C);
-    }
-    __syncthreads();
-  }
-}
-
-// ---- backward sweep (+ scatter to the caller's scenario-major vector) ---------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
-lu_backward_kernel(const LuDev S, const double* LU, double* YI, double* __restrict__ X, int mode,
-                   const int* __restrict__ map, const int* __restrict__ npos, const int* __restrict__ active) {
-  __shared__ double red[kWarps * kNB * kGroup];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n_groups = (*npos + kGroup - 1) / kGroup;
-  const Tabs T = make_tabs(S);
-  int wq0 = 0, wq1 = 0, mq0 = 0, mq1 = 0;
-  if (w < S.n_warp_lists) { wq0 = S.wl_ptr[w]; wq1 = S.wl_ptr[w + 1]; }
-  if (w < S.n_mid_lists) { mq0 = S.n_warp_sn + S.ml_ptr[w]; mq1 = S.n_warp_sn + S.ml_ptr[w + 1]; }
-  for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-    const int b = map[g * kGroup + lane];
-    Lane L;
-    L.valid = b >= 0 && (!active || active[b]);
-    L.lu = const_cast<double*>(LU) + static_cast<size_t>(g) * S.lu_size * kGroup + lane;
-    L.cb = nullptr;
-    L.y = YI + static_cast<size_t>(g) * S.n * kGroup + lane;
-    {
-      const Coop C{w, kWarps, true};
-      for (int q = S.n_sched - 1; q >= S.n_warp_sn + S.n_mid_sn; --q)
-        backward_front(L, load_front(T.fh, q), T, C, red + lane);
-    }
-    __syncthreads();
-    {
-      const Coop C{0, 1, false};
-      for (int q = mq1 - 1; q >= mq0; --q) backward_front(L, load_front(T.fh, q), T, C, red + lane);
-      __syncthreads();
-      for (int q = wq1 - 1; q >= wq0; --q) backward_front(L, load_front(T.fh, q), T, C, red + lane);
-    }
-    __syncthreads();
-    if (L.valid) {
-      double* xb = X + static_cast<size_t>(b) * S.n;
-      for (int k = w; k < S.n; k += kWarps) {
-        const double v = SZB_EL(L.y, k);
-        const int col = __ldg(S.colp + k);
-        if (mode == 1) xb[col] -= v; else xb[col] = v;
-      }
-    }
-    __syncthreads();
-  }
-}
+size_t smax(size_t a, size_t b) { return a > b ? a : b; }
 
 }  // namespace
 
 cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
-  int dev = 0, sms = 0;
+  int dev = 0, sms = 0, smem_max = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (S.n_warp_lists > kWarps || S.n_mid_lists > kWarps || S.warp_lines != kWarpLines ||
-      S.f_warp_max * (S.f_warp_max + 1) > kWarpLines)
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  // threads per CTA and warps per group were fixed by the host schedule (lu/schedule.py::plan_threads):
+  // the gather tables are laid out for exactly these group sizes
+  const int warps = S.threads >> 5;
+  if (S.threads <= 0 || (S.threads & 31) || warps > 32 || warps < S.n_warp_lists ||
+      S.wpg * S.n_group_lists > warps || (S.n_group_lists > 0 && S.wpg < 2))
     return cudaErrorInvalidConfiguration;
-  cfg->threads = kThreads;
-  cfg->smem = static_cast<size_t>(kSmemLines) * kGroup * sizeof(double);
-  const int sm_bytes = static_cast<int>(cfg->smem);
-  if ((e = cudaFuncSetAttribute(lu_factor_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lu_factor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(lu_factor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes)) != cudaSuccess) return e;
-  cfg->groups = (B + kGroup - 1) / kGroup;
-  cfg->grid = sms;                       // one CTA per SM (register file and shared memory are both full)
-  if (cfg->grid > cfg->groups) cfg->grid = cfg->groups > 0 ? cfg->groups : 1;
+  cfg->threads = S.threads;
+  if (S.f_warp_max > 32) return cudaErrorInvalidConfiguration;   // lane = row
+  if (S.n_group_lists > 7) return cudaErrorInvalidConfiguration;   // named barriers 1..7 (+8 for the phase barrier)
+  if (S.threads > SZB_FACTOR_THREADS) return cudaErrorInvalidConfiguration;
+  size_t fsm = static_cast<size_t>(S.n_warp_lists) * front_elems_warp(S.f_warp_max);
+  fsm = smax(fsm, static_cast<size_t>(S.n_group_lists) * group_elems(S.f_group_max));
+  if (fsm * sizeof(double) > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
+  cfg->top_in_global = 0;
+  cfg->big_elems = 0;
+  cfg->outer_nb = 0;
+  if (S.n_top > 0) {
+    const size_t top_sm = static_cast<size_t>(group_elems(S.f_top_max));
+    if (top_sm * sizeof(double) <= static_cast<size_t>(smem_max)) {
+      fsm = smax(fsm, top_sm);
+    } else {   // CTA-level fronts in a global workspace, side panels in shared memory
+      // CTA-level fronts that do not fit: global workspace + outer-blocked elimination whose side panel
+      // (outer_nb columns of -Lt) takes what shared memory there is
+      cfg->top_in_global = 1;
+      cfg->big_elems = static_cast<size_t>(front_elems_blk(S.f_top_max));
+      const size_t lts = static_cast<size_t>(lt_stride(S.f_top_max));
+      size_t nbo = (static_cast<size_t>(smem_max) / sizeof(double) - kDiagBuf) / lts;
+      nbo = nbo > 32 ? 32 : (nbo & ~static_cast<size_t>(3));
+      if (nbo < 4) return cudaErrorInvalidConfiguration;
+      cfg->outer_nb = static_cast<int>(nbo);
+      fsm = smax(fsm, nbo * lts + kDiagBuf);
+    }
+  }
+  cfg->smem_factor = fsm * sizeof(double);
+  if (cfg->smem_factor > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
+  // forward sweep: small CTAs, one scratch row vector per warp; the permuted vector in shared memory when
+  // at least two CTAs fit an SM
+  cfg->threads = S.threads;
+  cfg->threads_fwd = 128;
+  {
+    const size_t rvs = static_cast<size_t>(cfg->threads_fwd / 32) * S.f_max;
+    cfg->x_in_smem = (rvs + S.n) * sizeof(double) * 2 <= static_cast<size_t>(smem_max) ? 1 : 0;
+    cfg->smem_solve = (rvs + (cfg->x_in_smem ? S.n : 0)) * sizeof(double);
+    if (cfg->smem_solve > static_cast<size_t>(smem_max)) return cudaErrorInvalidConfiguration;
+  }
+  // backward sweep: small CTAs, the permuted vector in shared memory when at least two CTAs fit an SM
+  cfg->threads_bwd = 128;
+  cfg->bwd_x_in_smem = static_cast<size_t>(S.n) * sizeof(double) * 2 <= static_cast<size_t>(smem_max) ? 1 : 0;
+  cfg->smem_bwd = (cfg->bwd_x_in_smem ? static_cast<size_t>(S.n) * sizeof(double) : 0) +
+                  (S.n_top > 0 ? static_cast<size_t>(cfg->threads_bwd / 32 + 1) * S.s_top_max * sizeof(double) : 0);
+  e = cfg->top_in_global
+          ? cudaFuncSetAttribute(lu_factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(cfg->smem_factor))
+          : cudaFuncSetAttribute(lu_factor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(cfg->smem_factor));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(lu_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(cfg->smem_solve));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(lu_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(cfg->smem_bwd));
+  if (e != cudaSuccess) return e;
+  int occ_f = 1, occ_s = 1, occ_b = 1;
+  if (cfg->top_in_global) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lu_factor_kernel<true>, cfg->threads, cfg->smem_factor);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, lu_factor_kernel<false>, cfg->threads, cfg->smem_factor);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, lu_forward_kernel, cfg->threads_fwd, cfg->smem_solve);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, lu_backward_kernel, cfg->threads_bwd, cfg->smem_bwd);
+  if (occ_f < 1) occ_f = 1;
+  if (occ_s < 1) occ_s = 1;
+  if (occ_b < 1) occ_b = 1;
+  cfg->grid_factor = sms * occ_f;
+  cfg->grid_solve = sms * occ_s;
+  cfg->grid_bwd = sms * occ_b;
+  if (cfg->grid_factor > B) cfg->grid_factor = B > 0 ? B : 1;
+  if (cfg->grid_solve > B) cfg->grid_solve = B > 0 ? B : 1;
+  if (cfg->grid_bwd > B) cfg->grid_bwd = B > 0 ? B : 1;
   return cudaSuccess;
 }
 
-#ifdef SZB_LU_TIMING
-extern "C" __attribute__((visibility("default"))) int szb_debug_lu_cycles(unsigned long long* out24, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out24, g_lu_cycles, sizeof(unsigned long long) * 24);
-  if (reset) {
-    unsigned long long z[24] = {0};
-    cudaMemcpyToSymbol(g_lu_cycles, z, sizeof z);
-  }
-  return 0;
-}
-#endif
-
-cudaError_t lu_map_launch(const int* active, int B, int* map, int* npos, cudaStream_t st) {
+cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV, double* LU,
+                             double* CBW, double* FBW, const double* mvals, const double* slot_mask,
+                             const double* scale_b, double scale_const, const double* RHS, double* YOUT,
+                             int store_l, const int* active, int* flags, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  lu_map_kernel<<<1, 1024, 0, st>>>(active, B, map, npos);
+  if (cfg.top_in_global)
+    lu_factor_kernel<true><<<cfg.grid_factor, cfg.threads, cfg.smem_factor, st>>>(
+        S, JV, LU, CBW, FBW, mvals, slot_mask, scale_b, scale_const, RHS, YOUT, store_l, active, flags, B, cfg.outer_nb,
+        static_cast<int>(cfg.smem_factor / sizeof(double)));
+  else
+    lu_factor_kernel<false><<<cfg.grid_factor, cfg.threads, cfg.smem_factor, st>>>(
+        S, JV, LU, CBW, nullptr, mvals, slot_mask, scale_b, scale_const, RHS, YOUT, store_l, active, flags, B, 0, 0);
   return cudaGetLastError();
 }
 
-cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV, double* LU, double* CBW,
-                             const double* mvals, const double* slot_mask, const double* scale_b,
-                             double scale_const, const double* RHS, double* YI, const int* map, const int* npos,
-                             double* MON, int* flags, double growth_tol, cudaStream_t st) {
-  lu_factor_kernel<0><<<cfg.grid, cfg.threads, cfg.smem, st>>>(S, JV, LU, CBW, mvals, slot_mask, scale_b, scale_const,
-                                                               RHS, YI, map, npos, MON, flags, growth_tol);
-  lu_factor_kernel<1><<<cfg.grid, cfg.threads, cfg.smem, st>>>(S, JV, LU, CBW, mvals, slot_mask, scale_b, scale_const,
-                                                               RHS, YI, map, npos, MON, flags, growth_tol);
-  lu_factor_kernel<2><<<cfg.grid, cfg.threads, cfg.smem, st>>>(S, JV, LU, CBW, mvals, slot_mask, scale_b, scale_const,
-                                                               RHS, YI, map, npos, MON, flags, growth_tol);
-  return cudaGetLastError();
-}
-
-cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* LU, const double* RHS, double* X,
-                            double* CVW, double* YI, int do_fwd, int mode, const int* map, const int* npos,
-                            const int* active, cudaStream_t st) {
+cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* LU,
+                            const double* RHS, double* X, double* CVW, double* XW, double* YW, int do_fwd,
+                            int mode, const int* active, int B, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  const double* yp = RHS;
   if (do_fwd) {
-    lu_forward_kernel<<<cfg.grid, cfg.threads, 0, st>>>(S, LU, RHS, YI, CVW, map, npos, active);
+    lu_forward_kernel<<<cfg.grid_solve, cfg.threads_fwd, cfg.smem_solve, st>>>(
+        S, LU, RHS, YW, CVW, XW, cfg.x_in_smem, active, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    yp = YW;
   }
-  lu_backward_kernel<<<cfg.grid, cfg.threads, 0, st>>>(S, LU, YI, X, mode, map, npos, active);
+  lu_backward_kernel<<<cfg.grid_bwd, cfg.threads_bwd, cfg.smem_bwd, st>>>(
+      S, LU, yp, X, XW, cfg.bwd_x_in_smem, mode, active, B);
   return cudaGetLastError();
 }
 

@@ -1,61 +1,65 @@
-// szb_lu.cuh -- device-side view of the multifrontal schedule and launch prototypes of the
-// batch-interleaved LU (csrc/szb_lu.cu, csrc/szb_lu_front.cuh).
+// szb_lu.cuh -- device-side view of the multifrontal schedule and launch prototypes.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace szb {
 
-constexpr int kGroup = 32;   // scenarios per group = lanes of a warp
-
 // All arrays are device pointers (int32).  Built once per handle from szb_lu_symbolic.
 struct LuDev {
   int n, nnz_a, ns;
-  int lu_size, cb_size, cv_size;   // lines (of kGroup doubles) per group: factors, contribution ws, fwd ws
-  int n_warp_lists, n_warp_sn, n_mid_lists, n_mid_sn, n_sched;
-  int f_max, f_warp_max, warp_lines;
+  int lu_size, cb_size, cv_size;
+  int n_warp_lists, n_group_lists, n_top;
+  int n_warp_sn, n_group_sn;     // fronts in the warp lists / group lists (schedule order: warp, group, top)
+  int threads, wpg;              // threads per CTA, warps per group (fixed by the host schedule)
+  int f_warp_max, f_group_max, f_top_max, s_warp_max, s_group_max, s_top_max;
+  int f_max;                     // largest front order
   const int *rowp, *colp;
-  const int *idx, *rel;
-  const int *a_src, *a_dst;
-  const int *wl_ptr, *ml_ptr;
-  const int *atp, *tcp;   // tile tables of the tiled fronts (levels 1 and 2)
-  const int4* tce;
-  const int4* fh;   // front descriptors, 4 x int4 each, schedule order (lu/schedule.py)
-  const int4* ct;   // child table
+  const int *sn_piv0, *sn_s, *sn_f;
+  const int *idx_ptr, *idx, *rel_ptr, *rel, *child_ptr, *child;
+  const int *a_ptr, *a_src, *a_dst;
+  const int *lp_off, *up_off, *cb_off;
+  const int *ea_ptr, *ea_dst;   // per child: destination of every contribution-block element in the parent front
+  const int *wl_ptr, *wl, *gl_ptr, *gl, *top;
+  const int4* fh;                // front headers, 4 x int4 each, schedule order (lu/schedule.py)
+  const int2* ga;                // gather table: (tagged source, front position)
 };
 
 struct LuLaunchCfg {
-  int threads;      // threads per CTA
-  int grid;         // resident CTAs (persistent grid over the groups)
-  int groups;       // ceil(B / kGroup): groups the value arrays are sized for
-  size_t smem;
+  int threads;        // threads per block (multiple of 32, >= 32*n_warp_lists)
+  int grid_factor;    // resident blocks (persistent grid size)
+  size_t smem_factor; // dynamic shared memory of the factor kernel
+  int grid_solve;
+  size_t smem_solve;
+  int top_in_global;  // CTA-level fronts do not fit shared memory: they live in a per-CTA global workspace
+  size_t big_elems;   // doubles of that workspace per resident block
+  int outer_nb;       // pivots per outer block of the global-front elimination (side panel columns in shared memory)
+  int threads_fwd;    // forward sweep: threads per block
+  int x_in_smem;      // forward kernel keeps the permuted vector in shared memory
+  int threads_bwd;    // backward sweep: threads per block, resident blocks, dynamic shared memory
+  int grid_bwd;
+  size_t smem_bwd;
+  int bwd_x_in_smem;
 };
 
-// Chooses block/grid for this schedule on the current device; returns cudaError_t.
+// Chooses block/grid/smem for this schedule on the current device; returns cudaError_t.
 cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg);
 
-// map[p] = scenario at position p of the interleaved storage (active scenarios compacted in ascending
-// order, -1 behind them up to the end of the last group), *npos = number of active scenarios.
-// active == null: all B scenarios.
-cudaError_t lu_map_launch(const int* active, int B, int* map, int* npos, cudaStream_t st);
-
-// A(b) = scale(b) * slot_mask * JV[b] + mvals  ->  LU (interleaved by position, see lu_map_launch);
-// scale_b may be null (then scale_const).  RHS non-null: the right-hand side rides along (forward
-// substitution fused) and YI gets y = L^{-1} P b in pivot order (interleaved).  flags[b] = 2 for a zero /
-// non-finite pivot or an element growth max|u| / max|a| above growth_tol (MON: 3 doubles per position of
-// scratch for the monitors, carried across the three level kernels).
-cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV, double* LU, double* CBW,
-                             const double* mvals, const double* slot_mask, const double* scale_b,
-                             double scale_const, const double* RHS, double* YI, const int* map, const int* npos,
-                             double* MON, int* flags, double growth_tol, cudaStream_t st);
+// A(b) = scale(b) * JV[b] (+ mvals)  ->  LU[b];  scale_b may be null (then scale_const).
+// RHS / YOUT non-null: the right-hand side rides along (forward substitution fused), YOUT gets
+// y = L^{-1} P b in pivot order.  store_l == 0 skips writing the L21 rows (Newton never reuses L).
+cudaError_t lu_factor_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* JV,
+                             double* LU, double* CBW, double* FBW, const double* mvals, const double* slot_mask,
+                             const double* scale_b, double scale_const, const double* RHS, double* YOUT, int store_l,
+                             const int* active, int* flags, int B, cudaStream_t st);
 
 // mode 0:  X[b] <- A^{-1} RHS[b]         (X may alias RHS)
 // mode 1:  X[b] <- X[b] - A^{-1} RHS[b]  (Newton update y -= dx; X is Y)
-// do_fwd 1: RHS is b in original order, scenario-major (forward + backward sweep)
-// do_fwd 0: YI holds y in pivot order from a fused factorisation (backward sweep only)
-// map / npos: as left by the factorisation; active (may be null) masks scenarios on top of it
-cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* LU, const double* RHS, double* X,
-                            double* CVW, double* YI, int do_fwd, int mode, const int* map, const int* npos,
-                            const int* active, cudaStream_t st);
+// do_fwd 1: RHS is b in original order (forward + backward sweep)
+// do_fwd 0: RHS is y in pivot order from a fused factorisation (backward sweep only)
+// YW: [B][n] scratch for y in pivot order (used when do_fwd == 1)
+cudaError_t lu_solve_launch(const LuDev& S, const LuLaunchCfg& cfg, const double* LU,
+                            const double* RHS, double* X, double* CVW, double* XW, double* YW, int do_fwd,
+                            int mode, const int* active, int B, cudaStream_t st);
 
 }  // namespace szb

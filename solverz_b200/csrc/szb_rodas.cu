@@ -545,7 +545,7 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
     // lu = splu(M - dt*gamma*J) (:159), K[:,0] = lu.solve(rhs) (:163)
     if ((rc = szb_lu_refactor_masked(h, 0.0, S.scale, S.active, nullptr, nullptr, 1, st)) != SZB_OK) return rc;
     {
-      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->RHS, h->rd_K, h->CVW, h->ybuf, 1, 0, h->lu_map, h->lu_npos, S.active, st);
+      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->RHS, h->rd_K, h->CVW, h->XW, h->ybuf, 1, 0, S.active, B, st);
       if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
       h->launches[3]++;
     }
@@ -556,7 +556,7 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
       stage_rhs_kernel<<<eg, 256, 0, st>>>(h->RHS, h->F, use_dfdt ? h->rd_dfdt : nullptr, h->rd_sum2,
                                            h->rd_mcol, T.g[j], S, n, B);
       h->launches[4]++;
-      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->RHS, h->RHS, h->CVW, h->ybuf, 1, 0, h->lu_map, h->lu_npos, S.active, st);
+      cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->RHS, h->RHS, h->CVW, h->XW, h->ybuf, 1, 0, S.active, B, st);
       if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }
       h->launches[3]++;
       stage_post_kernel<<<eg, 256, 0, st>>>(h->rd_K + j * bn, h->RHS, h->rd_sum2, S, n, B);

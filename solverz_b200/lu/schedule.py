@@ -1,32 +1,29 @@
-"""Device schedule of the batch-interleaved multifrontal LU: front descriptors, child table, tile tables.
+"""Device schedule of the batched multifrontal LU: per-front descriptors and gather tables.
 
 ``solverz_b200.lu.symbolic.analyze`` fixes *what* is computed (pivots, ordering, supernodes, the
-two-level split of the elimination tree, the contribution-workspace layout).  This module lowers that
-result into the flat int32 tables the kernels of ``csrc/szb_lu.cu`` read.  Every table is the same
-for all scenarios, and since one warp instruction works on 32 scenarios (lane = scenario) each entry is
-decoded once per 32 scenarios:
+three-level split of the elimination tree).  This module lowers that result into the two flat int32
+tables the kernels of ``csrc/szb_lu.cu`` actually read, so that a front costs one descriptor load
+plus three streamed tables instead of a chain of dependent index look-ups:
 
-``fh``  front descriptors, 16 int32 each, in *schedule order*: the level-0 lists one after the other (list
-        ``w`` = the run ``wl_ptr[w]:wl_ptr[w+1]``), the level-1 lists (``n_warp_sn + ml_ptr[w]`` ..), then the
-        level-2 (CTA-level) list:
-        ``[s, f, piv0, lp_off, up_off, cb_off, a0, a1, c0, c1, idx_ptr, cv_off, atp0, tcp0, k, 0]``
-        ``a0:a1`` is the front's run of matrix entries in ``a_src`` / ``a_dst``, ``c0:c1`` its run of
-        rows in the child table, ``atp0`` / ``tcp0`` the starts of its tile pointers (-1: not a tiled front).
-``ct``  child table, 8 int32 per (parent, child) edge, children in schedule order:
-        ``[cb_off(child), u(child), rel_ptr(child), cv_off(child), 0, 0, 0, 0]``
-``a_src / a_dst``  matrix entries grouped by front: Jacobian slot and destination.  For a front that is
-        assembled in a shared-memory buffer (level 0) the destination is the offset in the factor storage;
-        for a TILED front (levels 1 and 2) the entries are sorted by the 8 x 8 tile they fall in and the
-        destination is the position inside that tile, ``r + 8 c``.
-``atp`` tiled fronts: ``atp[atp0 + tr + tc * nt]`` = first entry of tile (tr, tc); one extra pointer closes
-        the last tile.  Tile rows / columns 0..Tt-1 cover the pivots in steps of 8 (the last may be short),
-        Tt..nt-1 the update rows from ``s`` on.
-``tcp / tce``  tiled fronts: the CONTRIBUTORS of every tile.  ``tcp[tcp0 + tr + tc * nt]`` (``tc = nt`` is the
-        right-hand-side column) = first row of ``tce`` for that tile; a row of ``tce`` is one int4
-        ``[src, u_c, rowpack, colpack]``: the piece of a child's contribution block that lands in the tile starts
-        at workspace offset ``src`` (leading dimension ``u_c``), and nibble ``q`` of ``rowpack`` / ``colpack`` is
-        the position inside the tile of the piece's row / column ``q`` (0xF: the piece is shorter).  One load
-        per contributor replaces the walk over the child's relative indices.
+``fh``  front headers, 16 int32 each, in *schedule order* (warp lists, then group lists, then the
+        CTA-level list; list ``w`` of a level is the contiguous run ``ptr[w]:ptr[w+1]``):
+        ``[s, f, piv0, lp_off, up_off, cb_off, gaO, itO, gaC, itC, gaR, itR, k, n_src, idx_ptr, 0]``
+
+``ga``  gather tables, ``(src, dst)`` int32 pairs.  A front owns three blocks, each laid out
+        ``[iterations][G]`` (G = threads of the group that owns the front): in iteration ``it`` thread
+        ``r`` adds the value addressed by ``src`` to front position ``dst`` (``src == -1``: no-op).
+          O block  original data: Jacobian slots (scaled / masked / mass-shifted on the fly) and the
+                   rows of the right-hand side (ignored when no right-hand side rides along); none of
+                   it depends on the children, so its values are prefetched a front ahead,
+          C block  offsets in the contribution workspace (Schur parts of the children),
+          R block  the children's right-hand-side columns in the contribution workspace; skipped
+                   when no right-hand side rides along.
+        The three blocks of a front are contiguous, so a thread walks ONE stream of entries; bits 30-31
+        of ``src`` name the address space (0 contribution workspace, 1 Jacobian values, 2 right-hand
+        side), which makes the value fetch a pointer select instead of a branch.
+        Every destination is owned by exactly one thread across the three blocks, and a thread meets
+        its sources in a fixed order (matrix entry, children in schedule order), so the assembly
+        needs no barrier between children, no atomics, and is bitwise reproducible.
 
 This is what SuperLU's ``dgstrf`` re-derives inside every call of the reference's ``solve`` /
 ``lu_decomposition`` (Solverz/solvers/laesolver.py:11-45); here it is done once per model.
@@ -37,104 +34,121 @@ from typing import Dict
 
 import numpy as np
 
-__all__ = ["build_tables", "HDR_WORDS", "WARPS", "WARP_LINES", "TILE"]
+__all__ = ["plan_threads", "build_tables", "NOOP", "TAG_CB", "TAG_J", "TAG_RHS", "OFF_MASK"]
 
+NOOP = 0xFFFFFFFF
+TAG_CB, TAG_J, TAG_RHS = 0, 1, 2
+OFF_MASK = (1 << 30) - 1
 HDR_WORDS = 16
-WARPS = 8          # warps per CTA of the factor / sweep kernels (csrc/szb_lu.cu: kWarps)
-WARP_LINES = 110   # lines of 32 doubles in a warp's shared-memory front buffer (csrc/szb_lu.cu: kWarpLines)
-TILE = 8           # csrc/szb_lu_front.cuh: kNB
 
 
-def _tile_bounds(s: int, f: int) -> np.ndarray:
-    """Tile boundaries of a front in front-index space: 0, 8, .., (pivot tiles), s, s + 8, .., f."""
-    top = np.arange(0, s, TILE)
-    bot = np.arange(s, f, TILE)
-    return np.concatenate([top, bot, [f]]).astype(np.int64)
+def plan_threads(sym) -> Dict[str, int]:
+    """Threads per CTA and warps per group for this schedule (one warp per warp list, a whole
+    number of warps per group, at least 8 warps when CTA-level fronts exist)."""
+    warps = max(int(sym.n_warp_lists), 1)
+    wpg = 0
+    ngl = int(sym.n_group_lists)
+    if ngl > 0:
+        per = -(-warps // ngl)
+        wpg = max(2, per)
+        warps = wpg * ngl
+    if len(sym.top) > 0 and warps < 8:
+        if ngl > 0:
+            wpg = -(-8 // ngl)
+            warps = wpg * ngl
+        else:
+            warps = 8
+    if warps > 32:
+        raise ValueError(f"schedule needs {warps} warps per CTA (max 32)")
+    return dict(threads=32 * warps, wpg=wpg)
 
 
-def _pack(pos: np.ndarray) -> int:
-    """Nibble q = pos[q] for q < len(pos), 0xF beyond (two's-complement int32)."""
-    v = 0
-    for q in range(TILE):
-        v |= (int(pos[q]) if q < len(pos) else 0xF) << (4 * q)
-    return v - (1 << 32) if v >= (1 << 31) else v
+def _front_sources(sym, k: int):
+    """Sources of front k in assembly order: (dst, src, kind) with kind 0 = O, 1 = C, 2 = R."""
+    s, f = int(sym.sn_s[k]), int(sym.sn_f[k])
+    ld = int(sym.sn_ld[k])
+    a0, a1 = int(sym.a_ptr[k]), int(sym.a_ptr[k + 1])
+    dst = [np.asarray(sym.a_dst[a0:a1], dtype=np.int64)]
+    src = [np.asarray(sym.a_src[a0:a1], dtype=np.int64) | (TAG_J << 30)]
+    kind = [np.zeros(a1 - a0, dtype=np.int64)]
+    p0 = int(sym.sn_piv0[k])
+    dst.append(np.arange(s, dtype=np.int64) + f * ld)
+    src.append(np.asarray(sym.rowp[p0:p0 + s], dtype=np.int64) | (TAG_RHS << 30))
+    kind.append(np.zeros(s, dtype=np.int64))
+    for c in sym.child[sym.child_ptr[k]:sym.child_ptr[k + 1]]:
+        c = int(c)
+        uc = int(sym.sn_f[c] - sym.sn_s[c])
+        if uc == 0:
+            continue
+        e0 = int(sym.ea_ptr[c])
+        cnt = uc * (uc + 1)
+        if int(sym.cb_off[c]) + cnt > OFF_MASK:
+            raise ValueError("contribution workspace exceeds 2^30 doubles per resident scenario")
+        dst.append(np.asarray(sym.ea_dst[e0:e0 + cnt], dtype=np.int64))
+        off = int(sym.cb_off[c]) + np.arange(cnt, dtype=np.int64)
+        is_rhs = np.arange(cnt) >= uc * uc
+        src.append(off | (TAG_CB << 30))
+        kind.append(np.where(is_rhs, 2, 1).astype(np.int64))
+    return np.concatenate(dst), np.concatenate(src), np.concatenate(kind)
 
 
-def build_tables(sym) -> Dict[str, np.ndarray]:
-    """Returns fh, ct, a_src, a_dst, atp, tcp, tce (int32) and the counts n_sched, n_child, n_warp_sn, n_mid_sn."""
-    if max(int(sym.n_warp_lists), int(sym.n_mid_lists)) > WARPS:
-        raise ValueError(f"schedule has {sym.n_warp_lists} / {sym.n_mid_lists} warp lists, the kernels run "
-                         f"{WARPS} warps per CTA")
-    if int(sym.f_warp_max) * (int(sym.f_warp_max) + 1) > WARP_LINES:
-        raise ValueError(f"level-0 fronts of order {sym.f_warp_max} do not fit the {WARP_LINES}-line warp buffer")
-    seq = [int(k) for k in sym.wl] + [int(k) for k in sym.ml] + [int(k) for k in sym.top]
-    n_l0 = len(sym.wl)
-    fh = np.zeros((max(len(seq), 1), HDR_WORDS), dtype=np.int64)
-    a_src = np.asarray(sym.a_src, dtype=np.int64).copy()
-    a_dst = np.asarray(sym.a_dst, dtype=np.int64).copy()
-    ct, atp, tcp, tce = [], [], [], []
-    n_atp = n_tcp = n_tce = 0
-    for q, k in enumerate(seq):
-        s, f = int(sym.sn_s[k]), int(sym.sn_f[k])
-        tiled = q >= n_l0
-        kids = [int(c) for c in sym.child[sym.child_ptr[k]:sym.child_ptr[k + 1]]
-                if int(sym.sn_f[c] - sym.sn_s[c]) > 0]
-        c0 = len(ct)
-        for c in kids:
-            ct.append((int(sym.cb_off[c]), int(sym.sn_f[c] - sym.sn_s[c]), int(sym.rel_ptr[c]),
-                       int(sym.rel_ptr[c]), 0, 0, 0, 0))
-        atp0 = tcp0 = -1
-        a0, a1 = int(sym.a_ptr[k]), int(sym.a_ptr[k + 1])
-        if tiled:
-            tb = _tile_bounds(s, f)
-            nt = len(tb) - 1
-            lp, up = int(sym.lp_off[k]), int(sym.up_off[k])
-            d = a_dst[a0:a1]
-            in_p = d < up
-            off = np.where(in_p, d - lp, d - up)
-            c_ = np.where(in_p, off // f, s + off // max(s, 1))
-            r_ = np.where(in_p, off % f, off % max(s, 1))
-            tr = np.searchsorted(tb, r_, side="right") - 1
-            tc = np.searchsorted(tb, c_, side="right") - 1
-            tid = tr + tc * nt
-            order = np.argsort(tid, kind="stable")
-            a_src[a0:a1] = a_src[a0:a1][order]
-            a_dst[a0:a1] = ((r_ - tb[tr]) + TILE * (c_ - tb[tc]))[order]
-            cnt = np.bincount(tid, minlength=nt * nt)
-            atp0 = n_atp
-            ptr = a0 + np.concatenate([[0], np.cumsum(cnt)])
-            atp.append(ptr)
-            n_atp += len(ptr)
-            # contributors of every tile (rhs column = tile column nt), children in schedule order
-            per_tile = [[] for _ in range(nt * (nt + 1))]
-            for c in kids:
-                rl = np.asarray(sym.rel[sym.rel_ptr[c]:sym.rel_ptr[c + 1]], dtype=np.int64)
-                uc = len(rl)
-                cut = np.searchsorted(rl, tb, side="left")     # child rows below each tile boundary
-                cbo = int(sym.cb_off[c])
-                pieces = [(t, int(cut[t]), int(cut[t + 1])) for t in range(nt) if cut[t + 1] > cut[t]]
-                for (t_r, r_lo, r_hi) in pieces:
-                    rp = _pack(rl[r_lo:r_hi] - tb[t_r])
-                    for (t_c, c_lo, c_hi) in pieces:
-                        per_tile[t_r + t_c * nt].append((cbo + r_lo + c_lo * uc, uc, rp, _pack(rl[c_lo:c_hi] - tb[t_c])))
-                    per_tile[t_r + nt * nt].append((cbo + r_lo + uc * uc, uc, rp, _pack(np.zeros(1, dtype=np.int64))))
-            tcp0 = n_tcp
-            ptr = n_tce + np.concatenate([[0], np.cumsum([len(x) for x in per_tile])])
-            tcp.append(ptr)
-            n_tcp += len(ptr)
-            for x in per_tile:
-                tce.extend(x)
-                n_tce += len(x)
-        fh[q, :15] = (s, f, int(sym.sn_piv0[k]), int(sym.lp_off[k]), int(sym.up_off[k]), int(sym.cb_off[k]),
-                      a0, a1, c0, len(ct), int(sym.idx_ptr[k]), int(sym.rel_ptr[k]), atp0, tcp0, k)
-    if fh.max(initial=0) >= 2 ** 31 or max(n_atp, n_tcp, n_tce) >= 2 ** 29:
-        raise ValueError("LU schedule exceeds int32 offsets")
+def _schedule_front(dst: np.ndarray, src: np.ndarray, kind: np.ndarray, G: int):
+    """Assign sources to (block, iteration, thread): unique owner thread per destination, first-touch
+    round-robin so that consecutive sources of the first toucher land on consecutive threads."""
+    uniq, first, inv = np.unique(dst, return_index=True, return_inverse=True)
+    rank = np.empty(len(uniq), dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+    thread = (rank % G)[inv]
+    tabs = []
+    for kd in range(3):
+        sel = np.flatnonzero(kind == kd)
+        if len(sel) == 0:
+            tabs.append(np.zeros((0, G, 2), dtype=np.uint32))
+            continue
+        th = thread[sel]
+        order = np.argsort(th, kind="stable")          # sources of one thread stay in source order
+        th_sorted = th[order]
+        start = np.searchsorted(th_sorted, np.arange(G))
+        it_sorted = np.arange(len(sel)) - start[th_sorted]
+        iters = int(it_sorted.max()) + 1
+        tab = np.empty((iters, G, 2), dtype=np.uint32)
+        tab[:, :, 0] = NOOP
+        tab[:, :, 1] = 0
+        tab[it_sorted, th_sorted, 0] = src[sel][order].astype(np.uint32)
+        tab[it_sorted, th_sorted, 1] = dst[sel][order].astype(np.uint32)
+        tabs.append(tab)
+    return tabs
 
-    def flat(parts):
-        return np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(1), dtype=np.int32)
-    cta = np.array(ct, dtype=np.int64).reshape(-1, 8) if ct else np.zeros((1, 8), dtype=np.int64)
-    tcea = np.array(tce, dtype=np.int64).reshape(-1, 4) if tce else np.zeros((1, 4), dtype=np.int64)
-    return dict(fh=np.ascontiguousarray(fh, dtype=np.int32), ct=np.ascontiguousarray(cta, dtype=np.int32),
-                a_src=np.ascontiguousarray(a_src, dtype=np.int32), a_dst=np.ascontiguousarray(a_dst, dtype=np.int32),
-                atp=flat(atp), tcp=flat(tcp), tce=np.ascontiguousarray(tcea, dtype=np.int32),
-                n_sched=len(seq), n_child=len(ct), n_warp_sn=len(sym.wl), n_mid_sn=len(sym.ml))
+
+def build_tables(sym, threads: int, wpg: int) -> Dict[str, np.ndarray]:
+    """Returns ``dict(fh=int32[n_sched,16], ga=int32[n_entries,2], n_sched, n_entries, G_of)``."""
+    seqs = []
+    for w in range(int(sym.n_warp_lists)):
+        seqs += [(int(k), 32) for k in sym.wl[sym.wl_ptr[w]:sym.wl_ptr[w + 1]]]
+    for g in range(int(sym.n_group_lists)):
+        seqs += [(int(k), 32 * wpg) for k in sym.gl[sym.gl_ptr[g]:sym.gl_ptr[g + 1]]]
+    seqs += [(int(k), threads) for k in sym.top]
+    fh = np.zeros((max(len(seqs), 1), HDR_WORDS), dtype=np.int32)
+    blocks = []
+    cursor = 0
+    for q, (k, G) in enumerate(seqs):
+        dst, src, kind = _front_sources(sym, k)
+        tabs = _schedule_front(dst, src, kind, G)
+        fh[q, :6] = (int(sym.sn_s[k]), int(sym.sn_f[k]), int(sym.sn_piv0[k]), int(sym.lp_off[k]),
+                     int(sym.up_off[k]), int(sym.cb_off[k]))
+        for b, tab in enumerate(tabs):
+            fh[q, 6 + 2 * b] = cursor
+            fh[q, 7 + 2 * b] = tab.shape[0]
+            blocks.append(tab.reshape(-1, 2))
+            cursor += tab.shape[0] * G
+        fh[q, 12] = k
+        fh[q, 13] = len(dst)
+        fh[q, 14] = int(sym.idx_ptr[k])
+        if cursor >= 2 ** 31:
+            raise ValueError("gather table exceeds int32 offsets")
+    ga = np.concatenate(blocks) if blocks else np.zeros((0, 2), dtype=np.uint32)
+    if len(ga) == 0:
+        ga = np.full((1, 2), NOOP, dtype=np.uint32)
+    return dict(fh=fh, ga=np.ascontiguousarray(ga).view(np.int32), n_sched=len(seqs), n_entries=int(cursor),
+                G_of=np.array([g for _, g in seqs], dtype=np.int64),
+                ld_of=np.array([int(sym.sn_ld[k]) for k, _ in seqs], dtype=np.int64))

@@ -344,6 +344,14 @@ def _postorder(parent: np.ndarray, children: List[List[int]], key) -> np.ndarray
     return np.array(post, dtype=np.int64)
 
 
+def front_ld(f, level):
+    """Leading dimension of a front of order ``f`` scheduled at ``level`` (0 = warp, else multi-warp);
+    mirrors ld_warp / ld_blk of csrc/szb_lu.cu."""
+    f = np.asarray(f)
+    fp = f + 7      # multi-warp fronts carry 7 rows of zero padding (kPad): unmasked 8x8 tensor-core tiles
+    return np.where(np.asarray(level) == 0, f | 1, fp + ((2 - fp) & 3))
+
+
 @dataclasses.dataclass
 class LUSymbolic:
     """Frozen result of the analysis; the integer arrays are uploaded to the device once."""
@@ -355,6 +363,7 @@ class LUSymbolic:
     sn_piv0: np.ndarray       # first pivot of supernode
     sn_s: np.ndarray          # pivots in supernode
     sn_f: np.ndarray          # front order (s + u)
+    sn_ld: np.ndarray         # leading dimension of the front buffer (front_ld)
     sn_parent: np.ndarray     # parent supernode or -1
     idx_ptr: np.ndarray       # front index lists (permuted indices; first s are the pivots)
     idx: np.ndarray
@@ -364,40 +373,40 @@ class LUSymbolic:
     child: np.ndarray
     a_ptr: np.ndarray         # per supernode: J slots scattered into the front
     a_src: np.ndarray         # J slot (CSC position in the original matrix)
-    a_dst: np.ndarray         # offset in the factor storage: lp_off + r + c*f (c < s) or up_off + r + (c-s)*s
+    a_dst: np.ndarray         # r + c*f position in the column-major front
     lp_off: np.ndarray        # offset of the f x s column-major [L11\U11; L21] panel
     up_off: np.ndarray        # offset of the s x u column-major U12 panel
     lu_size: int              # doubles per scenario of factor storage (with padding)
     cb_off: np.ndarray        # offset of the u x (u+1) contribution block in the workspace
-    cb_size: int              # lines (32 scenarios each) of contribution workspace per resident CTA
-    sn_m: np.ndarray          # update rows of the supernode that are pivots of its parent
+    ea_ptr: np.ndarray        # extend-add destination tables, one run of u(u+1) entries per supernode
+    ea_dst: np.ndarray
+    cb_size: int              # doubles per resident scenario of contribution workspace
     nnz_lu: int               # true nnz(L+U) of the symbolic factor (no supernode padding)
     flops: float              # factor flops per scenario (2 per multiply-add)
     f_max: int
-    # schedule: warp-level subtrees (on-chip fronts), warp-level subtrees (tiled fronts), the CTA-level top
+    # schedule: warp-level subtrees, then group-level (a few warps) subtrees, then the CTA-level top
     n_warp_lists: int
-    wl_ptr: np.ndarray        # level-0 work lists (supernode ids, each list in postorder)
+    wl_ptr: np.ndarray        # warp work lists (supernode ids, each list in postorder)
     wl: np.ndarray
-    n_mid_lists: int
-    ml_ptr: np.ndarray        # level-1 work lists
-    ml: np.ndarray
-    top: np.ndarray           # level-2 (CTA-level) supernodes in postorder
+    n_group_lists: int
+    gl_ptr: np.ndarray        # group work lists
+    gl: np.ndarray
+    top: np.ndarray           # block-level supernodes in postorder
     f_warp_max: int
-    f_mid_max: int
+    f_group_max: int
     f_top_max: int
     ordering: str = ""
-    sched_version: int = 3    # layout of the schedule fields (rendered packages cache this object)
 
     @property
     def order(self) -> np.ndarray:
         """A valid sequential elimination order (children before parents)."""
-        return np.concatenate([self.wl, self.ml, self.top]).astype(np.int64)
+        return np.concatenate([self.wl, self.gl, self.top]).astype(np.int64)
 
     def stats(self) -> Dict[str, float]:
         return dict(n=self.n, nnzA=self.nnzA, nnz_lu=self.nnz_lu, lu_size=self.lu_size,
                     cb_size=self.cb_size, flops=self.flops, ns=self.ns, f_max=self.f_max,
-                    f_warp_max=self.f_warp_max, f_mid_max=self.f_mid_max, f_top_max=self.f_top_max,
-                    n_warp_sn=len(self.wl), n_mid_sn=len(self.ml), n_top=len(self.top),
+                    f_warp_max=self.f_warp_max, f_group_max=self.f_group_max, f_top_max=self.f_top_max,
+                    n_warp_sn=len(self.wl), n_group_sn=len(self.gl), n_top=len(self.top),
                     ordering=self.ordering)
 
 
@@ -407,8 +416,9 @@ def _flops_of(struct_sizes: np.ndarray) -> float:
 
 
 def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.ndarray,
-           relax_frac: float, relax_small: int, warp_front_max: int, mid_front_max: int, n_warps: int,
-           name: str, warp_fixed: float = 3000.0) -> LUSymbolic:
+           relax_frac: float, relax_small: int, warp_front_max: int, n_warps: int,
+           group_front_max: int, n_groups: int, name: str, warp_fixed: float = 3000.0,
+           group_fixed: float = 60000.0) -> LUSymbolic:
     n = A.shape[0]
     parent, children, struct = _symbolic_structs(S, order)
     size = np.array([len(s) for s in struct], dtype=np.int64)
@@ -534,27 +544,31 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         off += up_sz[k]
     lu_size = int(off)
 
-    # ---- schedule: three levels of the tree (csrc/szb_lu.cu: one CTA works on a GROUP of 32 scenarios,
-    # lane = scenario; one kernel per level).
-    #   level 0: every front of the subtree fits a warp-private shared-memory buffer (f <= warp_front_max): the
-    #            forest is split into independent subtrees dealt to the warps' work lists (longest processing
-    #            time first); a warp assembles and eliminates a front on chip, no synchronisation at all;
-    #   level 1: every front of the subtree has f <= mid_front_max: again independent subtrees dealt to the
-    #            warps, each front walked by ONE warp in register tiles (tiled path, operands from L2);
-    #   level 2: the top of the tree, one list in postorder, all warps of the CTA share a front (tiled path).
+    # ---- schedule: three levels of the tree.  A supernode is warp-level when every front in
+    # its subtree fits a warp-private buffer, group-level when every front fits a group buffer,
+    # CTA-level otherwise.  Each level's forest is split into independent subtrees that are
+    # assigned to work lists by longest-processing-time first.
     sub_fmax = sn_f.copy()
-    own_cost = (sn_s * sn_f * sn_f).astype(np.float64) + float(warp_fixed)
+    sub_cost = (sn_s * sn_f * sn_f).astype(np.float64)
+    own_cost = sub_cost.copy()
+    # warp level: a front costs a few thousand cycles of latency (descriptor, gather, write-out) whatever its
+    # size; with s f^2 alone the lists held 25 to 44 fronts and the longest set the level's time (measured:
+    # factor 11.25 -> 11.13 ms, sweeps 2.18 -> 2.14 ms with 3000 per front)
+    warp_cost = own_cost + warp_fixed
     for k in range(ns):  # postorder: children before parents
         p = sn_parent[k]
         if p >= 0:
             sub_fmax[p] = max(sub_fmax[p], sub_fmax[k])
-    level = np.where(sub_fmax <= warp_front_max, 0, np.where(sub_fmax <= mid_front_max, 1, 2))
-    a_dst = np.where(loc_c[by_owner] < sn_s[owner[by_owner]],
-                     lp_off[owner[by_owner]] + loc_r[by_owner] + loc_c[by_owner] * sn_f[owner[by_owner]],
-                     up_off[owner[by_owner]] + loc_r[by_owner]
-                     + (loc_c[by_owner] - sn_s[owner[by_owner]]) * sn_s[owner[by_owner]]).astype(np.int64)
-    assert np.all((loc_c[by_owner] < sn_s[owner[by_owner]]) | (loc_r[by_owner] < sn_s[owner[by_owner]])), \
-        "a matrix entry landed in the Schur block of its owner front"
+            sub_cost[p] += sub_cost[k]
+    level = np.where(sub_fmax <= warp_front_max, 0, np.where(sub_fmax <= group_front_max, 1, 2))
+    # leading dimension of the column-major front in shared memory (csrc/szb_lu.cu: ld_warp / ld_blk):
+    # warp-level fronts (lane = row, rank-1 steps): odd, so rows AND columns are conflict-free;
+    # multi-warp fronts (8x8 tensor-core tiles): ld >= f + 7 and ld = 2 (mod 4), which puts the four column
+    # pairs of an mma.m8n8k4 accumulator fragment on disjoint banks.
+    sn_ld = front_ld(sn_f, level)
+    a_dst = (loc_r[by_owner] + loc_c[by_owner] * sn_ld[owner[by_owner]]).astype(np.int64)
+    # (measured: lists balanced on s * f^2 finish within 5 % of each other; cost models with a per-front fixed
+    # part or per-panel barrier costs did not do better, profiles/r1_v6_factor_ncu.md)
 
     def make_lists(lv: int, n_max: int):
         mine = level == lv
@@ -565,9 +579,11 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
             if mine[k]:
                 p = sn_parent[k]
                 root_of[k] = k if (p < 0 or not mine[p]) else root_of[p]
+        # (group level: 60000 per front on the same scale, measured 11.13 -> 11.06 ms)
+        per_front = warp_cost if lv == 0 else (own_cost + group_fixed if lv == 1 else own_cost)
         for k in range(ns):
             if mine[k]:
-                cost[root_of[k]] += own_cost[k]
+                cost[root_of[k]] += per_front[k]
         n_lists = max(1, min(n_max, len(roots))) if roots else 0
         loads = np.zeros(max(n_lists, 1))
         assign = {}
@@ -586,87 +602,125 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
         return n_lists, lists, ptr, flat
 
     n_lists, lists, wl_ptr, wl = make_lists(0, n_warps)
-    n_mlists, mlists, ml_ptr, ml = make_lists(1, n_warps)
+    n_glists, glists, gl_ptr, gl = make_lists(1, n_groups)
     top = np.array([k for k in range(ns) if level[k] == 2], dtype=np.int64)
+    is_warp = level == 0
 
-    # ---- contribution-block workspace (one per group, in lines of 32 scenarios).  Each work list is a
-    # sequential postorder walk, so the classic multifrontal stack is valid per list: when a supernode
-    # starts, the blocks of its children (of the same list) are the top of the stack; they are absorbed and
-    # popped, and the supernode's own block is pushed in their place.  Blocks that cross from one list to a
-    # list of a higher level live in a persistent region A; the stacks of the three levels share addresses
-    # (the levels are separate kernel launches).
+    # ---- contribution-block workspace.  Each work list (and the top list) is a sequential
+    # postorder walk, so the classic multifrontal stack is valid per list: when a supernode
+    # starts, the blocks of its children (of the same list) are the top of the stack; they are
+    # absorbed into the front (which lives in shared memory) and popped, and the supernode's own
+    # block is pushed in their place once its pivots are eliminated.  Blocks that cross from a
+    # warp list to the top list live in a separate, never-reused region.
     cb_off = np.zeros(ns, dtype=np.int64)
     cb_need = sn_u * (sn_u + 1)   # u x u Schur block + one right-hand-side column
-    # The fronts are assembled IN PLACE: a parent's block is being accumulated while its children's blocks
-    # are still being read, so the two must not share addresses.  Two stacks by tree-depth parity give
-    # that for free: a node at depth d pushes on stack d mod 2 and pops its children (depth d + 1) from
-    # the other one; in a postorder walk the children are the top of their stack at that moment.
-    depth = np.zeros(ns, dtype=np.int64)
-    for k in range(ns - 1, -1, -1):
-        if sn_parent[k] >= 0:
-            depth[k] = depth[sn_parent[k]] + 1
+    cursor = 0
 
-    def alloc_list(seq: Sequence[int], bases) -> List[int]:
+    def alloc_list(seq: Sequence[int], base: int) -> int:
         inseq = set(int(s) for s in seq)
-        sp_ = [0, 0]
-        peak = [0, 0]
+        sp_ = 0
+        peak = 0
         start_of: Dict[int, int] = {}
         for k in seq:
-            par = int(depth[k] & 1)
             mine = [c for c in ch[k] if c in inseq]
             if mine:
-                sp_[1 - par] = min(start_of[c] for c in mine)      # pop the absorbed children
+                sp_ = min(start_of[c] for c in mine)      # pop the absorbed children
             if sn_parent[k] < 0 or int(sn_parent[k]) not in inseq:
-                continue                                            # crosses lists: persistent region
-            start_of[k] = sp_[par]
-            cb_off[k] = bases[par] + sp_[par]
-            sp_[par] += int(cb_need[k])
-            peak[par] = max(peak[par], sp_[par])
+                continue                                   # crosses lists: persistent region
+            start_of[k] = sp_
+            cb_off[k] = base + sp_
+            sp_ += int(cb_need[k])
+            peak = max(peak, sp_)
         return peak
 
-    level_lists = [[list(map(int, l)) for l in lists], [list(map(int, l)) for l in mlists], [list(map(int, top))]]
-    a_sz = 0
-    for lls in level_lists:
-        for seq in lls:
-            inseq = set(seq)
-            for k in seq:
-                p = int(sn_parent[k])
-                if p >= 0 and p not in inseq:
-                    cb_off[k] = a_sz
-                    a_sz += int(cb_need[k])
-    cb_size = a_sz
-    for lls in level_lists:
-        cursor = a_sz
-        for seq in lls:
-            pk = alloc_list(seq, (0, 0))
-            alloc_list(seq, (cursor, cursor + pk[0]))
-            cursor += pk[0] + pk[1]
-        cb_size = max(cb_size, cursor)
-    cb_size = int(cb_size)
+    # Blocks that cross lists go one level up or more (a list holds whole subtrees of its level), and the
+    # levels are separated by CTA-wide barriers in the factor kernel, so regions of different lifetimes
+    # share addresses.  The workspace of a resident CTA is what decides whether the contribution blocks
+    # stay in L2 (148 CTAs x cb_size: 114 MB without this sharing on the 1024-bus benchmark, 88 MB with it,
+    # against 126 MB of L2).
+    #   A  warp -> CTA level blocks      live: warp level .. CTA level
+    #   B  warp -> group level blocks    live: warp level .. group level
+    #   C  group -> CTA level blocks     live: group level .. CTA level
+    #   S0 / S1 / S2  stacks of the warp lists / group lists / CTA-level list, live within their level
+    # layout:  [A][B][S0 ...]            warp level
+    #          [A][B][S1][C]             group level  (S1 and C over S0)
+    #          [A][S2 ......][C]         CTA level    (S2 over B and S1 when it fits, else behind C)
+    all_lists = [list(map(int, l)) for l in lists] + [list(map(int, l)) for l in glists] + \
+                [list(map(int, top))]
+    list_level = [0] * len(lists) + [1] * len(glists) + [2]
+    lvl_of = {}
+    for seq, lv in zip(all_lists, list_level):
+        for k in seq:
+            lvl_of[k] = lv
+    cross = {"A": [], "B": [], "C": []}
+    for seq, lv in zip(all_lists, list_level):
+        inseq = set(seq)
+        for k in seq:
+            p = int(sn_parent[k])
+            if p >= 0 and p not in inseq:
+                kind = {(0, 2): "A", (0, 1): "B", (1, 2): "C"}.get((lv, lvl_of[p]))
+                if kind is None:
+                    raise AssertionError("a contribution block crosses lists of one level")
+                cross[kind].append(k)
+    size_of = lambda ks: int(sum(int(cb_need[k]) for k in ks))
+    a_sz, b_sz, c_sz = size_of(cross["A"]), size_of(cross["B"]), size_of(cross["C"])
 
-    # rows of a child's update set that fall inside the pivot block of its parent (rel is ascending)
-    sn_m = np.zeros(ns, dtype=np.int64)
+    def place(ks, base):
+        for k in ks:
+            cb_off[k] = base
+            base += int(cb_need[k])
+
+    def stacks(seqs, base):
+        top_ = base
+        for seq in seqs:
+            top_ += alloc_list(seq, top_)
+        return top_ - base
+
+    place(cross["A"], 0)
+    place(cross["B"], a_sz)
+    zone = a_sz + b_sz
+    s0_sz = stacks(all_lists[:len(lists)], zone)
+    s1_sz = stacks(all_lists[len(lists):len(lists) + len(glists)], zone)
+    place(cross["C"], zone + s1_sz)
+    c_end = zone + s1_sz + c_sz
+    # the CTA-level stack: measure, then put it over [B][S1] if it fits there
+    s2_sz = alloc_list(all_lists[-1], 0)
+    s2_base = a_sz if s2_sz <= b_sz + s1_sz else c_end
+    alloc_list(all_lists[-1], s2_base)
+    cursor = max(zone + s0_sz, c_end, s2_base + s2_sz)
+    cb_size = int(cursor)
+
+    # ---- extend-add destinations: element t = i + j*u of the u x (u+1) block of child c goes to
+    # rel[i] + col*ld_parent with col = rel[j] (Schur part) or f_parent (right-hand-side column)
+    ea_ptr = np.zeros(ns + 1, dtype=np.int64)
+    ea_ptr[1:] = np.cumsum(cb_need)
+    ea_dst = np.zeros(ea_ptr[-1], dtype=np.int64)
     for k in range(ns):
         p = sn_parent[k]
-        if p >= 0:
-            sn_m[k] = int(np.searchsorted(rel[rel_ptr[k]:rel_ptr[k + 1]], sn_s[p]))
+        uk = int(sn_u[k])
+        if p < 0 or uk == 0:
+            continue
+        rl = rel[rel_ptr[k]:rel_ptr[k + 1]]
+        ldp = int(sn_ld[p])
+        cols = np.concatenate([rl, [sn_f[p]]])
+        ea_dst[ea_ptr[k]:ea_ptr[k + 1]] = (rl[None, :] + cols[:, None] * ldp).reshape(-1)
 
     return LUSymbolic(
         n=n, nnzA=int(Ac.nnz), rowp=rowp, colp=colp, ns=ns, sn_piv0=sn_piv0, sn_s=sn_s,
-        sn_f=sn_f, sn_parent=sn_parent, idx_ptr=idx_ptr, idx=idx, rel_ptr=rel_ptr, rel=rel,
+        sn_f=sn_f, sn_ld=sn_ld, sn_parent=sn_parent, idx_ptr=idx_ptr, idx=idx, rel_ptr=rel_ptr, rel=rel,
         child_ptr=child_ptr, child=child, a_ptr=a_ptr, a_src=a_src, a_dst=a_dst, lp_off=lp_off,
-        up_off=up_off, lu_size=lu_size, cb_off=cb_off, cb_size=cb_size, sn_m=sn_m,
+        up_off=up_off, lu_size=lu_size, cb_off=cb_off, ea_ptr=ea_ptr, ea_dst=ea_dst, cb_size=cb_size,
         nnz_lu=nnz_lu,
         flops=flops, f_max=int(sn_f.max()), n_warp_lists=n_lists, wl_ptr=wl_ptr, wl=wl,
-        n_mid_lists=n_mlists, ml_ptr=ml_ptr, ml=ml, top=top,
+        n_group_lists=n_glists, gl_ptr=gl_ptr, gl=gl, top=top,
         f_warp_max=int(sn_f[level == 0].max()) if (level == 0).any() else 0,
-        f_mid_max=int(sn_f[level == 1].max()) if (level == 1).any() else 0,
+        f_group_max=int(sn_f[level == 1].max()) if (level == 1).any() else 0,
         f_top_max=int(sn_f[level == 2].max()) if (level == 2).any() else 0, ordering=name)
 
 
 def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
-            warp_front_max: int = 10, mid_front_max: int = 32, n_warps: int = 8,
-            orderings: Sequence[str] = ("nd", "mmd"), warp_fixed: float = 3000.0) -> LUSymbolic:
+            warp_front_max: int = 32, n_warps: int = 16, group_front_max: int = 72, n_groups: int = 4,
+            orderings: Sequence[str] = ("nd", "mmd"), warp_fixed: float = 3000.0, group_fixed: float = 60000.0) -> LUSymbolic:
     """Analyse the pattern (and representative values) of ``A``; see the module docstring."""
     A = sp.csc_matrix(A)
     A.sort_indices()
@@ -713,5 +767,5 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
             best = (fl, name, order)
     assert best is not None
     _, name, order = best
-    return _build(A, rowperm, S, order, relax_frac, relax_small, warp_front_max, max(mid_front_max, warp_front_max),
-                  n_warps, name, float(warp_fixed))
+    return _build(A, rowperm, S, order, relax_frac, relax_small, warp_front_max, n_warps,
+                  group_front_max, n_groups, name, float(warp_fixed), float(group_fixed))

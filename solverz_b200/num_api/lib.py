@@ -9,9 +9,9 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = Path(os.environ.get("SZB_LIB", str(_HERE.parent / "csrc" / "libszb.so")))   # SZB_LIB: instrumented builds of tools/
+LIB_PATH = _HERE.parent / "csrc" / "libszb.so"
 
-SZB_ABI_VERSION = 4
+SZB_ABI_VERSION = 3
 SZB_FLAG_EVENT = 8
 SLOT_Y, SLOT_F, SLOT_JV, SLOT_RHS, SLOT_PARAM0 = 0, 1, 2, 3, 16
 DTYPE_F64, DTYPE_I32 = 0, 1
@@ -24,10 +24,13 @@ _i32p = C.POINTER(C.c_int32)
 
 class LuSymbolicC(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n", "nnz_a", "ns", "lu_size", "cb_size", "cv_size", "n_warp_lists",
-                                         "n_warp_sn", "n_mid_lists", "n_mid_sn", "n_sched", "n_child", "n_idx",
-                                         "n_rel", "n_atp", "n_tcp", "n_tce", "warp_lines", "f_max", "f_warp_max")] + \
-               [(k, _i32p) for k in ("rowp", "colp", "idx", "rel", "a_src", "a_dst", "wl_ptr", "ml_ptr", "fh", "ct",
-                                     "atp", "tcp", "tce")]
+                                         "n_group_lists", "n_top", "f_warp_max", "f_group_max", "f_top_max",
+                                         "s_warp_max", "s_group_max", "s_top_max", "threads", "wpg",
+                                         "n_sched", "n_ga")] + \
+               [(k, _i32p) for k in ("rowp", "colp", "sn_piv0", "sn_s", "sn_f", "idx_ptr", "idx", "rel_ptr",
+                                     "rel", "child_ptr", "child", "a_ptr", "a_src", "a_dst", "lp_off",
+                                     "up_off", "cb_off", "ea_ptr", "ea_dst", "wl_ptr", "wl", "gl_ptr", "gl", "top",
+                                     "fh", "ga")]
 
 
 class DescC(C.Structure):
@@ -84,8 +87,6 @@ def load():
     lib.szb_eval_J.argtypes = [H, C.c_double, C.c_void_p]
     lib.szb_lu_refactor.argtypes = [H, C.c_double, C.c_void_p]
     lib.szb_lu_solve.argtypes = [H, C.c_int32, C.c_void_p]
-    lib.szb_lu_status.argtypes = [H, C.c_void_p, C.c_void_p]
-    lib.szb_set_growth_tol.argtypes = [H, C.c_double]
     lib.szb_newton.argtypes = [H, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.szb_newton_host.argtypes = [H, C.c_double, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]
@@ -110,29 +111,38 @@ def check(rc: int, handle=None, what: str = ""):
 
 
 def lu_symbolic_c(sym, keep: list) -> LuSymbolicC:
-    """Lower solverz_b200.lu.symbolic.LUSymbolic to the device schedule (lu/schedule.py) and wrap it in the C
-    struct (int32 arrays kept alive in `keep`)."""
+    """Convert solverz_b200.lu.symbolic.LUSymbolic into the C struct (int32 arrays kept alive in `keep`)."""
     s = LuSymbolicC()
     if sym is None:
         return s
-    from ..lu.schedule import WARP_LINES, build_tables
-    tabs = build_tables(sym)
-    if max(int(sym.lu_size), int(sym.cb_size)) * 32 >= 2 ** 31 * 32:
-        raise SzbError("LU schedule exceeds int32 offsets")
-    s.n, s.nnz_a, s.ns = sym.n, sym.nnzA, sym.ns
+    ns = sym.ns
+    s.n, s.nnz_a, s.ns = sym.n, sym.nnzA, ns
     s.lu_size, s.cb_size, s.cv_size = sym.lu_size, sym.cb_size, int(sym.rel_ptr[-1])
-    s.n_warp_lists, s.n_warp_sn = sym.n_warp_lists, tabs["n_warp_sn"]
-    s.n_mid_lists, s.n_mid_sn = sym.n_mid_lists, tabs["n_mid_sn"]
-    s.n_sched, s.n_child = tabs["n_sched"], len(tabs["ct"])
-    s.n_idx, s.n_rel = len(sym.idx), len(sym.rel)
-    s.n_atp, s.n_tcp, s.n_tce, s.warp_lines = len(tabs["atp"]), len(tabs["tcp"]), len(tabs["tce"]), WARP_LINES
-    s.f_max, s.f_warp_max = sym.f_max, sym.f_warp_max
-    arrays = dict(rowp=sym.rowp, colp=sym.colp, idx=sym.idx, rel=sym.rel, a_src=tabs["a_src"], a_dst=tabs["a_dst"],
-                  wl_ptr=sym.wl_ptr, ml_ptr=sym.ml_ptr, fh=tabs["fh"], ct=tabs["ct"], atp=tabs["atp"], tcp=tabs["tcp"], tce=tabs["tce"])
-    for name, a in arrays.items():
-        arr = np.ascontiguousarray(np.asarray(a), dtype=np.int32).reshape(-1)
+    s.n_warp_lists, s.n_group_lists, s.n_top = sym.n_warp_lists, sym.n_group_lists, len(sym.top)
+    s.f_warp_max, s.f_group_max, s.f_top_max = sym.f_warp_max, sym.f_group_max, sym.f_top_max
+
+    def smax(ids):
+        ids = np.asarray(ids, dtype=np.int64)
+        return int(sym.sn_s[ids].max()) if len(ids) else 0
+    s.s_warp_max, s.s_group_max, s.s_top_max = smax(sym.wl), smax(sym.gl), smax(sym.top)
+    if max(sym.lu_size, sym.cb_size, int(sym.a_dst.max(initial=0))) >= 2 ** 31:
+        raise SzbError("LU schedule exceeds int32 offsets")
+    for name in ("rowp", "colp", "sn_piv0", "sn_s", "sn_f", "idx_ptr", "idx", "rel_ptr", "rel", "child_ptr",
+                 "child", "a_ptr", "a_src", "a_dst", "lp_off", "up_off", "cb_off", "ea_ptr", "ea_dst", "wl_ptr",
+                 "wl", "gl_ptr", "gl", "top"):
+        arr = np.ascontiguousarray(np.asarray(getattr(sym, name)), dtype=np.int32)
         if arr.size == 0:
             arr = np.zeros(1, dtype=np.int32)
+        keep.append(arr)
+        setattr(s, name, arr.ctypes.data_as(_i32p))
+    # device schedule: front descriptors + gather tables for exactly this thread layout
+    from ..lu.schedule import build_tables, plan_threads
+    plan = plan_threads(sym)
+    tabs = build_tables(sym, plan["threads"], plan["wpg"])
+    s.threads, s.wpg = plan["threads"], plan["wpg"]
+    s.n_sched, s.n_ga = tabs["n_sched"], len(tabs["ga"])
+    for name in ("fh", "ga"):
+        arr = np.ascontiguousarray(tabs[name], dtype=np.int32)
         keep.append(arr)
         setattr(s, name, arr.ctypes.data_as(_i32p))
     return s

@@ -222,7 +222,7 @@ class CudaModel:
             np.add.at(mv, np.asarray(mass_slots, dtype=np.int64), 1.0)
             self.mass_vals = mv
         self.nstep = nstep
-        self._sym = symbolic if getattr(symbolic, "sched_version", 0) == 3 else None   # drop analyses cached by older renders
+        self._sym = symbolic if hasattr(symbolic, "sn_ld") else None   # analyses cached by older renders lack the ld table
         self._pkl_path = pkl_path
         self.lu_options = dict(lu_options or {})
         self._sessions: Dict[tuple, BatchSession] = {}

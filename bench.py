@@ -32,6 +32,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+CONFIGS = {"cfg2": dict(nx=32, batch=4096), "cfg3": dict(nx=100, batch=2048)}
 METRIC = "batched_newton_iters_per_s"
 UNIT = "iters/s"
 TOL = 1e-8
@@ -51,10 +52,24 @@ def _ncu_traffic(cls: str, nx: int, B: int):
     `ncu --set full` capture of this same workload (profiles/ncu_traffic.json); None when there is none."""
     p = ROOT / "profiles" / "ncu_traffic.json"
     if not p.exists():
-        return None
+        return None, "no capture committed"
     d = json.loads(p.read_text())
     e = d.get(f"{cls}@nx{nx}B{B}")
-    return float(e["dram_bytes_per_launch"]) if e else None
+    if not e:
+        return None, "no capture of this kernel class at this workload"
+    # a capture only describes the kernel it was taken from: the entry carries the hash of the kernel sources
+    # (tools/ncu_traffic.py writes it); after any change to them the number is reported as stale, not as traffic
+    if e.get("source_sha") != kernel_source_sha():
+        return None, f"stale: captured on kernel sources {e.get('source_sha')}, now {kernel_source_sha()}"
+    return float(e["dram_bytes_per_launch"]), "ncu capture of the same kernel sources"
+
+
+def kernel_source_sha() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "solverz_b200" / "csrc").glob("*.cu*")):
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
 
 
 # ------------------------------------------------------------------------------ clocks sampler
@@ -161,9 +176,21 @@ def _info_cache(nx):
     return _INFO[nx]
 
 
-def cpu_arm(nx: int, sample: int, cores: int, steps: int, warmup: int):
-    """Times the oracle port on `cores` host processes; returns (iters/s, iterations per step, s/step)."""
+def cpu_arm(nx: int, sample: int, cores: int, steps: int, warmup: int, kind: str = "auto"):
+    """Times the CPU path on `cores` host processes; returns (iters/s, iterations per step, s/step, scenarios
+    per step, kind, description).  kind "reference": the reference's own numba module + nr_method from the
+    private copy baseline/_ref (baseline/ref_pf.py); "port": the oracle restatement (numpy F/J + SciPy SuperLU),
+    used only when the reference copy is not there."""
     import multiprocessing as mp
+    if kind in ("auto", "reference"):
+        from baseline import ref_pf
+        why = ref_pf.available()
+        if not why:
+            v, its, sps_, used = ref_pf.timed_run(nx, sample, cores, steps, warmup, TOL)
+            return v, its, sps_, used, "reference", ("reference numba module (module_printer(jit=True)) + nr_method "
+                                                     "-> SciPy SuperLU spsolve, one process per core")
+        if kind == "reference":
+            raise SystemExit(f"bench.py: reference arm unavailable: {why}")
     per = max(1, sample // cores)
     blocks = [(nx, i * per, per) for i in range(cores)]
     ctx = mp.get_context("fork")
@@ -175,7 +202,8 @@ def cpu_arm(nx: int, sample: int, cores: int, steps: int, warmup: int):
         for _ in range(steps):
             total += sum(pool.map(cpu_solve_block, blocks))
         dt = time.perf_counter() - t0
-    return total / dt, total // max(steps, 1), dt / max(steps, 1), per * cores
+    return (total / dt, total // max(steps, 1), dt / max(steps, 1), per * cores, "port",
+            "oracle port (numpy F/J + SciPy SuperLU spsolve per iteration), one process per core")
 
 
 # ------------------------------------------------------------------------------ main
@@ -185,8 +213,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nx", type=int, default=32)
-    ap.add_argument("--batch", type=int, default=4096, help="scenarios per GPU")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS),
+                    help="BASELINE.json workload: cfg2 = configs[1] (the default N=1 line), cfg3 = configs[2] "
+                         "(10k-bus grid, 16384 scenarios over 8 GPUs = 2048 per GPU)")
+    ap.add_argument("--nx", type=int, default=0, help="lattice side (overrides --config)")
+    ap.add_argument("--batch", type=int, default=0, help="scenarios per GPU (overrides --config)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -199,7 +230,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    nx, B = args.nx, args.batch
+    nx = args.nx or CONFIGS[args.config]["nx"]
+    B = args.batch or CONFIGS[args.config]["batch"]
+    cpu_per_core = max(1, int(round(128 * (32.0 / nx) ** 3)))   # scenarios per core and step of the CPU arm
     workload = f"polar AC power flow, {nx * nx}-bus {nx}x{nx} lattice + 2% chords, n={2 * nx * nx}, " \
                f"{B} load scenarios per GPU, nr_method(ite_tol=1e-8), flat start"
 
@@ -207,15 +240,15 @@ def main():
         if rank != 0:
             return
         cores = os.cpu_count() or 1
-        sample = args.cpu_sample or min(B, 128 * cores)   # ~3-4 s of work per step on 16 cores
-        val, its, sps_, used = cpu_arm(nx, sample, cores, args.steps, max(args.warmup, 1))
+        sample = args.cpu_sample or min(B, cpu_per_core * cores)   # a few seconds of work per step
+        val, its, sps_, used, kind, what = cpu_arm(nx, sample, cores, args.steps, max(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps_ * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "sample_scenarios_per_step": used},
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"{used} scenarios per step ({its} Newton iterations), oracle port "
-                                           f"(numpy F/J + SciPy SuperLU spsolve), {cores} processes"},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                                 "sample": f"{used} scenarios per step ({its} Newton iterations), {what}, "
+                                           f"{cores} processes"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -224,11 +257,14 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = args.cpu_sample or min(B, 256 * cores)   # the whole batch where it fits: ~7-10 s on 16 cores
-        val, its, sps_, used = cpu_arm(nx, sample, cores, 1, 1)
-        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{used} of the {B} scenarios ({its} Newton iterations, {sps_:.1f} s), oracle port "
-                         f"(numpy F/J + SciPy SuperLU spsolve per iteration), {cores} processes"}
+        sample = args.cpu_sample or min(B, 2 * cpu_per_core * cores)   # ~10 s of CPU work
+        val, its, sps_, used, kind, what = cpu_arm(nx, sample, cores, 1, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{used} of the {B} scenarios ({its} Newton iterations, {sps_:.1f} s), {what}, "
+                         f"{cores} processes"}
+        if kind == "reference":          # the oracle port next to it (second number, same sample)
+            v2, _, s2, _, _, w2 = cpu_arm(nx, sample, cores, 1, 1, kind="port")
+            cpu["port"] = {"value": v2, "unit": UNIT, "seconds": s2, "what": w2}
 
     import torch
     import torch.distributed as dist
@@ -414,7 +450,8 @@ def main():
         roofline = {"bound": "hbm", "kernel": {"F": "szbm_F_kernel", "J": "szbm_J_kernel",
                                                "lu_refactor": "lu_factor_kernel", "lu_solve": "lu_backward_kernel"}[dom],
                     "achieved": classes[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": classes[dom]["frac"], "traffic": _ncu_traffic(dom, nx, B), "peak_source": peak_kind,
+                    "frac": classes[dom]["frac"], "traffic": _ncu_traffic(dom, nx, B)[0],
+                    "traffic_source": _ncu_traffic(dom, nx, B)[1], "peak_source": peak_kind,
                     "alg_bytes_per_launch": alg[dom] * units_per_launch, "classes": classes}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -175,3 +175,35 @@ def test_full_size_config2_properties(libszb, tmp_path_factory):
     mdl.p["Pinj"], mdl.p["Qinj"] = P[perm], Q[perm]
     sol2 = nr_method(mdl, Y0, Opt(ite_tol=1e-8))
     assert np.array_equal(sol2.y, sol.y[perm]) and np.array_equal(sol2.stats.nstep, sol.stats.nstep[perm])
+
+
+def test_full_size_config3_properties(libszb, tmp_path_factory):
+    """BASELINE.json configs[2] at its per-GPU size (10 000 buses, n = 20 000, 16 384 scenarios over 8 GPUs =
+    2048 per GPU; separator fronts up to 779 x 779 run out of the per-CTA global workspace): every scenario
+    converges, the ORACLE's residual of every GPU solution is below the tolerance, and 16 sampled scenarios
+    agree with the oracle's own Newton (solution 1e-10 relative, identical iteration counts)."""
+    from oracle.nr import nr_method as oracle_nr
+    from solverz_b200 import Opt, module_printer, nr_method
+    from solverz_b200.synthetic import pf_scenarios, polar_pf_model
+    d = tmp_path_factory.mktemp("mods100")
+    eqs, y0, info = polar_pf_model(100, 100)
+    module_printer(eqs, y0, "pfn100", directory=str(d)).render()
+    sys.path.insert(0, str(d))
+    mdl = importlib.import_module("pfn100").mdl
+    assert mdl.n == 20000
+    orc = _oracle(info)
+    B = 2048
+    P, Q = pf_scenarios(info, B)
+    mdl.p["Pinj"], mdl.p["Qinj"] = P, Q
+    sol = nr_method(mdl, np.tile(y0.array, (B, 1)), Opt(ite_tol=1e-8))
+    assert mdl.session(B).sym.f_top_max > 500
+    assert sol.stats.succeed.all() and (sol.stats.flag == 0).all()
+    assert sol.stats.nstep.min() >= 2 and sol.stats.nstep.max() <= 8
+    assert (sol.stats.nfeval == sol.stats.nstep + 1).all()
+    res = np.array([np.abs(orc.F(sol.y[b], P[b], Q[b])).max() for b in range(B)])
+    assert res.max() <= 1e-8
+    for b in range(0, B, 128):                          # 16 scenarios against the oracle's own Newton
+        ref = oracle_nr(lambda y: orc.F(y, P[b], Q[b]), orc.J, y0.array, 1e-8, 100)
+        assert np.abs(sol.y[b] - ref["y"]).max() <= 1e-10 * np.abs(ref["y"]).max()
+        assert int(sol.stats.nstep[b]) == ref["nstep"]
+    mdl.close()

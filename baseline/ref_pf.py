@@ -132,8 +132,9 @@ def timed_run(nx: int, sample: int, cores: int, steps: int, warmup: int, tol: fl
     per = max(1, sample // cores)
     blocks = [(nx, i * per, per, tol, False) for i in range(cores)]
     ctx = mp.get_context("spawn")          # numba + fork do not mix reliably
-    with ctx.Pool(cores) as pool:
-        for _ in range(max(warmup, 1)):    # imports the module in every worker (numba compile / cache load)
+    # the initializer imports the rendered module in EVERY worker (numba compile / cache load) before any timing
+    with ctx.Pool(cores, initializer=_load, initargs=(nx,)) as pool:
+        for _ in range(max(warmup, 1)):
             pool.map(solve_block, [(nx, 0, 1, tol, False)] * cores)
         t0 = time.perf_counter()
         total = 0

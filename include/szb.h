@@ -199,6 +199,11 @@ SZB_API int szb_eval_J(szb_handle* h, double t, szb_stream stream);
 /* numeric refactorisation of  A = J            (h_gamma == 0)
  *                             A = M - h_gamma*J (h_gamma != 0; M from desc.mass_vals) */
 SZB_API int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream);
+/* per-scenario status of the last szb_lu_refactor / szb_lu_refactor_masked_rows into flags_dev (device
+ * int32[B]): 0 ok, SZB_FLAG_SINGULAR = a zero / non-finite pivot or pivot growth beyond the monitor's bound
+ * under the static pivot order -- what the reference reports as SuperLU's RuntimeError("Factor is exactly
+ * singular") / MatrixRankWarning (laesolver.py:11-45 -> scipy linsolve.py) */
+SZB_API int szb_lu_status(szb_handle* h, int32_t* flags_dev, szb_stream stream);
 /* SLOT_RHS <- A^{-1} SLOT_RHS for nrhs right-hand sides stored as [nrhs][B][n] */
 SZB_API int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream);
 /* whole Newton solve, nr.py:45-64, on device buffers; iters/flags are device int32[B] */

@@ -28,13 +28,3 @@ def compile_model(cu_path, so_path, extra=()) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {cu_path}:\n{r.stdout}\n{r.stderr}")
     return str(so_path)
-
-
-def compile_host_check(cu_path, so_path) -> str:
-    """TEST ONLY: build the serial host version of the row functions (-DSZBM_HOST_CHECK)."""
-    cmd = ["g++", "-x", "c++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DSZBM_HOST_CHECK",
-           f"-I{INCLUDE_DIR}", "-o", str(so_path), str(cu_path), "-lm"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"g++ failed for {cu_path}:\n{r.stdout}\n{r.stderr}")
-    return str(so_path)

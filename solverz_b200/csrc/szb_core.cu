@@ -465,14 +465,25 @@ int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream) {
   if (!h) return SZB_EINVAL;
   if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
   SZB_CUDA(h, cudaSetDevice(h->device));
+  SZB_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * h->B, static_cast<cudaStream_t>(stream)));
   return szb_lu_refactor_masked(h, h_gamma, nullptr, nullptr, nullptr, nullptr, 1,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int szb_lu_status(szb_handle* h, int32_t* flags_dev, szb_stream stream) {
+  if (!h || !flags_dev) return SZB_EINVAL;
+  if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  SZB_CUDA(h, cudaMemcpyAsync(flags_dev, h->flags, sizeof(int) * h->B, cudaMemcpyDeviceToDevice,
+                              static_cast<cudaStream_t>(stream)));
+  return SZB_OK;
 }
 
 int szb_lu_refactor_masked_rows(szb_handle* h, const double* row_mask_dev, szb_stream stream) {
   if (!h) return SZB_EINVAL;
   if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
   SZB_CUDA(h, cudaSetDevice(h->device));
+  SZB_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * h->B, static_cast<cudaStream_t>(stream)));
   return szb_lu_refactor_masked(h, -1.0, nullptr, nullptr, nullptr, nullptr, 1,
                                 static_cast<cudaStream_t>(stream), row_mask_dev);
 }

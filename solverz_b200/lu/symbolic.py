@@ -27,13 +27,17 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import scipy.sparse as sp
 
-__all__ = ["LUSymbolic", "analyze"]
+__all__ = ["LUSymbolic", "analyze", "ANALYSIS_VERSION"]
+
+# bumped whenever the analysis or the tables derived from it change meaning: analyses cached next to a
+# rendered module (param_and_setting.pkl) with another version are recomputed
+ANALYSIS_VERSION = 2
 
 
 # --------------------------------------------------------------------------------------
 # 1. static pivoting
 # --------------------------------------------------------------------------------------
-def _heavy_matching(A: sp.csc_matrix) -> np.ndarray:
+def _heavy_matching(A: sp.csc_matrix, forced=None) -> np.ndarray:
     """Greedy heaviest-edge matching on |a_ij| / max_i |a_ij|, completed by augmenting paths that try
     heavy edges first.  Not guaranteed optimal for the product objective, but on diagonally strong
     matrices (power-flow, network, DAE Jacobians) it reproduces the optimum, and it costs O(nnz log nnz)
@@ -48,6 +52,9 @@ def _heavy_matching(A: sp.csc_matrix) -> np.ndarray:
     order = np.argsort(-ratio, kind="stable")
     row_of = np.full(n, -1, dtype=np.int64)      # column -> matched row
     col_of = np.full(n, -1, dtype=np.int64)      # row -> matched column
+    if forced is not None:                       # pre-assigned (row, column) pairs: never displaced below
+        row_of[forced[1]] = forced[0]
+        col_of[forced[0]] = forced[1]
     for i, j, r in zip(W.row[order].tolist(), W.col[order].tolist(), ratio[order].tolist()):
         if r <= 0.0:
             break
@@ -55,6 +62,10 @@ def _heavy_matching(A: sp.csc_matrix) -> np.ndarray:
             row_of[j] = i
             col_of[i] = j
     free = np.flatnonzero(row_of < 0)
+    is_forced_row = None
+    if forced is not None:
+        is_forced_row = np.zeros(n, dtype=bool)
+        is_forced_row[forced[0]] = True
     if len(free):
         Ac = sp.csc_matrix((ratio, (W.row, W.col)), shape=(n, n))
         indptr, indices, data = Ac.indptr, Ac.indices, Ac.data
@@ -79,6 +90,8 @@ def _heavy_matching(A: sp.csc_matrix) -> np.ndarray:
                     reached_from[i] = j
                     if col_of[i] < 0:
                         found = i
+                    elif is_forced_row is not None and is_forced_row[i]:
+                        continue                     # a forced pair is not re-matched
                     else:
                         j2 = int(col_of[i])
                         stack.append((j2, nbrs(j2)))
@@ -100,8 +113,13 @@ def _heavy_matching(A: sp.csc_matrix) -> np.ndarray:
     return row_of
 
 
-def static_row_matching(A: sp.csc_matrix, exact_below: int = 1500) -> np.ndarray:
+def static_row_matching(A: sp.csc_matrix, exact_below: int = 1500, forced=None) -> np.ndarray:
     """Return ``rowperm`` with ``rowperm[c]`` = the original row matched to column ``c``.
+
+    ``forced = (rows, cols)``: pairs that must be matched to each other whatever their values.  A DAE passes
+    the unit entries of its mass matrix: the matrices factored on this order are ``M - h*gamma*J`` for every
+    step size and the row-masked ``M + diag(alg rows) J`` of the consistent initialisation, and the only
+    entries of a differential row that survive in ALL of them are the mass entries.
 
     Maximises prod |a_{rowperm[c], c}| (MC64 job-5 style objective), so the permuted
     matrix has a zero-free, large diagonal.  Structural zeros that are stored explicitly
@@ -109,11 +127,24 @@ def static_row_matching(A: sp.csc_matrix, exact_below: int = 1500) -> np.ndarray
     ``exact_below`` unknowns the exact assignment solver is replaced by ``_heavy_matching``.
     """
     n = A.shape[0]
+    if forced is not None:
+        forced = (np.asarray(forced[0], dtype=np.int64), np.asarray(forced[1], dtype=np.int64))
+        if len(forced[0]) == 0:
+            forced = None
     if n >= exact_below:
-        return _heavy_matching(A)
+        return _heavy_matching(A, forced)
     from scipy.sparse.csgraph import min_weight_full_bipartite_matching
 
     W = sp.coo_matrix(A)
+    if forced is not None:                       # keep only the forced entry in its row and in its column
+        fr = np.zeros(n, dtype=bool)
+        fc = np.zeros(n, dtype=bool)
+        fr[forced[0]] = True
+        fc[forced[1]] = True
+        pair_col = np.full(n, -1, dtype=np.int64)
+        pair_col[forced[0]] = forced[1]
+        keep = (~fr[W.row] & ~fc[W.col]) | (pair_col[W.row] == W.col)
+        W = sp.coo_matrix((W.data[keep], (W.row[keep], W.col[keep])), shape=(n, n))
     absd = np.abs(W.data)
     colmax = np.zeros(n)
     np.maximum.at(colmax, W.col, absd)
@@ -396,6 +427,7 @@ class LUSymbolic:
     f_group_max: int
     f_top_max: int
     ordering: str = ""
+    version: int = ANALYSIS_VERSION
 
     @property
     def order(self) -> np.ndarray:
@@ -720,14 +752,15 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
 
 def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
             warp_front_max: int = 32, n_warps: int = 16, group_front_max: int = 72, n_groups: int = 4,
-            orderings: Sequence[str] = ("nd", "mmd"), warp_fixed: float = 3000.0, group_fixed: float = 60000.0) -> LUSymbolic:
+            orderings: Sequence[str] = ("nd", "mmd"), warp_fixed: float = 3000.0, group_fixed: float = 60000.0,
+            forced_pairs=None) -> LUSymbolic:
     """Analyse the pattern (and representative values) of ``A``; see the module docstring."""
     A = sp.csc_matrix(A)
     A.sort_indices()
     n = A.shape[0]
     if A.shape[0] != A.shape[1]:
         raise ValueError("square matrix expected")
-    rowperm = static_row_matching(A)
+    rowperm = static_row_matching(A, forced=forced_pairs)
     B = A.tocsr()[rowperm]
     S = _sym_pattern(B)
     label, nc = _compress(S)

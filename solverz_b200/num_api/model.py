@@ -151,6 +151,12 @@ class BatchSession:
     def lu_refactor(self, h_gamma: float = 0.0):
         L.check(self.lib.szb_lu_refactor(self.h, float(h_gamma), self._stream()), self.h, "szb_lu_refactor")
 
+    def lu_status(self):
+        """Per-scenario status of the last refactorisation (device int32[B]; 0 ok, 2 singular / unstable)."""
+        L.check(self.lib.szb_lu_status(self.h, C.c_void_p(self.flags.data_ptr()), self._stream()), self.h,
+                "szb_lu_status")
+        return self.flags
+
     def lu_solve(self, nrhs: int = 1):
         L.check(self.lib.szb_lu_solve(self.h, int(nrhs), self._stream()), self.h, "szb_lu_solve")
         return self.RHS
@@ -222,7 +228,8 @@ class CudaModel:
             np.add.at(mv, np.asarray(mass_slots, dtype=np.int64), 1.0)
             self.mass_vals = mv
         self.nstep = nstep
-        self._sym = symbolic if hasattr(symbolic, "sn_ld") else None   # analyses cached by older renders lack the ld table
+        from ..lu.symbolic import ANALYSIS_VERSION
+        self._sym = symbolic if getattr(symbolic, "version", 0) == ANALYSIS_VERSION else None   # stale cached analyses are redone
         self._pkl_path = pkl_path
         self.lu_options = dict(lu_options or {})
         self._sessions: Dict[tuple, BatchSession] = {}
@@ -328,7 +335,8 @@ class CudaModel:
             if not np.all(np.isfinite(jv)):
                 raise L.SzbError("the Jacobian at y0 is not finite; cannot fix the static pivot order")
             A = sps.csc_matrix((jv, self.indices, self.indptr), shape=(self.n, self.n))
-            self._sym = analyze(A, **self.lu_options)
+            # a DAE pins every differential row to its mass entry (see static_row_matching)
+            self._sym = analyze(A, forced_pairs=self.mass, **self.lu_options)
             if self._pkl_path is not None:
                 try:
                     with open(self._pkl_path, "rb") as f:

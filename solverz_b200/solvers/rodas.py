@@ -60,6 +60,11 @@ def dae_ic(sess, t0: float, rtol: float):
         sess.eval_J(t0)
         L.check(sess.lib.szb_lu_refactor_masked_rows(sess.h, C.c_void_p(mask.data_ptr()), sess._stream()),
                 sess.h, "szb_lu_refactor_masked_rows")
+        bad = sess.lu_status() != 0
+        if bool(bad.any()):
+            # the reference's spsolve raises / warns on a singular J[AlgEqn, AlgVar] (daeic.py:38 -> laesolver.py:11-15)
+            raise ValueError(f"DaeIc: the algebraic sub-Jacobian is singular for scenario(s) "
+                             f"{torch.nonzero(bad).flatten().tolist()[:8]} (index > 1, or an inconsistent model)")
         sess.RHS.zero_()
         sess.RHS[:, alg_eqn] = rhs_alg
         x = sess.lu_solve(1)

@@ -52,6 +52,31 @@ def test_symbolic_schedule_solves(nx, opts):
         assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
 
 
+@pytest.mark.parametrize("nx,opts", [(8, {}), (12, dict(warp_front_max=8, group_front_max=20, n_warps=4, n_groups=2))])
+def test_device_tables_walk(nx, opts):
+    """The tables the kernels read (front headers, O-block gather entries, child records + rel vectors) walked in
+    numpy exactly as szb_lu.cu does: same factors as the plain supernode walk, and the fused right-hand side
+    column equals the forward substitution."""
+    import mf_emulate as E
+    from solverz_b200.lu.schedule import build_tables, plan_threads
+    from solverz_b200.lu.symbolic import analyze
+    J, _ = _pf_jacobian(nx)
+    sym = analyze(J, **opts)
+    plan = plan_threads(sym)
+    tabs = build_tables(sym, plan["threads"], plan["wpg"])
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal(sym.n)
+    lu_t, y = E.factor_tables(sym, tabs, J.data, rhs=b)
+    lu = E.factor(sym, J.data)
+    assert np.abs(lu_t - lu).max() <= 1e-11 * np.abs(lu).max()
+    x = E.solve(sym, lu_t, b)
+    xr = sla.spsolve(J, b)
+    assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
+    # y = L^{-1} P b: finishing with the backward sweep alone must give the same x
+    lu_n, _ = E.factor_tables(sym, tabs, J.data, rhs=None)
+    assert np.abs(lu_n - lu).max() <= 1e-11 * np.abs(lu).max()
+
+
 def test_symbolic_shifted_matrix_and_singular_pattern():
     import mf_emulate as E
     from solverz_b200.lu.symbolic import analyze
@@ -84,34 +109,7 @@ def test_symbolic_shifted_matrix_and_singular_pattern():
 
 
 # ----------------------------------------------------------------------------- printer via host check
-def _host_lib(eqs, name, tmp_path):
-    from solverz_b200.code_printer.cuda import compile_host_check, print_model
-    from solverz_b200.jacobian import derive_jacobian
-    ir = eqs.to_ir()
-    pat = derive_jacobian(ir)
-    src = print_model(ir, pat, name)
-    cu = tmp_path / f"{name}.cu"
-    cu.write_text(src)
-    so = compile_host_check(cu, tmp_path / f"{name}_host.so")
-    return ir, pat, ctypes.CDLL(so), src
-
-
-def _eval(lib, ir, pat, Y, params, t=0.0):
-    Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=float)
-    B = Y.shape[0]
-    vals = []
-    for p in ir.params.values():
-        v = params.get(p.name, p.value)
-        v = np.ascontiguousarray(v, dtype=np.float64 if p.dtype == "f64" else np.int32)
-        if p.per_scenario and v.ndim == 1:
-            v = np.ascontiguousarray(np.tile(v, (B, 1)))
-        vals.append(v)
-    ptrs = (ctypes.c_void_p * max(len(vals), 1))(*[v.ctypes.data for v in vals])
-    F = np.zeros((B, ir.n))
-    JV = np.zeros((B, pat.nnz))
-    lib.szbm_host_F(B, ctypes.c_double(t), Y.ctypes.data_as(ctypes.c_void_p), ptrs, F.ctypes.data_as(ctypes.c_void_p))
-    lib.szbm_host_J(B, ctypes.c_double(t), Y.ctypes.data_as(ctypes.c_void_p), ptrs, JV.ctypes.data_as(ctypes.c_void_p))
-    return F, JV
+from host_check import host_lib as _host_lib, host_eval as _eval  # noqa: E402
 
 
 def test_printer_pf_matches_reference_golden(tmp_path):

@@ -131,3 +131,69 @@ def test_rodas_swing_ensemble_vs_reference_golden(libszb):
         on_ramp = np.array([np.min(np.abs(t - tst[b][1:5])) < 2e-3 for t in g["tspan"]])
         assert d[~on_ramp].max() < 1e-6, (b, d)
         assert d.max() < 1e-4 * max(1.0, np.abs(g["Y"][b]).max()), (b, d)
+
+
+def test_dae_ic_inconsistent_start_vs_oracle(libszb):
+    """DaeIc (daeic.py:24-68) from an INCONSISTENT y0: swing-type toy whose differential rows carry Jacobian
+    entries far larger than their mass entry (J[delta, omega] = 314), so a value-based static matching would
+    pivot those rows off the mass entries and the row-masked matrix of the initialisation would be singular.
+    Every scenario of the batch against the oracle's daeic (Newton on J[AlgEqn, AlgVar] with the three-probe
+    halving line search), then a Rodas run from the same inconsistent start against the oracle's Rodas."""
+    from oracle.rodas import daeic as oracle_daeic, rodas as oracle_rodas
+    from solverz_b200 import Eqn, Model, Ode, Opt, Param, Rodas, Var, cos, made_numerical, sin
+    from solverz_b200.solvers.rodas import dae_ic
+    from solverz_b200.solvers.rodas_param import Rodas_param
+    B = 5
+    pm = np.linspace(0.5, 0.9, B).reshape(B, 1)
+    m = Model()
+    m.delta = Var('delta', [0.3])
+    m.omega = Var('omega', [1.0])
+    m.z = Var('z', [1.0, 1.0])                       # inconsistent on purpose
+    m.Pm = Param('Pm', [0.8], per_scenario=True)
+    m.f1 = Ode('f1', 314 * (m.omega - 1), diff_var=m.delta)
+    m.f2 = Ode('f2', (m.Pm - m.z[0] * sin(m.delta) - 2 * (m.omega - 1)) / 5, diff_var=m.omega)
+    m.g1 = Eqn('g1', m.z[0] - 1.2 + 0.3 * m.z[1] * cos(m.delta))
+    m.g2 = Eqn('g2', m.z[1] ** 2 + m.z[0] * m.z[1] - 2)
+    dae, y0 = m.create_instance()
+    nd = made_numerical(dae, y0, sparse=True)
+    nd.p["Pm"] = pm
+    s = nd.session(B)
+    assert sorted(zip(*[list(map(int, a)) for a in nd.mass])) == [(0, 0), (1, 1)]
+    sym = s.sym
+    # the differential rows are pivoted on their mass entries whatever the values say
+    assert int(sym.rowp[list(sym.colp).index(0)]) == 0 and int(sym.rowp[list(sym.colp).index(1)]) == 1
+    s.set_params(nd.p)
+    s.set_y(np.tile(y0.array, (B, 1)))
+    dae_ic(s, 0.0, 1e-3)
+    got = s.Y.cpu().numpy()
+    M = nd.M
+
+    def FJ(b):
+        p = pm[b, 0]
+
+        def F(t, y):
+            d, w, z0, z1 = y
+            return np.array([314 * (w - 1), (p - z0 * np.sin(d) - 2 * (w - 1)) / 5,
+                             z0 - 1.2 + 0.3 * z1 * np.cos(d), z1 ** 2 + z0 * z1 - 2])
+
+        def J(t, y):
+            d, w, z0, z1 = y
+            return sps.csc_matrix(np.array([[0, 314, 0, 0],
+                                            [-z0 * np.cos(d) / 5, -2 / 5, -np.sin(d) / 5, 0],
+                                            [-0.3 * z1 * np.sin(d), 0, 1, 0.3 * np.cos(d)],
+                                            [0, 0, z1, 2 * z1 + z0]]))
+        return F, J
+    for b in range(B):
+        F, J = FJ(b)
+        ref = oracle_daeic(F, J, M, y0.array, 0.0, 1e-3)
+        assert np.linalg.norm(F(0.0, y0.array)[2:]) > 1e-2          # the start really is inconsistent
+        assert np.abs(got[b] - ref).max() <= 1e-12, (b, got[b], ref)
+    tsp = np.linspace(0, 1, 11)
+    sol = Rodas(nd, tsp, np.tile(y0.array, (B, 1)), Opt(rtol=1e-4, atol=1e-7))
+    rp = Rodas_param("rodas4")
+    for b in range(B):
+        F, J = FJ(b)
+        yi = oracle_daeic(F, J, M, y0.array, 0.0, 1e-4)
+        ref = oracle_rodas(F, J, M, tsp, yi, rp, rtol=1e-4, atol=1e-7, dfdt_mode=0)
+        assert int(sol.stats.nstep[b]) == ref["stats"]["nstep"] and int(sol.stats.nreject[b]) == ref["stats"]["nreject"]
+        assert np.max(np.abs(sol.Y[b] - ref["Y"])) < 1e-8

@@ -204,6 +204,18 @@ SZB_API int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream);
  * under the static pivot order -- what the reference reports as SuperLU's RuntimeError("Factor is exactly
  * singular") / MatrixRankWarning (laesolver.py:11-45 -> scipy linsolve.py) */
 SZB_API int szb_lu_status(szb_handle* h, int32_t* flags_dev, szb_stream stream);
+/* factor storage of scenario b of the last szb_lu_refactor into out_dev (device double[SZB_Q_LU_SIZE]): per
+ * supernode the f x s panel [L11\U11; L21] (column-major, 1/u_pp on the diagonal) followed by the s x u panel
+ * U12 -- what the host needs to present the reference object's .L / .U (laesolver.py:37-42) */
+SZB_API int szb_lu_factors(szb_handle* h, int32_t b, double* out_dev, szb_stream stream);
+/* a-posteriori check of a solve under the static pivot order:  relres_dev[b] = max|rhs_b - A_b x_b| /
+ * max|rhs_b|  with A = J (h_gamma == 0) or M - h_gamma*J, assembled slot by slot from SLOT_JV
+ * (slot_row_dev / slot_col_dev: device int32[nnz_j], row and column of every CSC slot).  rhs_dev / x_dev:
+ * device double[B][n] in the original row / column order.  SuperLU's partial pivoting, which the reference
+ * gets per call (laesolver.py:11-15), bounds this residual; a fixed pivot sequence does not -- callers
+ * re-analyse the scenarios whose residual is large with their own values (solvers/laesolver.py, nr.py). */
+SZB_API int szb_lu_residual(szb_handle* h, double h_gamma, const int32_t* slot_row_dev, const int32_t* slot_col_dev,
+                            const double* rhs_dev, const double* x_dev, double* relres_dev, szb_stream stream);
 /* SLOT_RHS <- A^{-1} SLOT_RHS for nrhs right-hand sides stored as [nrhs][B][n] */
 SZB_API int szb_lu_solve(szb_handle* h, int32_t nrhs, szb_stream stream);
 /* whole Newton solve, nr.py:45-64, on device buffers; iters/flags are device int32[B] */

@@ -171,6 +171,58 @@ int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b,
   return SZB_OK;
 }
 
+// relres[b] = max_i |rhs_i - (A x)_i| / max(max_i |rhs_i|, tiny) with A = scale * JV[b] (+ mass) given slot by slot
+// (row / column index per CSC slot).  One CTA per scenario, the residual vector in shared memory (fp64 atomicAdd:
+// the order of the additions is irrelevant for a check).  This is the a-posteriori stability test of the static
+// pivot order: SuperLU's partial pivoting (the reference, laesolver.py:11-45) guarantees a small residual, a fixed
+// pivot sequence does not, so the solve is CHECKED instead.
+__global__ void __launch_bounds__(256)
+lin_residual_kernel(const double* __restrict__ JV, const double* __restrict__ mvals, double scale,
+                    const int* __restrict__ srow, const int* __restrict__ scol, const double* __restrict__ RHS,
+                    const double* __restrict__ X, double* __restrict__ relres, int n, int nnz, int B) {
+  extern __shared__ double rs[];
+  __shared__ double red[2][8];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const double* __restrict__ jv = JV + static_cast<size_t>(b) * nnz;
+    const double* __restrict__ rhs = RHS + static_cast<size_t>(b) * n;
+    const double* __restrict__ x = X + static_cast<size_t>(b) * n;
+    __syncthreads();
+    double bm = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double v = rhs[i];
+      rs[i] = v;
+      const double a = fabs(v);
+      bm = (a > bm || a != a) ? a : bm;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < nnz; p += blockDim.x) {
+      double a = scale * jv[p];
+      if (mvals) a += mvals[p];
+      atomicAdd(&rs[srow[p]], -a * x[scol[p]]);
+    }
+    __syncthreads();
+    double rm = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double a = fabs(rs[i]);
+      rm = (a > rm || a != a) ? a : rm;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double t1 = __shfl_xor_sync(0xffffffffu, rm, o), t2 = __shfl_xor_sync(0xffffffffu, bm, o);
+      rm = (t1 > rm || t1 != t1) ? t1 : rm;
+      bm = (t2 > bm || t2 != t2) ? t2 : bm;
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = rm; red[1][threadIdx.x >> 5] = bm; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) {
+        rm = (red[0][w] > rm || red[0][w] != red[0][w]) ? red[0][w] : rm;
+        bm = (red[1][w] > bm || red[1][w] != red[1][w]) ? red[1][w] : bm;
+      }
+      relres[b] = rm / fmax(bm, 1e-300);
+    }
+  }
+}
+
 // G = M (y - y_prev) - c (F + kappa F_prev) and max|G| per scenario (NaN-propagating); one CTA per scenario
 __global__ void __launch_bounds__(256)
 implicit_residual_kernel(const double* __restrict__ F, const double* __restrict__ Y, const double* __restrict__ Y0,
@@ -468,6 +520,46 @@ int szb_lu_refactor(szb_handle* h, double h_gamma, szb_stream stream) {
   SZB_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * h->B, static_cast<cudaStream_t>(stream)));
   return szb_lu_refactor_masked(h, h_gamma, nullptr, nullptr, nullptr, nullptr, 1,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int szb_lu_residual(szb_handle* h, double h_gamma, const int32_t* slot_row_dev, const int32_t* slot_col_dev,
+                    const double* rhs_dev, const double* x_dev, double* relres_dev, szb_stream stream) {
+  if (!h || !slot_row_dev || !slot_col_dev || !rhs_dev || !x_dev || !relres_dev) return SZB_EINVAL;
+  if (h->B <= 0) { szb_set_error(h, "call szb_set_batch first"); return SZB_ESTATE; }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  const double* mv = nullptr;
+  double scale = 1.0;
+  if (h_gamma != 0.0) {
+    if (!h->mass_vals) { szb_set_error(h, "szb_lu_residual: h_gamma != 0 needs desc.mass_vals"); return SZB_EINVAL; }
+    mv = h->mass_vals;
+    scale = -h_gamma;
+  }
+  const size_t smem = sizeof(double) * static_cast<size_t>(h->n);
+  int smem_max = 0;
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  if (smem > static_cast<size_t>(smem_max)) {
+    szb_set_error(h, "szb_lu_residual: n = %d does not fit the shared-memory residual vector", h->n);
+    return SZB_EINVAL;
+  }
+  SZB_CUDA(h, cudaFuncSetAttribute(lin_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int grid = h->B < 4 * sms ? h->B : 4 * sms;
+  lin_residual_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      h->JV, mv, scale, slot_row_dev, slot_col_dev, rhs_dev, x_dev, relres_dev, h->n, h->nnz_j, h->B);
+  SZB_CUDA(h, cudaGetLastError());
+  h->launches[4]++;
+  return SZB_OK;
+}
+
+int szb_lu_factors(szb_handle* h, int32_t b, double* out_dev, szb_stream stream) {
+  if (!h || !out_dev) return SZB_EINVAL;
+  if (!h->factored) { szb_set_error(h, "szb_lu_factors before szb_lu_refactor"); return SZB_ESTATE; }
+  if (b < 0 || b >= h->B) { szb_set_error(h, "szb_lu_factors: scenario %d outside the batch", b); return SZB_EINVAL; }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  SZB_CUDA(h, cudaMemcpyAsync(out_dev, h->LU + static_cast<size_t>(b) * h->S.lu_size, sizeof(double) * h->S.lu_size,
+                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return SZB_OK;
 }
 
 int szb_lu_status(szb_handle* h, int32_t* flags_dev, szb_stream stream) {

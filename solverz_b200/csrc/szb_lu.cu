@@ -180,8 +180,8 @@ template <bool PLAIN>
 __device__ __forceinline__ double asm_fetch(const unsigned sr, const FactorArgs& A) {
   const unsigned tag = sr >> 30;
   const int off = static_cast<int>(sr & 0x3fffffffu);
-  if (PLAIN) {   // A = J: the value fetch is a pointer select
-    const double* base = tag == 0u ? A.cb : (tag == 1u ? A.jv : A.rhs);
+  if (PLAIN) {   // A = J: the value fetch is a pointer select (tags 0 and 3: contribution workspace)
+    const double* base = tag == 1u ? A.jv : (tag == 2u ? A.rhs : A.cb);
     return base[off];
   } else {
     if (tag == 1u) {
@@ -189,7 +189,7 @@ __device__ __forceinline__ double asm_fetch(const unsigned sr, const FactorArgs&
       const double mk = A.smask ? A.smask[off] : 1.0;
       return fma(A.scale * mk, A.jv[off], mv);
     }
-    const double* base = tag == 0u ? A.cb : A.rhs;
+    const double* base = tag == 2u ? A.rhs : A.cb;
     return base[off];
   }
 }
@@ -203,7 +203,7 @@ __device__ __forceinline__ void assemble_stream(const AsmPre& P, const int rank,
   const int2* __restrict__ e = ga + H.gaO + rank;
   // an entry is dead when it is padding, or a right-hand-side row while no right-hand side rides along
   auto live = [=](const int2 en) {
-    return en.x != -1 && (with_rhs || (static_cast<unsigned>(en.x) >> 30) != 2u);
+    return en.x != -1 && (with_rhs || (static_cast<unsigned>(en.x) >> 30) < 2u);   // tags 2, 3: right-hand-side data
   };
   // Most fronts of the tree are tiny: their whole stream is one or two entries per thread.  The first
   // batch is therefore specialised on its length (2, 4 or 8 slots) -- an unrolled 8-slot batch executes
@@ -417,16 +417,33 @@ __device__ __forceinline__ void lt_tile(const double* __restrict__ Fm, double* _
 // column tiles cg, cg + CW, ... < ct_end of the 8-column tiles right of the panel.  No masks and no
 // predicates (a predicated variant costs spills): tiles that overhang the front live in its zero padding
 // (kPad).  Per strip: 1 + 2R loads, R DMMAs, 2R stores, all with immediate offsets from two running pointers.
-template <int R>
+// FUSED: the warp computes the -Lt fragments of its own rows itself (A21 D^{-1} as one DMMA per row tile, the
+// accumulator layout turned into the A-fragment layout by two shuffles), instead of reading them from the side
+// panel that a separate phase A wrote: no side panel traffic and ONE barrier per panel instead of two.  bd is the
+// B fragment of D^{-1} of this panel.
+template <int R, bool FUSED>
 __device__ __forceinline__ void trailing_strips(double* __restrict__ Fm, const double* __restrict__ lt,
                                                 const int lts, const int p0, const int nb, const int ld,
                                                 const int row0, const int cg, const int CW, const int ct_end,
-                                                const int lane) {
+                                                const int lane, const double bd) {
   const int r0 = p0 + nb;
   const int q = lane & 3, g8 = lane >> 2;
   double xa[R];
+  if (FUSED) {
+    const double* __restrict__ ap = Fm + r0 + row0 + g8 + (p0 + (q < nb ? q : 0)) * ld;
+    const int src = (lane & ~3) | (q >> 1);
 #pragma unroll
-  for (int r = 0; r < R; ++r) xa[r] = lt[q * lts + row0 + 8 * r + g8];
+    for (int r = 0; r < R; ++r) {
+      const double a0 = q < nb ? ap[8 * r] : 0.0;          // rows beyond the front: zero padding
+      double c0 = 0.0, c1 = 0.0;
+      dmma(c0, c1, a0, bd);
+      const double s0 = __shfl_sync(0xffffffffu, c0, src), s1 = __shfl_sync(0xffffffffu, c1, src);
+      xa[r] = -((q & 1) ? s1 : s0);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) xa[r] = lt[q * lts + row0 + 8 * r + g8];
+  }
   const int cstep = 8 * CW * ld;
   const double* __restrict__ bp = Fm + p0 + (q < nb ? q : 0) + (r0 + 8 * cg + g8) * ld;   // stays inside the panel rows
   double* __restrict__ cp = Fm + r0 + row0 + g8 + (r0 + 8 * cg + 2 * q) * ld;
@@ -451,14 +468,16 @@ __device__ __forceinline__ void trailing_strips(double* __restrict__ Fm, const d
 }
 
 // up to four row tiles from row0: as many as hold rows of the trailing block (m rows)
+template <bool FUSED>
 __device__ __forceinline__ void trailing_rows(double* __restrict__ Fm, const double* __restrict__ lt, const int lts,
                                               const int p0, const int nb, const int m, const int ld, const int row0,
-                                              const int cg, const int CW, const int ct_end, const int lane) {
+                                              const int cg, const int CW, const int ct_end, const int lane,
+                                              const double bd) {
   const int nt = (m - row0 + 7) >> 3;
-  if (nt >= 4) trailing_strips<4>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
-  else if (nt == 3) trailing_strips<3>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
-  else if (nt == 2) trailing_strips<2>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
-  else if (nt == 1) trailing_strips<1>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane);
+  if (nt >= 4) trailing_strips<4, FUSED>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane, bd);
+  else if (nt == 3) trailing_strips<3, FUSED>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane, bd);
+  else if (nt == 2) trailing_strips<2, FUSED>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane, bd);
+  else if (nt == 1) trailing_strips<1, FUSED>(Fm, lt, lts, p0, nb, ld, row0, cg, CW, ct_end, lane, bd);
 }
 
 // deferred triangular solves of the U rows: for every panel and every column right of it
@@ -515,6 +534,70 @@ __device__ long long g_el[8 * 8];
 // prefetched assembly state is saved once per front).  The buffers are passed as offsets into the
 // dynamic shared memory so that the compiler keeps the LDS / STS forms; SM_FRONT = false: the front
 // itself lives in a global workspace (FmG), only the side panel and the inverse are on chip.
+// one panel of eliminate_blocked (phase A + barrier when !FUSED, then phase B + barrier)
+template <bool FUSED>
+__device__ __forceinline__ void blocked_panel(const PanelGrp& g, double* __restrict__ Fm, double* __restrict__ lt,
+                                              const int lts, double* __restrict__ dinv_cur,
+                                              double* __restrict__ dinv_next, double* __restrict__ Lg, const int t,
+                                              const int npan, const int s, const int f, const int ncol,
+                                              const int ld, int* flag) {
+  const int lane = g.lane(), w = g.warp(), nw = g.nw;
+  const int q = lane & 3, g8 = lane >> 2;
+  const int p0 = t * kNB;
+  const int nb = min(kNB, s - p0);
+  const int r0 = p0 + nb;
+  const bool has_next = t + 1 < npan;
+  const int m = f - r0;
+  const double bd = g8 < kNB ? dinv_cur[q + kNB * g8] : 0.0;               // B[k][col] = Dinv[k][col]
+  if (!FUSED) {
+    // ---- phase A
+    const int nrt = (m + 7) >> 3;
+    if (w < nrt) {
+      double bl = 0.0;
+      if (Lg != nullptr)                                 // B[k][col] = L11[k][col] (unit lower, identity-padded)
+        bl = q == g8 ? 1.0 : ((q > g8 && q < nb) ? Fm[(p0 + q) + (p0 + g8) * ld] : 0.0);
+      for (int rt = w; rt < nrt; rt += nw) lt_tile(Fm, lt, lts, Lg, p0, nb, f, ld, rt, bd, bl, lane);
+    }
+    g.sync();
+  }
+  // ---- phase B
+  if (has_next && w == 0) {
+    // the diagonal warp: panel t applied to the 8x8 tile around the next diagonal block, then LU + inverse
+    trailing_strips<1, FUSED>(Fm, lt, lts, p0, nb, ld, 0, 0, 1, 1, lane, bd);
+    __syncwarp();
+    diag_block(Fm, dinv_next, r0, min(kNB, s - r0), ld, lane, flag);
+  } else if (m > 0) {
+    const int W = has_next ? nw - 1 : nw;            // worker warps
+    const int ww = has_next ? w - 1 : w;
+    const int nch = (m + 31) >> 5;                   // row groups of 32 rows
+    const int nct = (ncol - r0 + 7) >> 3;            // column tiles
+    const int CW = max(1, min(W / nch, nct));        // warps that share a row group, striding over the column tiles
+    const int ntile = nch * CW;
+    const float inv_cw = 1.0f / static_cast<float>(CW);
+    for (int tile = ww; tile < ntile; tile += W) {
+      const int tr = nch == 1 ? 0 : fdiv(tile, inv_cw);
+      const int cg = tile - tr * CW;
+      if (tile == 0 && has_next) {                   // tile (0, 0) belongs to the diagonal warp
+        const int n3 = min(3, (m - 1) >> 3);          // rows 8.. of the first column tile
+        if (n3 == 3) trailing_strips<3, FUSED>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane, bd);
+        else if (n3 == 2) trailing_strips<2, FUSED>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane, bd);
+        else if (n3 == 1) trailing_strips<1, FUSED>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane, bd);
+        trailing_rows<FUSED>(Fm, lt, lts, p0, nb, m, ld, 0, CW, CW, nct, lane, bd);
+      } else {
+        trailing_rows<FUSED>(Fm, lt, lts, p0, nb, m, ld, tr << 5, cg, CW, nct, lane, bd);
+      }
+    }
+  }
+  g.sync();
+}
+
+// Not inlined on purpose: the elimination gets the full register budget to itself (the caller's
+// prefetched assembly state is saved once per front).  The buffers are passed as offsets into the
+// dynamic shared memory so that the compiler keeps the LDS / STS forms.  When L is not wanted (Newton: the
+// forward substitution rides along as a front column) the panels run FUSED: no phase A, no side panel, one
+// barrier per panel; the explicit inverse of the diagonal block is then double-buffered (the diagonal warp
+// writes the next one while slower warps still read the current one) -- the second buffer is the head of
+// the unused side panel.
 template <bool SM_FRONT>
 __device__ __noinline__ void eliminate_blocked(const PanelGrp g, double* FmG, const int fm_off, const int lt_off,
                                                const int lts, double* __restrict__ Lg, const int s, const int f,
@@ -524,73 +607,20 @@ __device__ __noinline__ void eliminate_blocked(const PanelGrp g, double* FmG, co
   double* __restrict__ lt = sm + lt_off;
   double* __restrict__ dinv = lt + kNB * lts;
   const int lane = g.lane(), w = g.warp(), nw = g.nw;
-  const int q = lane & 3, g8 = lane >> 2;
   const int npan = (s + kNB - 1) / kNB;
-#ifdef SZB_FINE_TIMING
-  const bool dbg_ = blockIdx.x == 0 && g.id == 0 && (threadIdx.x & 127) == 0;
-  long long el_[7] = {0, 0, 0, 0, 0, 0, 0};
-  long long te_ = clock64();
-#endif
   if (w == 0) diag_block(Fm, dinv, 0, min(kNB, s), ld, lane, flag);
   g.sync();
-  SZB_E(0)
-  for (int t = 0; t < npan; ++t) {
-    const int p0 = t * kNB;
-    const int nb = min(kNB, s - p0);
-    const int r0 = p0 + nb;
-    const bool has_next = t + 1 < npan;
-    const int m = f - r0;
-    // ---- phase A
-    const int nrt = (m + 7) >> 3;
-    if (w < nrt) {
-      const double bd = g8 < kNB ? dinv[q + kNB * g8] : 0.0;               // B[k][col] = Dinv[k][col]
-      double bl = 0.0;
-      if (Lg != nullptr)                                 // B[k][col] = L11[k][col] (unit lower, identity-padded)
-        bl = q == g8 ? 1.0 : ((q > g8 && q < nb) ? Fm[(p0 + q) + (p0 + g8) * ld] : 0.0);
-      for (int rt = w; rt < nrt; rt += nw) lt_tile(Fm, lt, lts, Lg, p0, nb, f, ld, rt, bd, bl, lane);
-    }
-    SZB_E(2)
-    g.sync();
-    SZB_E(3)
-    // ---- phase B
-    if (has_next && w == 0) {
-      // the diagonal warp: panel t applied to the 8x8 tile around the next diagonal block, then LU + inverse
-      trailing_strips<1>(Fm, lt, lts, p0, nb, ld, 0, 0, 1, 1, lane);
-      __syncwarp();
-      diag_block(Fm, dinv, r0, min(kNB, s - r0), ld, lane, flag);
-      SZB_E(1)
-    } else if (m > 0) {
-      const int W = has_next ? nw - 1 : nw;            // worker warps
-      const int ww = has_next ? w - 1 : w;
-      const int nch = (m + 31) >> 5;                   // row groups of 32 rows
-      const int nct = (ncol - r0 + 7) >> 3;            // column tiles
-      const int CW = max(1, min(W / nch, nct));        // warps that share a row group, striding over the column tiles
-      const int ntile = nch * CW;
-      const float inv_cw = 1.0f / static_cast<float>(CW);
-      for (int tile = ww; tile < ntile; tile += W) {
-        const int tr = nch == 1 ? 0 : fdiv(tile, inv_cw);
-        const int cg = tile - tr * CW;
-        if (tile == 0 && has_next) {                   // tile (0, 0) belongs to the diagonal warp
-          const int n3 = min(3, (m - 1) >> 3);          // rows 8.. of the first column tile
-          if (n3 == 3) trailing_strips<3>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane);
-          else if (n3 == 2) trailing_strips<2>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane);
-          else if (n3 == 1) trailing_strips<1>(Fm, lt, lts, p0, nb, ld, 8, 0, 1, 1, lane);
-          trailing_rows(Fm, lt, lts, p0, nb, m, ld, 0, CW, CW, nct, lane);
-        } else {
-          trailing_rows(Fm, lt, lts, p0, nb, m, ld, tr << 5, cg, CW, nct, lane);
-        }
-      }
-    }
-    SZB_E(4)
-    g.sync();
-    SZB_E(5)
+  if (Lg == nullptr) {
+    double* __restrict__ dinv2 = lt;                   // second inverse buffer (kDiagBuf doubles of the side panel)
+    for (int t = 0; t < npan; ++t)
+      blocked_panel<true>(g, Fm, lt, lts, (t & 1) ? dinv2 : dinv, (t & 1) ? dinv : dinv2, nullptr, t, npan, s, f,
+                          ncol, ld, flag);
+  } else {
+    for (int t = 0; t < npan; ++t)
+      blocked_panel<false>(g, Fm, lt, lts, dinv, dinv, Lg, t, npan, s, f, ncol, ld, flag);
   }
   finalize_u(Fm, s, ncol, ld, lane, w, nw);
   g.sync();
-  SZB_E(6)
-#ifdef SZB_FINE_TIMING
-  if (dbg_) for (int i = 0; i < 7; ++i) g_el[8 * (threadIdx.x >> 7 & 7) + i] += el_[i];
-#endif
 }
 
 

@@ -42,6 +42,16 @@ struct State {
   double* ev_val;   // [B][SZB_MAX_EVENTS] event values at the end of the last accepted step (rodas.py:203)
 };
 
+// A scenario whose M - dt*gamma*J met a zero / non-finite static pivot stops with SZB_FLAG_SINGULAR -- the
+// per-scenario form of the RuntimeError that lu_decomposition raises inside the reference's step (rodas.py:159-162)
+__global__ void rodas_lu_check_kernel(State S, const int* __restrict__ lu_flags, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && S.active[b] && lu_flags[b] == SZB_FLAG_SINGULAR) {
+    S.active[b] = 0;
+    S.stats[8 * b + 6] = SZB_FLAG_SINGULAR;
+  }
+}
+
 // rodas.py:127-146 -- failure exits, end stretch, fixed step; prepares LU scale and the J mask
 __global__ void step_begin_kernel(State S, Ctl C, double gamma, int* __restrict__ n_active, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -518,7 +528,12 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
   S.nrec = S.inext + B; S.stats = S.nrec + B;
   S.ev_val = h->rd_ev;
 
+  if (B > 65535) {   // the stage kernels index the scenario through gridDim.y
+    szb_set_error(h, "szb_rodas: at most 65535 scenarios per call (got %d); split the batch", B);
+    return SZB_EINVAL;
+  }
   const dim3 eg((n + 255) / 256 > 64 ? 64 : (n + 255) / 256, B);
+  SZB_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * B, st));
   rodas_init_kernel<<<B, 128, 0, st>>>(S, *out, h->Y, o->t0, dt0, o->facmax, o->n_out, o->record_cap, C, n, B);
   h->launches[4]++;
   int rc;
@@ -544,6 +559,8 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
     h->launches[4]++;
     // lu = splu(M - dt*gamma*J) (:159), K[:,0] = lu.solve(rhs) (:163)
     if ((rc = szb_lu_refactor_masked(h, 0.0, S.scale, S.active, nullptr, nullptr, 1, st)) != SZB_OK) return rc;
+    rodas_lu_check_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, h->flags, B);
+    h->launches[4]++;
     {
       cudaError_t e = szb::lu_solve_launch(h->S, h->cfg, h->LU, h->RHS, h->rd_K, h->CVW, h->XW, h->ybuf, 1, 0, S.active, B, st);
       if (e != cudaSuccess) { szb_set_error(h, "LU solve launch: %s", cudaGetErrorString(e)); return SZB_ECUDA; }

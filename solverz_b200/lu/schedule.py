@@ -9,21 +9,21 @@ plus three streamed tables instead of a chain of dependent index look-ups:
         CTA-level list; list ``w`` of a level is the contiguous run ``ptr[w]:ptr[w+1]``):
         ``[s, f, piv0, lp_off, up_off, cb_off, gaO, itO, gaC, itC, gaR, itR, k, n_src, idx_ptr, 0]``
 
-``ga``  gather tables, ``(src, dst)`` int32 pairs.  A front owns three blocks, each laid out
-        ``[iterations][G]`` (G = threads of the group that owns the front): in iteration ``it`` thread
-        ``r`` adds the value addressed by ``src`` to front position ``dst`` (``src == -1``: no-op).
-          O block  original data: Jacobian slots (scaled / masked / mass-shifted on the fly) and the
-                   rows of the right-hand side (ignored when no right-hand side rides along); none of
-                   it depends on the children, so its values are prefetched a front ahead,
-          C block  offsets in the contribution workspace (Schur parts of the children),
-          R block  the children's right-hand-side columns in the contribution workspace; skipped
-                   when no right-hand side rides along.
-        The three blocks of a front are contiguous, so a thread walks ONE stream of entries; bits 30-31
-        of ``src`` name the address space (0 contribution workspace, 1 Jacobian values, 2 right-hand
-        side), which makes the value fetch a pointer select instead of a branch.
-        Every destination is owned by exactly one thread across the three blocks, and a thread meets
-        its sources in a fixed order (matrix entry, children in schedule order), so the assembly
-        needs no barrier between children, no atomics, and is bitwise reproducible.
+``ga``  gather table, ``(src, dst)`` int32 pairs.  A front owns ONE block laid out ``[iterations][G]`` (G = threads
+        of the group that owns the front; offset / iterations in ``gaO / itO``, the C and R fields of the header
+        are zero): in iteration ``it`` thread ``r`` adds the value addressed by ``src`` to front position ``dst``
+        (``src == -1``: no-op).  Bits 30-31 of ``src`` name the address space, which makes the value fetch a
+        pointer select instead of a branch:
+          1  Jacobian slot (scaled / masked / mass-shifted on the fly),
+          2  row of the right-hand side          } ignored when no right-hand side rides along
+          3  contribution workspace, a child's right-hand-side column }
+          0  contribution workspace, Schur part of a child.
+        Every destination is owned by exactly one thread, and a thread meets the sources of a destination in a
+        fixed order (matrix entry, children in schedule order), so the assembly needs no barrier between
+        children, no atomics, and is bitwise reproducible.  Destinations are dealt to the threads by source-count
+        class (see ``_schedule_front``), so the per-thread entry counts of the whole stream are balanced: the
+        iteration count is within a few per cent of entries / G (three separately padded blocks in first-touch
+        order left 35 % of the slots empty).
 
 This is what SuperLU's ``dgstrf`` re-derives inside every call of the reference's ``solve`` /
 ``lu_decomposition`` (Solverz/solvers/laesolver.py:11-45); here it is done once per model.
@@ -34,10 +34,10 @@ from typing import Dict
 
 import numpy as np
 
-__all__ = ["plan_threads", "build_tables", "NOOP", "TAG_CB", "TAG_J", "TAG_RHS", "OFF_MASK"]
+__all__ = ["plan_threads", "build_tables", "NOOP", "TAG_CB", "TAG_J", "TAG_RHS", "TAG_CBR", "OFF_MASK"]
 
 NOOP = 0xFFFFFFFF
-TAG_CB, TAG_J, TAG_RHS = 0, 1, 2
+TAG_CB, TAG_J, TAG_RHS, TAG_CBR = 0, 1, 2, 3
 OFF_MASK = (1 << 30) - 1
 HDR_WORDS = 16
 
@@ -87,17 +87,21 @@ def _front_sources(sym, k: int):
         dst.append(np.asarray(sym.ea_dst[e0:e0 + cnt], dtype=np.int64))
         off = int(sym.cb_off[c]) + np.arange(cnt, dtype=np.int64)
         is_rhs = np.arange(cnt) >= uc * uc
-        src.append(off | (TAG_CB << 30))
-        kind.append(np.where(is_rhs, 2, 1).astype(np.int64))
+        src.append(np.where(is_rhs, off | (TAG_CBR << 30), off | (TAG_CB << 30)))
+        kind.append(np.zeros(cnt, dtype=np.int64))      # one block: the whole stream is balanced together
     return np.concatenate(dst), np.concatenate(src), np.concatenate(kind)
 
 
 def _schedule_front(dst: np.ndarray, src: np.ndarray, kind: np.ndarray, G: int):
     """Assign sources to (block, iteration, thread): unique owner thread per destination, first-touch
     round-robin so that consecutive sources of the first toucher land on consecutive threads."""
-    uniq, first, inv = np.unique(dst, return_index=True, return_inverse=True)
+    uniq, first, inv, cnt = np.unique(dst, return_index=True, return_inverse=True, return_counts=True)
+    # destinations with the same number of sources are dealt round-robin in first-touch order: every thread gets
+    # the same number (+-1) of 3-source, 2-source, 1-source destinations, so the per-thread entry counts -- whose
+    # maximum is the iteration count every thread walks -- are balanced (first-touch order alone left 35 % of the
+    # slots as padding), and neighbours in first-touch order still sit on neighbouring threads (coalesced sources)
     rank = np.empty(len(uniq), dtype=np.int64)
-    rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+    rank[np.lexsort((first, -cnt))] = np.arange(len(uniq))
     thread = (rank % G)[inv]
     tabs = []
     for kd in range(3):

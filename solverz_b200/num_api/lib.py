@@ -88,6 +88,9 @@ def load():
     lib.szb_lu_refactor.argtypes = [H, C.c_double, C.c_void_p]
     lib.szb_lu_solve.argtypes = [H, C.c_int32, C.c_void_p]
     lib.szb_lu_status.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.szb_lu_factors.argtypes = [H, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.szb_lu_residual.argtypes = [H, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]
     lib.szb_newton.argtypes = [H, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.szb_newton_host.argtypes = [H, C.c_double, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]

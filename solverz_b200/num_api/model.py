@@ -35,7 +35,9 @@ def _torch():
 class BatchSession:
     """One szb handle + the torch tensors bound to it, for a fixed batch size on one device."""
 
-    def __init__(self, model: "CudaModel", B: int, device: Optional[int] = None, with_lu: bool = True):
+    def __init__(self, model: "CudaModel", B: int, device: Optional[int] = None, with_lu: bool = True, sym=None):
+        """``sym``: a symbolic LU analysis to use instead of the model's own (the pivot fallback of nr_method
+        re-analyses on the Jacobian of a scenario the model's static pivots failed on)."""
         torch = _torch()
         self.model = model
         self.B = int(B)
@@ -49,7 +51,8 @@ class BatchSession:
         desc.n = model.n
         desc.nnz_j = model.nnz_j
         desc.model_lib = str(model.so_path).encode()
-        sym = model.symbolic(self.device) if with_lu else None
+        if sym is None:
+            sym = model.symbolic(self.device) if with_lu else None
         self.sym = sym
         desc.lu = L.lu_symbolic_c(sym, self._keep)
         if model.mass_vals is not None:
@@ -156,6 +159,27 @@ class BatchSession:
         L.check(self.lib.szb_lu_status(self.h, C.c_void_p(self.flags.data_ptr()), self._stream()), self.h,
                 "szb_lu_status")
         return self.flags
+
+    def slot_rows_cols(self):
+        """Row and column of every Jacobian slot as device int32 tensors (CSC order of the frozen pattern)."""
+        if getattr(self, "_slot_rc", None) is None:
+            torch = _torch()
+            m = self.model
+            cols = np.repeat(np.arange(m.n, dtype=np.int32), np.diff(m.indptr))
+            self._slot_rc = (torch.as_tensor(m.indices.astype(np.int32)).to(self.Y.device),
+                             torch.as_tensor(cols).to(self.Y.device))
+        return self._slot_rc
+
+    def lu_residual(self, rhs, x, h_gamma: float = 0.0):
+        """``max|rhs - A x| / max|rhs|`` per scenario for A = J (or M - h_gamma J) of the current SLOT_JV."""
+        torch = _torch()
+        rows, cols = self.slot_rows_cols()
+        out = torch.empty(self.B, dtype=torch.float64, device=self.Y.device)
+        L.check(self.lib.szb_lu_residual(self.h, float(h_gamma), C.c_void_p(rows.data_ptr()),
+                                         C.c_void_p(cols.data_ptr()), C.c_void_p(rhs.data_ptr()),
+                                         C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), self._stream()),
+                self.h, "szb_lu_residual")
+        return out
 
     def lu_solve(self, nrhs: int = 1):
         L.check(self.lib.szb_lu_solve(self.h, int(nrhs), self._stream()), self.h, "szb_lu_solve")

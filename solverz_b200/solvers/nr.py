@@ -18,6 +18,57 @@ from .solution import aesol
 from .stats import Stats
 
 
+def _pivot_fallback(eqn: CudaModel, s, y_start, y_res, it, fl, opt, rounds: int = 3):
+    """Scenarios that did not converge are solved again with a pivot order of their OWN: the static order of the
+    model comes from the Jacobian at (y0, default parameters), while the reference pivots inside every call
+    (laesolver.py:11-15 -> SuperLU, partial pivoting), so a scenario far from the representative point may have
+    failed on the pivots rather than on the problem.  The symbolic analysis is redone on the Jacobian of the first
+    failed scenario at ITS start, the failed ones are re-run from their starts on that schedule (still on the
+    GPU); up to ``rounds`` times.  A scenario that also fails there keeps its original result and flag."""
+    import torch
+    from ..lu.symbolic import analyze
+    from ..num_api.model import BatchSession
+    import scipy.sparse as sps
+    for _ in range(rounds):
+        bad = np.flatnonzero(fl != 0)
+        if len(bad) == 0:
+            break
+        idx = torch.as_tensor(bad, device=y_start.device)
+        one = eqn.session(1, s.device, with_lu=False)
+        one.set_params({k: (v[int(bad[0])] if eqn_param_is_batched(eqn, k, v, s.B) else v) for k, v in s.P.items()})
+        one.set_y(y_start[int(bad[0])])
+        jv = one.eval_J(0.0)[0].cpu().numpy()
+        if not np.all(np.isfinite(jv)):
+            break
+        A = sps.csc_matrix((jv, eqn.indices, eqn.indptr), shape=(eqn.n, eqn.n))
+        try:
+            sym = analyze(A, forced_pairs=eqn.mass, **eqn.lu_options)
+        except ValueError:
+            break
+        fb = BatchSession(eqn, len(bad), s.device, sym=sym)
+        try:
+            fb.set_params({k: (v[idx] if eqn_param_is_batched(eqn, k, v, s.B) else v) for k, v in s.P.items()})
+            fb.set_y(y_start[idx])
+            it2, fl2 = fb.newton(opt.ite_tol, opt.max_it)
+            it2 = it2.cpu().numpy().astype(np.int64)
+            fl2 = fl2.cpu().numpy().astype(np.int64)
+            ok = fl2 == 0
+            if not ok.any():
+                break
+            good = torch.as_tensor(bad[ok], device=y_res.device)
+            y_res[good] = fb.Y[torch.as_tensor(np.flatnonzero(ok), device=y_res.device)]
+            it[bad[ok]] = it2[ok]
+            fl[bad[ok]] = 0
+        finally:
+            fb.close()
+    return y_res, it, fl
+
+
+def eqn_param_is_batched(eqn: CudaModel, name: str, tns, B: int) -> bool:
+    pm = next((p for p in eqn.params_meta if p["name"] == name), None)
+    return bool(pm and pm["per_scenario"] and tns.ndim == 2 and tns.shape[0] == B)
+
+
 def nr_method(eqn: CudaModel, y, opt: Opt = None):
     if opt is None:
         opt = Opt()
@@ -40,11 +91,15 @@ def nr_method(eqn: CudaModel, y, opt: Opt = None):
     s = eqn.session(B)
     s.set_params(eqn.p)
     s.set_y(y_arr)
+    y_start = s.Y.clone() if getattr(opt, "pivot_fallback", True) else None
     iters, flags = s.newton(opt.ite_tol, opt.max_it)
     stats = Stats('Newton')
     it = iters.cpu().numpy().astype(np.int64)
     fl = flags.cpu().numpy().astype(np.int64)
-    y_out = s.Y.clone() if on_device else s.Y.cpu().numpy()
+    y_res = s.Y
+    if y_start is not None and (fl != 0).any():
+        y_res, it, fl = _pivot_fallback(eqn, s, y_start, y_res.clone(), it, fl, opt)
+    y_out = y_res.clone() if on_device else y_res.cpu().numpy()
     if single:
         stats.nstep = int(it[0])
         stats.nfeval = stats.nstep + 1

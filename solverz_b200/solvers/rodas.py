@@ -192,6 +192,8 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
         o.t_out = _dp(tsp)
         y_out = torch.zeros((len(tspan), B, n), dtype=torch.float64, device=dev)
         out.y_out = y_out.data_ptr()
+        n_rows_all = torch.zeros(B, dtype=torch.int32, device=dev)     # rows of y_out each scenario filled
+        out.n_rows = n_rows_all.data_ptr()
     elif single:
         cap = int(getattr(opt, "record_cap", 10001))
         o.record_cap = cap
@@ -213,7 +215,7 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
         ev_t = torch.full((B, cap), float("nan"), dtype=torch.float64, device=dev)
         ev_i = torch.full((B, cap), -1, dtype=torch.int32, device=dev)
         ev_y = torch.zeros((B, cap, n), dtype=torch.float64, device=dev)
-        n_rows = torch.zeros(B, dtype=torch.int32, device=dev)
+        n_rows = n_rows_all if dense else torch.zeros(B, dtype=torch.int32, device=dev)
         out.ev_count, out.ev_t, out.ev_i, out.ev_y = ev_count.data_ptr(), ev_t.data_ptr(), ev_i.data_ptr(), ev_y.data_ptr()
         out.n_rows = n_rows.data_ptr()
     y_init = s.Y.clone()
@@ -231,10 +233,18 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
     if dense:
         Yh = y_out.permute(1, 0, 2).contiguous()          # [B, nt, n]
         T = tspan.copy()
+        rows_all = n_rows_all.cpu().numpy().astype(np.int64)
         if single:
-            reached = int(torch.as_tensor(st[0, 6] == 0))
+            # a scenario that stops early (dt underflow, > 100 rejects, singular matrix) returns what it reached,
+            # like the reference's T[0:nt+1], Y[0:nt+1] (rodas.py:329-344) -- not zero rows
             Y = Yh[0].cpu().numpy()
+            if failed[0]:
+                T, Y = T[:rows_all[0]], Y[:rows_all[0]]
         else:
+            short = torch.as_tensor(rows_all, device=Yh.device)[:, None] <= torch.arange(len(tspan), device=Yh.device)[None, :]
+            if bool(short.any()):                          # rows a scenario never reached: nan, not zeros
+                Yh[short] = float("nan")
+            stats.n_rows = rows_all
             Y = Yh if on_device else Yh.cpu().numpy()
     elif single:
         nrec = int(st[0, 7])
@@ -248,6 +258,11 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
     if dev_events is not None:
         cnt = ev_count.cpu().numpy().astype(np.int64)
         stats.nevent = int(cnt[0]) if single else cnt.copy()
+        if int(cnt.max(initial=0)) > dev_events.max_events:
+            import warnings
+            warnings.warn(f"ComponentEvents: {int(cnt.max())} events located but only max_events = "
+                          f"{dev_events.max_events} are recorded per scenario; te / ye / ie hold the first ones",
+                          RuntimeWarning, stacklevel=2)
         if single:
             k = min(int(cnt[0]), dev_events.max_events)
             if k > 0:
@@ -263,7 +278,8 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
         else:                                             # [B, cap] padded with nan / -1; rows of Y past n_rows are zero
             te, ie = ev_t.cpu().numpy(), ev_i.cpu().numpy()
             ye = ev_y if on_device else ev_y.cpu().numpy()
-            stats.n_rows = n_rows.cpu().numpy().astype(np.int64) if dense else None
+            if not dense:
+                stats.n_rows = None
     if vars_in is not None and not isinstance(Y, torch.Tensor):
         Y = TimeVars(vars_in.a, Y)
         if ye is not None and single:

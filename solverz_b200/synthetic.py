@@ -237,37 +237,50 @@ def dhs_fdae_model(nx: int, ny: int, ns=None, seed: int = 0, dt: float = 60.0):
                 pipes.append((node(ix, iy), node(ix, iy + 1)))
     n_pipe = len(pipes)
     pidx = {p: k for k, p in enumerate(pipes)}
-    V = np.zeros((n_node, n_pipe))
-    for k, (a, b) in enumerate(pipes):
-        V[a, k] = -1.0
-        V[b, k] = 1.0
-    loops = []
+    # incidence / loop / selection matrices as sparse triplets (50 000 pipes: the dense forms would need 10 GB each)
+    pa = np.array([p[0] for p in pipes])
+    pb = np.array([p[1] for p in pipes])
+    ar = np.arange(n_pipe)
+    V = sps.csr_matrix((np.concatenate([-np.ones(n_pipe), np.ones(n_pipe)]),
+                        (np.concatenate([pa, pb]), np.concatenate([ar, ar]))), shape=(n_node, n_pipe))
+    lr, lc, lv = [], [], []
+    nl = 0
     for ix in range(nx - 1):
-        for iy in range(ny - 1):
-            row = np.zeros(n_pipe)                       # around the cell: +x, +y, -x, -y
-            row[pidx[(node(ix, iy), node(ix + 1, iy))]] = 1.0
-            row[pidx[(node(ix + 1, iy), node(ix + 1, iy + 1))]] = 1.0
-            row[pidx[(node(ix, iy + 1), node(ix + 1, iy + 1))]] = -1.0
-            row[pidx[(node(ix, iy), node(ix, iy + 1))]] = -1.0
-            loops.append(row)
-    Lm = np.array(loops)
+        for iy in range(ny - 1):                         # around the cell: +x, +y, -x, -y
+            lc += [pidx[(node(ix, iy), node(ix + 1, iy))], pidx[(node(ix + 1, iy), node(ix + 1, iy + 1))],
+                   pidx[(node(ix, iy + 1), node(ix + 1, iy + 1))], pidx[(node(ix, iy), node(ix, iy + 1))]]
+            lv += [1.0, 1.0, -1.0, -1.0]
+            lr += [nl] * 4
+            nl += 1
+    Lm = sps.csr_matrix((lv, (lr, lc)), shape=(nl, n_pipe))
     K = rng.uniform(0.5, 2.0, n_pipe)
     load = rng.uniform(0.5, 1.5, n_node - 1)            # withdrawals at the non-source nodes (flow into the node)
-    V_ns = V[1:, :]
-    Vin = np.maximum(V_ns, 0.0)                         # pipes that end at the node
-    Vf = np.zeros((n_pipe, n_node))                     # the node a pipe starts from
-    for k, (a, b) in enumerate(pipes):
-        Vf[k, a] = 1.0
+    V_ns = V[1:, :].tocsr()
+    Vin = V_ns.maximum(0.0).tocsr()                     # pipes that end at the node
+    Vin.eliminate_zeros()
+    Vf = sps.csr_matrix((np.ones(n_pipe), (ar, pa)), shape=(n_pipe, n_node))   # the node a pipe starts from
     # steady state of the nominal load: hydraulic Newton, then temperatures node by node (lattice order is topological)
-    mflow = np.linalg.lstsq(np.vstack([V_ns, Lm]), np.concatenate([load, np.zeros(len(loops))]), rcond=None)[0]
+    rhs0 = np.concatenate([load, np.zeros(nl)])
+    if n_pipe <= 4000:                                   # the small fixtures keep their dense start bit for bit
+        mflow = np.linalg.lstsq(np.vstack([V_ns.toarray(), Lm.toarray()]), rhs0, rcond=None)[0]
+    else:
+        import scipy.sparse.linalg as sla
+        mflow = sla.spsolve(sps.vstack([V_ns, Lm]).tocsc(), rhs0)
     for _ in range(50):
         res = np.concatenate([V_ns @ mflow - load, Lm @ (K * mflow * np.abs(mflow))])
-        Jh = np.vstack([V_ns, Lm * (2 * K * np.abs(mflow))[None, :]])
-        mflow = mflow - np.linalg.solve(Jh, res)
+        if n_pipe <= 4000:
+            Jh = np.vstack([V_ns.toarray(), Lm.toarray() * (2 * K * np.abs(mflow))[None, :]])
+            mflow = mflow - np.linalg.solve(Jh, res)
+        else:
+            Jh = sps.vstack([V_ns, Lm @ sps.diags(2 * K * np.abs(mflow))]).tocsc()
+            dm = sla.spsolve(Jh, res)
+            mflow = mflow - dm
+            if np.abs(dm).max() <= 1e-14 * max(1.0, np.abs(mflow).max()):
+                break
     cth, lam, Ta, Ts = 0.08 * dt / 60.0, 0.01 * dt / 60.0, 10.0, 90.0
     Tn = np.full(n_node, Ts)
     Tout = np.full(n_pipe, Ts)
-    for _ in range(200):                                  # fixed point of the steady thermal equations
+    for _ in range(max(200, 2 * (nx + ny))):              # fixed point of the steady thermal equations
         Tin = Vf @ Tn
         Tout = (cth * mflow * Tin + lam * Ta) / (cth * mflow + lam)
         Tn[1:] = (Vin @ (mflow * Tout)) / (Vin @ mflow)
@@ -279,7 +292,7 @@ def dhs_fdae_model(nx: int, ny: int, ns=None, seed: int = 0, dt: float = 60.0):
     m.Tin = ns.Var('Tin', Vf @ Tn)
     m.Tout0 = ns.AliasVar('Tout', value=Tout, step=1) if own else ns.AliasVar('Tout', step=1, value=Tout)
     for nm, A in (("V_ns", V_ns), ("L", Lm), ("Vin", Vin), ("Vf", Vf)):
-        setattr(m, nm, ns.Param(nm, sps.csc_array(A), dim=2, sparse=True))
+        setattr(m, nm, ns.Param(nm, sps.csc_array(A), dim=2, sparse=True))   # structural zeros are not stored
     m.K = ns.Param('K', K)
     m.m_inj = ns.Param('m_inj', load)
     m.sc = ns.TimeSeriesParam('sc', v_series=[1.0, 1.0, 1.2, 1.2], time_series=[0.0, dt, 3 * dt, 1e6], **kw)

@@ -140,7 +140,7 @@ def eliminate_blocked(F, s, f, ncol, NB=4):
 
 def factor_tables(sym, tabs, jv, rhs=None, mvals=None, scale=1.0, store_l=True):
     """Walks the schedule of ``build_tables``; returns (lu, y) with y = L^{-1} P rhs in pivot order."""
-    from solverz_b200.lu.schedule import NOOP, OFF_MASK, TAG_CB, TAG_J, TAG_RHS
+    from solverz_b200.lu.schedule import NOOP, OFF_MASK, TAG_CB, TAG_CBR, TAG_J, TAG_RHS
     lu = np.zeros(sym.lu_size)
     cb = np.full(max(sym.cb_size, 1), np.nan)
     y = np.zeros(sym.n)
@@ -155,7 +155,7 @@ def factor_tables(sym, tabs, jv, rhs=None, mvals=None, scale=1.0, store_l=True):
         ncol = f + 1
         Fm = np.zeros(ld * ncol)
         owner = {}
-        for b in range(3 if with_rhs else 2):
+        for b in range(1):
             g0, iters = int(fh[q, 6 + 2 * b]), int(fh[q, 7 + 2 * b])
             blk = ga[g0:g0 + iters * G].reshape(iters, G, 2)
             for it in range(iters):
@@ -169,12 +169,15 @@ def factor_tables(sym, tabs, jv, rhs=None, mvals=None, scale=1.0, store_l=True):
                 m = live & (tag == TAG_CB)
                 v[m] = cb[off[m]]
                 m = live & (tag == TAG_J)
-                assert b == 0 or not m.any()
                 v[m] = scale * jv[off[m]] + (mvals[off[m]] if mvals is not None else 0.0)
                 m = live & (tag == TAG_RHS)
-                assert b == 0 or not m.any()
                 if with_rhs:
                     v[m] = rhs[off[m]]
+                else:
+                    live = live & ~m
+                m = live & (tag == TAG_CBR)
+                if with_rhs:
+                    v[m] = cb[off[m]]
                 else:
                     live = live & ~m
                 Fm[dst[live]] += v[live]

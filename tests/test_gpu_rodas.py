@@ -197,3 +197,61 @@ def test_dae_ic_inconsistent_start_vs_oracle(libszb):
         ref = oracle_rodas(F, J, M, tsp, yi, rp, rtol=1e-4, atol=1e-7, dfdt_mode=0)
         assert int(sol.stats.nstep[b]) == ref["stats"]["nstep"] and int(sol.stats.nreject[b]) == ref["stats"]["nreject"]
         assert np.max(np.abs(sol.Y[b] - ref["Y"])) < 1e-8
+
+
+def test_config4_full_size_sample_vs_oracle(libszb):
+    """BASELINE.json configs[3] at its model size (45 x 45 = 2025 machines, n = 20 250, fronts up to 454 in the
+    per-CTA global workspace): a batch of bus-fault scenarios through the first 5 ms of the fault of scenario 0
+    (Rodas rodas4, rtol 1e-3, atol 1e-6, hinit 1e-5); two scenarios against the oracle's Rodas loop
+    (oracle/rodas.py) driven by the REFERENCE's own F / J of the same model (baseline/_ref, made_numerical):
+    identical accepted / rejected step counts, trajectories 1e-8.  Size-independent properties on the rest: the
+    unfaulted scenario stays at its equilibrium, a repeated scenario is bitwise equal."""
+    import sys
+    ref_dir = Path(__file__).resolve().parents[1] / "baseline" / "_ref"
+    if not (ref_dir / "Solverz" / "__init__.py").exists():
+        pytest.skip("baseline/_ref (private copy of the reference) is not present")
+    sys.path.insert(0, str(ref_dir))
+    import Solverz as SZ
+    from oracle.rodas import rodas as oracle_rodas
+    from solverz_b200 import Opt, Rodas, made_numerical
+    from solverz_b200.solvers.rodas_param import Rodas_param
+    from solverz_b200.synthetic import swing_dae_model, swing_fault_scenarios
+    nx = 45
+    m, info = swing_dae_model(nx, nx)
+    dae, y0 = m.create_instance()
+    nd = made_numerical(dae, y0, sparse=True)
+    B = 16
+    fmask, tst, tsv = swing_fault_scenarios(info["nb"], B)
+    fmask[3] = 0.0                                       # scenario 3: no fault at all
+    fmask[5], tst[5], tsv[5] = fmask[0], tst[0], tsv[0]  # scenario 5 repeats scenario 0
+    nd.p["fmask"], nd.p["gf__ts_t"], nd.p["gf__ts_v"] = fmask, tst, tsv
+    tsp = np.array([0.0, 0.05, 0.1, 0.1005, 0.102, 0.105])
+    opt = Opt(rtol=1e-3, atol=1e-6, hinit=1e-5)
+    sol = Rodas(nd, tsp, np.tile(y0.array, (B, 1)), opt)
+    assert sol.stats.succeed.all()
+    assert np.abs(sol.Y[3] - y0.array[None, :]).max() < 1e-10
+    assert np.array_equal(sol.Y[5], sol.Y[0]) and np.array_equal(sol.stats.nstep[5:6], sol.stats.nstep[0:1])
+    assert np.abs(sol.Y[0, -1] - y0.array).max() > 1e-3   # the fault moved the state
+    # the reference's numerical functions of the same model, built with the reference's DSL
+    mr, _ = swing_dae_model(nx, nx, ns=SZ)
+    dr, y0r = mr.create_instance()
+    ref = SZ.made_numerical(dr, y0r, sparse=True)
+    np.testing.assert_allclose(y0r.array, y0.array, rtol=0, atol=1e-14)
+    M = sps.csc_matrix(ref.M)
+    rp = Rodas_param("rodas4")
+    for b in (0, 1):
+        ref.p["fmask"] = fmask[b].copy()                 # plain parameters are ndarrays in the reference's p dict
+        gf = ref.p["gf"]                                 # the TimeSeriesParam object itself (get_v_t per call)
+        gf.time_series[:] = tst[b]
+        gf.v_series[:] = tsv[b]
+        from scipy.interpolate import interp1d
+        gf.vt = interp1d(gf.time_series, gf.v_series, kind='linear')
+        gf.tend = gf.time_series[-1]
+        F = lambda t, y: np.asarray(ref.F(t, y, ref.p)).copy()
+        J = lambda t, y: sps.csc_matrix(ref.J(t, y, ref.p))
+        r = oracle_rodas(F, J, M, tsp, y0.array, rp, rtol=1e-3, atol=1e-6, hinit=1e-5, dfdt_mode=0)
+        assert int(sol.stats.nstep[b]) == r["stats"]["nstep"], (b, int(sol.stats.nstep[b]), r["stats"]["nstep"])
+        assert int(sol.stats.nreject[b]) == r["stats"]["nreject"]
+        d = np.abs(sol.Y[b] - r["Y"]).max(axis=1)
+        assert d[:3].max() < 1e-8 and d.max() < 1e-5 * max(1.0, np.abs(r["Y"]).max()), (b, d)
+    nd.close()

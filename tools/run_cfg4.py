@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--nx", type=int, default=45)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--tend", type=float, default=0.12)
+    ap.add_argument("--rtol", type=float, default=1e-3)      # SURVEY.md 8d cfg#4: rodas4, rtol 1e-3, atol 1e-6, hinit 1e-5
+    ap.add_argument("--atol", type=float, default=1e-6)
+    ap.add_argument("--hinit", type=float, default=1e-5)
     a = ap.parse_args()
     import torch
     from solverz_b200 import Opt, Rodas, made_numerical
@@ -42,15 +45,31 @@ def main():
     tsp = np.linspace(0.0, a.tend, 7)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    sol = Rodas(nd, tsp, Y0, Opt(rtol=1e-4, atol=1e-7, hinit=1e-4))
+    sol = Rodas(nd, tsp, Y0, Opt(rtol=a.rtol, atol=a.atol, hinit=a.hinit))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     st = sol.stats
     drift = float(np.max(np.abs(sol.Y[0] - y0.array[None, :])))
     same = bool(np.array_equal(sol.Y[1], sol.Y[2]))
     moved = float(np.max(np.abs(sol.Y[1, -1] - y0.array)))
-    line = {"workload": f"swing/flux-decay/exciter DAE, {info['nb']} machines, n={info['n']}, Rodas rodas4, "
-                        f"{B} bus-fault scenarios, tspan [0, {a.tend}]",
+    peak = 6539.2
+    try:
+        peak = float(json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+    except Exception:
+        pass
+    nnzj, nnzlu, n, s_ = int(nd.nnz_j), int(sess.sym.nnz_lu), int(nd.n), 6
+    # algorithmic bytes of one Rodas step per scenario: 8 (nnzJ + nnzJ + nnzLU + s nnzLU + (6 s + 6) n)
+    step_bytes = 8 * (2 * nnzj + (1 + s_) * nnzlu + (6 * s_ + 6) * n)
+    attempts = int(st.nstep.sum() + st.nreject.sum())
+    line = {"metric": "rodas_accepted_steps_per_s", "value": float(st.nstep.sum() / dt), "unit": "steps/s",
+            "workload": f"swing/flux-decay/exciter DAE, {info['nb']} machines, n={info['n']}, Rodas rodas4 "
+                        f"(rtol {a.rtol}, atol {a.atol}, hinit {a.hinit}), {B} bus-fault scenarios, tspan [0, {a.tend}]",
+            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "alg_bytes_per_step_per_scenario": step_bytes,
+                         "achieved": step_bytes * attempts / dt / 1e9,
+                         "frac": step_bytes * attempts / dt / 1e9 / peak,
+                         "note": "whole step (1 J + 1 LU + s solves + s F), attempted steps (accepted + rejected) x "
+                                 "algorithmic bytes / wall time of the whole call"},
+            "nnz_J": nnzj, "attempted_steps": attempts,
             "accepted_steps_per_s": float(st.nstep.sum() / dt), "stage_solves_per_s": float(st.nsolve.sum() / dt),
             "seconds": dt, "steps_min_max": [int(st.nstep.min()), int(st.nstep.max())],
             "rejected_total": int(st.nreject.sum()), "all_finished": bool(st.succeed.all()),

@@ -266,7 +266,7 @@ class _Translator:
         raise NotImplementedError(f"{self.eq}: index expression {k!r}")
 
 
-def _param_from_reference(name: str, p) -> S.Param:
+def _param_from_reference(name: str, p, per_scenario: bool = False) -> S.Param:
     if getattr(p, "triggerable", False):
         raise NotImplementedError(f"parameter {name}: triggerable parameters (equation/param.py:16) are host "
                                   f"callbacks evaluated between calls; update mdl.p[...] between solves instead")
@@ -276,7 +276,7 @@ def _param_from_reference(name: str, p) -> S.Param:
         if dim != 1:
             raise NotImplementedError(f"parameter {name}: 2-D TimeSeriesParam")
         return S.TimeSeriesParam(name, np.asarray(p.v_series, dtype=float), np.asarray(p.time_series, dtype=float),
-                                 value=np.asarray(p.v, dtype=float), index=p.index)
+                                 value=np.asarray(p.v, dtype=float), index=p.index, per_scenario=per_scenario)
     if getattr(p, "is_alias", False):
         base, _, k = name.rpartition("_tag_")
         return S.AliasVar(base, step=int(k) + 1, value=None if p.v is None else np.asarray(p.v, dtype=float))
@@ -285,13 +285,24 @@ def _param_from_reference(name: str, p) -> S.Param:
         v = p.v
         M = sps.csr_matrix(v) if sps.issparse(v) else sps.csr_matrix(np.asarray(v, dtype=float))
         return S.Param(name, M, dim=2, sparse=True)
-    return S.Param(name, np.asarray(p.v), dtype=int if is_int else float)
+    if per_scenario and is_int:
+        raise ValueError(f"parameter {name}: integer (index) parameters are shared by all scenarios")
+    return S.Param(name, np.asarray(p.v), dtype=int if is_int else float, per_scenario=per_scenario and not is_int)
 
 
-def from_solverz(eqs, y0) -> Tuple[Equations, Vars]:
-    """Lower a Solverz ``AE`` / ``DAE`` / ``FDAE`` and its ``Vars`` (module docstring)."""
+def from_solverz(eqs, y0, per_scenario=()) -> Tuple[Equations, Vars]:
+    """Lower a Solverz ``AE`` / ``DAE`` / ``FDAE`` and its ``Vars`` (module docstring).
+
+    ``per_scenario``: names of the 1-D parameters (``Param`` values, or the knots of a ``TimeSeriesParam``) that
+    differ between the scenarios of a batch -- the one declaration the reference has no word for (there a user
+    mutates ``mdl.p[name]`` between solves); ``mdl.p[name]`` then takes ``[B, len]`` values.  Everything else is
+    shared by the batch."""
     if not is_solverz_object(eqs):
         raise TypeError(f"from_solverz expects a Solverz AE / DAE / FDAE, got {type(eqs).__name__}")
+    per_scenario = set(per_scenario or ())
+    unknown = per_scenario - set(eqs.PARAM)
+    if unknown:
+        raise ValueError(f"per_scenario names that are not parameters of the model: {sorted(unknown)}")
     kind = type(eqs).__name__
     cls = {"AE": AE, "DAE": DAE, "FDAE": FDAE}.get(kind)
     if cls is None:
@@ -309,7 +320,7 @@ def from_solverz(eqs, y0) -> Tuple[Equations, Vars]:
         helper = next((nm[:-len(sfx)] for sfx in _MATRIX_HELPER_SUFFIXES if nm.endswith(sfx)), None)
         if helper is not None and helper in eqs.PARAM and int(getattr(eqs.PARAM[helper], "dim", 1)) == 2:
             continue
-        mine = _param_from_reference(nm, p)
+        mine = _param_from_reference(nm, p, nm in per_scenario)
         params[mine.name] = mine
     # equations
     eqns: List[Eqn] = []

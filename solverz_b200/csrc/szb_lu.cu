@@ -571,9 +571,12 @@ __device__ __forceinline__ void blocked_panel(const PanelGrp& g, double* __restr
     const int ww = has_next ? w - 1 : w;
     const int nch = (m + 31) >> 5;                   // row groups of 32 rows
     const int nct = (ncol - r0 + 7) >> 3;            // column tiles
-    const int CW = max(1, min(W / nch, nct));        // warps that share a row group, striding over the column tiles
+    // W / nch without an integer division (W <= 32: the multiply-shift forms are exact): this runs once per
+    // panel and warp, and a generic division is ~25 instructions
+    const int wq = nch == 1 ? W : (nch == 2 ? W >> 1 : (nch == 3 ? (W * 43) >> 7 : (nch == 4 ? W >> 2 : W / nch)));
+    const int CW = max(1, min(wq, nct));             // warps that share a row group, striding over the column tiles
     const int ntile = nch * CW;
-    const float inv_cw = 1.0f / static_cast<float>(CW);
+    const float inv_cw = __frcp_rn(static_cast<float>(CW));
     for (int tile = ww; tile < ntile; tile += W) {
       const int tr = nch == 1 ? 0 : fdiv(tile, inv_cw);
       const int cg = tile - tr * CW;
@@ -808,7 +811,7 @@ __device__ __noinline__ void eliminate_global(const PanelGrp g, double* __restri
         const int nchR = (nrR + 3) >> 2;
         const int ncR = max(0, tcmax - tb + 1);                         // column tiles behind the block
         const int JC = ncC * nchC, J = JC + ncR * nchR;
-        const float inv_c = 1.0f / static_cast<float>(max(nchC, 1)), inv_r = 1.0f / static_cast<float>(max(nchR, 1));
+        const float inv_c = __frcp_rn(static_cast<float>(max(nchC, 1))), inv_r = __frcp_rn(static_cast<float>(max(nchR, 1)));
         for (int j = ww; j < J; j += W) {
           int tc, tr, nt;
           if (j < JC) {
@@ -834,7 +837,7 @@ __device__ __noinline__ void eliminate_global(const PanelGrp g, double* __restri
       if (ntr > 0 && ntc > 0) {
         const int nch = (ntr + 3) >> 2;                // chunks of 4 row tiles
         const int npair = (ntc + 1) >> 1;              // pairs of column tiles
-        const float inv = 1.0f / static_cast<float>(nch);
+        const float inv = __frcp_rn(static_cast<float>(nch));
         for (int j = w; j < nch * npair; j += nw) {
           const int a = fdiv(j, inv);
           const int tc = tb + 2 * a, tr = tb + 4 * (j - a * nch);
@@ -894,7 +897,7 @@ __device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre
   double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
   {
     const int rows = A.store_l ? f : s;
-    const float invr = 1.0f / static_cast<float>(rows);
+    const float invr = __frcp_rn(static_cast<float>(rows));
     for (int t = lane; t < rows * s; t += kWarp) {
       const int p = fdiv(t, invr);
       const int i = t - p * rows;
@@ -906,8 +909,8 @@ __device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre
     double* __restrict__ Up = A.lu + H.up_off;           // U12, s x u column-major: Up[r + c*s]
     double* C = A.cb + H.cb_off;                         // u x (u+1), column-major
     const int nc = u + with_rhs;
-    const float invu = 1.0f / static_cast<float>(u);
-    const float invs = 1.0f / static_cast<float>(s);
+    const float invu = __frcp_rn(static_cast<float>(u));
+    const float invs = __frcp_rn(static_cast<float>(s));
     for (int t = lane; t < u * s; t += kWarp) {
       const int c = fdiv(t, invs);
       const int rr = t - c * s;
@@ -978,7 +981,7 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
     // lanes over the long dimension, pointer walks over the short one: no index arithmetic inside
     double* __restrict__ Up = A.lu + H.up_off;           // U12, s x u column-major: Up[r + c*s]
     {
-      const float invs = 1.0f / static_cast<float>(s);
+      const float invs = __frcp_rn(static_cast<float>(s));
       for (int t = r; t < u * s; t += G_) {
         const int c = fdiv(t, invs);
         const int rr = t - c * s;

@@ -54,7 +54,8 @@ def test_power_flow_same_model_object_both_backends(libszb, tmp_path):
     # back-end 1: the reference's renderer
     SZ.module_printer(spf, y0, "ga_pf_ref", directory=str(tmp_path), jit=True).render()
     # back-end 2: this package's renderer, same objects, lang='cuda'
-    SB.module_printer(spf, y0, "ga_pf_cuda", lang='cuda', directory=str(tmp_path)).render()
+    SB.module_printer(spf, y0, "ga_pf_cuda", lang='cuda', directory=str(tmp_path),
+                      per_scenario=("Pinj", "Qinj")).render()     # the scenario inputs of this batch
     sys.path.insert(0, str(tmp_path))
     ref = importlib.import_module("ga_pf_ref")
     dev = importlib.import_module("ga_pf_cuda")

@@ -92,7 +92,7 @@ def test_newton_pivot_fallback(libszb):
     m = Model()
     m.x = Var('x', [1.0, 1.0, 1.0])
     m.a = Param('a', [4.0], per_scenario=True)
-    m.b = Param('b', [6.0, 5.0, 4.0], per_scenario=True)
+    m.b = Param('b', [2.0, 5.0, 6.0], per_scenario=True)
     # J = [[a, 1, 0], [1, 3, 1], [0, 1, 2 x2]]: the order chosen at a = 4 pivots on a first
     m.e0 = Eqn('e0', m.a * m.x[0] + m.x[1] - m.b[0])
     m.e1 = Eqn('e1', m.x[0] + 3 * m.x[1] + m.x[2] - m.b[1])
@@ -100,7 +100,7 @@ def test_newton_pivot_fallback(libszb):
     eqs, y0 = m.create_instance()
     mdl = made_numerical(eqs, y0, sparse=True)
     a = np.array([[4.0], [0.0], [3.0], [1e-18]])
-    bb = np.tile(np.array([6.0, 5.0, 4.0]), (4, 1))
+    bb = np.tile(np.array([2.0, 5.0, 6.0]), (4, 1))
     mdl.p["a"], mdl.p["b"] = a, bb
     Y0 = np.tile(y0.array, (4, 1))
     opt = Opt(ite_tol=1e-10)
@@ -108,8 +108,9 @@ def test_newton_pivot_fallback(libszb):
     assert sol.stats.succeed.all(), sol.stats.flag
     for k in range(4):
         x = sol.y[k]
-        r = np.array([a[k, 0] * x[0] + x[1] - 6.0, x[0] + 3 * x[1] + x[2] - 5.0, x[1] + x[2] ** 2 - 4.0])
+        r = np.array([a[k, 0] * x[0] + x[1] - 2.0, x[0] + 3 * x[1] + x[2] - 5.0, x[1] + x[2] ** 2 - 6.0])
         assert np.abs(r).max() <= 1e-10
+    assert np.allclose(sol.y[1], [-3.0, 2.0, 2.0], atol=1e-9) and int(sol.stats.nstep[1]) == 5   # numpy's Newton with pivoting
     opt2 = Opt(ite_tol=1e-10)
     opt2.pivot_fallback = False
     sol2 = nr_method(mdl, Y0, opt2)

@@ -292,20 +292,28 @@ def main():
     Y0 = torch.as_tensor(np.tile(y0.array, (B, 1))).to(dev)
     sess.set_params({"Pinj": P, "Qinj": Q})
     sess.set_profile(True)
-    gathered_it = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
-    gathered_fl = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
-    gathered_Y = [torch.zeros_like(sess.Y) for _ in range(world)] if (world > 1 and rank == 0) else None
+    from solverz_b200.parallel import gather_results_async
+    pending = [None]
 
     def step():
         sess.Y.copy_(Y0)
         it, fl = sess.newton(TOL, MAX_IT)
         if world > 1:
-            dist.all_gather(gathered_it, it)
-            dist.all_gather(gathered_fl, fl)
-            dist.gather(sess.Y, gathered_Y, dst=0)
+            # the product's multi-GPU path (solverz_b200/parallel.py): the gather of solutions, iteration counts and
+            # flags is ISSUED here from private send buffers and completes while the next step's kernels run; every
+            # step's gather is waited for inside the timed region (the last one before the closing barrier)
+            if pending[0] is not None:
+                pending[0].wait()
+            pending[0] = gather_results_async(sess.Y, it, fl, B * world)
         return it, fl
 
+    def drain():
+        if pending[0] is not None:
+            pending[0].wait()
+            pending[0] = None
+
     def sync_all():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -332,6 +340,7 @@ def main():
         for k in prof:
             prof[k]["ms"] += pr[k]["ms"]
             prof[k]["units"] += pr[k]["units"]
+    drain()
     e1.record()
     sync_all()
     clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None

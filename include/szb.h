@@ -50,7 +50,7 @@ extern "C" {
 #define SZB_API
 #endif
 
-#define SZB_ABI_VERSION 3
+#define SZB_ABI_VERSION 4
 
 /* error codes */
 #define SZB_OK 0
@@ -169,6 +169,14 @@ typedef struct szb_rodas_opt {
   const int32_t* ev_term;    /* host [n_events]: 1 = the scenario stops at this event */
   double event_duration;     /* events closer than this to the step start are dropped (rodas.py:257-259) */
   int32_t ev_cap;            /* events recorded per scenario (rows of ev_t / ev_i / ev_y) */
+  /* Step-wise driving, for event functions that are Python callbacks (rodas.py:99-107: value, isterminal,
+   * direction = events(t, y)): the host has to see every accepted step.  resume = 1 keeps the controller state
+   * of the previous call on this handle (t, dt, facmax, reject counter, dense-output cursor, statistics) instead
+   * of initialising from t0 / hinit; stop_after_accepted > 0 pauses a scenario (it stays SZB_FLAG_RUNNING) after
+   * that many accepted steps of this call.  Between calls the host may move a scenario back to an event time
+   * with szb_rodas_state_set and by writing its state into SLOT_Y. */
+  int32_t resume;
+  int32_t stop_after_accepted;
 } szb_rodas_opt;
 
 typedef struct szb_rodas_out {
@@ -241,6 +249,17 @@ SZB_API int szb_newton_host(szb_handle* h, double tol, int32_t max_it, double* y
 /* batched Rodas (rodas.py:7-344): integrates every scenario of SLOT_Y from t0 to tend with its own
  * adaptive step; SLOT_Y holds the final states on return. */
 SZB_API int szb_rodas(szb_handle* h, const szb_rodas_opt* opt, const szb_rodas_out* out, szb_stream stream);
+/* controller state after a szb_rodas call, host arrays of B entries each (NULL: skipped): time reached, start
+ * and size of the last accepted step, dense-output cursor (index of the next requested time), the [B][8]
+ * statistics block of szb_rodas_out.stats */
+SZB_API int szb_rodas_state_get(szb_handle* h, double* t_host, double* told_host, double* dt_host,
+                                int32_t* inext_host, int32_t* stats_host);
+/* scenario b continues from time t (its state: SLOT_Y); inext >= 0 rewinds the dense-output cursor; flag >= 0
+ * sets its status (SZB_FLAG_EVENT stops it, SZB_FLAG_RUNNING lets a resume call continue it) */
+SZB_API int szb_rodas_state_set(szb_handle* h, int32_t b, double t, int32_t inext, int32_t flag);
+/* stage vectors K [s][B][n] of the last attempted step into K_out_dev (device double[s*B*n]; s = stages of the
+ * scheme of the last call) -- the data of the dense output ntrp1 (rodas.py:383-386) */
+SZB_API int szb_rodas_stages(szb_handle* h, double* K_out_dev, szb_stream stream);
 /* row_col[r] = column of the unit entry of M in row r, or -1 for an algebraic row (host int32[n]);
  * needed once before szb_rodas */
 SZB_API int szb_set_mass_rows(szb_handle* h, const int32_t* row_col, int32_t n);

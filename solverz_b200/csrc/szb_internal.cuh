@@ -56,6 +56,7 @@ struct szb_handle {
   double *rd_K = nullptr, *rd_y1 = nullptr, *rd_sum2 = nullptr, *rd_dfdt = nullptr, *rd_F1 = nullptr;
   double *rd_dbl = nullptr, *rd_tout = nullptr, *rd_ev = nullptr;
   int *rd_int = nullptr, *rd_mcol = nullptr;
+  bool rodas_started = false;   // a szb_rodas call has initialised the controller state of this batch
   int rd_tout_cap = 0;
   bool rd_mcol_ready = false;
   std::vector<int> mass_row_col;   // row -> column of the unit mass entry, -1 for algebraic rows

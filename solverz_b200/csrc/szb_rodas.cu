@@ -28,6 +28,7 @@ struct Tableau {
 struct Ctl {  // scalars of the step controller
   double tend, rtol, atol, f_savety, fac1, fac2, hmax, hmin, uround, hinit;
   int fix_h, n_out, record_cap, max_steps;
+  int stop_after;   // > 0: a scenario pauses after this many accepted steps of the current call (szb_rodas_opt)
   // component-threshold events (szb.h): value_i = y[ev_idx[i]] - ev_thr[i]
   int n_events, ev_cap;
   double event_duration;
@@ -37,8 +38,9 @@ struct Ctl {  // scalars of the step controller
 
 // per-scenario state, struct of arrays
 struct State {
-  double *t, *dt, *told, *facmax, *scale, *tstage, *ddt;
+  double *t, *dt, *told, *facmax, *scale, *tstage, *ddt, *dtacc;   // dtacc: step size of the last accepted step
   int *reject, *active, *jmask, *inext, *nrec, *stats;  // stats: [B][8]
+  int* acc_left;   // accepted steps this scenario may still take in the current call (stop_after_accepted)
   double* ev_val;   // [B][SZB_MAX_EVENTS] event values at the end of the last accepted step (rodas.py:203)
 };
 
@@ -219,11 +221,14 @@ step_finish_kernel(const double* __restrict__ K, double* __restrict__ Y, Tableau
       S.reject[b] = 0;
       S.told[b] = S.t[b];
       S.t[b] = S.t[b] + dt;
+      S.dtacc[b] = dt;
       st[0] += 1;
       S.facmax[b] = C.fac2;                         // :321
       if (fabs(C.tend - S.t[b]) < C.uround) {       // :318
         S.active[b] = 0;
         st[6] = SZB_FLAG_CONVERGED;
+      } else if (C.stop_after > 0 && --S.acc_left[b] <= 0) {
+        S.active[b] = 0;                            // paused: still SZB_FLAG_RUNNING, a resume call continues it
       }
     } else {                                        // :323-326
       S.reject[b] += 1;
@@ -414,6 +419,15 @@ __global__ void rodas_init_kernel(State S, szb_rodas_out O, const double* __rest
   }
 }
 
+// resume = 1: the controller state of the previous call stays; scenarios that were only paused run again
+__global__ void rodas_resume_kernel(State S, int stop_after, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    S.active[b] = S.stats[8 * b + 6] == SZB_FLAG_RUNNING ? 1 : 0;
+    S.acc_left[b] = stop_after;
+  }
+}
+
 __global__ void rodas_finalize_kernel(State S, double* t_end, int* stats_out, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
@@ -454,8 +468,8 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
     h->rd_sum2 = static_cast<double*>(alloc(sizeof(double) * bn));
     h->rd_dfdt = static_cast<double*>(alloc(sizeof(double) * bn));
     h->rd_F1 = static_cast<double*>(alloc(sizeof(double) * bn));
-    h->rd_dbl = static_cast<double*>(alloc(sizeof(double) * 7 * B));
-    h->rd_int = static_cast<int*>(alloc(sizeof(int) * (5 + 8) * B));
+    h->rd_dbl = static_cast<double*>(alloc(sizeof(double) * 8 * B));
+    h->rd_int = static_cast<int*>(alloc(sizeof(int) * (6 + 8) * B));
     h->rd_mcol = static_cast<int*>(alloc(sizeof(int) * n));
     h->rd_ev = static_cast<double*>(alloc(sizeof(double) * SZB_MAX_EVENTS * B));
     h->rd_tout = nullptr;
@@ -467,6 +481,7 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
     h->rodas_B = B;
     h->rodas_stages = s;
     h->rd_mcol_ready = false;
+    h->rodas_started = false;
   }
   if (!h->rd_mcol_ready) {
     if (h->mass_row_col.size() != static_cast<size_t>(n)) { szb_set_error(h, "szb_rodas: mass row map missing; call szb_set_mass_rows"); return SZB_ESTATE; }
@@ -501,6 +516,7 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
   C.uround = DBL_EPSILON;                                                // spacing(1.0), :81
   C.fix_h = o->fix_h; C.hinit = o->hinit; C.n_out = o->n_out; C.record_cap = o->record_cap;
   C.max_steps = o->max_steps > 0 ? o->max_steps : 1000000;
+  C.stop_after = o->stop_after_accepted > 0 ? o->stop_after_accepted : 0;
   C.n_events = o->n_events;
   C.ev_cap = o->ev_cap;
   C.event_duration = o->event_duration;
@@ -523,9 +539,9 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
 
   State S{};
   S.t = h->rd_dbl; S.dt = S.t + B; S.told = S.dt + B; S.facmax = S.told + B; S.scale = S.facmax + B;
-  S.tstage = S.scale + B; S.ddt = S.tstage + B;
+  S.tstage = S.scale + B; S.ddt = S.tstage + B; S.dtacc = S.ddt + B;
   S.reject = h->rd_int; S.active = S.reject + B; S.jmask = S.active + B; S.inext = S.jmask + B;
-  S.nrec = S.inext + B; S.stats = S.nrec + B;
+  S.nrec = S.inext + B; S.acc_left = S.nrec + B; S.stats = S.acc_left + B;
   S.ev_val = h->rd_ev;
 
   if (B > 65535) {   // the stage kernels index the scenario through gridDim.y
@@ -534,7 +550,14 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
   }
   const dim3 eg((n + 255) / 256 > 64 ? 64 : (n + 255) / 256, B);
   SZB_CUDA(h, cudaMemsetAsync(h->flags, 0, sizeof(int) * B, st));
-  rodas_init_kernel<<<B, 128, 0, st>>>(S, *out, h->Y, o->t0, dt0, o->facmax, o->n_out, o->record_cap, C, n, B);
+  if (o->resume) {
+    if (!h->rodas_started) { szb_set_error(h, "szb_rodas: resume without a previous call on this handle"); return SZB_ESTATE; }
+    rodas_resume_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, C.stop_after, B);
+  } else {
+    rodas_init_kernel<<<B, 128, 0, st>>>(S, *out, h->Y, o->t0, dt0, o->facmax, o->n_out, o->record_cap, C, n, B);
+    rodas_resume_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, C.stop_after, B);
+    h->rodas_started = true;
+  }
   h->launches[4]++;
   int rc;
   const bool use_dfdt = o->dfdt_mode != 0;
@@ -586,6 +609,44 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
   rodas_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, out->t_end, out->stats, B);
   h->launches[4]++;
   SZB_CUDA(h, cudaStreamSynchronize(st));
+  return SZB_OK;
+}
+
+// ---- step-wise driving (callback events, solvers/rodas_event.py): controller state of the last call
+extern "C" int szb_rodas_state_get(szb_handle* h, double* t_host, double* told_host, double* dt_host,
+                                   int32_t* inext_host, int32_t* stats_host) {
+  if (!h) return SZB_EINVAL;
+  if (!h->rodas_started || h->rodas_B != h->B) { szb_set_error(h, "szb_rodas_state_get before szb_rodas"); return SZB_ESTATE; }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  const int B = h->B;
+  const double* d = h->rd_dbl;      // t, dt, told, facmax, scale, tstage, ddt, dtacc
+  const int* i = h->rd_int;         // reject, active, jmask, inext, nrec, acc_left, stats[8]
+  if (t_host) SZB_CUDA(h, cudaMemcpy(t_host, d, sizeof(double) * B, cudaMemcpyDeviceToHost));
+  if (told_host) SZB_CUDA(h, cudaMemcpy(told_host, d + 2 * B, sizeof(double) * B, cudaMemcpyDeviceToHost));
+  if (dt_host) SZB_CUDA(h, cudaMemcpy(dt_host, d + 7 * B, sizeof(double) * B, cudaMemcpyDeviceToHost));
+  if (inext_host) SZB_CUDA(h, cudaMemcpy(inext_host, i + 3 * B, sizeof(int) * B, cudaMemcpyDeviceToHost));
+  if (stats_host) SZB_CUDA(h, cudaMemcpy(stats_host, i + 6 * B, sizeof(int) * 8 * B, cudaMemcpyDeviceToHost));
+  return SZB_OK;
+}
+
+extern "C" int szb_rodas_state_set(szb_handle* h, int32_t b, double t, int32_t inext, int32_t flag) {
+  if (!h) return SZB_EINVAL;
+  if (!h->rodas_started || h->rodas_B != h->B) { szb_set_error(h, "szb_rodas_state_set before szb_rodas"); return SZB_ESTATE; }
+  if (b < 0 || b >= h->B) { szb_set_error(h, "szb_rodas_state_set: scenario %d outside the batch", b); return SZB_EINVAL; }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  const int B = h->B;
+  SZB_CUDA(h, cudaMemcpy(h->rd_dbl + b, &t, sizeof(double), cudaMemcpyHostToDevice));
+  if (inext >= 0) SZB_CUDA(h, cudaMemcpy(h->rd_int + 3 * B + b, &inext, sizeof(int), cudaMemcpyHostToDevice));
+  if (flag >= 0) SZB_CUDA(h, cudaMemcpy(h->rd_int + 6 * B + 8 * b + 6, &flag, sizeof(int), cudaMemcpyHostToDevice));
+  return SZB_OK;
+}
+
+extern "C" int szb_rodas_stages(szb_handle* h, double* K_out_dev, szb_stream stream) {
+  if (!h || !K_out_dev) return SZB_EINVAL;
+  if (!h->rodas_started) { szb_set_error(h, "szb_rodas_stages before szb_rodas"); return SZB_ESTATE; }
+  SZB_CUDA(h, cudaSetDevice(h->device));
+  SZB_CUDA(h, cudaMemcpyAsync(K_out_dev, h->rd_K, sizeof(double) * static_cast<size_t>(h->rodas_stages) * h->B * h->n,
+                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return SZB_OK;
 }
 

@@ -11,8 +11,9 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE.parent / "csrc" / "libszb.so"
 
-SZB_ABI_VERSION = 3
-SZB_FLAG_EVENT = 8
+SZB_ABI_VERSION = 4
+SZB_FLAG_CONVERGED, SZB_FLAG_MAXIT, SZB_FLAG_SINGULAR, SZB_FLAG_DTMIN, SZB_FLAG_REJECTS = 0, 1, 2, 3, 4
+SZB_FLAG_NAN, SZB_FLAG_RUNNING, SZB_FLAG_NOTCONV, SZB_FLAG_EVENT = 5, 6, 7, 8
 SLOT_Y, SLOT_F, SLOT_JV, SLOT_RHS, SLOT_PARAM0 = 0, 1, 2, 3, 16
 DTYPE_F64, DTYPE_I32 = 0, 1
 FLAG_NAMES = {0: "converged", 1: "max_it", 2: "singular", 3: "dt_min", 4: "rejects", 5: "nan", 6: "running",
@@ -50,7 +51,7 @@ class RodasOptC(C.Structure):
                 ("gammatilde", _dp), ("a", _dp), ("g", _dp), ("b", _dp), ("bd", _dp), ("c", _dp), ("d", _dp),
                 ("e", _dp), ("n_events", C.c_int32), ("ev_idx", C.POINTER(C.c_int32)), ("ev_thr", _dp),
                 ("ev_dir", C.POINTER(C.c_int32)), ("ev_term", C.POINTER(C.c_int32)), ("event_duration", C.c_double),
-                ("ev_cap", C.c_int32)]
+                ("ev_cap", C.c_int32), ("resume", C.c_int32), ("stop_after_accepted", C.c_int32)]
 
 
 class RodasOutC(C.Structure):
@@ -96,6 +97,9 @@ def load():
                                     C.c_void_p, C.c_void_p, C.c_void_p]
     lib.szb_rodas.argtypes = [H, C.POINTER(RodasOptC), C.POINTER(RodasOutC), C.c_void_p]
     lib.szb_set_mass_rows.argtypes = [H, C.POINTER(C.c_int32), C.c_int32]
+    lib.szb_rodas_state_get.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.szb_rodas_state_set.argtypes = [H, C.c_int32, C.c_double, C.c_int32, C.c_int32]
+    lib.szb_rodas_stages.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.szb_lu_refactor_masked_rows.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.szb_query.argtypes = [H, C.c_int32, C.POINTER(C.c_int64)]
     lib.szb_set_time.argtypes = [H, C.c_double]

@@ -107,29 +107,59 @@ def dae_ic(sess, t0: float, rtol: float):
     raise ValueError("Need Better y0")
 
 
-def _rodas_events(dae: CudaModel, tspan, y0, opt: Opt):
-    """``Opt(event=...)``: the reference's event functions are Python callbacks on one trajectory
-    (rodas.py:99-107, 200-271), so this path takes one scenario and keeps the step controller on the
-    host; F, J, the factorisation and the stage solves are device calls (solvers/rodas_event.py)."""
-    from .rodas_event import DeviceOps, rodas_with_events
-    vars_in = y0 if isinstance(y0, Vars) else None
-    y_arr = np.asarray(y0.array if isinstance(y0, Vars) else y0, dtype=float)
-    if y_arr.ndim != 1:
-        raise NotImplementedError("event callbacks take one trajectory (rodas.py:200-271): pass a 1-D y0, or run "
-                                  "the batch without events")
-    s = dae.session(1)
-    s.set_params(dae.p)
-    s.set_y(y_arr)
-    dae_ic(s, float(tspan[0]), opt.rtol)
-    if opt.hmax is None:
-        opt.hmax = abs(float(tspan[-1]) - float(tspan[0]))          # rodas.py:76-77
-    y_init = s.Y[0].cpu().numpy().copy()
-    sol = rodas_with_events(DeviceOps(s), dae.M, tspan, y_init, opt, dfdt_mode=getattr(opt, "dfdt", "module") == "fd")
-    if vars_in is not None:                                         # parser.py:100-104
-        sol.Y = TimeVars(vars_in.a, sol.Y)
-        if sol.te is not None:
-            sol.ye = TimeVars(vars_in.a, sol.ye)
-    return sol
+def _finish_callback_events(dae, s, tspan, opt, rp, o, out, y_out, stats_d, single, dense, vars_in, on_device):
+    """``Opt(event=callable)``: ``szb_rodas`` one accepted step per call, the callback in between
+    (solvers/rodas_event.py); assembles the reference's return value (rodas.py:329-342)."""
+    from .rodas_event import rodas_callback_events
+    B, n = s.B, dae.n
+    o.stop_after_accepted = 1
+
+    def run_call(resume: bool):
+        o.resume = 1 if resume else 0
+        L.check(s.lib.szb_rodas(s.h, C.byref(o), C.byref(out), s._stream()), s.h, "szb_rodas")
+
+    _, st, loc, T_steps, Y_steps = rodas_callback_events(dae, s, tspan, opt, rp, run_call, single, vars_in)
+    st = st.astype(np.int64)
+    stats = Stats(opt.scheme)
+    for i, k in enumerate(("nstep", "nfeval", "nJeval", "ndecomp", "nreject", "nsolve")):
+        setattr(stats, k, int(st[0, i]) if single else st[:, i].copy())
+    stats.flag = int(st[0, 6]) if single else st[:, 6].copy()
+    failed = (st[:, 6] != 0) & (st[:, 6] != L.SZB_FLAG_EVENT)
+    stats.ret = ("failed" if failed[0] else None) if single else np.where(failed, "failed", None)
+    stats.succeed = False if single else ~failed
+    nev = np.array([len(l.te) for l in loc], dtype=np.int64)
+    stats.nevent = int(nev[0]) if single else nev
+    Ts, Ys = [], []
+    for b in range(B):
+        if dense:
+            te_last = loc[b].te[-1] if loc[b].terminal else None
+            rows = len(tspan) if te_last is None else int(np.searchsorted(tspan, te_last, side='right'))
+            if failed[b]:
+                rows = min(rows, int(np.searchsorted(tspan, T_steps[b][-1], side='right')))
+            Tb = tspan[:rows].copy()
+            Yb = y_out[:rows, b].cpu().numpy()
+            if te_last is not None and (rows == 0 or Tb[-1] < te_last):     # the event point closes T (rodas.py:291-299)
+                Tb = np.append(Tb, te_last)
+                Yb = np.vstack([Yb, loc[b].ye[-1][None, :]])
+        else:
+            Tb, Yb = np.array(T_steps[b]), np.array(Y_steps[b])
+        Ts.append(Tb)
+        Ys.append(Yb)
+    if single:
+        T, Y = Ts[0], Ys[0]
+        te = np.array(loc[0].te) if loc[0].te else None
+        ye = np.array(loc[0].ye) if loc[0].te else None
+        ie = np.array(loc[0].ie, dtype=float) if loc[0].te else None
+        if vars_in is not None:
+            Y = TimeVars(vars_in.a, Y)
+            if ye is not None:
+                ye = TimeVars(vars_in.a, ye)
+        return daesol(T, Y, te, ye, ie, stats=stats)
+    # a batch: ragged results as lists (one entry per scenario)
+    te = [np.array(l.te) for l in loc]
+    ye = [np.array(l.ye) for l in loc]
+    ie = [np.array(l.ie, dtype=float) for l in loc]
+    return daesol(Ts, Ys, te, ye, ie, stats=stats)
 
 
 def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
@@ -146,8 +176,7 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
     dense = len(tspan) > 2
     from .rodas_event import ComponentEvents
     dev_events = opt.event if isinstance(opt.event, ComponentEvents) and rp.has_dense_output else None
-    if opt.event is not None and dev_events is None:
-        return _rodas_events(dae, tspan, y0, opt)
+    callback = opt.event if (opt.event is not None and dev_events is None) else None
     if dense and not rp.has_dense_output:
         raise NotImplementedError(f"dense output of {opt.scheme} (ntrp2, rodas.py:389-393) is not built")
     vars_in = y0 if isinstance(y0, Vars) else None
@@ -194,7 +223,7 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
         out.y_out = y_out.data_ptr()
         n_rows_all = torch.zeros(B, dtype=torch.int32, device=dev)     # rows of y_out each scenario filled
         out.n_rows = n_rows_all.data_ptr()
-    elif single:
+    elif single and callback is None:
         cap = int(getattr(opt, "record_cap", 10001))
         o.record_cap = cap
         y_steps = torch.zeros((cap, B, n), dtype=torch.float64, device=dev)
@@ -219,6 +248,9 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
         out.ev_count, out.ev_t, out.ev_i, out.ev_y = ev_count.data_ptr(), ev_t.data_ptr(), ev_i.data_ptr(), ev_y.data_ptr()
         out.n_rows = n_rows.data_ptr()
     y_init = s.Y.clone()
+    if callback is not None:
+        return _finish_callback_events(dae, s, tspan, opt, rp, o, out, y_out, stats_d, single, dense, vars_in,
+                                       on_device)
     L.check(s.lib.szb_rodas(s.h, C.byref(o), C.byref(out), s._stream()), s.h, "szb_rodas")
     st = stats_d.cpu().numpy().astype(np.int64)
     stats = Stats(opt.scheme)

@@ -1,15 +1,20 @@
-"""Rodas with event functions, one scenario (``Opt(event=callable)``).
+"""Event functions for the batched Rodas (``Opt(event=...)``).
 
-Reference: Solverz/solvers/daesolver/rodas/rodas.py:99-107 (event set-up), 200-271 (sign-change
-detection, secant start + bisection on the dense output ``ntrp``), 273-303 (dense output clipped at a
-terminal event), 329-342 (``te / ye / ie`` of the returned ``daesol``).
+Reference behaviour: Solverz/solvers/daesolver/rodas/rodas.py:99-107 (``value, isterminal, direction =
+events(t, y)``), 200-271 (what an event does to a step), 273-303 (dense output up to a terminal event), 329-342
+(``te / ye / ie`` of the returned ``daesol``).
 
-The event function is a *Python callback* in the reference (``value, isterminal, direction =
-events(t, y)`` with ``y`` a 1-D ndarray), so the step controller that consumes it runs on the host
-here as well; every numerical piece of a step -- F, J, the refactorisation of ``M - dt*gamma*J`` and
-the stage solves -- is a call into the device library (``szb_eval_F / szb_eval_J / szb_lu_refactor /
-szb_lu_solve``) on a one-scenario session.  Batched ensembles without events go through
-``szb_rodas`` (solvers/rodas.py), where the whole loop stays on the device.
+Two kinds of event function:
+
+* ``ComponentEvents`` -- thresholds on components of ``y``.  Their form is known, so detection, root search and the
+  roll-back to the event time run per scenario inside the step kernel (``csrc/szb_rodas.cu``).
+* any Python callable -- the reference's own interface.  A callback can only be asked on the host, so the device
+  integrates ONE accepted step per running scenario (``szb_rodas`` with ``stop_after_accepted = 1``, resumed call
+  after call: the whole step -- J, F, the refactorisation of ``M - dt*gamma*J``, the stage solves, the error
+  controller -- stays in ``szb_rodas``), then ``EventLocator`` below asks the callback about the new states of all
+  scenarios, brackets sign changes, finds the event time on the step's dense output (the stage vectors are read
+  from the device), and moves a scenario back to its event (``szb_rodas_state_set`` + its row of ``SLOT_Y``) before
+  the next call.  Any batch size; the cost is one host round trip per accepted step, which the callback needs anyway.
 """
 from __future__ import annotations
 
@@ -19,7 +24,7 @@ from .rodas_param import Rodas_param
 from .solution import daesol
 from .stats import Stats
 
-__all__ = ["rodas_with_events", "DeviceOps", "ComponentEvents"]
+__all__ = ["ComponentEvents", "EventLocator", "rodas_callback_events"]
 
 
 class ComponentEvents:
@@ -45,227 +50,163 @@ class ComponentEvents:
         return y[self.index] - self.threshold, self.terminal, self.direction
 
 
-class DeviceOps:
-    """F, J-refresh, factor and solve of one scenario on the device session."""
-
-    def __init__(self, sess):
-        import torch
-        self.s = sess
-        self.torch = torch
-
-    def F(self, t, y):
-        self.s.set_y(y)
-        return self.s.eval_F(float(t))[0].cpu().numpy().copy()
-
-    def J(self, t, y):
-        self.s.set_y(y)
-        self.s.eval_J(float(t))          # values stay in SLOT_JV for the next refactorisation
-
-    def factor(self, dt_gamma):
-        self.s.lu_refactor(float(dt_gamma))   # A = M - dt*gamma*J (szb.h)
-
-    def solve(self, rhs):
-        self.s.RHS.copy_(self.torch.as_tensor(rhs).reshape(1, -1))
-        return self.s.lu_solve(1)[0].cpu().numpy().copy()
-
-
 def _ntrp1(y0, tau, dt, K, rp):
-    # rodas.py:383-386
+    """Dense output of the schemes with interpolation coefficients (rodas.py:383-386); K: [n, s]."""
     return y0 + tau * dt * K @ (rp.b + (tau - 1) * (rp.c + tau * (rp.d + tau * rp.e)))
 
 
 def _ntrp2(y0, y1, F0, F1, tau, dt):
-    # rodas.py:389-393
+    """Cubic Hermite output of rodas3 (rodas.py:389-393)."""
     return ((1 - tau) * y0 + tau * y1 +
             tau * (tau - 1) * ((1 - 2 * tau) * (y1 - y0) + (tau - 1) * dt * F0 + tau * dt * F1))
 
 
-def rodas_with_events(dev, M, tspan, y0, opt, dfdt_mode: bool = False):
-    """``dev``: the four device operations of one scenario (``DeviceOps`` over a one-scenario
-    BatchSession whose parameters are set; the tests drive the same controller with a stub to check
-    the host logic without a GPU); ``y0``: consistent initial value (``dae_ic`` ran); ``M``: scipy
-    mass matrix; returns ``daesol``."""
-    events = opt.event
-    stats = Stats(opt.scheme)
-    rp = Rodas_param(opt.scheme)
-    tspan = np.asarray(tspan, dtype=float)
-    tend, t0 = tspan[-1], tspan[0]
-    n = y0.shape[0]
-    nt = 0
-    t = t0
-    hmin = 16 * np.spacing(t0)
-    uround = np.spacing(1.0)
-    T = [t0]
-    Y = [y0.copy()]
-    dense_output = len(tspan) > 2
-    told = t0
-    inext, tnext = 1, (tspan[1] if dense_output else None)
-    value, isterminal, direction = events(t, y0)                      # :102-103
-    stop = 0
-    tevent = None
-    te, ye, ie = [], [], []
-    dt = 1e-6 * (tend - t0) if opt.hinit is None else opt.hinit      # :110-117
-    dt = np.maximum(dt, hmin)
-    dt = np.minimum(dt, opt.hmax)
-    facmax = opt.facmax
-    done = False
-    reject = 0
+class EventLocator:
+    """What the reference does with ``events`` after one accepted step of one scenario (rodas.py:200-271), as a
+    function of that step alone: ``after_step`` gets the step ``[told, told + dt]`` with its end states and a
+    callable ``interp(tau)`` for the dense output, and returns where the scenario continues from.
 
-    def ntrp(y0_, ynew_, told_, dt_, K_, tau_):
-        if opt.scheme != 'rodas3':
-            return _ntrp1(y0_, tau_, dt_, K_, rp)
-        return _ntrp2(y0_, ynew_, dev.F(told_, y0_), dev.F(told_ + dt_, ynew_), tau_, dt_)   # :363-380
+    Semantics kept exactly (they decide which later sign changes are seen): only components whose value changed
+    sign over the step and moves in the watched ``direction`` are searched, in index order; the first guess is the
+    secant point, then the bracket is bisected until it is shorter than 128 ulp of the step ends; an event closer
+    than ``event_duration`` to the step start ends the search of this step; after an event the step ENDS at the
+    event (later components are tested against the shortened step), and the values remembered for the next step are
+    those at the ORIGINAL step end."""
 
-    while not done:
-        if np.abs(dt) < uround:                                       # :127-130
-            stats.ret = 'failed'
-            break
-        if reject > 100:                                              # :132-135
-            stats.ret = 'failed'
-            break
-        if t + dt >= tend:                                            # :138-141
-            dt = tend - t
-        else:
-            dt = np.minimum(dt, 0.5 * (tend - t))
-        if opt.fix_h:
-            dt = opt.hinit
-        K = np.zeros((n, rp.s))
-        if reject == 0:                                               # :150-152
-            dev.J(t, y0)
-            stats.nJeval += 1
-        if dfdt_mode:                                                 # :154, :347-352
-            tscale = np.maximum(0.1 * np.abs(t), 1e-8)
-            ddt = t + np.sqrt(np.spacing(1)) * tscale - t
-            dfdt0 = dt * (dev.F(t + ddt, y0) - dev.F(t, y0)) / ddt
-        else:
-            dfdt0 = np.zeros(n)
-        rhs = dev.F(t, y0) + rp.g[0] * dfdt0
-        stats.nfeval += 1
-        dev.factor(dt * rp.gamma)                                     # :159
-        stats.ndecomp += 1
-        K[:, 0] = dev.solve(rhs)
-        for j in range(1, rp.s):                                      # :165-173
-            sum_1 = K @ rp.alpha[:, j]
-            sum_2 = K @ rp.gammatilde[:, j]
-            y1 = y0 + dt * sum_1
-            rhs = dev.F(t + dt * rp.a[j], y1) + M @ sum_2 + rp.g[j] * dfdt0
-            stats.nfeval += 1
-            K[:, j] = dev.solve(rhs) - sum_2
-        stats.nsolve += rp.s
-        sum_1 = K @ (dt * rp.b)
-        ynew = y0 + sum_1
-        if not opt.fix_h:                                             # :177-188
-            sum_2 = K @ (dt * rp.bd)
-            SK = opt.atol + opt.rtol * np.abs(ynew)
-            with np.errstate(invalid='ignore', divide='ignore'):
-                err = np.max(np.abs((sum_1 - sum_2) / SK))
-            if np.any(np.isinf(ynew)) or np.any(np.isnan(ynew)) or np.isnan(err):
-                err = 1.0e6
-            err = np.maximum(err, 1.0e-6)
-            fac = opt.f_savety / (err ** (1 / rp.pord))
-            fac = np.minimum(facmax, np.maximum(opt.fac1, fac))
-            dtnew = dt * fac
-        else:
-            err = 1.0
-            dtnew = dt
+    def __init__(self, events, event_duration: float, t0: float, y0: np.ndarray):
+        self.events = events
+        self.event_duration = float(event_duration)
+        self.value = np.asarray(events(t0, y0)[0], dtype=float)
+        self.te, self.ye, self.ie = [], [], []
+        self.terminal = False
 
-        if err <= 1.0:
-            reject = 0
-            told = t
-            t = t + dt
-            stats.nstep += 1
-            # ---- events (:200-271)
-            valueold = value
-            value, isterminal, direction = events(t, ynew)
-            value_save = value
-            ff = np.where(np.asarray(value) * np.asarray(valueold) < 0)[0]
-            for i in ff:
-                v0 = valueold[i]
-                v1 = value[i]
-                detect = 1
-                if direction[i] < 0 and v0 <= v1:
-                    detect = 0
-                if direction[i] > 0 and v0 >= v1:
-                    detect = 0
-                if not detect:
-                    continue
-                iterate = 1
-                tL, tR = told, t
-                if np.abs(v1 - v0) > uround:
-                    tevent = told - v0 * dt / (v1 - v0)               # secant start, :223
+    def after_step(self, told: float, dt: float, t_end: float, y_end: np.ndarray, interp):
+        """Returns ``(t, y, moved)``: the time / state the scenario continues from and whether they differ from the
+        step end."""
+        before = self.value
+        now, isterminal, direction = self.events(t_end, y_end)
+        now = np.asarray(now, dtype=float)
+        at_step_end = now
+        t, y, moved = t_end, y_end, False
+        eps = np.spacing(1.0)
+        for i in np.flatnonzero(now * before < 0):
+            lo_v, hi_v = before[i], now[i]
+            if (direction[i] < 0 and lo_v <= hi_v) or (direction[i] > 0 and lo_v >= hi_v):
+                continue
+            lo_t, hi_t = told, t
+            width_tol = min(128 * max(np.spacing(told), np.spacing(t)), abs(t - told))
+            if abs(hi_v - lo_v) > eps:
+                guess = told - lo_v * dt / (hi_v - lo_v)
+                y_guess = y
+                for _ in range(100):
+                    y_guess = interp((guess - told) / dt)
+                    now, isterminal, direction = self.events(guess, y_guess)
+                    mid_v = now[i]
+                    if hi_v * mid_v < 0:
+                        lo_t, lo_v, guess = guess, mid_v, 0.5 * (guess + hi_t)
+                    elif lo_v * mid_v < 0:
+                        hi_t, hi_v, guess = guess, mid_v, 0.5 * (lo_t + guess)
+                    else:
+                        break
+                    if hi_t - lo_t < width_tol:
+                        break
                 else:
-                    iterate = 0
-                    tevent = t
-                    ynext = ynew
-                tol = 128 * np.max([np.spacing(told), np.spacing(t)])
-                tol = np.min([tol, np.abs(t - told)])
-                while iterate > 0:
-                    iterate += 1
-                    tau = (tevent - told) / dt
-                    ynext = ntrp(y0, ynew, told, dt, K, tau)
-                    value, isterminal, direction = events(tevent, ynext)
-                    if v1 * value[i] < 0:
-                        tL = tevent
-                        tevent = 0.5 * (tevent + tR)
-                        v0 = value[i]
-                    elif v0 * value[i] < 0:
-                        tR = tevent
-                        tevent = 0.5 * (tL + tevent)
-                        v1 = value[i]
-                    else:
-                        iterate = 0
-                    if (tR - tL) < tol:
-                        iterate = 0
-                    if iterate > 100:
-                        print(f"Lost Event in interval [{told}, {t}].\n")
-                        break
-                if np.abs(tevent - told) < opt.event_duration:        # :257-259
-                    break
-                t = tevent
-                ynew = ynext
-                te.append(tevent)
-                ie.append(i)
-                ye.append(np.array(ynext, dtype=float))
-                value, isterminal, direction = events(tevent, ynext)
-                value = value_save
-                if isterminal[i]:                                     # :267-271
-                    if dense_output and tnext >= tevent:
-                        tnext = tevent
-                    stop = 1
-                    break
-            # ---- output (:273-309)
-            if dense_output:
-                while t >= tnext > told:
-                    tau = (tnext - told) / dt
-                    ynext = ntrp(y0, ynew, told, dt, K, tau)
-                    nt += 1
-                    T.append(tnext)
-                    Y.append(ynext)
-                    if stop and tnext >= tevent:
-                        break
-                    inext += 1
-                    if inext <= len(tspan) - 1:
-                        tnext = tspan[inext]
-                        if stop and tnext >= tevent:
-                            tnext = tevent
-                    else:
-                        tnext = tend + dt
+                    print(f"Lost Event in interval [{told}, {t}].\n")
             else:
-                nt += 1
-                T.append(t)
-                Y.append(ynew.copy())
-            if np.abs(tend - t) < uround or stop:                     # :318-319
-                done = True
-            y0 = ynew
-            facmax = opt.fac2
-        else:
-            reject += 1
-            stats.nreject += 1
-            facmax = 1
-        dt = np.min([opt.hmax, np.max([hmin, dtnew])])                # :327
+                guess, y_guess = t, y
+            if abs(guess - told) < self.event_duration:
+                at_step_end = now          # the reference leaves `value` at its last evaluation here (rodas.py:257-259)
+                break
+            t, y, moved = guess, y_guess, True
+            self.te.append(guess)
+            self.ie.append(int(i))
+            self.ye.append(np.array(y_guess, dtype=float))
+            isterminal = self.events(guess, y_guess)[1]
+            now = at_step_end
+            if isterminal[i]:
+                self.terminal = True
+                break
+        self.value = at_step_end
+        return t, y, moved
 
-    T = np.array(T)
-    Y = np.array(Y)
-    if te:
-        return daesol(T, Y, np.array(te), np.array(ye), np.array(ie, dtype=float), stats)
-    return daesol(T, Y, stats=stats)
+
+def rodas_callback_events(dae, sess, tspan, opt, rp, run_call, single: bool, vars_in):
+    """Drives ``szb_rodas`` one accepted step at a time for ``Opt(event=callable)`` (module docstring).
+
+    ``run_call(resume)`` performs one ``szb_rodas`` call with ``stop_after_accepted = 1`` and returns the tensors it
+    writes (``solvers/rodas.py`` owns the option / output structs); this function owns the event logic and the
+    assembly of ``T / Y / te / ye / ie`` in the reference's layout."""
+    import ctypes as C
+    import torch
+    from ..num_api import lib as L
+    B, n = sess.B, dae.n
+    dense = len(tspan) > 2
+    t0 = float(tspan[0])
+    Y0 = sess.Y.cpu().numpy()
+    loc = [EventLocator(opt.event, opt.event_duration, t0, Y0[k].copy()) for k in range(B)]
+    T_steps = [[t0] for _ in range(B)]
+    Y_steps = [[Y0[k].copy()] for k in range(B)]
+    y_prev = Y0.copy()
+    nstep_prev = np.zeros(B, dtype=np.int64)
+    tt = np.zeros(B)
+    told = np.zeros(B)
+    dts = np.zeros(B)
+    inext = np.zeros(B, dtype=np.int32)
+    stats = np.zeros((B, 8), dtype=np.int32)
+    out = None
+    resume = False
+    probe = [None]
+    while True:
+        out = run_call(resume)
+        resume = True
+        L.check(sess.lib.szb_rodas_state_get(sess.h, tt.ctypes.data, told.ctypes.data, dts.ctypes.data,
+                                             inext.ctypes.data, stats.ctypes.data), sess.h, "szb_rodas_state_get")
+        stepped = np.flatnonzero(stats[:, 0] > nstep_prev)
+        if len(stepped):
+            Yh = sess.Y.cpu().numpy()
+            K_host = None
+            F_ends = None
+            for b in stepped.tolist():
+                y_start, y_end = y_prev[b], Yh[b].copy()
+
+                def interp(tau, b=b, y_start=y_start, y_end=y_end):
+                    nonlocal K_host, F_ends
+                    if opt.scheme != 'rodas3':
+                        if K_host is None:            # stage vectors of the step just taken: [s, B, n] on the device
+                            buf = torch.empty((rp.s, B, n), dtype=torch.float64, device=sess.Y.device)
+                            L.check(sess.lib.szb_rodas_stages(sess.h, C.c_void_p(buf.data_ptr()), sess._stream()),
+                                    sess.h, "szb_rodas_stages")
+                            K_host = buf.cpu().numpy()
+                        return _ntrp1(y_start, tau, dts[b], K_host[:, b, :].T, rp)
+                    if F_ends is None:
+                        F_ends = {}
+                    if b not in F_ends:               # rodas3: Hermite data = F at both ends of the step
+                        if probe[0] is None:          # a private one-scenario session (model.session() would retire `sess`)
+                            from ..num_api.model import BatchSession
+                            probe[0] = BatchSession(dae, 1, sess.device, with_lu=False)
+                        one = probe[0]
+                        one.set_params({k: (v[b] if (v.ndim == 2 and v.shape[0] == B) else v) for k, v in sess.P.items()})
+                        one.set_y(y_start)
+                        f0 = one.eval_F(float(told[b]))[0].cpu().numpy().copy()
+                        one.set_y(y_end)
+                        f1 = one.eval_F(float(told[b] + dts[b]))[0].cpu().numpy().copy()
+                        F_ends[b] = (f0, f1)
+                    return _ntrp2(y_start, y_end, F_ends[b][0], F_ends[b][1], tau, dts[b])
+
+                t_b, y_b, moved = loc[b].after_step(float(told[b]), float(dts[b]), float(tt[b]), y_end, interp)
+                if moved:
+                    sess.Y[b].copy_(torch.as_tensor(y_b))
+                    nxt = int(np.searchsorted(tspan, t_b, side='right')) if dense else -1
+                    flag = L.SZB_FLAG_EVENT if loc[b].terminal else L.SZB_FLAG_RUNNING
+                    L.check(sess.lib.szb_rodas_state_set(sess.h, b, float(t_b), nxt, flag), sess.h, "szb_rodas_state_set")
+                    stats[b, 6] = flag
+                    Yh[b] = y_b
+                T_steps[b].append(t_b)
+                Y_steps[b].append(np.array(y_b, dtype=float))
+            y_prev = Yh
+            nstep_prev = stats[:, 0].astype(np.int64)
+        if not (stats[:, 6] == L.SZB_FLAG_RUNNING).any():
+            break
+    if probe[0] is not None:
+        probe[0].close()
+    return out, stats, loc, T_steps, Y_steps

@@ -350,7 +350,7 @@ def test_c_abi_exports_every_declared_symbol(libszb):
     out = subprocess.run(["nm", "-D", "--defined-only", str(L.LIB_PATH)], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (szb_\w+)", out))
     assert declared <= exported, declared - exported
-    assert libszb.szb_abi_version() == L.SZB_ABI_VERSION == 3
+    assert libszb.szb_abi_version() == L.SZB_ABI_VERSION == 4
     # error convention: NULL handle -> negative code, never a crash
     assert libszb.szb_set_batch(None, 4) < 0
     assert libszb.szb_destroy(None) == 0
@@ -430,7 +430,7 @@ def test_shard_plan_gloo_world2(tmp_path):
     script.write_text('''
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, %r)
-from solverz_b200.parallel import shard_range, gather_results
+from solverz_b200.parallel import shard_range, gather_results, gather_results_async
 dist.init_process_group("gloo")
 r, w = dist.get_rank(), dist.get_world_size()
 B, n = 11, 3
@@ -441,6 +441,11 @@ fl = torch.zeros(hi - lo, dtype=torch.int32)
 Y, IT, FL = gather_results(y, it, fl, B)
 assert Y.shape == (B, n) and torch.equal(Y[:, 0], torch.arange(B, dtype=torch.float64) + 0.5)
 assert torch.equal(IT, torch.arange(B, dtype=torch.int32) %% 4) and int(FL.sum()) == 0
+# the asynchronous form: the shard buffers may be overwritten as soon as the gather is issued
+pend = gather_results_async(y, it, fl, B)
+y.fill_(-1.0); it.fill_(-1)
+Y2, IT2, FL2 = pend.wait()
+assert torch.equal(Y2, Y) and torch.equal(IT2, IT) and torch.equal(FL2, FL)
 dist.destroy_process_group()
 sys.stdout.write("rank " + str(r) + " ok " + str(lo) + " " + str(hi) + chr(10)); sys.stdout.flush()
 ''' % str(ROOT))

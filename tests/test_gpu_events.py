@@ -98,7 +98,10 @@ def test_orbit(libszb, scheme):
     np.testing.assert_allclose(sol.Y.array, g[f"orbit_{scheme}_Y"], rtol=1e-5, atol=1e-7)
 
 
-def test_events_need_one_trajectory(libszb):
+def test_callback_events_on_a_batch(libszb):
+    """The reference's callback interface on MORE than one trajectory: every scenario is asked after each of its
+    accepted steps (szb_rodas one accepted step per call); five launch speeds, each against the single-trajectory
+    run of the same call path and the closed form t = 2 v0 / g."""
     from solverz_b200 import Model, Ode, Opt, Rodas, Var, made_numerical
     m = Model()
     m.x = Var('x', [0, 20])
@@ -106,11 +109,20 @@ def test_events_need_one_trajectory(libszb):
     m.f2 = Ode('f2', -9.8, m.x[1])
     bball, y0 = m.create_instance()
     nb = made_numerical(bball, y0, sparse=True)
-    with pytest.raises(NotImplementedError):
-        Rodas(nb, [0, 1], np.tile(y0.array, (3, 1)), Opt(event=ball_events))
+    v0 = np.array([20.0, 10.0, 35.0, 5.0, 27.5])
+    Y0 = np.stack([np.zeros_like(v0), v0], axis=1)
+    tsp = np.linspace(0, 30, 100)
+    sol = Rodas(nb, tsp, Y0, Opt(event=ball_events))
+    assert (sol.stats.flag == 8).all() and (sol.stats.nevent == 1).all()
+    for b in range(len(v0)):
+        one = Rodas(nb, tsp, Y0[b], Opt(event=ball_events))
+        assert abs(sol.te[b][0] - 2 * v0[b] / 9.8) < 1e-8
+        assert sol.te[b][0] == one.te[0] and int(sol.stats.nstep[b]) == one.stats.nstep
+        np.testing.assert_array_equal(sol.T[b], one.T)
+        np.testing.assert_array_equal(sol.Y[b], one.Y)
+        assert sol.T[b][-1] == sol.te[b][0]                      # the event point closes T (rodas.py:291-299)
 
 
-# ---------------------------------------------------------------------------- device-side events
 def test_device_events_readme_ball(libszb):
     """The README case again, with the event given as a ComponentEvents object: detection, bisection and the
     roll-back run inside the step kernel (szb_rodas) instead of the host loop; same fixture."""

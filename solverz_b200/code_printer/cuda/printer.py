@@ -76,6 +76,12 @@ class _CPrinter(C99CodePrinter):
             return prod if e > 0 else f"1.0/({prod})"
         return super()._print_Pow(expr)
 
+    def _print_Min(self, expr):
+        # sympy's C printer dispatches on the class NAME and would treat our two-argument Min (functions.py:502-520)
+        # as its own variadic Min (nested fmin of re-built one-argument nodes)
+        a, b = expr.args
+        return f"szb_min({self._print(a)}, {self._print(b)})"
+
     def _print_sign(self, expr):
         return f"szb_sign({self._print(expr.args[0])})"
 

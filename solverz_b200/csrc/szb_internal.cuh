@@ -55,6 +55,7 @@ struct szb_handle {
   int rodas_B = 0, rodas_stages = 0;
   double *rd_K = nullptr, *rd_y1 = nullptr, *rd_sum2 = nullptr, *rd_dfdt = nullptr, *rd_F1 = nullptr;
   double *rd_dbl = nullptr, *rd_tout = nullptr, *rd_ev = nullptr;
+  double *rd_y0s = nullptr, *rd_F0s = nullptr;   // Hermite dense output (rodas3): y and F at the start of the step
   int *rd_int = nullptr, *rd_mcol = nullptr;
   bool rodas_started = false;   // a szb_rodas call has initialised the controller state of this batch
   int rd_tout_cap = 0;

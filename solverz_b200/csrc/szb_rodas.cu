@@ -28,6 +28,7 @@ struct Tableau {
 struct Ctl {  // scalars of the step controller
   double tend, rtol, atol, f_savety, fac1, fac2, hmax, hmin, uround, hinit;
   int fix_h, n_out, record_cap, max_steps;
+  int hermite;      // dense output by the cubic Hermite form ntrp2 (rodas3: no interpolation coefficients)
   int stop_after;   // > 0: a scenario pauses after this many accepted steps of the current call (szb_rodas_opt)
   // component-threshold events (szb.h): value_i = y[ev_idx[i]] - ev_thr[i]
   int n_events, ev_cap;
@@ -41,6 +42,7 @@ struct State {
   double *t, *dt, *told, *facmax, *scale, *tstage, *ddt, *dtacc;   // dtacc: step size of the last accepted step
   int *reject, *active, *jmask, *inext, *nrec, *stats;  // stats: [B][8]
   int* acc_left;   // accepted steps this scenario may still take in the current call (stop_after_accepted)
+  int* acc_now;    // 1: this attempt was accepted (ntrp2 dense output runs after the F evaluation at the new point)
   double* ev_val;   // [B][SZB_MAX_EVENTS] event values at the end of the last accepted step (rodas.py:203)
 };
 
@@ -328,8 +330,9 @@ step_finish_kernel(const double* __restrict__ K, double* __restrict__ Y, Tableau
     __syncthreads();
     if (threadIdx.x == 0) O.ev_count[b] = base + s_nev;
   }
+  if (C.hermite && threadIdx.x == 0) S.acc_now[b] = 1;   // ntrp2 needs F at the new point: hermite_output_kernel
   // dense output at the requested times inside (told, t]   (:273-303, ntrp1 :383-386)
-  if (C.n_out > 0) {
+  if (C.n_out > 0 && !C.hermite) {
     int inext = S.inext[b];
     while (inext < C.n_out) {
       const double tn = t_out[inext];
@@ -419,6 +422,53 @@ __global__ void rodas_init_kernel(State S, szb_rodas_out O, const double* __rest
   }
 }
 
+// ---- rodas3 dense output (ntrp2, rodas.py:389-393): cubic Hermite over the accepted step from y0, y1 and
+// F0 = F(told, y0), F1 = F(told + dt, y1).  The step start (y0, F0) is saved before the stages overwrite F; after an
+// accepted step F is evaluated once more at the new point (only in this mode), then the requested times inside
+// (told, t] are written.  alias_F = 1 reproduces the reference's rendered-module path, where both F calls of ntrp
+// return the module's one shared buffer, so F0 IS F1 there (the same aliasing as in dfdt).
+__global__ void hermite_save_kernel(const double* __restrict__ Y, const double* __restrict__ F, double* __restrict__ Y0s,
+                                    double* __restrict__ F0s, State S, int n, int B) {
+  const int b = blockIdx.y;
+  if (!S.active[b]) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) S.acc_now[b] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const size_t q = static_cast<size_t>(b) * n + i;
+    Y0s[q] = Y[q];
+    F0s[q] = F[q];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+hermite_output_kernel(const double* __restrict__ Y0s, const double* __restrict__ F0s, const double* __restrict__ Y1,
+                      const double* __restrict__ F1, State S, Ctl C, szb_rodas_out O, const double* __restrict__ t_out,
+                      int alias_F, int n, int B) {
+  const int b = blockIdx.x;
+  if (!S.acc_now[b]) return;
+  const double told = S.told[b], dt = S.dtacc[b], tnew = S.t[b];
+  const size_t o = static_cast<size_t>(b) * n;
+  int inext = S.inext[b];
+  while (inext < C.n_out) {
+    const double tn = t_out[inext];
+    if (!(tnew >= tn && tn > told)) break;                       // while t >= tnext > told (:274)
+    const double tau = (tn - told) / dt;
+    double* dst = O.y_out + (static_cast<size_t>(inext) * B + b) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double y0 = Y0s[o + i], y1 = Y1[o + i], f1 = F1[o + i];
+      const double f0 = alias_F ? f1 : F0s[o + i];
+      dst[i] = (1.0 - tau) * y0 + tau * y1 +
+               tau * (tau - 1.0) * ((1.0 - 2.0 * tau) * (y1 - y0) + (tau - 1.0) * dt * f0 + tau * dt * f1);
+    }
+    ++inext;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    S.inext[b] = inext;
+    if (O.n_rows) O.n_rows[b] = inext;
+    S.acc_now[b] = 0;
+  }
+}
+
 // resume = 1: the controller state of the previous call stays; scenarios that were only paused run again
 __global__ void rodas_resume_kernel(State S, int stop_after, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,8 +518,10 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
     h->rd_sum2 = static_cast<double*>(alloc(sizeof(double) * bn));
     h->rd_dfdt = static_cast<double*>(alloc(sizeof(double) * bn));
     h->rd_F1 = static_cast<double*>(alloc(sizeof(double) * bn));
+    h->rd_y0s = nullptr;
+    h->rd_F0s = nullptr;
     h->rd_dbl = static_cast<double*>(alloc(sizeof(double) * 8 * B));
-    h->rd_int = static_cast<int*>(alloc(sizeof(int) * (6 + 8) * B));
+    h->rd_int = static_cast<int*>(alloc(sizeof(int) * (7 + 8) * B));
     h->rd_mcol = static_cast<int*>(alloc(sizeof(int) * n));
     h->rd_ev = static_cast<double*>(alloc(sizeof(double) * SZB_MAX_EVENTS * B));
     h->rd_tout = nullptr;
@@ -487,6 +539,17 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
     if (h->mass_row_col.size() != static_cast<size_t>(n)) { szb_set_error(h, "szb_rodas: mass row map missing; call szb_set_mass_rows"); return SZB_ESTATE; }
     SZB_CUDA(h, cudaMemcpyAsync(h->rd_mcol, h->mass_row_col.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
     h->rd_mcol_ready = true;
+  }
+  if (o->n_out > 0 && !(o->c && o->d && o->e) && !h->rd_y0s) {   // Hermite dense output: start state of the step
+    void *p0 = nullptr, *p1 = nullptr;
+    if (cudaMalloc(&p0, sizeof(double) * bn) != cudaSuccess || cudaMalloc(&p1, sizeof(double) * bn) != cudaSuccess) {
+      szb_set_error(h, "szb_rodas: out of device memory for the Hermite dense output");
+      return SZB_ENOMEM;
+    }
+    h->rodas_owned.push_back(p0);
+    h->rodas_owned.push_back(p1);
+    h->rd_y0s = static_cast<double*>(p0);
+    h->rd_F0s = static_cast<double*>(p1);
   }
   double* tout_dev = nullptr;
   if (o->n_out > 0) {
@@ -517,6 +580,7 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
   C.fix_h = o->fix_h; C.hinit = o->hinit; C.n_out = o->n_out; C.record_cap = o->record_cap;
   C.max_steps = o->max_steps > 0 ? o->max_steps : 1000000;
   C.stop_after = o->stop_after_accepted > 0 ? o->stop_after_accepted : 0;
+  C.hermite = (o->n_out > 0 && !(o->c && o->d && o->e)) ? 1 : 0;
   C.n_events = o->n_events;
   C.ev_cap = o->ev_cap;
   C.event_duration = o->event_duration;
@@ -541,7 +605,7 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
   S.t = h->rd_dbl; S.dt = S.t + B; S.told = S.dt + B; S.facmax = S.told + B; S.scale = S.facmax + B;
   S.tstage = S.scale + B; S.ddt = S.tstage + B; S.dtacc = S.ddt + B;
   S.reject = h->rd_int; S.active = S.reject + B; S.jmask = S.active + B; S.inext = S.jmask + B;
-  S.nrec = S.inext + B; S.acc_left = S.nrec + B; S.stats = S.acc_left + B;
+  S.nrec = S.inext + B; S.acc_left = S.nrec + B; S.stats = S.acc_left + B; S.acc_now = S.stats + 8 * B;
   S.ev_val = h->rd_ev;
 
   if (B > 65535) {   // the stage kernels index the scenario through gridDim.y
@@ -572,6 +636,10 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
     if ((rc = szb_launch_J(h, 0.0, S.t, h->Y, h->JV, S.jmask, st)) != SZB_OK) return rc;
     // F(t, y0) and the time derivative term (:154-156)
     if ((rc = szb_launch_F(h, 0.0, S.t, h->Y, h->F, nullptr, S.active, st)) != SZB_OK) return rc;
+    if (C.hermite) {                                 // ntrp2: the step start (y0, F0) before the stages overwrite F
+      hermite_save_kernel<<<eg, 256, 0, st>>>(h->Y, h->F, h->rd_y0s, h->rd_F0s, S, n, B);
+      h->launches[4]++;
+    }
     if (use_dfdt) {
       if ((rc = szb_launch_F(h, 0.0, S.tstage, h->Y, h->rd_F1, nullptr, S.active, st)) != SZB_OK) return rc;
       dfdt_kernel<<<eg, 256, 0, st>>>(h->F, h->rd_F1, h->rd_dfdt, S, n, B);
@@ -604,6 +672,12 @@ extern "C" int szb_rodas(szb_handle* h, const szb_rodas_opt* o, const szb_rodas_
     }
     step_finish_kernel<<<B, 256, 0, st>>>(h->rd_K, h->Y, T, C, S, *out, tout_dev, n, B);
     h->launches[4]++;
+    if (C.hermite) {                                 // F at the new point of the accepted scenarios, then ntrp2
+      if ((rc = szb_launch_F(h, 0.0, S.t, h->Y, h->rd_F1, nullptr, S.acc_now, st)) != SZB_OK) return rc;
+      hermite_output_kernel<<<B, 256, 0, st>>>(h->rd_y0s, h->rd_F0s, h->Y, h->rd_F1, S, C, *out, tout_dev,
+                                               o->dfdt_mode == 0 ? 1 : 0, n, B);
+      h->launches[4]++;
+    }
     SZB_CUDA(h, cudaGetLastError());
   }
   rodas_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, out->t_end, out->stats, B);

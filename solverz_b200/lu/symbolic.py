@@ -38,10 +38,10 @@ ANALYSIS_VERSION = 2
 # 1. static pivoting
 # --------------------------------------------------------------------------------------
 def _heavy_matching(A: sp.csc_matrix, forced=None) -> np.ndarray:
-    """Greedy heaviest-edge matching on |a_ij| / max_i |a_ij|, completed by augmenting paths that try
-    heavy edges first.  Not guaranteed optimal for the product objective, but on diagonally strong
-    matrices (power-flow, network, DAE Jacobians) it reproduces the optimum, and it costs O(nnz log nnz)
-    where SciPy's assignment solver needs minutes for n ~ 10^4."""
+    """Greedy heaviest-edge matching on |a_ij| / max_i |a_ij|; when it leaves columns unmatched, a bottleneck
+    matching takes over.  Not guaranteed optimal for the product objective, but on diagonally strong
+    matrices (power-flow, network, DAE Jacobians) the greedy pass reproduces the optimum, and it costs
+    O(nnz log nnz) where SciPy's assignment solver needs minutes for n ~ 10^4."""
     n = A.shape[0]
     W = sp.coo_matrix(A)
     absd = np.abs(W.data)
@@ -62,11 +62,21 @@ def _heavy_matching(A: sp.csc_matrix, forced=None) -> np.ndarray:
             row_of[j] = i
             col_of[i] = j
     free = np.flatnonzero(row_of < 0)
+    if len(free) > 64:
+        # many columns without a heavy partner (blocks with no natural diagonal, e.g. incidence matrices, where the
+        # scaled weights are flat anyway): bottleneck matching -- the largest threshold tau such that the entries
+        # with ratio >= tau still admit a perfect matching, found by bisection with Hopcroft-Karp probes
+        # (lu/matching.py, O(E sqrt(V)) each); forced pairs stay.  The augmenting-path completion below is O(free * nnz) in
+        # Python: fine for the handful of columns a diagonally strong matrix leaves over, minutes for thousands.
+        return _bottleneck_matching(sp.csr_matrix((ratio, (W.row, W.col)), shape=(n, n)), forced)
     is_forced_row = None
     if forced is not None:
         is_forced_row = np.zeros(n, dtype=bool)
         is_forced_row[forced[0]] = True
     if len(free):
+        # a few columns left: augmenting paths from the greedy matching that try heavy edges first (keeps the heavy
+        # pairs; a bottleneck matching from scratch would only protect the SMALLEST entry and was measured to give
+        # the power-flow lattices pivot orders Newton does not survive)
         Ac = sp.csc_matrix((ratio, (W.row, W.col)), shape=(n, n))
         indptr, indices, data = Ac.indptr, Ac.indices, Ac.data
 
@@ -110,6 +120,48 @@ def _heavy_matching(A: sp.csc_matrix, forced=None) -> np.ndarray:
                 if j == j0:
                     break
                 i = prev
+    return row_of
+
+
+def _bottleneck_matching(R: sp.csr_matrix, forced=None) -> np.ndarray:
+    """rowperm (column -> row) of a perfect matching of the bipartite graph of ``R`` (rows x columns, entries = scaled
+    magnitudes in (0, 1]) whose SMALLEST entry is as large as possible."""
+    n = R.shape[0]
+    R = sp.coo_matrix(R)
+    keep = R.data > 0
+    rows, cols, vals = R.row[keep], R.col[keep], R.data[keep]
+    row_of = np.full(n, -1, dtype=np.int64)
+    if forced is not None:
+        row_of[forced[1]] = forced[0]
+        fr = np.zeros(n, dtype=bool)
+        fc = np.zeros(n, dtype=bool)
+        fr[forced[0]] = True
+        fc[forced[1]] = True
+        k2 = ~fr[rows] & ~fc[cols]
+        rows, cols, vals = rows[k2], cols[k2], vals[k2]
+    need = int((row_of < 0).sum())
+
+    from .matching import max_matching
+
+    def probe(tau):
+        m = vals >= tau
+        match = max_matching(rows[m], cols[m], n)                   # match[j] = row of column j, or -1
+        return match if int((match >= 0).sum()) == need else None
+
+    best = probe(0.0)
+    if best is None:
+        raise ValueError("Jacobian pattern is structurally singular: no full matching")
+    cand = np.unique(vals)
+    lo, hi = 0, len(cand) - 1                      # invariant: cand[lo] is feasible (the smallest entry always is)
+    while lo < hi:
+        mid = (lo + hi + 1) // 2
+        m_ = probe(cand[mid])
+        if m_ is not None:
+            best, lo = m_, mid
+        else:
+            hi = mid - 1
+    free = row_of < 0
+    row_of[free] = best[free]
     return row_of
 
 

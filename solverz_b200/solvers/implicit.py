@@ -19,7 +19,7 @@ from ..num_api import lib as L
 from ..num_api.model import CudaModel
 from ..variables import TimeVars, Vars
 from .option import Opt
-from .rodas import dae_ic
+from .rodas import dae_ic, _profiled
 from .solution import daesol
 from .stats import Stats
 
@@ -102,9 +102,11 @@ def _run(dae: CudaModel, tspan, y0, opt: Opt, mode: int, scheme: str):
     return daesol(T, Y, stats=stats)
 
 
+@_profiled
 def backward_euler(dae: CudaModel, tspan, y0, opt: Opt = None):
     return _run(dae, tspan, y0, opt, 1, 'Backward Euler')
 
 
+@_profiled
 def implicit_trapezoid(dae: CudaModel, tspan, y0, opt: Opt = None):
     return _run(dae, tspan, y0, opt, 2, 'Trapezoidal')

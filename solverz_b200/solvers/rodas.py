@@ -162,6 +162,27 @@ def _finish_callback_events(dae, s, tspan, opt, rp, o, out, y_out, stats_d, sing
     return daesol(Ts, Ys, te, ye, ie, stats=stats)
 
 
+def _profiled(fn):
+    """``Opt(profile=True)``: wall time of the whole call, printed like the reference's dae_io_parser does
+    (solvers/parser.py:91-96)."""
+    import functools
+    import time
+
+    @functools.wraps(fn)
+    def wrapper(dae, tspan, y0, opt: Opt = None, **kw):
+        if opt is not None and getattr(opt, "profile", False):
+            import torch
+            torch.cuda.synchronize()
+            start = time.perf_counter()
+            sol = fn(dae, tspan, y0, opt, **kw)
+            torch.cuda.synchronize()
+            print(f"Time elapsed: {time.perf_counter() - start}s")
+            return sol
+        return fn(dae, tspan, y0, opt, **kw)
+    return wrapper
+
+
+@_profiled
 def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
     if opt is None:
         opt = Opt()
@@ -177,8 +198,11 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
     from .rodas_event import ComponentEvents
     dev_events = opt.event if isinstance(opt.event, ComponentEvents) and rp.has_dense_output else None
     callback = opt.event if (opt.event is not None and dev_events is None) else None
-    if dense and not rp.has_dense_output:
-        raise NotImplementedError(f"dense output of {opt.scheme} (ntrp2, rodas.py:389-393) is not built")
+    if dense and opt.scheme == "rodas3d":
+        # the reference's tableau of rodas3d defines no interpolation coefficients (param.py:171-199: commented out),
+        # so its ntrp1 raises there too; rodas3 interpolates with the Hermite form ntrp2 on the device
+        raise NotImplementedError("dense output of rodas3d: the scheme has no interpolation coefficients "
+                                  "(rodas/param.py:171-199)")
     vars_in = y0 if isinstance(y0, Vars) else None
     y_arr = y0.array if isinstance(y0, Vars) else y0
     on_device = isinstance(y_arr, torch.Tensor)
@@ -210,6 +234,8 @@ def Rodas(dae: CudaModel, tspan, y0, opt: Opt = None):
             ("alpha", "gammatilde", "a", "g", "b", "bd", "c", "d", "e")]
     o.s, o.pord, o.gamma = rp.s, rp.pord, rp.gamma
     (o.alpha, o.gammatilde, o.a, o.g, o.b, o.bd, o.c, o.d, o.e) = [_dp(k) for k in keep]
+    if not rp.has_dense_output:          # no interpolation coefficients: szb_rodas interpolates with ntrp2 (rodas3)
+        o.c = o.d = o.e = None
     out = L.RodasOutC()
     t_end = torch.zeros(B, dtype=torch.float64, device=dev)
     stats_d = torch.zeros((B, 8), dtype=torch.int32, device=dev)

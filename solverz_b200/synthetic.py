@@ -261,14 +261,14 @@ def dhs_fdae_model(nx: int, ny: int, ns=None, seed: int = 0, dt: float = 60.0):
     Vf = sps.csr_matrix((np.ones(n_pipe), (ar, pa)), shape=(n_pipe, n_node))   # the node a pipe starts from
     # steady state of the nominal load: hydraulic Newton, then temperatures node by node (lattice order is topological)
     rhs0 = np.concatenate([load, np.zeros(nl)])
-    if n_pipe <= 4000:                                   # the small fixtures keep their dense start bit for bit
+    if n_pipe <= 500:                                   # the small fixtures keep their dense start bit for bit
         mflow = np.linalg.lstsq(np.vstack([V_ns.toarray(), Lm.toarray()]), rhs0, rcond=None)[0]
     else:
         import scipy.sparse.linalg as sla
         mflow = sla.spsolve(sps.vstack([V_ns, Lm]).tocsc(), rhs0)
     for _ in range(50):
         res = np.concatenate([V_ns @ mflow - load, Lm @ (K * mflow * np.abs(mflow))])
-        if n_pipe <= 4000:
+        if n_pipe <= 500:
             Jh = np.vstack([V_ns.toarray(), Lm.toarray() * (2 * K * np.abs(mflow))[None, :]])
             mflow = mflow - np.linalg.solve(Jh, res)
         else:

@@ -461,3 +461,27 @@ if __name__ == "__main__":
     if "sicnm" in which:
         golden_sicnm()
     print("golden fixtures written to", HERE)
+
+
+def golden_rodas3_dense():
+    """rodas3 dense output (ntrp2, rodas.py:389-393) of the reference on its tests/test_dae.py model: the inline
+    path (made_numerical: two distinct F evaluations) and the rendered-module path (both F calls of ntrp return the
+    module's one shared buffer, so F0 is F1 there)."""
+    from Solverz import Eqn, Model, Ode, Opt, Rodas, Var, made_numerical, module_printer
+    m = Model()
+    m.x = Var('x', 1)
+    m.y = Var('y', 1)
+    m.f = Ode(name='f', f=-m.x ** 3 + 0.5 * m.y ** 2, diff_var=m.x)
+    m.g = Eqn(name='g', eqn=m.x ** 2 + m.y ** 2 - 2)
+    dae, y0 = m.create_instance()
+    tsp = np.linspace(0, 20, 41)
+    nd = made_numerical(dae, y0, sparse=True)
+    s_inline = Rodas(nd, tsp, y0, Opt(hinit=0.1, scheme='rodas3'))
+    d = tempfile.mkdtemp()
+    module_printer(dae, y0, "gold_r3", directory=d, jit=True).render()
+    sys.path.insert(0, d)
+    mod = importlib.import_module("gold_r3")
+    s_module = Rodas(mod.mdl, tsp, mod.y, Opt(hinit=0.1, scheme='rodas3'))
+    st = lambda s: np.array([s.stats.nstep, s.stats.nfeval, s.stats.nJeval, s.stats.ndecomp, s.stats.nreject, s.stats.nsolve])
+    np.savez(HERE / "rodas3_dense_ref.npz", tspan=tsp, Y_inline=s_inline.Y.array, Y_module=s_module.Y.array,
+             stats_inline=st(s_inline), stats_module=st(s_module))

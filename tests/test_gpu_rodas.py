@@ -255,3 +255,23 @@ def test_config4_full_size_sample_vs_oracle(libszb):
         d = np.abs(sol.Y[b] - r["Y"]).max(axis=1)
         assert d[:3].max() < 1e-8 and d.max() < 1e-5 * max(1.0, np.abs(r["Y"]).max()), (b, d)
     nd.close()
+
+
+def test_rodas3_dense_output_ntrp2(libszb):
+    """Dense output of rodas3 -- the cubic Hermite form ntrp2 (rodas.py:389-393) -- on the device, against the
+    reference's own runs (tests/golden/rodas3_dense_ref.npz): 'fd' mode = the inline made_numerical path (two distinct
+    F evaluations), 'module' mode = the rendered-module path, where both F calls of ntrp return one shared buffer
+    (F0 is F1 there; the two fixtures differ by 1.7e-3, so the test tells the modes apart)."""
+    from solverz_b200 import Opt, Rodas
+    g = np.load(GOLD / "rodas3_dense_ref.npz")
+    nd, y0 = _dae_test_model()
+    for mode, key in (("fd", "inline"), ("module", "module")):
+        opt = Opt(hinit=0.1, scheme="rodas3")
+        opt.dfdt = mode
+        sol = Rodas(nd, g["tspan"], y0, opt)
+        got = [sol.stats.nstep, sol.stats.nfeval, sol.stats.nJeval, sol.stats.ndecomp, sol.stats.nreject, sol.stats.nsolve]
+        assert got == g[f"stats_{key}"].tolist()
+        assert np.max(np.abs(sol.Y.array - g[f"Y_{key}"])) < 1e-8, mode
+    # a batch takes the same path
+    sol = Rodas(nd, g["tspan"], np.tile(y0.array, (3, 1)), Opt(hinit=0.1, scheme="rodas3"))
+    assert np.max(np.abs(sol.Y[1] - g["Y_module"])) < 1e-8

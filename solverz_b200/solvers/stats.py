@@ -18,11 +18,5 @@ class Stats:
         self.flag = None
 
     def __repr__(self):
-        return (f"Scheme: {self.scheme}, "
-                f"succeed: {self.succeed}, "
-                f"nstep: {self.nstep}, "
-                f"nfeval: {self.nfeval}, "
-                f"nJeval: {self.nJeval}, "
-                f"ndecomp: {self.ndecomp}, "
-                f"nreject: {self.nreject}."
-                f"nsolve: {self.nsolve}")
+        fields = ("succeed", "nstep", "nfeval", "nJeval", "ndecomp", "nreject", "nsolve")
+        return f"Stats({self.scheme}: " + ", ".join(f"{k}={getattr(self, k)}" for k in fields) + ")"

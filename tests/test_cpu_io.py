@@ -65,3 +65,31 @@ def test_xlsx_needs_openpyxl_or_one_trajectory(tmp_path):
             save_result(sol, "one", str(tmp_path), f="xlsx")
     else:
         assert save_result(sol, "one", str(tmp_path), f="xlsx").exists()
+
+
+def test_daesol_window_and_append():
+    """daesol[i], daesol[a:b] (events inside the window) and daesol.append (restart chains), the contract of the
+    reference's container (solvers/solution.py:40-99)."""
+    from solverz_b200.solvers.solution import daesol
+    from solverz_b200.solvers.stats import Stats
+    T = np.linspace(0.0, 1.0, 11)
+    Y = np.stack([T, T ** 2], axis=1)
+    st = Stats("rodas4")
+    st.nstep, st.nfeval = 10, 60
+    sol = daesol(T, Y, te=np.array([0.25, 0.75]), ye=np.array([[0.25, 0.0625], [0.75, 0.5625]]), ie=np.array([0.0, 1.0]),
+                 stats=st)
+    w = sol[2:6]
+    assert np.array_equal(w.T, T[2:6]) and np.array_equal(w.Y, Y[2:6])
+    assert w.te.tolist() == [0.25] and w.ie.tolist() == [0.0] and w.ye.shape == (1, 2)
+    assert sol[8:].te.size == 0 and sol[3].T == T[3]
+    with pytest.raises(NotImplementedError):
+        sol["x"]
+    st2 = Stats("rodas4")
+    st2.nstep, st2.nfeval = 5, 30
+    more = daesol(T[:6] + 1.0, Y[:6], te=np.array([1.3]), ye=np.array([[1.3, 1.69]]), ie=np.array([0.0]), stats=st2)
+    sol.append(more)
+    assert len(sol.T) == 17 and sol.Y.shape == (17, 2) and sol.te.tolist() == [0.25, 0.75, 1.3]
+    assert sol.stats.nstep == 15 and sol.stats.nfeval == 90
+    empty = daesol()
+    empty.append(more)
+    assert empty.stats.scheme == "rodas4" and np.array_equal(empty.T, more.T) and empty.te.tolist() == [1.3]

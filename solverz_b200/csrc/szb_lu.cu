@@ -194,7 +194,17 @@ __device__ __forceinline__ double asm_fetch(const unsigned sr, const FactorArgs&
   }
 }
 
-template <bool PLAIN>
+// GLOBAL_FM: the front lives in the per-CTA global workspace.  `Fm[d] += v` would be load (an L2 round trip the
+// compiler cannot overlap with the previous store to the same array) + add + store per entry; a result-less atomicAdd
+// is a fire-and-forget reduction executed at the L2 instead.  Every destination is owned by ONE thread and reductions
+// of one thread to one address are applied in program order, so the sums keep their fixed order (bitwise reproducible).
+template <bool GLOBAL_FM>
+__device__ __forceinline__ void front_add(double* __restrict__ Fm, const int d, const double v) {
+  if (GLOBAL_FM) atomicAdd(Fm + d, v);
+  else Fm[d] += v;
+}
+
+template <bool PLAIN, bool GLOBAL_FM>
 __device__ __forceinline__ void assemble_stream(const AsmPre& P, const int rank, const int G_, const FrontHdr& H,
                                                 const int2* __restrict__ ga, double* __restrict__ Fm,
                                                 const FactorArgs& A) {
@@ -218,7 +228,7 @@ __device__ __forceinline__ void assemble_stream(const AsmPre& P, const int rank,
     }
 #pragma unroll
     for (int q = 0; q < N; ++q)
-      if (live(P.en[q])) Fm[P.en[q].y] += v[q];
+      if (live(P.en[q])) front_add<GLOBAL_FM>(Fm, P.en[q].y, v[q]);
   };
   if (iters <= 2) { first_batch(std::integral_constant<int, 2>{}); return; }
   if (iters <= 4) { first_batch(std::integral_constant<int, 4>{}); return; }
@@ -237,17 +247,20 @@ __device__ __forceinline__ void assemble_stream(const AsmPre& P, const int rank,
     for (int q = 0; q < kAsm; ++q) v[q] = live(en[q]) ? asm_fetch<PLAIN>(static_cast<unsigned>(en[q].x), A) : 0.0;
 #pragma unroll
     for (int q = 0; q < kAsm; ++q)
-      if (live(en[q])) Fm[en[q].y] += v[q];
+      if (live(en[q])) front_add<GLOBAL_FM>(Fm, en[q].y, v[q]);
 #pragma unroll
     for (int q = 0; q < kAsm; ++q) en[q] = nx[q];
   }
 }
 
+template <bool GLOBAL_FM>
 __device__ __forceinline__ void assemble_front(const AsmPre& P, const int rank, const int G_, const FrontHdr& H,
                                                const int2* __restrict__ ga, double* __restrict__ Fm,
                                                const FactorArgs& A) {
-  if (A.mvals == nullptr && A.smask == nullptr && A.scale == 1.0) assemble_stream<true>(P, rank, G_, H, ga, Fm, A);
-  else assemble_stream<false>(P, rank, G_, H, ga, Fm, A);
+  if (A.mvals == nullptr && A.smask == nullptr && A.scale == 1.0)
+    assemble_stream<true, GLOBAL_FM>(P, rank, G_, H, ga, Fm, A);
+  else
+    assemble_stream<false, GLOBAL_FM>(P, rank, G_, H, ga, Fm, A);
 }
 
 // ---- single warp, fronts with at most 32 rows: right-looking rank-1 steps, lane = row.  When the
@@ -887,7 +900,7 @@ __device__ void factor_front_warp(const FrontHdr H, const FrontHdr Hnext, AsmPre
   const int ncol = f + with_rhs;
   clear_front(Fm, ld * (f + 1), lane, kWarp);
   __syncwarp();
-  assemble_front(P, lane, kWarp, H, ga, Fm, A);
+  assemble_front<false>(P, lane, kWarp, H, ga, Fm, A);
   asm_prefetch(P, Hnext, ga, lane, kWarp, with_rhs != 0);   // in flight during the elimination
   __syncwarp();
   SZB_T(0)
@@ -948,7 +961,7 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
 #ifdef SZB_PHASE_TIMING
   const long long tfg1_ = clock64();
 #endif
-  assemble_front(P, r, G_, H, ga, Fm, A);
+  assemble_front<!SM_FRONT>(P, r, G_, H, ga, Fm, A);
   g.sync();
   SZB_T(0)
   double* __restrict__ Lp = A.lu + H.lp_off;             // f x s, column-major, ld = f
@@ -981,11 +994,24 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
     // lanes over the long dimension, pointer walks over the short one: no index arithmetic inside
     double* __restrict__ Up = A.lu + H.up_off;           // U12, s x u column-major: Up[r + c*s]
     {
+      // four elements per thread in flight (a front in the global workspace pays an L2 round trip per load)
       const float invs = __frcp_rn(static_cast<float>(s));
-      for (int t = r; t < u * s; t += G_) {
+      const int tot = u * s;
+      int t = r;
+      for (; t + 3 * G_ < tot; t += 4 * G_) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tq = t + q * G_;
+          const int c = fdiv(tq, invs);
+          v[q] = Fm[(tq - c * s) + (s + c) * ld];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) __stcs(Up + t + q * G_, v[q]);
+      }
+      for (; t < tot; t += G_) {
         const int c = fdiv(t, invs);
-        const int rr = t - c * s;
-        __stcs(Up + t, Fm[rr + (s + c) * ld]);
+        __stcs(Up + t, Fm[(t - c * s) + (s + c) * ld]);
       }
     }
     double* C = A.cb + H.cb_off;                         // u x (u+1), column-major
@@ -993,7 +1019,17 @@ __device__ FrontHdr factor_front_group(const PanelGrp g, const FrontHdr H, const
     for (int i = lane; i < u; i += kWarp) {
       const double* __restrict__ src = Fm + (s + i) + (s + w) * ld;
       double* dst = C + i + w * u;
-      for (int j = w; j < nc; j += nw, src += nw * ld, dst += nw * u) *dst = *src;
+      int j = w;
+      // eight columns per batch: loads first, then stores (C is written and re-read by this CTA, so it is not
+      // restrict and the compiler would otherwise issue one dependent load / store pair at a time)
+      for (; j + 7 * nw < nc; j += 8 * nw, src += 8 * nw * ld, dst += 8 * nw * u) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = src[q * nw * ld];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q * nw * u] = v[q];
+      }
+      for (; j < nc; j += nw, src += nw * ld, dst += nw * u) *dst = *src;
     }
   }
   if (with_rhs)

@@ -179,8 +179,12 @@ int szb_lu_refactor_masked(szb_handle* h, double h_gamma, const double* scale_b,
 __global__ void __launch_bounds__(256)
 lin_residual_kernel(const double* __restrict__ JV, const double* __restrict__ mvals, double scale,
                     const int* __restrict__ srow, const int* __restrict__ scol, const double* __restrict__ RHS,
-                    const double* __restrict__ X, double* __restrict__ relres, int n, int nnz, int B) {
-  extern __shared__ double rs[];
+                    const double* __restrict__ X, double* __restrict__ relres, double* rs_global, int n, int nnz,
+                    int B) {
+  extern __shared__ double rs_shared[];
+  // the residual vector of the scenario in flight: shared memory when n doubles fit, else this CTA's slice of a
+  // global scratch (L2; the same atomics, slower)
+  double* rs = rs_global ? rs_global + static_cast<size_t>(blockIdx.x) * n : rs_shared;
   __shared__ double red[2][8];
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const double* __restrict__ jv = JV + static_cast<size_t>(b) * nnz;
@@ -534,19 +538,24 @@ int szb_lu_residual(szb_handle* h, double h_gamma, const int32_t* slot_row_dev, 
     mv = h->mass_vals;
     scale = -h_gamma;
   }
-  const size_t smem = sizeof(double) * static_cast<size_t>(h->n);
+  size_t smem = sizeof(double) * static_cast<size_t>(h->n);
   int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
-  if (smem > static_cast<size_t>(smem_max)) {
-    szb_set_error(h, "szb_lu_residual: n = %d does not fit the shared-memory residual vector", h->n);
-    return SZB_EINVAL;
-  }
-  SZB_CUDA(h, cudaFuncSetAttribute(lin_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  const int grid = h->B < 4 * sms ? h->B : 4 * sms;
+  int grid = h->B < 4 * sms ? h->B : 4 * sms;
+  double* scratch = nullptr;
+  if (smem > static_cast<size_t>(smem_max)) {          // large n: one slice of global scratch per resident CTA
+    grid = h->B < sms ? h->B : sms;
+    SZB_CUDA(h, cudaMallocAsync(reinterpret_cast<void**>(&scratch), sizeof(double) * static_cast<size_t>(grid) * h->n,
+                                static_cast<cudaStream_t>(stream)));
+    smem = 0;
+  }
+  SZB_CUDA(h, cudaFuncSetAttribute(lin_residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem > 0 ? smem : 8)));
   lin_residual_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      h->JV, mv, scale, slot_row_dev, slot_col_dev, rhs_dev, x_dev, relres_dev, h->n, h->nnz_j, h->B);
+      h->JV, mv, scale, slot_row_dev, slot_col_dev, rhs_dev, x_dev, relres_dev, scratch, h->n, h->nnz_j, h->B);
+  if (scratch) SZB_CUDA(h, cudaFreeAsync(scratch, static_cast<cudaStream_t>(stream)));
   SZB_CUDA(h, cudaGetLastError());
   h->launches[4]++;
   return SZB_OK;

@@ -53,6 +53,9 @@ def fdae_solver(fdae: CudaModel, tspan, y0, opt: Opt = None, **kwargs):
         hist.append((tj.reshape(1, -1).expand(B, -1) if tj.ndim == 1 else tj).clone())
     T = [float(t_init)]
     Ys = [s.Y.clone()]
+    # backend knob for batches whose whole trajectory does not fit the device: opt.trajectory = 'last' keeps the
+    # first and the last node (Y is [B, 2, n], T = [t0, tend]); the default keeps every node like the reference
+    keep_all = getattr(opt, "trajectory", "all") != "last"
     tt = t0 = float(t_init)
     uround = np.spacing(1.0)
     it_sum = torch.zeros(B, dtype=torch.int64, device=s.Y.device)
@@ -71,7 +74,10 @@ def fdae_solver(fdae: CudaModel, tspan, y0, opt: Opt = None, **kwargs):
         ok &= flags == 0
         tt = tt + dt
         T.append(float(tt))
-        Ys.append(s.Y.clone())
+        if keep_all:
+            Ys.append(s.Y.clone())
+        else:                                                 # opt.trajectory = 'last': first and last node only
+            Ys[1:] = [s.Y.clone()]
         t0 = tt
         hist = [s.Y.clone()] + hist[:nhist - 1]
         if np.abs(tend - tt) < uround:
@@ -89,7 +95,7 @@ def fdae_solver(fdae: CudaModel, tspan, y0, opt: Opt = None, **kwargs):
         stats.nJeval, stats.ndecomp, stats.nsolve = it.copy(), it.copy(), it.copy()
         stats.succeed = ok.cpu().numpy()
     Y = torch.stack(Ys, dim=1)                                # [B, nt+1, n]
-    T = np.array(T)
+    T = np.array(T) if keep_all else np.array([T[0], T[-1]])
     if single:
         Y = Y[0].cpu().numpy()
         if vars_in is not None:

@@ -53,7 +53,9 @@ def main():
     Y0 = torch.as_tensor(np.tile(y0.array, (B, 1))).to(dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    sol = fdae_solver(mdl, [0, a.steps * dt], Y0, Opt(step_size=dt, ite_tol=1e-8))
+    opt = Opt(step_size=dt, ite_tol=1e-8)
+    opt.trajectory = "last"                              # 61 nodes x B x n doubles would not fit next to the factors
+    sol = fdae_solver(mdl, [0, a.steps * dt], Y0, opt)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     st = sol.stats

@@ -277,6 +277,22 @@ def dhs_fdae_model(nx: int, ny: int, ns=None, seed: int = 0, dt: float = 60.0):
             mflow = mflow - dm
             if np.abs(dm).max() <= 1e-14 * max(1.0, np.abs(mflow).max()):
                 break
+    # The thermal part fixes the upwind direction of every pipe, so every pipe must carry its flow from its first to
+    # its second node: pipes whose nominal flow came out negative (loop flows on a large lattice) are turned round.
+    # The loads of a scenario are scaled uniformly, and with quadratic resistances m(sc) = sc m(1) exactly, so the
+    # orientation holds for every scenario and time.  (The small fixtures have no such pipe: nothing changes there.)
+    flip = mflow < 0
+    if flip.any():
+        sgn = np.where(flip, -1.0, 1.0)
+        mflow = np.abs(mflow)
+        pa, pb = np.where(flip, pb, pa), np.where(flip, pa, pb)
+        V = sps.csr_matrix(V @ sps.diags(sgn))
+        Lm = sps.csr_matrix(Lm @ sps.diags(sgn))
+        V_ns = V[1:, :].tocsr()
+        Vin = V_ns.maximum(0.0).tocsr()
+        Vin.eliminate_zeros()
+        Vf = sps.csr_matrix((np.ones(n_pipe), (ar, pa)), shape=(n_pipe, n_node))
+        assert np.abs(V_ns @ mflow - load).max() < 1e-9 and np.abs(Lm @ (K * mflow * np.abs(mflow))).max() < 1e-9
     cth, lam, Ta, Ts = 0.08 * dt / 60.0, 0.01 * dt / 60.0, 10.0, 90.0
     Tn = np.full(n_node, Ts)
     Tout = np.full(n_pipe, Ts)

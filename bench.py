@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-sessions", type=int, default=2,
+    ap.add_argument("--e2e-sessions", type=int, default=4,
                     help="end-to-end arm: concurrent sessions (host thread + stream each) the batch is split over, so that "
                          "one session's host<->device copies overlap the other's kernels")
     ap.add_argument("--lu-opt", default="", help="JSON dict of lu.symbolic.analyze options (experiments)")

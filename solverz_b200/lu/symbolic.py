@@ -24,6 +24,8 @@ from __future__ import annotations
 import dataclasses
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -32,6 +34,10 @@ __all__ = ["LUSymbolic", "analyze", "ANALYSIS_VERSION"]
 # bumped whenever the analysis or the tables derived from it change meaning: analyses cached next to a
 # rendered module (param_and_setting.pkl) with another version are recomputed
 ANALYSIS_VERSION = 2
+
+# the "mmd" candidate is read off SuperLU (perm_c of a throw-away factorisation) up to this many compressed vertices;
+# above it that factorisation costs minutes (20 at n = 69 400) and lu/amd.py orders the graph instead
+MMD_SUPERLU_MAX = 25000
 
 
 # --------------------------------------------------------------------------------------
@@ -378,6 +384,23 @@ def _order_mmd_superlu(S: sp.csr_matrix) -> np.ndarray:
     lu = sla.splu(M, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0,
                   options=dict(SymmetricMode=True))
     return np.argsort(lu.perm_c).astype(np.int64)
+
+
+def _order_amd_candidates(Sc: sp.csr_matrix, wc: np.ndarray, starts: int = 6):
+    """Approximate-minimum-degree orderings of the compressed graph (lu/amd.py) from several vertex numberings.  On
+    lattice-like patterns the fill of a minimum-degree ordering is decided by how ties are broken (measured on the
+    district-heating graph, n = 33 880: 1.36e8 ... 1.93e8 flops over six numberings, SuperLU's MMD 1.59e8), and one
+    ordering costs milliseconds, so the caller keeps the best of a few."""
+    from .amd import amd_order
+    nc = Sc.shape[0]
+    rng = np.random.default_rng(20250101)
+    out = []
+    for trial in range(max(1, starts)):
+        perm = np.arange(nc) if trial == 0 else (np.arange(nc)[::-1].copy() if trial == 1 else rng.permutation(nc))
+        Sp = Sc[perm][:, perm].tocsr()
+        Sp.sort_indices()
+        out.append(perm[amd_order(Sp.indptr, Sp.indices, wc[perm])])
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -835,11 +858,13 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
     for o in orderings:
         if o == "nd":
             cands.append(("nd", expand(_nested_dissection(adjc, wc))))
-        elif o == "mmd":
+        elif o == "mmd" and nc <= MMD_SUPERLU_MAX:
             try:
                 cands.append(("mmd", expand(_order_mmd_superlu(Sc))))
             except Exception:  # pragma: no cover - SuperLU hack unavailable
                 pass
+        elif o in ("amd", "mmd"):         # "mmd" above the size SuperLU's detour is affordable for
+            cands.extend(("amd", expand(oc)) for oc in _order_amd_candidates(Sc, wc))
         elif o == "natural":
             cands.append(("natural", np.arange(n, dtype=np.int64)))
         else:
@@ -848,6 +873,8 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
     for name, order in cands:
         _, _, struct = _symbolic_structs(S, order)
         fl = _flops_of(np.array([len(s) for s in struct]))
+        if os.environ.get("SZB_ANALYZE_VERBOSE"):
+            print(f"[analyze] candidate {name}: flops {fl:.4g}, widest column structure {max(len(s) for s in struct)}")
         if best is None or fl < best[0]:
             best = (fl, name, order)
     assert best is not None

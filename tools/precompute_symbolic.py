@@ -8,6 +8,8 @@ with the same arguments num_api/model.py::symbolic passes).
 
     python tools/precompute_symbolic.py dhs 158        # -> build/models/dhs_lattice_158x158
     python tools/precompute_symbolic.py swing 45       # -> build/models/swing_lattice_45x45
+    python tools/precompute_symbolic.py dhs 100 --force   # redo a stored analysis (after a change of lu/symbolic.py)
+    python tools/precompute_symbolic.py pf 32 --dry nd,mmd nd,amd   # compare ordering sets, store nothing
 """
 import pickle
 import sys
@@ -25,6 +27,8 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 def main():
     kind, nx = sys.argv[1], int(sys.argv[2])
+    force = "--force" in sys.argv
+    dry = sys.argv[sys.argv.index("--dry") + 1:] if "--dry" in sys.argv else None
     from host_check import host_eval, host_lib
     from solverz_b200 import module_printer
     from solverz_b200.lu.symbolic import analyze
@@ -50,7 +54,7 @@ def main():
     pkl = Path(pkg) / "param_and_setting.pkl"
     st = pickle.load(open(pkl, "rb"))
     from solverz_b200.lu.symbolic import ANALYSIS_VERSION
-    if getattr(st.get("symbolic"), "version", 0) == ANALYSIS_VERSION:
+    if getattr(st.get("symbolic"), "version", 0) == ANALYSIS_VERSION and not force and dry is None:
         print("analysis already cached")
         return
     with tempfile.TemporaryDirectory() as tmp:
@@ -69,6 +73,13 @@ def main():
         np.add.at(mv, np.asarray(st["mass_slots"], dtype=np.int64), 1.0)
         jv = np.where(mv != 0, jv + mv, jv)
     A = sps.csc_matrix((jv, st["indices"], st["indptr"]), shape=(st["n"], st["n"]))
+    if dry is not None:
+        for ords in dry:
+            t0 = time.time()
+            sym = analyze(A, forced_pairs=mass, **{**(st.get("lu_options") or {}), "orderings": tuple(ords.split(","))})
+            print(f"{ords}: {time.time() - t0:.1f} s  ordering={sym.ordering} nnz_lu={sym.nnz_lu} lu_size={sym.lu_size} "
+                  f"flops={sym.flops:.4g} f_top_max={sym.f_top_max}", flush=True)
+        return
     t0 = time.time()
     sym = analyze(A, forced_pairs=mass, **(st.get("lu_options") or {}))
     print(f"analysis {time.time() - t0:.1f} s: n={sym.n} nnz_lu={sym.nnz_lu} lu_size={sym.lu_size} flops={sym.flops:.3g} "

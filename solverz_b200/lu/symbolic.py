@@ -33,11 +33,16 @@ __all__ = ["LUSymbolic", "analyze", "ANALYSIS_VERSION"]
 
 # bumped whenever the analysis or the tables derived from it change meaning: analyses cached next to a
 # rendered module (param_and_setting.pkl) with another version are recomputed
-ANALYSIS_VERSION = 2
+ANALYSIS_VERSION = 3
 
 # the "mmd" candidate is read off SuperLU (perm_c of a throw-away factorisation) up to this many compressed vertices;
 # above it that factorisation costs minutes (20 at n = 69 400) and lu/amd.py orders the graph instead
 MMD_SUPERLU_MAX = 25000
+# the multi-start AMD candidates (lu/amd.py) compete only where the factorisation is flop-dominated.  Measured on the
+# B200 (profiles/r2_ordering_experiment.md): cfg#3 (6.0e8 flops under MMD) 380 -> 339 ms per refactor with the best AMD
+# start (4.8e8 flops); cfg#2 (5.2e6 flops) 10.42 -> 10.78 ms although AMD has 12.6 % fewer flops -- at that size the
+# kernel time is assembly and write-out of many small fronts, and AMD's top fronts are larger (154 against 128)
+AMD_MIN_FLOPS = 5.0e7
 
 
 # --------------------------------------------------------------------------------------
@@ -827,7 +832,7 @@ def _build(A: sp.csc_matrix, rowperm: np.ndarray, S: sp.csr_matrix, order: np.nd
 
 def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
             warp_front_max: int = 32, n_warps: int = 16, group_front_max: int = 72, n_groups: int = 4,
-            orderings: Sequence[str] = ("nd", "mmd"), warp_fixed: float = 3000.0, group_fixed: float = 60000.0,
+            orderings: Sequence[str] = ("nd", "mmd", "amd?"), warp_fixed: float = 3000.0, group_fixed: float = 60000.0,
             forced_pairs=None) -> LUSymbolic:
     """Analyse the pattern (and representative values) of ``A``; see the module docstring."""
     A = sp.csc_matrix(A)
@@ -855,6 +860,7 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
         return np.array([v for g in oc for v in members[g]], dtype=np.int64)
 
     cands: List[Tuple[str, np.ndarray]] = []
+    maybe_amd = False
     for o in orderings:
         if o == "nd":
             cands.append(("nd", expand(_nested_dissection(adjc, wc))))
@@ -865,18 +871,28 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
                 pass
         elif o in ("amd", "mmd"):         # "mmd" above the size SuperLU's detour is affordable for
             cands.extend(("amd", expand(oc)) for oc in _order_amd_candidates(Sc, wc))
+        elif o == "amd?":                 # AMD only where flops decide (see AMD_MIN_FLOPS); evaluated below
+            maybe_amd = True
         elif o == "natural":
             cands.append(("natural", np.arange(n, dtype=np.int64)))
         else:
             raise ValueError(f"unknown ordering {o!r}")
     best = None
-    for name, order in cands:
-        _, _, struct = _symbolic_structs(S, order)
-        fl = _flops_of(np.array([len(s) for s in struct]))
-        if os.environ.get("SZB_ANALYZE_VERBOSE"):
-            print(f"[analyze] candidate {name}: flops {fl:.4g}, widest column structure {max(len(s) for s in struct)}")
-        if best is None or fl < best[0]:
-            best = (fl, name, order)
+
+    def compete(some):
+        nonlocal best
+        for name, order in some:
+            _, _, struct = _symbolic_structs(S, order)
+            fl = _flops_of(np.array([len(s) for s in struct]))
+            if os.environ.get("SZB_ANALYZE_VERBOSE"):
+                print(f"[analyze] candidate {name}: flops {fl:.4g}, widest column structure "
+                      f"{max(len(s) for s in struct)}")
+            if best is None or fl < best[0]:
+                best = (fl, name, order)
+
+    compete(cands)
+    if maybe_amd and not any(nm == "amd" for nm, _ in cands) and (best is None or best[0] >= AMD_MIN_FLOPS):
+        compete([("amd", expand(oc)) for oc in _order_amd_candidates(Sc, wc)])
     assert best is not None
     _, name, order = best
     return _build(A, rowperm, S, order, relax_frac, relax_small, warp_front_max, n_warps,

@@ -37,6 +37,7 @@
 //     CTA-level chain at the top of the tree is walked by all warps of the CTA in both sweeps.
 //   The sparse structure is never reshaped into a dense contraction; the frontal matrices of the
 //   multifrontal method ARE dense, and their rank-4 updates are what the DMMA path is used for.
+#include <cstdlib>
 #include "szb_lu.cuh"
 
 #include <cstdio>
@@ -811,11 +812,11 @@ __device__ __noinline__ void eliminate_global(const PanelGrp g, double* __restri
       g.sync();
       // ---- phase B, the L-shaped band: tiles (tr, tc) with tr0 <= tr, tc and (tr < tb or tc < tb)
       const bool look = has_next && tr0 < tb;          // the next diagonal block lies inside the band
+      if (look && r0 == cend) next_done = true;        // decided by every warp alike: it guards a group barrier below
       if (look && w == 0) {
         strip_abs<1>(Fm, ltk, lts, p0, nb, r0, ld, tr0, tr0, lane);
         __syncwarp();
         diag_block(Fm, dinv, r0, min(kNB, s - r0), ld, lane, flag);
-        if (r0 == cend) next_done = true;
       } else {
         const int W = look ? nw - 1 : nw, ww = look ? w - 1 : w;
         const int ncC = max(0, min(tb, tcmax + 1) - tr0);               // column tiles inside the block
@@ -1701,8 +1702,14 @@ cudaError_t lu_plan(const LuDev& S, int B, LuLaunchCfg* cfg) {
       cfg->big_elems = static_cast<size_t>(front_elems_blk(S.f_top_max));
       const size_t lts = static_cast<size_t>(lt_stride(S.f_top_max));
       size_t nbo = (static_cast<size_t>(smem_max) / sizeof(double) - kDiagBuf) / lts;
-      nbo = nbo > 32 ? 32 : (nbo & ~static_cast<size_t>(3));
-      if (nbo < 4) return cudaErrorInvalidConfiguration;
+      // whole 8-row tiles per outer block: a block that ends inside a tile (nbo = 28 at f = 950) made only the
+      // diagonal warp skip the barrier that follows the block -- fixed above, and avoided here as well
+      nbo = nbo > 32 ? 32 : (nbo & ~static_cast<size_t>(7));
+      if (const char* cap = getenv("SZB_OUTER_NB")) {   // test hook: the short outer blocks of very large fronts
+        const size_t v = static_cast<size_t>(atoi(cap)) & ~static_cast<size_t>(7);
+        if (v >= 8 && v < nbo) nbo = v;
+      }
+      if (nbo < 8) return cudaErrorInvalidConfiguration;
       cfg->outer_nb = static_cast<int>(nbo);
       fsm = smax(fsm, nbo * lts + kDiagBuf);
     }

@@ -142,6 +142,41 @@ def test_large_fronts_in_global_memory(libszb, tmp_path_factory):
         assert int(sol.stats.nstep[b]) == ref["nstep"]
 
 
+@pytest.mark.parametrize("outer_nb", [8, 24])
+def test_large_fronts_with_short_outer_blocks(libszb, tmp_path_factory, monkeypatch, outer_nb):
+    """Fronts beyond ~1100 rows leave room for fewer than 32 side-panel columns in shared memory, so the outer blocks
+    of the global-memory elimination get shorter (24, 16, 8 pivots).  The SZB_OUTER_NB test hook of lu_plan forces
+    those block lengths on the 40 x 40 lattice: factor + solve against SuperLU.  (The district-heating model at
+    49 612 pipes, front 950, was the first to get a block length below 32 -- 28, not a whole number of 8-row tiles --
+    and found a group barrier that only some warps executed; block lengths are whole tiles since.)"""
+    import torch
+    from solverz_b200 import module_printer
+    from solverz_b200.synthetic import polar_pf_model
+    monkeypatch.setenv("SZB_OUTER_NB", str(outer_nb))
+    d = tmp_path_factory.mktemp(f"mods40nb{outer_nb}")
+    eqs, y0, info = polar_pf_model(40, 40)
+    name = f"pfn40nb{outer_nb}"
+    module_printer(eqs, y0, name, directory=str(d)).render()
+    sys.path.insert(0, str(d))
+    mdl = importlib.import_module(name).mdl
+    orc = _oracle(info)
+    B = 4
+    s = mdl.session(B)
+    assert s.sym.f_top_max > 167
+    rng = np.random.default_rng(11)
+    Y = y0.array[None, :] + 0.05 * rng.standard_normal((B, mdl.n))
+    s.set_y(Y)
+    s.eval_J()
+    rhs = rng.standard_normal((B, mdl.n))
+    s.RHS.copy_(torch.as_tensor(rhs))
+    s.lu_refactor(0.0)
+    assert (s.lu_status().cpu().numpy() == 0).all()
+    X = s.lu_solve(1).cpu().numpy()
+    for b in range(B):
+        xr = sla.spsolve(orc.J(Y[b]), rhs[b])
+        assert np.abs(X[b] - xr).max() <= 1e-10 * np.abs(xr).max()
+
+
 def test_full_size_config2_properties(libszb, tmp_path_factory):
     """BASELINE.json configs[1] at full size (1024 buses, n = 2048, 4096 load scenarios) through properties
     that do not need 4096 oracle solves: every scenario converges; the ORACLE's residual of every GPU

@@ -69,7 +69,9 @@ def fdae_solver(fdae: CudaModel, tspan, y0, opt: Opt = None, **kwargs):
         for nm, (tag, sl) in alias.items():                   # F(t0 + dt, y, p, Y[nt], Y[nt-1], ...)
             s.P[nm].copy_(hist[tag][:, sl])
         s.set_time(t0 + dt)
-        iters, flags = s.newton(opt.ite_tol, 100)             # nr_method(ae, y0, Opt(ite_tol=...)), :108
+        # nr_method(ae, y0, Opt(ite_tol=...)), :108 -- the reference always runs it with its default max_it = 100;
+        # an Opt(max_it=...) below that is honoured here (bounds the time a stagnating scenario can hold the batch)
+        iters, flags = s.newton(opt.ite_tol, min(100, int(getattr(opt, "max_it", 100))))
         it_sum += iters.to(torch.int64)
         ok &= flags == 0
         tt = tt + dt

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--nx", type=int, default=158)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--tol", type=float, default=1e-8, help="Opt.ite_tol (absolute, on max |F|)")
+    ap.add_argument("--max-it", type=int, default=100, help="Newton iterations per time step at most")
     a = ap.parse_args()
     import torch
     from solverz_b200 import Opt, fdae_solver, module_printer
@@ -53,7 +55,7 @@ def main():
     Y0 = torch.as_tensor(np.tile(y0.array, (B, 1))).to(dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    opt = Opt(step_size=dt, ite_tol=1e-8)
+    opt = Opt(step_size=dt, ite_tol=a.tol, max_it=a.max_it)
     opt.trajectory = "last"                              # 61 nodes x B x n doubles would not fit next to the factors
     sol = fdae_solver(mdl, [0, a.steps * dt], Y0, opt)
     torch.cuda.synchronize()
@@ -80,6 +82,7 @@ def main():
             "time_steps_per_s": B * a.steps / wall, "seconds": wall, "newton_iterations": its,
             "iterations_per_step_min_max": [int(np.asarray(st.nsolve).min()), int(np.asarray(st.nsolve).max())],
             "all_converged": bool(np.asarray(st.succeed).all()),
+            "converged_scenarios": int(np.asarray(st.succeed).sum()), "ite_tol": a.tol, "max_it": a.max_it,
             "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "alg_bytes_per_iteration": it_bytes,
                          "achieved": it_bytes * its / wall / 1e9, "frac": it_bytes * its / wall / 1e9 / peak,
                          "note": "whole Newton iteration (F + J + LU refactor + solve + update), algorithmic bytes x "

@@ -452,6 +452,9 @@ def main():
                           "launches": prof[k]["launches"],
                           "ms_per_launch": prof[k]["ms"] / max(1, prof[k]["launches"]),
                           "achieved_gbs": gbs, "frac": gbs / peak}
+    if "lu_refactor" in classes:     # the arithmetic side of the same launches (fp64, DMMA + FMA), for the large fronts
+        classes["lu_refactor"]["fp64_tflops"] = (float(sym.flops) * prof["lu_refactor"]["units"]
+                                                 / (prof["lu_refactor"]["ms"] * 1e-3) / 1e12)
     dom = max(classes, key=lambda k: classes[k]["ms_per_step"]) if classes else None
     roofline = None
     if dom:

@@ -158,7 +158,7 @@ class BatchSession:
         """Per-scenario status of the last refactorisation (device int32[B]; 0 ok, 2 singular / unstable)."""
         L.check(self.lib.szb_lu_status(self.h, C.c_void_p(self.flags.data_ptr()), self._stream()), self.h,
                 "szb_lu_status")
-        return self.flags
+        return self.flags.clone()      # self.flags is also where newton() reports: hand out a snapshot, not the buffer
 
     def slot_rows_cols(self):
         """Row and column of every Jacobian slot as device int32 tensors (CSC order of the frozen pattern)."""

@@ -3,7 +3,11 @@
 dram__bytes_read.sum + dram__bytes_write.sum per launch, tagged with the hash of the kernel sources so that bench.py
 can tell a capture of the current kernels from a stale one.
 
-    python tools/ncu_traffic.py gpurun_out/r2k_factor.ncu-rep lu_refactor 32 4096"""
+    python tools/ncu_traffic.py gpurun_out/r2k_factor.ncu-rep lu_refactor 32 4096
+    python tools/ncu_traffic.py <report> lu_refactor 100 2048 "ncu --metrics dram__bytes_read.sum,... one launch"
+
+(optional fifth argument: how the report was taken, when it was not a --set full capture -- the large workloads are
+captured with the three metrics alone, because every replay pass of --set full saves and restores 40 GB of factors)"""
 import csv
 import io
 import json
@@ -32,7 +36,8 @@ def main():
     d = json.loads(p.read_text()) if p.exists() else {}
     d[f"{cls}@nx{nx}B{B}"] = {"kernel": vals[col["Kernel Name"]], "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd,
                               "dram_bytes_write": wr, "gpu_time_ms": get("gpu__time_duration.sum"),
-                              "source": f"ncu --set full --clock-control none, one launch, report {Path(rep).name}",
+                              "source": (sys.argv[5] if len(sys.argv) > 5 else "ncu --set full --clock-control none, one launch")
+                              + f", report {Path(rep).name}",
                               "source_sha": bench.kernel_source_sha()}
     p.write_text(json.dumps(d, indent=1))
     print(d[f"{cls}@nx{nx}B{B}"])

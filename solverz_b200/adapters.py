@@ -30,8 +30,14 @@ multi-argument products of FROZEN matrices (``Mat_Mul(A, Mat_Mul(B, x))``, ``Mat
 formed once on the host -- 2-D parameters are immutable in the reference too), and ``Diag(v)`` factors on either
 side of one matrix (``Mat_Mul(Diag(u), A, Diag(v), x) = u * (A @ (v * x))``).  A matrix applied to a vector that
 itself depends NON-linearly on another matrix product is rejected with ``NotImplementedError``.  ``Ones(n)``
-broadcasts (``functions.py:726-749``) and becomes the scalar 1 of the row template.  Triggerable parameters
-(``param.py:16``) are host callbacks evaluated between calls; they are rejected.
+broadcasts (``functions.py:726-749``) and becomes the scalar 1 of the row template.
+
+Triggerable parameters (``param.py:16-59``: ``Param(..., triggerable=True, trigger_var=[...], trigger_fun=f)``): the
+reference's generated ``F_`` / ``J_`` overwrite the parameter with ``f(trigger variables)`` at every call
+(``code_printer/python/utilities.py:118-129``), and the Jacobian treats it as a parameter (no derivative through
+``f``).  Here the parameter is replaced, inside the expressions, by ``frozen(f(...))`` -- a function whose value is its
+argument and whose derivative is zero -- when ``f`` can be written symbolically: a numpy ufunc of the table below, or
+any callable that accepts symbols (``lambda x: 2 * x + 1``).  Opaque host callbacks are rejected with a message.
 """
 from __future__ import annotations
 
@@ -45,7 +51,64 @@ from . import sym as S
 from .equations import AE, DAE, FDAE, Eqn, Equations, LoopEqn, LoopOde, Ode
 from .variables import Vars
 
-__all__ = ["from_solverz", "is_solverz_object"]
+__all__ = ["from_solverz", "is_solverz_object", "frozen"]
+
+
+class frozen(sp.Function):
+    """``frozen(e)`` has the value of ``e`` and no derivative: how a triggerable parameter ``p = f(vars)`` of the
+    reference enters F (its current value) and J (a constant)."""
+    nargs = 1
+    is_real = True
+
+    def fdiff(self, argindex=1):
+        return sp.Integer(0)
+
+    def _eval_derivative(self, s):
+        return sp.Integer(0)
+
+    def _cudacode(self, printer):
+        return f"({printer._print(self.args[0])})"
+
+
+# numpy ufuncs a trigger_fun may be (called on symbols they raise); anything else is tried on the symbols directly
+_TRIGGER_UFUNCS = {"sin": sp.sin, "cos": sp.cos, "tan": sp.tan, "exp": sp.exp, "log": sp.log, "sqrt": sp.sqrt,
+                   "absolute": sp.Abs, "fabs": sp.Abs, "sign": S.Sign, "tanh": sp.tanh, "sinh": sp.sinh,
+                   "cosh": sp.cosh, "arctan": sp.atan, "arctan2": sp.atan2, "square": lambda x: x ** 2,
+                   "negative": lambda x: -x, "reciprocal": lambda x: 1 / x}
+
+
+def _trigger_expression(name: str, p, variables: Dict[str, S.Var]):
+    """The symbolic form of ``p.trigger_fun(*trigger variables)`` over this backend's variable symbols."""
+    tv = list(p.trigger_var or [])
+    fun = p.trigger_fun
+    if not tv or fun is None:
+        raise ValueError(f"parameter {name}: triggerable=True needs trigger_var and trigger_fun")
+    missing = [v for v in tv if v not in variables]
+    if missing:
+        raise NotImplementedError(f"parameter {name}: trigger_var {missing} are not variables of the model "
+                                  f"(parameters as trigger inputs are not lowered)")
+    args = [variables[v].sym for v in tv]
+    lens = {variables[v].size for v in tv if variables[v].size != 1}
+    size = int(np.size(p.v)) if p.v is not None else None
+    if size is not None and size != 1 and lens and lens != {size}:
+        raise NotImplementedError(f"parameter {name}: trigger variables of length {sorted(lens)} for a parameter of "
+                                  f"length {size}; only elementwise trigger functions are lowered")
+    uf = getattr(fun, "__name__", "") if isinstance(fun, np.ufunc) else None
+    if uf is not None:
+        if uf not in _TRIGGER_UFUNCS:
+            raise NotImplementedError(f"parameter {name}: numpy ufunc {uf} has no symbolic counterpart here")
+        return _TRIGGER_UFUNCS[uf](*args)
+    try:
+        e = fun(*args)
+    except Exception as ex:
+        raise NotImplementedError(f"parameter {name}: trigger_fun {getattr(fun, '__name__', fun)!r} is an opaque host "
+                                  f"callback ({type(ex).__name__} when called on symbols); the device cannot call "
+                                  f"it.  Write it with operators / solverz_b200 functions, or update mdl.p[{name!r}] "
+                                  f"between solves instead") from None
+    try:
+        return sp.sympify(e)
+    except Exception:
+        raise NotImplementedError(f"parameter {name}: trigger_fun returned {type(e).__name__}, not an expression")
 
 _MATRIX_HELPER_SUFFIXES = ("_data", "_indices", "_indptr", "_shape0")
 
@@ -67,10 +130,11 @@ def is_solverz_object(obj) -> bool:
 
 
 class _Translator:
-    def __init__(self, variables: Dict[str, S.Var], params: Dict[str, S.Param], eq_name: str):
+    def __init__(self, variables: Dict[str, S.Var], params: Dict[str, S.Param], eq_name: str, triggered=None):
         self.vars = variables
         self.params = params
         self.eq = eq_name
+        self.triggered = triggered or {}        # name -> symbolic f(trigger variables)
         self._counter = 0
 
     # ---- leaves -------------------------------------------------------------------------------
@@ -107,12 +171,17 @@ class _Translator:
         if isinstance(e, (sp.Number, sp.NumberSymbol)):
             return e
         if cname in ("iVar", "Para", "iAliasVar", "idx"):
+            if e.name in self.triggered:
+                return frozen(self.triggered[e.name])
             b = self._base(e.name)
             if isinstance(b, S.Param) and b.dim == 2:
                 raise NotImplementedError(f"{self.eq}: the 2-D parameter {e.name} may only appear as a factor of "
                                           f"Mat_Mul")
             return b.sym
         if cname in ("IdxVar", "IdxPara", "IdxAliasVar", "Idxidx"):
+            if e.name0 in self.triggered:
+                raise NotImplementedError(f"{self.eq}: the triggerable parameter {e.name0} is used with an index; only "
+                                          f"whole-parameter uses are lowered")
             return self._base(e.name0)[self._plain_index(e.index)]
         if isinstance(e, sp.Symbol):
             if e.name == "t":
@@ -267,9 +336,6 @@ class _Translator:
 
 
 def _param_from_reference(name: str, p, per_scenario: bool = False) -> S.Param:
-    if getattr(p, "triggerable", False):
-        raise NotImplementedError(f"parameter {name}: triggerable parameters (equation/param.py:16) are host "
-                                  f"callbacks evaluated between calls; update mdl.p[...] between solves instead")
     cname = type(p).__name__
     dim = int(getattr(p, "dim", 1))
     if cname == "TimeSeriesParam":
@@ -316,7 +382,11 @@ def from_solverz(eqs, y0, per_scenario=()) -> Tuple[Equations, Vars]:
         variables[nm] = S.Var(nm, np.asarray(y0[nm], dtype=float))
     # parameters
     params: Dict[str, S.Param] = {}
+    triggered: Dict[str, sp.Expr] = {}
     for nm, p in eqs.PARAM.items():
+        if getattr(p, "triggerable", False):
+            triggered[nm] = _trigger_expression(nm, p, variables)
+            continue
         helper = next((nm[:-len(sfx)] for sfx in _MATRIX_HELPER_SUFFIXES if nm.endswith(sfx)), None)
         if helper is not None and helper in eqs.PARAM and int(getattr(eqs.PARAM[helper], "dim", 1)) == 2:
             continue
@@ -325,9 +395,12 @@ def from_solverz(eqs, y0, per_scenario=()) -> Tuple[Equations, Vars]:
     # equations
     eqns: List[Eqn] = []
     for nm, e in eqs.EQNs.items():
-        tr = _Translator(variables, params, nm)
+        tr = _Translator(variables, params, nm, triggered)
         cname = type(e).__name__
         if cname in ("LoopEqn", "LoopOde"):
+            used = [k for k in e.var_map if k in triggered]
+            if used:
+                raise NotImplementedError(f"equation {nm}: triggerable parameters {used} inside a loop body")
             for vm_name, obj in e.var_map.items():           # Set parameters that only the body rewriter registered
                 if vm_name not in variables and vm_name not in params:
                     mine = _param_from_reference(vm_name, obj)

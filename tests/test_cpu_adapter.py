@@ -187,15 +187,50 @@ def test_module_printer_accepts_reference_objects(tmp_path):
     assert st["n"] == 2 and st["nnz_j"] == 4 and (Path(pkg) / st["so"]).exists()
 
 
+def test_triggerable_parameters(tmp_path):
+    """Param(triggerable=True, trigger_var, trigger_fun) (equation/param.py:16-59): the reference's generated F_ / J_
+    overwrite the parameter with trigger_fun(variables) at every call and differentiate as if it were a constant
+    (module test expectations: code_printer/python/module/test/test_module_printer.py:20-60).  The adapter writes
+    it as frozen(f(vars)): same F, same J."""
+    SZ = _SZ()
+    from solverz_b200.adapters import from_solverz, frozen
+    import sympy as sp
+    m = SZ.Model()
+    m.x = SZ.Var('x', [0.3, -0.7, 1.1])
+    m.y = SZ.Var('y', [1.0, 2.0, -0.5])
+    m.ax = SZ.Param('ax', [0.0, 0.0, 0.0], triggerable=True, trigger_var=['x'], trigger_fun=np.sin)
+    m.bq = SZ.Param('bq', [0.0, 0.0, 0.0], triggerable=True, trigger_var=['x', 'y'],
+                    trigger_fun=lambda x, y: 2 * x * y + 1)
+    m.c = SZ.Param('c', [0.5, 1.5, 2.5])
+    m.e1 = SZ.Eqn('e1', m.ax * m.y + m.x ** 2 - m.c)
+    m.e2 = SZ.Eqn('e2', m.y * m.bq - SZ.exp(m.x) * m.ax + m.c * m.y)
+    spf, y0 = m.create_instance()
+    ref = SZ.made_numerical(spf, y0, sparse=True)
+    mine, y = from_solverz(spf, y0)
+    assert "ax" not in mine.PARAM and "bq" not in mine.PARAM and "c" in mine.PARAM
+    x = sp.Symbol('x')
+    assert sp.diff(frozen(sp.sin(x)) * x, x) == frozen(sp.sin(x))
+    rng = np.random.default_rng(8)
+    pts = [(None, y0.array)] + [(None, y0.array + 0.3 * rng.standard_normal(6)) for _ in range(3)]
+    _compare(ref, mine, "ad_trig", tmp_path, pts)
+
+
 def test_rejections():
     SZ = _SZ()
     from solverz_b200.adapters import from_solverz
     m = SZ.Model()
     m.x = SZ.Var('x', [1.0, 2.0])
-    m.p = SZ.Param('p', [1.0, 1.0], triggerable=True, trigger_var='x', trigger_fun=lambda x: x)
+    m.p = SZ.Param('p', [1.0, 1.0], triggerable=True, trigger_var='x', trigger_fun=lambda x: np.where(x > 0, x, 0.0))
     m.e = SZ.Eqn('e', m.x - m.p)
     spf, y0 = m.create_instance()
-    with pytest.raises(NotImplementedError, match="triggerable"):
+    with pytest.raises(NotImplementedError, match="opaque host callback|not an expression"):
         from_solverz(spf, y0)
+    m2 = SZ.Model()
+    m2.x = SZ.Var('x', [1.0, 2.0])
+    m2.p = SZ.Param('p', [1.0, 1.0], triggerable=True, trigger_var='x', trigger_fun=np.sin)
+    m2.e = SZ.Eqn('e', m2.x - m2.p[0:1] * 2)
+    spf2, y02 = m2.create_instance()
+    with pytest.raises(NotImplementedError, match="used with an index"):
+        from_solverz(spf2, y02)
     with pytest.raises(TypeError):
         from_solverz(object(), None)

@@ -93,3 +93,30 @@ def test_dae_same_model_object_rodas(libszb):
     assert s2.stats.nstep == s1.stats.nstep and s2.stats.nreject == s1.stats.nreject
     np.testing.assert_allclose(s2.T, s1.T, rtol=1e-10)
     assert np.abs(np.asarray(s2.Y) - s1.Y.array).max() < 1e-8
+
+
+def test_triggerable_parameter_on_the_device(libszb, tmp_path):
+    """Param(triggerable=True) (equation/param.py:16-59) lowered as frozen(f(vars)): F, J on the device and the whole
+    Newton iteration (which sees a Jacobian WITHOUT the derivative through f, like the reference's) against the
+    reference's made_numerical + nr_method: same solution, same iteration count."""
+    import Solverz as SZ
+    import solverz_b200 as SB
+    m = SZ.Model()
+    m.x = SZ.Var('x', [0.3, 0.7, 1.1])
+    m.y = SZ.Var('y', [1.0, 2.0, 0.5])
+    m.ax = SZ.Param('ax', [0.0, 0.0, 0.0], triggerable=True, trigger_var=['x'], trigger_fun=np.sin)
+    m.c = SZ.Param('c', [0.5, 1.5, 2.5])
+    m.e1 = SZ.Eqn('e1', 0.1 * m.ax * m.y + 2 * m.x - m.c)
+    m.e2 = SZ.Eqn('e2', 3 * m.y - 0.2 * m.ax + m.x * m.y - m.c)
+    spf, y0 = m.create_instance()
+    ref = SZ.made_numerical(spf, y0, sparse=True)
+    dev = SB.made_numerical(spf, y0, sparse=True)
+    yp = y0.array + 0.1 * np.random.default_rng(2).standard_normal(6)
+    Fr, Jr = np.asarray(ref.F(yp, ref.p)).copy(), sps.csc_matrix(ref.J(yp, ref.p))
+    Fd, Jd = dev.F(yp, dev.p), sps.csc_matrix(dev.J(yp, dev.p))
+    assert np.abs(Fd - Fr).max() <= 1e-13 and abs(Jd - Jr).max() <= 1e-13
+    rs = SZ.nr_method(ref, y0, SZ.Opt(ite_tol=1e-10))
+    ds = SB.nr_method(dev, y0.array, SB.Opt(ite_tol=1e-10))
+    assert bool(rs.stats.succeed) and bool(np.all(ds.stats.succeed))
+    np.testing.assert_allclose(np.asarray(ds.y).ravel(), rs.y.array, rtol=0, atol=1e-12)
+    assert int(np.asarray(ds.stats.nstep).ravel()[0]) == int(rs.stats.nstep)

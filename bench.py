@@ -465,6 +465,9 @@ def main():
                     "frac": classes[dom]["frac"], "traffic": _ncu_traffic(dom, nx, B)[0],
                     "traffic_source": _ncu_traffic(dom, nx, B)[1], "peak_source": peak_kind,
                     "alg_bytes_per_launch": alg[dom] * units_per_launch, "classes": classes}
+        if roofline["traffic"]:      # what the launch really moved through DRAM (ncu), as bandwidth and share of the peak
+            roofline["traffic_gbs"] = roofline["traffic"] / (classes[dom]["ms_per_launch"] * 1e-3) / 1e9
+            roofline["traffic_frac"] = roofline["traffic_gbs"] / peak
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,

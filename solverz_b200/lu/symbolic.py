@@ -436,6 +436,74 @@ def _symbolic_structs(S: sp.csr_matrix, order: np.ndarray):
     return parent, children, struct
 
 
+def _col_counts_py(n, indptr, indices):
+    """len(struct[j]) of ``_symbolic_structs`` for the already permuted pattern (CSC, sorted), without the Python
+    sets: the structures live in one append-only pool, a marker array removes duplicates.  O(nnz(L)); used to rank
+    the ordering candidates, where only the counts matter."""
+    cnt = np.zeros(n, np.int64)
+    mark = np.full(n, -1, np.int64)
+    head = np.full(n, -1, np.int64)          # children of j as a linked list
+    nxt = np.full(n, -1, np.int64)
+    s0 = np.zeros(n, np.int64)
+    s1 = np.zeros(n, np.int64)
+    pool = np.empty(max(4 * len(indices), 1024), np.int64)
+    top = 0
+    for j in range(n):
+        start = top
+        mark[j] = j
+        mn = n
+        need = indptr[j + 1] - indptr[j]
+        c = head[j]
+        while c >= 0:
+            need += s1[c] - s0[c]
+            c = nxt[c]
+        if top + need > len(pool):
+            grown = np.empty(max(2 * len(pool), top + need), np.int64)
+            grown[:top] = pool[:top]
+            pool = grown
+        for k in range(indptr[j], indptr[j + 1]):
+            i = indices[k]
+            if i > j and mark[i] != j:
+                mark[i] = j
+                pool[top] = i
+                top += 1
+                if i < mn:
+                    mn = i
+        c = head[j]
+        while c >= 0:
+            for q in range(s0[c], s1[c]):
+                i = pool[q]
+                if mark[i] != j:
+                    mark[i] = j
+                    pool[top] = i
+                    top += 1
+                    if i < mn:
+                        mn = i
+            c = nxt[c]
+        s0[j] = start
+        s1[j] = top
+        cnt[j] = top - start
+        if top > start:
+            nxt[j] = head[mn]
+            head[mn] = j
+    return cnt
+
+
+try:  # pragma: no cover - exercised wherever numba is installed
+    import numba as _nb
+
+    _col_counts = _nb.njit(cache=True)(_col_counts_py)
+except Exception:  # pragma: no cover
+    _col_counts = _col_counts_py
+
+
+def _struct_sizes(S: sp.csr_matrix, order: np.ndarray) -> np.ndarray:
+    """Column counts of the factor of pattern(S) under ``order`` (same numbers as ``_symbolic_structs``)."""
+    Sp = S[order][:, order].tocsc()
+    Sp.sort_indices()
+    return _col_counts(S.shape[0], Sp.indptr.astype(np.int64), Sp.indices.astype(np.int64))
+
+
 def _postorder(parent: np.ndarray, children: List[List[int]], key) -> np.ndarray:
     n = len(parent)
     post = []
@@ -882,11 +950,10 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
     def compete(some):
         nonlocal best
         for name, order in some:
-            _, _, struct = _symbolic_structs(S, order)
-            fl = _flops_of(np.array([len(s) for s in struct]))
+            sizes = _struct_sizes(S, order)
+            fl = _flops_of(sizes)
             if os.environ.get("SZB_ANALYZE_VERBOSE"):
-                print(f"[analyze] candidate {name}: flops {fl:.4g}, widest column structure "
-                      f"{max(len(s) for s in struct)}")
+                print(f"[analyze] candidate {name}: flops {fl:.4g}, widest column structure {int(sizes.max())}")
             if best is None or fl < best[0]:
                 best = (fl, name, order)
 

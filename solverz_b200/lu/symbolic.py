@@ -43,6 +43,7 @@ MMD_SUPERLU_MAX = 25000
 # start (4.8e8 flops); cfg#2 (5.2e6 flops) 10.42 -> 10.78 ms although AMD has 12.6 % fewer flops -- at that size the
 # kernel time is assembly and write-out of many small fronts, and AMD's top fronts are larger (154 against 128)
 AMD_MIN_FLOPS = 5.0e7
+ND_MAX = 30000
 
 
 # --------------------------------------------------------------------------------------
@@ -931,7 +932,11 @@ def analyze(A: sp.spmatrix, *, relax_frac: float = 0.3, relax_small: int = 4,
     maybe_amd = False
     for o in orderings:
         if o == "nd":
-            cands.append(("nd", expand(_nested_dissection(adjc, wc))))
+            # the BFS dissection is interpreted Python (18 s at 173 800 vertices) and has not won on any pattern of
+            # that size (2x the flops of AMD on the district-heating graphs): above ND_MAX it only runs when it is
+            # the sole candidate asked for
+            if nc <= ND_MAX or all(x == "nd" for x in orderings):
+                cands.append(("nd", expand(_nested_dissection(adjc, wc))))
         elif o == "mmd" and nc <= MMD_SUPERLU_MAX:
             try:
                 cands.append(("mmd", expand(_order_mmd_superlu(Sc))))

@@ -106,3 +106,34 @@ def test_analysis_takes_the_amd_candidates_on_request_and_factorises_correctly()
     A.sort_indices()
     x = E.solve(sym, E.factor(sym, A.data), b)
     np.testing.assert_allclose(x, np.linalg.solve(A.toarray(), b), rtol=1e-10, atol=1e-12)
+
+
+def test_large_pattern_is_analysed_without_superlu_or_python_dissection():
+    """Above MMD_SUPERLU_MAX / ND_MAX vertices the analysis must not detour through SuperLU's numeric factorisation
+    (54 minutes at n = 173 800 before lu/amd.py) nor through the interpreted BFS dissection: a 182 x 182 lattice
+    (33 124 unknowns) is analysed by the AMD candidates alone, in seconds, and the schedule it yields is consistent."""
+    import time
+    from solverz_b200.lu import symbolic as SY
+    nx = 182
+    n = nx * nx
+    idx = np.arange(n).reshape(nx, nx)
+    S = _sym(n, np.concatenate([idx[:, :-1].ravel(), idx[:-1, :].ravel()]),
+             np.concatenate([idx[:, 1:].ravel(), idx[1:, :].ravel()]))
+    rng = np.random.default_rng(9)
+    A = (S.multiply(sp.csr_matrix((rng.uniform(-1, 1, S.nnz), S.indices, S.indptr), shape=S.shape))
+         + sp.diags(rng.uniform(4, 5, n))).tocsc()
+    assert n > SY.MMD_SUPERLU_MAX and n > SY.ND_MAX
+    called = []
+    orig_mmd, orig_nd = SY._order_mmd_superlu, SY._nested_dissection
+    SY._order_mmd_superlu = lambda *a, **k: called.append("mmd") or orig_mmd(*a, **k)
+    SY._nested_dissection = lambda *a, **k: called.append("nd") or orig_nd(*a, **k)
+    try:
+        t0 = time.perf_counter()
+        sym = SY.analyze(A)
+        dt = time.perf_counter() - t0
+    finally:
+        SY._order_mmd_superlu, SY._nested_dissection = orig_mmd, orig_nd
+    assert called == [] and sym.ordering == "amd"
+    assert dt < 120.0, dt
+    assert sorted(sym.colp.tolist()) == list(range(n)) and sorted(sym.rowp.tolist()) == list(range(n))
+    assert int(sym.sn_s.sum()) == n and sym.nnz_lu < 40 * A.nnz
